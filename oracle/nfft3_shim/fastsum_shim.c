@@ -1,0 +1,743 @@
+/* ORACLE (test infrastructure, not product code).
+ *
+ * CPU restatement (C + OpenMP, self-contained radix-2 FFT instead of FFTW3) of
+ * the NFFT3 `fastsum` entry points the reference calls from
+ * SRC/external/nfft_interface.c (plan build :223-254 / :359-390, execute :426 and
+ * :533-534, teardown :56-59, :93-98, :110-113).  NFFT3 is an external, un-pinned
+ * dependency that is absent from /root/reference and cannot be installed here
+ * (no network): PARITY UNPINNED at this boundary.  What is restated is the
+ * published algorithm, with the parameters the reference fixes
+ * (nfft_interface.c:18-27): expansion degree N=32, oversampled FFT length 64,
+ * window cut-off m=4, eps_I=eps_B=0 (no near field, no boundary regularisation),
+ * NFFT3's default Kaiser-Bessel window with PRE_PHI_HUT | PRE_PSI.
+ *
+ *   fastsum_trafo:   f(y_i) = sum_k b_k * ( sum_j alpha_j e^{+2 pi i k x_j} ) e^{-2 pi i k y_i}
+ *     1. adjoint NFFT  : g[l] += alpha_j * prod_t psi_t(x_j - l_t/n_os)   over (2m+2)^d taps
+ *                        g_hat = unnormalised DFT with e^{+...};  f_hat_k = g_hat_k / prod phi_hat(k_t)
+ *     2. f_hat_k *= b_k,  b = fftshift(FFT_forward(fftshift(K(min(|j/N - 1/2|, 1/2)) / N^d)))
+ *     3. NFFT trafo    : g_hat_k = f_hat_k / prod phi_hat(k_t) zero-padded; g = DFT with e^{-...};
+ *                        f_i = sum_taps g[l] * prod_t psi_t(y_i - l_t/n_os)
+ * 
+ */
+#include "fastsum.h"
+#include "kernels.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846264338327950288
+#endif
+
+/* ------------------------------------------------------------------ */
+/* allocation (nfft3.h)                                                */
+/* ------------------------------------------------------------------ */
+void *nfft_malloc(size_t n)
+{
+   void *p = NULL;
+   if (n == 0)
+      n = 1;
+   if (posix_memalign(&p, 64, n) != 0 || p == NULL)
+   {
+      fprintf(stderr, "oracle shim: nfft_malloc(%zu) failed\n", n);
+      exit(EXIT_FAILURE);
+   }
+   return p;
+}
+
+void nfft_free(void *p) { free(p); }
+
+/* ------------------------------------------------------------------ */
+/* radial kernels (kernels.h); only der == 0 is evaluated when          */
+/* eps_I == eps_B == 0                                                  */
+/* ------------------------------------------------------------------ */
+static void shim_der_guard(int der, const char *name)
+{
+   if (der != 0)
+   {
+      fprintf(stderr, "oracle shim: %s derivative order %d not restated (eps_I = eps_B = 0 never needs it)\n", name, der);
+      exit(EXIT_FAILURE);
+   }
+}
+
+C gaussian(R x, int der, const R *param)
+{
+   R c = param[0];
+   shim_der_guard(der, "gaussian");
+   return exp(-x * x / (c * c));
+}
+
+C xx_gaussian(R x, int der, const R *param)
+{
+   R c = param[0];
+   shim_der_guard(der, "xx_gaussian");
+   return x * x / (c * c) * exp(-x * x / (c * c));
+}
+
+C laplacian_rbf(R x, int der, const R *param)
+{
+   R c = param[0];
+   shim_der_guard(der, "laplacian_rbf");
+   return exp(-fabs(x) / c);
+}
+
+C der_laplacian_rbf(R x, int der, const R *param)
+{
+   R c = param[0];
+   shim_der_guard(der, "der_laplacian_rbf");
+   return fabs(x) / c * exp(-fabs(x) / c);
+}
+
+/* ------------------------------------------------------------------ */
+/* Kaiser-Bessel window, sigma = n_os / N = 2, b = pi (2 - 1/sigma)     */
+/* ------------------------------------------------------------------ */
+static R shim_kb_b(void) { return M_PI * (2.0 - 1.0 / 2.0); }
+
+/* modified Bessel function I0 by its power series: all terms positive, so
+ * the sum is accurate to a few ulp for the arguments met here (<= 19). */
+static R shim_bessel_i0(R x)
+{
+   R q = 0.25 * x * x;
+   R term = 1.0, sum = 1.0;
+   int k;
+   for (k = 1; k < 500; k++)
+   {
+      term *= q / ((R)k * (R)k);
+      sum += term;
+      if (term < 1e-20 * sum)
+         break;
+   }
+   return sum;
+}
+
+R shim_kb_phi(R x, int n_os, int m)
+{
+   R b = shim_kb_b();
+   R t = x * (R)n_os;
+   R d2 = (R)m * (R)m - t * t;
+   if (d2 > 0.0)
+   {
+      R s = sqrt(d2);
+      return sinh(b * s) / (M_PI * s);
+   }
+   else if (d2 < 0.0)
+   {
+      R s = sqrt(-d2);
+      return sin(b * s) / (M_PI * s);
+   }
+   return b / M_PI;
+}
+
+R shim_kb_phi_hut(int k, int n_os, int m)
+{
+   R b = shim_kb_b();
+   R w = 2.0 * M_PI * (R)k / (R)n_os;
+   return shim_bessel_i0((R)m * sqrt(b * b - w * w));
+}
+
+/* ------------------------------------------------------------------ */
+/* self-contained power-of-two FFT                                      */
+/* ------------------------------------------------------------------ */
+static int shim_ilog2(int n)
+{
+   int l = 0;
+   while ((1 << l) < n)
+      l++;
+   if ((1 << l) != n)
+   {
+      fprintf(stderr, "oracle shim: FFT length %d is not a power of two\n", n);
+      exit(EXIT_FAILURE);
+   }
+   return l;
+}
+
+/* w[j] = exp(sign * 2 pi i j / n), j < n/2, evaluated in long double */
+static void shim_twiddles(C *w, int n, int sign)
+{
+   int j;
+   for (j = 0; j < n / 2; j++)
+   {
+      long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n;
+      w[j] = (R)cosl(a) + I * (R)(sign * sinl(a));
+   }
+}
+
+static void shim_fft1(C *a, int n, int logn, const C *w)
+{
+   int i, j, len;
+   /* bit reversal */
+   for (i = 1, j = 0; i < n; i++)
+   {
+      int bit = n >> 1;
+      for (; j & bit; bit >>= 1)
+         j ^= bit;
+      j ^= bit;
+      if (i < j)
+      {
+         C t = a[i];
+         a[i] = a[j];
+         a[j] = t;
+      }
+   }
+   (void)logn;
+   for (len = 2; len <= n; len <<= 1)
+   {
+      int half = len >> 1, step = n / len;
+      for (i = 0; i < n; i += len)
+      {
+         for (j = 0; j < half; j++)
+         {
+            C u = a[i + j];
+            C v = a[i + j + half] * w[j * step];
+            a[i + j] = u + v;
+            a[i + j + half] = u - v;
+         }
+      }
+   }
+}
+
+/* in-place d-dimensional unnormalised DFT of an n^d row-major array
+ * (last index fastest); sign = -1: e^{-2 pi i ...} (FFTW_FORWARD), +1: FFTW_BACKWARD */
+void shim_fft_nd(C *data, int d, int n, int sign)
+{
+   int logn = shim_ilog2(n);
+   size_t total = 1;
+   int t;
+   C *w = (C *)nfft_malloc(sizeof(C) * (size_t)(n / 2 + 1));
+   shim_twiddles(w, n, sign);
+   for (t = 0; t < d; t++)
+      total *= (size_t)n;
+   for (t = 0; t < d; t++)
+   {
+      size_t stride = 1, npencil = total / (size_t)n;
+      int u;
+      long long pidx;
+      for (u = t + 1; u < d; u++)
+         stride *= (size_t)n;
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+      {
+         C *buf = (C *)nfft_malloc(sizeof(C) * (size_t)n);
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+         for (pidx = 0; pidx < (long long)npencil; pidx++)
+         {
+            size_t hi = (size_t)pidx / stride, lo = (size_t)pidx % stride;
+            size_t base = hi * stride * (size_t)n + lo;
+            int i;
+            for (i = 0; i < n; i++)
+               buf[i] = data[base + (size_t)i * stride];
+            shim_fft1(buf, n, logn, w);
+            for (i = 0; i < n; i++)
+               data[base + (size_t)i * stride] = buf[i];
+         }
+         nfft_free(buf);
+      }
+   }
+   nfft_free(w);
+}
+
+/* fftshift of an n^d array with even n: swap halves along every dimension */
+static void shim_fftshift_nd(C *data, int d, int n)
+{
+   size_t total = 1, idx;
+   int t;
+   C *tmp;
+   for (t = 0; t < d; t++)
+      total *= (size_t)n;
+   tmp = (C *)nfft_malloc(sizeof(C) * total);
+   for (idx = 0; idx < total; idx++)
+   {
+      size_t rem = idx, dst = 0, mul = 1;
+      for (t = d - 1; t >= 0; t--)
+      {
+         int c = (int)(rem % (size_t)n);
+         rem /= (size_t)n;
+         c = (c + n / 2) % n;
+         dst += (size_t)c * mul;
+         mul *= (size_t)n;
+      }
+      tmp[dst] = data[idx];
+   }
+   memcpy(data, tmp, sizeof(C) * total);
+   nfft_free(tmp);
+}
+
+/* ------------------------------------------------------------------ */
+/* plan life cycle                                                      */
+/* ------------------------------------------------------------------ */
+static size_t shim_ipow(int n, int d)
+{
+   size_t r = 1;
+   int t;
+   for (t = 0; t < d; t++)
+      r *= (size_t)n;
+   return r;
+}
+
+void fastsum_init_guru_kernel(fastsum_plan *ths, int d, kernel k, R *param,
+                              unsigned flags, int nn, int p, R eps_I, R eps_B)
+{
+   if (eps_I != 0.0 || eps_B != 0.0)
+   {
+      fprintf(stderr, "oracle shim: only eps_I = eps_B = 0 is restated (reference: nfft_interface.c:21,228)\n");
+      exit(EXIT_FAILURE);
+   }
+   if (d < 1 || d > 4)
+   {
+      fprintf(stderr, "oracle shim: dimension %d not supported\n", d);
+      exit(EXIT_FAILURE);
+   }
+   memset(ths, 0, sizeof(*ths));
+   ths->d = d;
+   ths->k = k;
+   ths->kernel_param = param;
+   ths->flags = flags;
+   ths->n = nn;
+   ths->p = p;
+   ths->eps_I = eps_I;
+   ths->eps_B = eps_B;
+   ths->b = (C *)nfft_malloc(sizeof(C) * shim_ipow(nn, d));
+   ths->f_hat = (C *)nfft_malloc(sizeof(C) * shim_ipow(nn, d));
+   ths->b_ready = 0;
+   ths->g = NULL;
+}
+
+static void shim_nodes_free(shim_nfft_nodes *nd)
+{
+   if (nd->psi)
+      nfft_free(nd->psi);
+   if (nd->cell)
+      nfft_free(nd->cell);
+   nd->psi = NULL;
+   nd->cell = NULL;
+   nd->M = 0;
+   nd->ready = 0;
+}
+
+static void shim_ensure_grid(fastsum_plan *ths, int n_os)
+{
+   if (ths->g == NULL)
+      ths->g = (C *)nfft_malloc(sizeof(C) * shim_ipow(n_os, ths->d));
+}
+
+void fastsum_init_guru_source_nodes(fastsum_plan *ths, int N_total, int nn_oversampled, int m)
+{
+   ths->N_total = N_total;
+   ths->x = (R *)nfft_malloc(sizeof(R) * (size_t)ths->d * (size_t)N_total);
+   ths->alpha = (C *)nfft_malloc(sizeof(C) * (size_t)N_total);
+   ths->n_os_src = nn_oversampled;
+   ths->m_src = m;
+   memset(&ths->src, 0, sizeof(ths->src));
+   shim_ensure_grid(ths, nn_oversampled);
+}
+
+void fastsum_init_guru_target_nodes(fastsum_plan *ths, int M_total, int nn_oversampled, int m)
+{
+   ths->M_total = M_total;
+   ths->y = (R *)nfft_malloc(sizeof(R) * (size_t)ths->d * (size_t)M_total);
+   ths->f = (C *)nfft_malloc(sizeof(C) * (size_t)M_total);
+   ths->n_os_tgt = nn_oversampled;
+   ths->m_tgt = m;
+   memset(&ths->tgt, 0, sizeof(ths->tgt));
+   shim_ensure_grid(ths, nn_oversampled);
+}
+
+void fastsum_finalize_source_nodes(fastsum_plan *ths)
+{
+   if (ths->x)
+      nfft_free(ths->x);
+   if (ths->alpha)
+      nfft_free(ths->alpha);
+   ths->x = NULL;
+   ths->alpha = NULL;
+   shim_nodes_free(&ths->src);
+}
+
+void fastsum_finalize_target_nodes(fastsum_plan *ths)
+{
+   if (ths->y)
+      nfft_free(ths->y);
+   if (ths->f)
+      nfft_free(ths->f);
+   ths->y = NULL;
+   ths->f = NULL;
+   shim_nodes_free(&ths->tgt);
+}
+
+void fastsum_finalize_kernel(fastsum_plan *ths)
+{
+   if (ths->b)
+      nfft_free(ths->b);
+   if (ths->f_hat)
+      nfft_free(ths->f_hat);
+   if (ths->g)
+      nfft_free(ths->g);
+   ths->b = NULL;
+   ths->f_hat = NULL;
+   ths->g = NULL;
+}
+
+/* Fourier coefficients of the (un-regularised, eps = 0) kernel:
+ * B[j] = K(min(||j/N - 1/2||, 1/2)) / N^d on the N^d grid, then
+ * b = fftshift(FFT_forward(fftshift(B))).   */
+void fastsum_precompute_kernel(fastsum_plan *ths)
+{
+   int d = ths->d, n = ths->n, t;
+   size_t total = shim_ipow(n, d);
+   long long j;
+#ifdef _OPENMP
+#pragma omp parallel for private(t) schedule(static)
+#endif
+   for (j = 0; j < (long long)total; j++)
+   {
+      if (d == 1)
+      {
+         R xx = -((R)j / (R)n - 0.5);
+         if (xx < -0.5)
+            xx = -0.5;
+         if (xx > 0.5)
+            xx = 0.5;
+         ths->b[j] = ths->k(xx, 0, ths->kernel_param) / (R)total;
+      }
+      else
+      {
+         size_t kk = (size_t)j;
+         R r2 = 0.0, r;
+         for (t = 0; t < d; t++)
+         {
+            R c = (R)(kk % (size_t)n) / (R)n - 0.5;
+            r2 += c * c;
+            kk /= (size_t)n;
+         }
+         r = sqrt(r2);
+         if (r >= 0.5)
+            r = 0.5;
+         ths->b[j] = ths->k(r, 0, ths->kernel_param) / (R)total;
+      }
+   }
+   shim_fftshift_nd(ths->b, d, n);
+   shim_fft_nd(ths->b, d, n, -1);
+   shim_fftshift_nd(ths->b, d, n);
+   ths->b_ready = 1;
+}
+
+/* PRE_PSI: psi[(j*d + t)*(2m+2) + lj] = phi(x_jt - l/n_os), l = floor(n_os x_jt) - m + lj */
+static void shim_precompute_nodes(shim_nfft_nodes *nd, const R *x, int M, int d, int n_os, int m)
+{
+   int taps = 2 * m + 2;
+   long long j;
+   shim_nodes_free(nd);
+   nd->M = M;
+   nd->psi = (R *)nfft_malloc(sizeof(R) * (size_t)M * (size_t)d * (size_t)taps);
+   nd->cell = (int *)nfft_malloc(sizeof(int) * (size_t)M * (size_t)d);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+   for (j = 0; j < (long long)M; j++)
+   {
+      int t, lj;
+      for (t = 0; t < d; t++)
+      {
+         R xj = x[(size_t)j * d + t];
+         int c = (int)lrint(floor(xj * (R)n_os));
+         int u = c - m;
+         nd->cell[(size_t)j * d + t] = c;
+         for (lj = 0; lj < taps; lj++)
+            nd->psi[((size_t)j * d + t) * taps + lj] = shim_kb_phi(xj - (R)(u + lj) / (R)n_os, n_os, m);
+      }
+   }
+   nd->ready = 1;
+}
+
+void fastsum_precompute_source_nodes(fastsum_plan *ths)
+{
+   shim_precompute_nodes(&ths->src, ths->x, ths->N_total, ths->d, ths->n_os_src, ths->m_src);
+}
+
+void fastsum_precompute_target_nodes(fastsum_plan *ths)
+{
+   shim_precompute_nodes(&ths->tgt, ths->y, ths->M_total, ths->d, ths->n_os_tgt, ths->m_tgt);
+}
+
+void fastsum_precompute(fastsum_plan *ths)
+{
+   fastsum_precompute_kernel(ths);
+   fastsum_precompute_source_nodes(ths);
+   fastsum_precompute_target_nodes(ths);
+}
+
+/* ------------------------------------------------------------------ */
+/* window spread (B^T) and interpolation (B)                            */
+/* ------------------------------------------------------------------ */
+static inline int shim_wrap(int l, int n)
+{
+   int r = l % n;
+   return r < 0 ? r + n : r;
+}
+
+/* g (n_os^d, zeroed here) += sum_j f_j * prod_t psi */
+static void shim_spread(const shim_nfft_nodes *nd, const C *fj, C *g, int d, int n_os, int m)
+{
+   int taps = 2 * m + 2;
+   size_t gtotal = shim_ipow(n_os, d);
+   int nthreads = 1;
+   C *priv = NULL;
+#ifdef _OPENMP
+   nthreads = omp_in_parallel() ? 1 : omp_get_max_threads();
+   if (nthreads > 64)
+      nthreads = 64;
+   if ((long long)nd->M < 4096)
+      nthreads = 1;
+#endif
+   memset(g, 0, sizeof(C) * gtotal);
+   if (nthreads > 1)
+   {
+      priv = (C *)nfft_malloc(sizeof(C) * gtotal * (size_t)(nthreads - 1));
+      memset(priv, 0, sizeof(C) * gtotal * (size_t)(nthreads - 1));
+   }
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads)
+#endif
+   {
+      int tid = 0, nt = 1;
+      C *gt;
+      long long j, j0, j1;
+      int idx[4][32];
+#ifdef _OPENMP
+      tid = omp_get_thread_num();
+      nt = omp_get_num_threads();
+#endif
+      gt = (tid == 0) ? g : priv + (size_t)(tid - 1) * gtotal;
+      j0 = (long long)nd->M * tid / nt;
+      j1 = (long long)nd->M * (tid + 1) / nt;
+      for (j = j0; j < j1; j++)
+      {
+         const R *psi = nd->psi + (size_t)j * d * taps;
+         C a = fj[j];
+         int t, l0, l1, l2, l3;
+         for (t = 0; t < d; t++)
+         {
+            int u = nd->cell[(size_t)j * d + t] - m;
+            for (l0 = 0; l0 < taps; l0++)
+               idx[t][l0] = shim_wrap(u + l0, n_os);
+         }
+         if (d == 1)
+         {
+            for (l0 = 0; l0 < taps; l0++)
+               gt[idx[0][l0]] += a * psi[l0];
+         }
+         else if (d == 2)
+         {
+            for (l0 = 0; l0 < taps; l0++)
+            {
+               C a0 = a * psi[l0];
+               size_t b0 = (size_t)idx[0][l0] * n_os;
+               for (l1 = 0; l1 < taps; l1++)
+                  gt[b0 + idx[1][l1]] += a0 * psi[taps + l1];
+            }
+         }
+         else if (d == 3)
+         {
+            for (l0 = 0; l0 < taps; l0++)
+            {
+               C a0 = a * psi[l0];
+               size_t b0 = (size_t)idx[0][l0] * n_os;
+               for (l1 = 0; l1 < taps; l1++)
+               {
+                  C a1 = a0 * psi[taps + l1];
+                  size_t b1 = (b0 + idx[1][l1]) * n_os;
+                  for (l2 = 0; l2 < taps; l2++)
+                     gt[b1 + idx[2][l2]] += a1 * psi[2 * taps + l2];
+               }
+            }
+         }
+         else
+         {
+            for (l0 = 0; l0 < taps; l0++)
+            {
+               C a0 = a * psi[l0];
+               size_t b0 = (size_t)idx[0][l0] * n_os;
+               for (l1 = 0; l1 < taps; l1++)
+               {
+                  C a1 = a0 * psi[taps + l1];
+                  size_t b1 = (b0 + idx[1][l1]) * n_os;
+                  for (l2 = 0; l2 < taps; l2++)
+                  {
+                     C a2 = a1 * psi[2 * taps + l2];
+                     size_t b2 = (b1 + idx[2][l2]) * n_os;
+                     for (l3 = 0; l3 < taps; l3++)
+                        gt[b2 + idx[3][l3]] += a2 * psi[3 * taps + l3];
+                  }
+               }
+            }
+         }
+      }
+   }
+   if (nthreads > 1)
+   {
+      long long i;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+      for (i = 0; i < (long long)gtotal; i++)
+      {
+         int t;
+         C s = g[i];
+         for (t = 0; t < nthreads - 1; t++)
+            s += priv[(size_t)t * gtotal + (size_t)i];
+         g[i] = s;
+      }
+      nfft_free(priv);
+   }
+}
+
+/* f_j = sum_taps g[l] * prod_t psi */
+static void shim_interp(const shim_nfft_nodes *nd, const C *g, C *fj, int d, int n_os, int m)
+{
+   int taps = 2 * m + 2;
+   long long j;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) if (!omp_in_parallel())
+#endif
+   for (j = 0; j < (long long)nd->M; j++)
+   {
+      const R *psi = nd->psi + (size_t)j * d * taps;
+      int idx[4][32];
+      int t, l0, l1, l2, l3;
+      C acc = 0.0;
+      for (t = 0; t < d; t++)
+      {
+         int u = nd->cell[(size_t)j * d + t] - m;
+         for (l0 = 0; l0 < taps; l0++)
+            idx[t][l0] = shim_wrap(u + l0, n_os);
+      }
+      if (d == 1)
+      {
+         for (l0 = 0; l0 < taps; l0++)
+            acc += g[idx[0][l0]] * psi[l0];
+      }
+      else if (d == 2)
+      {
+         for (l0 = 0; l0 < taps; l0++)
+         {
+            C s1 = 0.0;
+            size_t b0 = (size_t)idx[0][l0] * n_os;
+            for (l1 = 0; l1 < taps; l1++)
+               s1 += g[b0 + idx[1][l1]] * psi[taps + l1];
+            acc += s1 * psi[l0];
+         }
+      }
+      else if (d == 3)
+      {
+         for (l0 = 0; l0 < taps; l0++)
+         {
+            C s1 = 0.0;
+            size_t b0 = (size_t)idx[0][l0] * n_os;
+            for (l1 = 0; l1 < taps; l1++)
+            {
+               C s2 = 0.0;
+               size_t b1 = (b0 + idx[1][l1]) * n_os;
+               for (l2 = 0; l2 < taps; l2++)
+                  s2 += g[b1 + idx[2][l2]] * psi[2 * taps + l2];
+               s1 += s2 * psi[taps + l1];
+            }
+            acc += s1 * psi[l0];
+         }
+      }
+      else
+      {
+         for (l0 = 0; l0 < taps; l0++)
+         {
+            C s1 = 0.0;
+            size_t b0 = (size_t)idx[0][l0] * n_os;
+            for (l1 = 0; l1 < taps; l1++)
+            {
+               C s2 = 0.0;
+               size_t b1 = (b0 + idx[1][l1]) * n_os;
+               for (l2 = 0; l2 < taps; l2++)
+               {
+                  C s3 = 0.0;
+                  size_t b2 = (b1 + idx[2][l2]) * n_os;
+                  for (l3 = 0; l3 < taps; l3++)
+                     s3 += g[b2 + idx[3][l3]] * psi[3 * taps + l3];
+                  s2 += s3 * psi[2 * taps + l2];
+               }
+               s1 += s2 * psi[taps + l1];
+            }
+            acc += s1 * psi[l0];
+         }
+      }
+      fj[j] = acc;
+   }
+}
+
+/* copy between the centred N^d coefficient cube (index k_t + N/2) and the
+ * wrapped positions of the n_os^d FFT array, dividing by prod phi_hat(k_t).
+ * dir = 0: g -> f_hat (adjoint, read), dir = 1: f_hat -> g (trafo, write; g pre-zeroed) */
+static void shim_deconvolve(C *g, C *f_hat, int d, int N, int n_os, int m, int dir)
+{
+   size_t total = shim_ipow(N, d);
+   R *ph = (R *)nfft_malloc(sizeof(R) * (size_t)N);
+   long long idx;
+   int k;
+   for (k = 0; k < N; k++)
+      ph[k] = 1.0 / shim_kb_phi_hut(k - N / 2, n_os, m);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+   for (idx = 0; idx < (long long)total; idx++)
+   {
+      size_t rem = (size_t)idx, gi = 0, mul = 1;
+      R scale = 1.0;
+      int t;
+      for (t = d - 1; t >= 0; t--)
+      {
+         int kc = (int)(rem % (size_t)N);
+         int kk = kc - N / 2;
+         rem /= (size_t)N;
+         scale *= ph[kc];
+         gi += (size_t)(kk < 0 ? kk + n_os : kk) * mul;
+         mul *= (size_t)n_os;
+      }
+      if (dir == 0)
+         f_hat[idx] = g[gi] * scale;
+      else
+         g[gi] = f_hat[idx] * scale;
+   }
+   nfft_free(ph);
+}
+
+void fastsum_trafo(fastsum_plan *ths)
+{
+   int d = ths->d;
+   size_t nhat = shim_ipow(ths->n, d);
+   long long k;
+   if (!ths->b_ready || !ths->src.ready || !ths->tgt.ready)
+   {
+      fprintf(stderr, "oracle shim: fastsum_trafo before fastsum_precompute\n");
+      exit(EXIT_FAILURE);
+   }
+   /* 1. adjoint NFFT at the source nodes */
+   shim_spread(&ths->src, ths->alpha, ths->g, d, ths->n_os_src, ths->m_src);
+   shim_fft_nd(ths->g, d, ths->n_os_src, +1);
+   shim_deconvolve(ths->g, ths->f_hat, d, ths->n, ths->n_os_src, ths->m_src, 0);
+   /* 2. multiply by the kernel's Fourier coefficients */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+   for (k = 0; k < (long long)nhat; k++)
+      ths->f_hat[k] *= ths->b[k];
+   /* 3. NFFT trafo at the target nodes */
+   memset(ths->g, 0, sizeof(C) * shim_ipow(ths->n_os_tgt, d));
+   shim_deconvolve(ths->g, ths->f_hat, d, ths->n, ths->n_os_tgt, ths->m_tgt, 1);
+   shim_fft_nd(ths->g, d, ths->n_os_tgt, -1);
+   shim_interp(&ths->tgt, ths->g, ths->f, d, ths->n_os_tgt, ths->m_tgt);
+}
