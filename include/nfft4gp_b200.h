@@ -1,0 +1,229 @@
+/*
+ * nfft4gp_b200.h -- C ABI of libnfft4gp_b200.so, the B200-native (sm_100a) replacement for the
+ * hot path of the nfft4gp C library: the NFFT-accelerated additive-kernel matrix-vector product
+ * and the preconditioned CG solve built on it.
+ *
+ * Every entry point in part 1 has EXACTLY the name, argument meaning, return convention
+ * (0 = ok, -1 = error + printf message) and ownership rules of the reference function it replaces;
+ * the reference file:line is cited next to each declaration (paths relative to the reference
+ * repository).  A maintainer of the reference swaps the objects listed in INTEGRATION.md for this
+ * library and keeps every caller (solvers, GP optimizer, TESTS drivers) unchanged.
+ *
+ * Part 2 ("Nfft4GPB200*") are additive extensions: device selection, device-resident vectors,
+ * factor upload for the preconditioners, multi-GPU sharding, and debug taps used by the parity tests.
+ *
+ * Plain C: pointers and sizes only.  All floating point is fp64, all indices are 32-bit int
+ * (reference: NFFT4GP_DOUBLE = double, SRC/utils/utils.h:28-32).
+ */
+#ifndef NFFT4GP_B200_H
+#define NFFT4GP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef NFFT4GP_DOUBLE
+#define NFFT4GP_DOUBLE double
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Part 0: the plug-point types (INC/_solvers.h:23,51; INC/_linearalg.h:404; INC/_utils.h:430-438)
+ * ------------------------------------------------------------------------------------------ */
+typedef int (*func_solve)(void *precond, int n, double *x, double *rhs);                                  /* _solvers.h:23  */
+typedef int (*func_symmatvec)(void *matrix, int n, double alpha, double *x, double beta, double *y);      /* _solvers.h:51  */
+typedef int (*func_kernel)(void *str, NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *permr, int kr,
+                           int *permc, int kc, NFFT4GP_DOUBLE **Kp, NFFT4GP_DOUBLE **dKp);                /* _linearalg.h:404 */
+typedef void *(*func_create)(void);                                                                      /* _utils.h:430   */
+typedef void (*func_free)(void *str);                                                                    /* _utils.h:438   */
+typedef int (*precond_kernel_setup)(NFFT4GP_DOUBLE *data, int n, int ldim, int d, func_kernel fkernel,
+                                    void *fkernel_params, int require_grad, void *precond);              /* _preconds.h:41-42 */
+
+/* Generic kernel handle.  The callers of the reference write `_params[0]` (f), `_params[1]` (l) and
+ * `_noise_level` (mu) DIRECTLY before every kernel build (SRC/optimizer/gp_loss.c:145-150,
+ * TESTS/TEST1/foo.cpp:222-224), so the field order and types are part of the ABI
+ * (INC/_linearalg.h:420-450).  `_external` points at this library's private state. */
+#ifndef NFFT4GP_KERNEL_MAX_PARAMS
+#define NFFT4GP_KERNEL_MAX_PARAMS 5
+#endif
+typedef struct NFFT4GP_KERNEL_STRUCT
+{
+   NFFT4GP_DOUBLE _params[NFFT4GP_KERNEL_MAX_PARAMS];
+   int _iparams[NFFT4GP_KERNEL_MAX_PARAMS];
+   int _max_n;
+   int _omp;
+   NFFT4GP_DOUBLE _noise_level;
+   int _own_buffer;
+   NFFT4GP_DOUBLE *_buffer;
+   int _own_dbuffer;
+   NFFT4GP_DOUBLE *_dbuffer;
+   func_kernel _fkernel_buffer;
+   int **_ibufferp;
+   size_t *_libufferp;
+   int _own_fkernel_buffer_params;
+   void *_fkernel_buffer_params;
+   size_t _ldwork;
+   NFFT4GP_DOUBLE *_dwork;
+   void *_external;
+} nfft4gp_kernel, *pnfft4gp_kernel;
+
+/* ------------------------------------------------------------------------------------------
+ * Part 1a: NFFT interface (INC/_external.h, SRC/external/nfft_interface.c)
+ * ------------------------------------------------------------------------------------------ */
+
+/* nfft_interface.c:622-674 (_external.h:176).  `data` is feature-major (d columns of ldim values);
+ * `windows` holds nwindows*dwindows feature ids read flat, -1 pads a short LAST window.  The handle
+ * keeps the caller's `windows` pointer (not copied, not freed) and a private copy of the columns. */
+void *Nfft4GPNFFTAdditiveKernelParamCreate(NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *windows, int nwindows, int dwindows);
+
+/* nfft_interface.c:676-734 / 736-794 (_external.h:198,220): func_kernel-shaped plan (re)build.  Reads f, l, mu
+ * from the handle; requires n == ldim and non-NULL Kp, dKp; ignores permr/permc; returns the handle itself in
+ * *Kp and *dKp (freed by the no-op Nfft4GPNFFTKernelFree). */
+int Nfft4GPNFFTAdditiveKernelGaussianKernel(void *str, NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *permr, int kr,
+                                            int *permc, int kc, NFFT4GP_DOUBLE **Kp, NFFT4GP_DOUBLE **dKp);
+int Nfft4GPNFFTAdditiveKernelMatern12Kernel(void *str, NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *permr, int kr,
+                                            int *permc, int kc, NFFT4GP_DOUBLE **Kp, NFFT4GP_DOUBLE **dKp);
+
+/* nfft_interface.c:796-817 (_external.h:233): y <- beta*y + alpha*f^2*((1/P) sum_w K_w + mu I) x.  x, y host, length n. */
+int Nfft4GPAdditiveNFFTMatSymv(void *data, int n, NFFT4GP_DOUBLE alpha, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE beta, NFFT4GP_DOUBLE *y);
+/* nfft_interface.c:819-840 (_external.h:246): y (3n) = [dK/df x ; dK/dl x ; dK/dmu x]. */
+int Nfft4GPAdditiveNFFTGradMatSymv(void *data, int n, NFFT4GP_DOUBLE alpha, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE beta, NFFT4GP_DOUBLE *y);
+/* nfft_interface.c:842-856 (_external.h:254) and :79-82 (_external.h:75, no-op). */
+void Nfft4GPAdditiveNFFTKernelFree(void *str);
+void Nfft4GPNFFTKernelFree(void *str);
+
+/* single-window equivalents: nfft_interface.c:3-42, 44-77, 129-263, 265-398, 400-497, 499-620 (_external.h:60-161).
+ * `data` for the kernel builders is the window's own feature-major n x d block; Mat(Grad)Symv take the
+ * pointer returned in *Kp / *dKp. */
+void *Nfft4GPNFFTKernelParamCreate(int max_n, int dim);
+void Nfft4GPNFFTKernelParamFree(void *kernel);
+int Nfft4GPNFFTKernelGaussianKernel(void *str, NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *permr, int kr,
+                                    int *permc, int kc, NFFT4GP_DOUBLE **Kp, NFFT4GP_DOUBLE **dKp);
+int Nfft4GPNFFTKernelMatern12Kernel(void *str, NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *permr, int kr,
+                                    int *permc, int kc, NFFT4GP_DOUBLE **Kp, NFFT4GP_DOUBLE **dKp);
+int Nfft4GPNFFTMatSymv(void *data, int n, NFFT4GP_DOUBLE alpha, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE beta, NFFT4GP_DOUBLE *y);
+int Nfft4GPNFFTGradMatSymv(void *data, int n, NFFT4GP_DOUBLE alpha, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE beta, NFFT4GP_DOUBLE *y);
+
+/* ------------------------------------------------------------------------------------------
+ * Part 1b: Krylov solver (INC/_solvers.h:102, SRC/solvers/pcg.c:3-206)
+ * Same control flow and quirks as the reference (true-residual recheck with an extra matvec, *piter = 0
+ * unless convergence is confirmed, rel_res_v[ii] overwritten with the ABSOLUTE true residual at the
+ * recheck; *prel_res_v is callee-allocated with malloc, caller frees).  When `matvec` / `precondfunc` are
+ * this library's own entry points the whole iteration runs device-resident with fused vector kernels;
+ * any other function pointers are called on host vectors exactly as the reference does.
+ * ------------------------------------------------------------------------------------------ */
+int Nfft4GPSolverPcg(void *mat_data, int n, func_symmatvec matvec, void *prec_data, func_solve precondfunc,
+                     NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs, int maxits, int atol, NFFT4GP_DOUBLE tol,
+                     NFFT4GP_DOUBLE *prel_res, NFFT4GP_DOUBLE **prel_res_v, int *piter, int print_level);
+
+/* ------------------------------------------------------------------------------------------
+ * Part 1c: preconditioners (INC/_preconds.h; SRC/preconds/nys.c, fsai.c, afn.c/afn.h)
+ * Handles are opaque here (the reference's callers only use the functions).
+ * ------------------------------------------------------------------------------------------ */
+void *Nfft4GPPrecondNysCreate(void);                                     /* nys.c:3-33    (_preconds.h:358) */
+void Nfft4GPPrecondNysFree(void *str);                                   /* nys.c:35-76   (:365) */
+void Nfft4GPPrecondNysReset(void *str);                                  /* nys.c:78-98   (:372) */
+void Nfft4GPPrecondNysSetRank(void *str, int k);                         /* nys.c:100-105 (:380) */
+void Nfft4GPPrecondNysSetPerm(void *str, int *perm, int own_perm);       /* nys.c:107-113 (:389) */
+int Nfft4GPPrecondNysSolve(void *vnys_mat, int n, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs);   /* nys.c:115-173 (:400) */
+int Nfft4GPPrecondNysSetupWithKernel(NFFT4GP_DOUBLE *data, int n, int ldim, int d, func_kernel fkernel,
+                                     void *fkernel_params, int require_grad, void *vnys_mat); /* nys.c:518-660 (:444) */
+
+void *Nfft4GPPrecondFsaiCreate(void);                                    /* fsai.c:7-30    (_preconds.h:187) */
+void Nfft4GPPrecondFsaiFree(void *str);                                  /* fsai.c:32-66   (:194) */
+void Nfft4GPPrecondFsaiReset(void *str);                                 /* fsai.c:68-98   (:201) */
+void Nfft4GPPrecondFsaiSetLfil(void *str, int lfil);                     /* fsai.c:100-104 (:209) */
+int Nfft4GPPrecondFsaiSolve(void *vfsai_mat, int n, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs); /* fsai.c:106-123 (:220) */
+int Nfft4GPPrecondFsaiSetupWithKernel(NFFT4GP_DOUBLE *data, int n, int ldim, int d, func_kernel fkernel,
+                                      void *fkernel_params, int require_grad, void *vfsai_mat); /* fsai.c:302-673 (:264) */
+
+/* AFN: SRC/preconds/afn.c is not compiled by the reference (SURVEY.md finding 2); names follow afn.h:65-132,
+ * the algorithm follows MATLAB afn_setup.m:30-109 / afn_solve.m:39-69. */
+void *Nfft4GPPrecondAFNCreate(void);
+void Nfft4GPPrecondAFNFree(void *str);
+void Nfft4GPPrecondAFNSetRank(void *str, int max_k);
+void Nfft4GPPrecondAFNSetLfil(void *str, int lfil);
+int Nfft4GPPrecondAFNSolve(void *vafn_mat, int n, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs);
+int Nfft4GPPrecondAFNSetupWithKernel(NFFT4GP_DOUBLE *data, int n, int ldim, int d, func_kernel fkernel,
+                                     void *fkernel_params, int require_grad, void *vafn_mat);
+
+/* Dense additive kernel used by the preconditioner setups (SRC/linearalg/kernels.c:3046-3494; _linearalg.h:717,740).
+ * Same func_kernel contract: full lower (permr NULL), K(permr,permr) lower, K(permr,permc) full, column-major;
+ * Kp only (dKp must be NULL in this library: the gradient blocks belong to the optimizer, out of scope). */
+void *Nfft4GPKernelAdditiveKernelParamCreate(NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *windows, int nwindows,
+                                             int dwindows, func_kernel fkernel);
+int Nfft4GPKernelAdditiveKernel(void *str, NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *permr, int kr,
+                                int *permc, int kc, NFFT4GP_DOUBLE **Kp, NFFT4GP_DOUBLE **dKp);
+int Nfft4GPKernelGaussianKernel(void *str, NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *permr, int kr,
+                                int *permc, int kc, NFFT4GP_DOUBLE **Kp, NFFT4GP_DOUBLE **dKp);   /* kernels.c:680  */
+int Nfft4GPKernelMatern12Kernel(void *str, NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *permr, int kr,
+                                int *permc, int kc, NFFT4GP_DOUBLE **Kp, NFFT4GP_DOUBLE **dKp);   /* kernels.c:2390 */
+void Nfft4GPKernelParamFree(void *str);                                                           /* kernels.c (_linearalg.h:458) */
+
+/* ------------------------------------------------------------------------------------------
+ * Part 2: B200 extensions
+ * ------------------------------------------------------------------------------------------ */
+
+/* Select the CUDA device (default: device 0, or LOCAL_RANK when set).  Fails loudly (-1 + message) when no
+ * sm_100 device is visible: there is NO CPU fallback anywhere in this library. */
+int Nfft4GPB200Init(int device);
+int Nfft4GPB200DeviceCount(void);
+const char *Nfft4GPB200Version(void);
+/* number of kernels this library has launched since load / since the last reset (bench.py: gpu_launches) */
+long long Nfft4GPB200LaunchCount(void);
+void Nfft4GPB200LaunchCountReset(void);
+
+/* pinned host and device memory helpers for callers that want device-resident vectors */
+void *Nfft4GPB200HostAlloc(size_t bytes);
+void Nfft4GPB200HostFree(void *p);
+void *Nfft4GPB200DeviceAlloc(size_t bytes);
+void Nfft4GPB200DeviceFree(void *p);
+int Nfft4GPB200MemcpyH2D(void *dst_dev, const void *src_host, size_t bytes);
+int Nfft4GPB200MemcpyD2H(void *dst_host, const void *src_dev, size_t bytes);
+int Nfft4GPB200DeviceSynchronize(void);
+/* CUDA-event timing on the library's stream (the stream every kernel of this library is launched on) */
+void *Nfft4GPB200EventCreate(void);
+void Nfft4GPB200EventDestroy(void *ev);
+int Nfft4GPB200EventRecord(void *ev);
+float Nfft4GPB200EventElapsedMs(void *start, void *stop); /* synchronises on `stop` */
+
+/* Device-resident variants of the plug points: same semantics, x / y / rhs are DEVICE pointers. */
+int Nfft4GPB200AdditiveNFFTMatSymvDevice(void *data, int n, double alpha, const double *d_x, double beta, double *d_y);
+int Nfft4GPB200AdditiveNFFTGradMatSymvDevice(void *data, int n, double alpha, const double *d_x, double beta, double *d_y);
+int Nfft4GPB200PrecondSolveDevice(void *prec, func_solve which, int n, double *d_x, const double *d_rhs);
+/* PCG with device-resident x (in: initial guess, out: solution) and rhs. Other arguments as Nfft4GPSolverPcg. */
+int Nfft4GPB200SolverPcgDevice(void *mat_data, int n, func_symmatvec matvec, void *prec_data, func_solve precondfunc,
+                               double *d_x, const double *d_rhs, int maxits, int atol, double tol,
+                               double *prel_res, double **prel_res_v, int *piter, int print_level);
+
+/* Upload precomputed factors (e.g. produced by the reference's CPU setup) instead of running the setup here. */
+int Nfft4GPB200PrecondNysSetFactors(void *nys, int n, int k, const int *perm, const double *U /* n x k col-major */,
+                                    const double *s /* k */, double eta);
+int Nfft4GPB200PrecondFsaiSetFactors(void *fsai, int n, const int *ia, const int *ja, const double *a);
+int Nfft4GPB200PrecondAFNSetFactors(void *afn, int n, int k, const int *perm, const double *L /* k x k lower, col-major */,
+                                    const double *K12 /* k x (n-k) col-major */, const int *ia, const int *ja, const double *a);
+/* read factors back (parity tests of the setups); any output pointer may be NULL */
+int Nfft4GPB200PrecondNysGetFactors(void *nys, int *n, int *k, int *perm, double *U, double *s, double *eta);
+int Nfft4GPB200PrecondFsaiGetFactors(void *fsai, int *n, int *nnz, int *ia, int *ja, double *a);
+
+/* Multi-GPU (one process per GPU).  The NCCL communicator is created from a unique id that the caller
+ * broadcasts (128 bytes).  mode 0: replicate; 1: shard by feature window, allreduce(sum) of y per matvec;
+ * 2: shard by point block, allreduce(sum) of the oversampled grids per matvec (y complete on every rank). */
+int Nfft4GPB200CommGetUniqueId(void *id128);
+int Nfft4GPB200CommInit(int rank, int nranks, const void *id128);
+int Nfft4GPB200CommFinalize(void);
+int Nfft4GPB200SetSharding(void *additive_handle, int mode);
+
+/* Debug taps for the stage-by-stage parity tests (host output buffers). */
+int Nfft4GPB200DebugWindowInfo(void *additive_handle, int w, int *dim, double *scale, int *nseg);
+int Nfft4GPB200DebugSpread(void *additive_handle, int w, double alpha, const double *x, double *grid /* 64^dim */);
+int Nfft4GPB200DebugCoeff(void *additive_handle, int w, int which, double *c /* 2 * 32^dim: b_k/phi_hat^2 interleaved */);
+int Nfft4GPB200DebugGridAfterFFT(void *additive_handle, int w, double alpha, const double *x, double *h /* 64^dim */);
+/* tuning knobs (bench / A-B tests): name in {"spread3d","gather3d"}; variant 0 = generic, 1 = tiled (default) */
+int Nfft4GPB200SetVariant(const char *name, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFFT4GP_B200_H */

@@ -1,0 +1,320 @@
+"""ctypes mirror of include/nfft4gp_b200.h -- same names, argument meaning and error behaviour as the reference's
+C interface (INC/_external.h, INC/_solvers.h, INC/_preconds.h), so that the parity tests read like the reference's
+own drivers (TESTS/TEST1/foo.cpp:209-251)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnfft4gp_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+FUNC_SYMMATVEC = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_double, c_double_p, C.c_double, c_double_p)
+FUNC_SOLVE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, c_double_p, c_double_p)
+
+
+class Nfft4GPKernel(C.Structure):
+    """nfft4gp_kernel (include/nfft4gp_b200.h; reference INC/_linearalg.h:420-450)."""
+    _fields_ = [
+        ("_params", C.c_double * 5), ("_iparams", C.c_int * 5), ("_max_n", C.c_int), ("_omp", C.c_int),
+        ("_noise_level", C.c_double), ("_own_buffer", C.c_int), ("_buffer", c_double_p), ("_own_dbuffer", C.c_int),
+        ("_dbuffer", c_double_p), ("_fkernel_buffer", C.c_void_p), ("_ibufferp", C.c_void_p), ("_libufferp", C.c_void_p),
+        ("_own_fkernel_buffer_params", C.c_int), ("_fkernel_buffer_params", C.c_void_p), ("_ldwork", C.c_size_t),
+        ("_dwork", c_double_p), ("_external", C.c_void_p),
+    ]
+
+
+def build_library(force=False):
+    """Compile libnfft4gp_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", os.path.join(HERE, "csrc"), "-j8"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the C-ABI library.  Fails loudly when it is missing -- there is no fallback implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a).  nfft4gp_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i, d = C.c_void_p, C.c_int, C.c_double
+    kargs = [vp, c_double_p, i, i, i, c_int_p, i, c_int_p, i, C.POINTER(vp), C.POINTER(vp)]
+    margs = [vp, i, d, c_double_p, d, c_double_p]
+    sig = {
+        "Nfft4GPNFFTAdditiveKernelParamCreate": (vp, [c_double_p, i, i, i, c_int_p, i, i]),
+        "Nfft4GPNFFTAdditiveKernelGaussianKernel": (i, kargs),
+        "Nfft4GPNFFTAdditiveKernelMatern12Kernel": (i, kargs),
+        "Nfft4GPAdditiveNFFTMatSymv": (i, margs),
+        "Nfft4GPAdditiveNFFTGradMatSymv": (i, margs),
+        "Nfft4GPAdditiveNFFTKernelFree": (None, [vp]),
+        "Nfft4GPNFFTKernelFree": (None, [vp]),
+        "Nfft4GPNFFTKernelParamCreate": (vp, [i, i]),
+        "Nfft4GPNFFTKernelParamFree": (None, [vp]),
+        "Nfft4GPNFFTKernelGaussianKernel": (i, kargs),
+        "Nfft4GPNFFTKernelMatern12Kernel": (i, kargs),
+        "Nfft4GPNFFTMatSymv": (i, margs),
+        "Nfft4GPNFFTGradMatSymv": (i, margs),
+        "Nfft4GPSolverPcg": (i, [vp, i, vp, vp, vp, c_double_p, c_double_p, i, i, d, c_double_p, C.POINTER(c_double_p), c_int_p, i]),
+        "Nfft4GPPrecondNysCreate": (vp, []), "Nfft4GPPrecondNysFree": (None, [vp]), "Nfft4GPPrecondNysReset": (None, [vp]),
+        "Nfft4GPPrecondNysSetRank": (None, [vp, i]), "Nfft4GPPrecondNysSetPerm": (None, [vp, c_int_p, i]),
+        "Nfft4GPPrecondNysSolve": (i, [vp, i, c_double_p, c_double_p]),
+        "Nfft4GPPrecondNysSetupWithKernel": (i, [c_double_p, i, i, i, vp, vp, i, vp]),
+        "Nfft4GPPrecondFsaiCreate": (vp, []), "Nfft4GPPrecondFsaiFree": (None, [vp]), "Nfft4GPPrecondFsaiReset": (None, [vp]),
+        "Nfft4GPPrecondFsaiSetLfil": (None, [vp, i]),
+        "Nfft4GPPrecondFsaiSolve": (i, [vp, i, c_double_p, c_double_p]),
+        "Nfft4GPPrecondFsaiSetupWithKernel": (i, [c_double_p, i, i, i, vp, vp, i, vp]),
+        "Nfft4GPPrecondAFNCreate": (vp, []), "Nfft4GPPrecondAFNFree": (None, [vp]),
+        "Nfft4GPPrecondAFNSetRank": (None, [vp, i]), "Nfft4GPPrecondAFNSetLfil": (None, [vp, i]),
+        "Nfft4GPPrecondAFNSolve": (i, [vp, i, c_double_p, c_double_p]),
+        "Nfft4GPPrecondAFNSetupWithKernel": (i, [c_double_p, i, i, i, vp, vp, i, vp]),
+        "Nfft4GPKernelAdditiveKernelParamCreate": (vp, [c_double_p, i, i, i, c_int_p, i, i, vp]),
+        "Nfft4GPKernelAdditiveKernel": (i, kargs), "Nfft4GPKernelGaussianKernel": (i, kargs),
+        "Nfft4GPKernelMatern12Kernel": (i, kargs), "Nfft4GPKernelParamFree": (None, [vp]),
+        "Nfft4GPB200Init": (i, [i]), "Nfft4GPB200DeviceCount": (i, []), "Nfft4GPB200Version": (C.c_char_p, []),
+        "Nfft4GPB200LaunchCount": (C.c_longlong, []), "Nfft4GPB200LaunchCountReset": (None, []),
+        "Nfft4GPB200HostAlloc": (vp, [C.c_size_t]), "Nfft4GPB200HostFree": (None, [vp]),
+        "Nfft4GPB200DeviceAlloc": (vp, [C.c_size_t]), "Nfft4GPB200DeviceFree": (None, [vp]),
+        "Nfft4GPB200MemcpyH2D": (i, [vp, vp, C.c_size_t]), "Nfft4GPB200MemcpyD2H": (i, [vp, vp, C.c_size_t]),
+        "Nfft4GPB200DeviceSynchronize": (i, []),
+        "Nfft4GPB200EventCreate": (vp, []), "Nfft4GPB200EventDestroy": (None, [vp]), "Nfft4GPB200EventRecord": (i, [vp]),
+        "Nfft4GPB200EventElapsedMs": (C.c_float, [vp, vp]),
+        "Nfft4GPB200AdditiveNFFTMatSymvDevice": (i, [vp, i, d, vp, d, vp]),
+        "Nfft4GPB200AdditiveNFFTGradMatSymvDevice": (i, [vp, i, d, vp, d, vp]),
+        "Nfft4GPB200PrecondSolveDevice": (i, [vp, vp, i, vp, vp]),
+        "Nfft4GPB200SolverPcgDevice": (i, [vp, i, vp, vp, vp, vp, vp, i, i, d, c_double_p, C.POINTER(c_double_p), c_int_p, i]),
+        "Nfft4GPB200PrecondNysSetFactors": (i, [vp, i, i, c_int_p, c_double_p, c_double_p, d]),
+        "Nfft4GPB200PrecondFsaiSetFactors": (i, [vp, i, c_int_p, c_int_p, c_double_p]),
+        "Nfft4GPB200PrecondAFNSetFactors": (i, [vp, i, i, c_int_p, c_double_p, c_double_p, c_int_p, c_int_p, c_double_p]),
+        "Nfft4GPB200PrecondNysGetFactors": (i, [vp, c_int_p, c_int_p, c_int_p, c_double_p, c_double_p, c_double_p]),
+        "Nfft4GPB200PrecondFsaiGetFactors": (i, [vp, c_int_p, c_int_p, c_int_p, c_int_p, c_double_p]),
+        "Nfft4GPB200CommGetUniqueId": (i, [vp]), "Nfft4GPB200CommInit": (i, [i, i, vp]), "Nfft4GPB200CommFinalize": (i, []),
+        "Nfft4GPB200SetSharding": (i, [vp, i]),
+        "Nfft4GPB200DebugWindowInfo": (i, [vp, i, c_int_p, c_double_p, c_int_p]),
+        "Nfft4GPB200DebugSpread": (i, [vp, i, d, c_double_p, c_double_p]),
+        "Nfft4GPB200DebugCoeff": (i, [vp, i, i, c_double_p]),
+        "Nfft4GPB200DebugGridAfterFFT": (i, [vp, i, d, c_double_p, c_double_p]),
+        "Nfft4GPB200SetVariant": (i, [C.c_char_p, i]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError here = the library does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    L._signatures = sig
+    L.free = C.CDLL(None).free
+    L.free.argtypes = [vp]
+    L.free.restype = None
+    _lib = L
+    return L
+
+
+def dptr(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def iptr(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+class AdditiveNFFTKernel:
+    """The reference call sequence for the additive NFFT kernel (TESTS/TEST1/foo.cpp:216-251):
+    ParamCreate -> write f, l, mu into the handle -> {Gaussian,Matern12}Kernel -> MatSymv / GradMatSymv -> Free.
+    X is feature-major (d, n) like the reference's data files; windows flat int32 with -1 padding the last window."""
+
+    def __init__(self, X, windows, nwindows, dwindows, kernel="gaussian"):
+        L = lib()
+        self.X = np.ascontiguousarray(X, dtype=np.float64)
+        self.d, self.n = self.X.shape
+        self.windows = np.ascontiguousarray(windows, dtype=np.int32)
+        self.kernel = kernel
+        self.h = L.Nfft4GPNFFTAdditiveKernelParamCreate(dptr(self.X), self.n, self.n, self.d, iptr(self.windows), nwindows, dwindows)
+        if not self.h:
+            raise RuntimeError("Nfft4GPNFFTAdditiveKernelParamCreate failed")
+        self.K = C.c_void_p()
+        self.dK = C.c_void_p()
+
+    def build(self, f, l, mu):
+        L = lib()
+        k = Nfft4GPKernel.from_address(self.h)
+        k._params[0] = f
+        k._params[1] = l
+        k._noise_level = mu
+        fn = L.Nfft4GPNFFTAdditiveKernelGaussianKernel if self.kernel == "gaussian" else L.Nfft4GPNFFTAdditiveKernelMatern12Kernel
+        self.K, self.dK = C.c_void_p(), C.c_void_p()
+        rc = fn(self.h, dptr(self.X), self.n, self.n, self.d, None, 0, None, 0, C.byref(self.K), C.byref(self.dK))
+        if rc != 0:
+            raise RuntimeError("NFFT additive kernel build failed (no CUDA device?)")
+        return self
+
+    def matvec(self, x, alpha=1.0, beta=0.0, y=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros(self.n) if y is None else np.array(y, dtype=np.float64)
+        if lib().Nfft4GPAdditiveNFFTMatSymv(self.K, self.n, alpha, dptr(x), beta, dptr(y)) != 0:
+            raise RuntimeError("Nfft4GPAdditiveNFFTMatSymv failed")
+        return y
+
+    def grad_matvec(self, x, alpha=1.0, beta=0.0, y=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros(3 * self.n) if y is None else np.array(y, dtype=np.float64)
+        if lib().Nfft4GPAdditiveNFFTGradMatSymv(self.dK, self.n, alpha, dptr(x), beta, dptr(y)) != 0:
+            raise RuntimeError("Nfft4GPAdditiveNFFTGradMatSymv failed")
+        return y
+
+    def matvec_device(self, d_x, d_y, alpha=1.0, beta=0.0):
+        """x, y are raw device pointers (ints), e.g. torch_tensor.data_ptr()."""
+        if lib().Nfft4GPB200AdditiveNFFTMatSymvDevice(self.K, self.n, alpha, d_x, beta, d_y) != 0:
+            raise RuntimeError("Nfft4GPB200AdditiveNFFTMatSymvDevice failed")
+
+    def window_info(self, w):
+        dim, scale, nseg = C.c_int(), C.c_double(), C.c_int()
+        assert lib().Nfft4GPB200DebugWindowInfo(self.h, w, C.byref(dim), C.byref(scale), C.byref(nseg)) == 0
+        return dim.value, scale.value, nseg.value
+
+    def debug_spread(self, w, x, alpha=1.0):
+        dim, _, _ = self.window_info(w)
+        g = np.zeros(64 ** dim)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert lib().Nfft4GPB200DebugSpread(self.h, w, alpha, dptr(x), dptr(g)) == 0
+        return g.reshape((64,) * dim)
+
+    def debug_grid_after_fft(self, w, x, alpha=1.0):
+        dim, _, _ = self.window_info(w)
+        g = np.zeros(64 ** dim)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert lib().Nfft4GPB200DebugGridAfterFFT(self.h, w, alpha, dptr(x), dptr(g)) == 0
+        return g.reshape((64,) * dim)
+
+    def debug_coeff(self, w, which=0):
+        dim, _, _ = self.window_info(w)
+        c = np.zeros(2 * 32 ** dim)
+        assert lib().Nfft4GPB200DebugCoeff(self.h, w, which, dptr(c)) == 0
+        c = c.reshape(-1, 2)
+        return (c[:, 0] + 1j * c[:, 1]).reshape((32,) * dim)
+
+    def matvec_fn(self):
+        return C.cast(lib().Nfft4GPAdditiveNFFTMatSymv, C.c_void_p)
+
+    def free(self):
+        if self.h:
+            lib().Nfft4GPAdditiveNFFTKernelFree(self.h)
+            self.h = None
+
+
+class NysPrecond:
+    def __init__(self):
+        self.h = lib().Nfft4GPPrecondNysCreate()
+        self._keep = []
+
+    def set_factors(self, perm, U, s, eta):
+        n, k = U.shape
+        Uf = np.asfortranarray(U, dtype=np.float64)
+        perm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        rc = lib().Nfft4GPB200PrecondNysSetFactors(self.h, n, k, iptr(perm) if perm is not None else None,
+                                                   Uf.ctypes.data_as(c_double_p), dptr(s), eta)
+        if rc != 0:
+            raise RuntimeError("Nfft4GPB200PrecondNysSetFactors failed")
+        self.n = n
+
+    def solve(self, rhs):
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        x = np.zeros_like(rhs)
+        if lib().Nfft4GPPrecondNysSolve(self.h, rhs.size, dptr(x), dptr(rhs)) != 0:
+            raise RuntimeError("Nfft4GPPrecondNysSolve failed")
+        return x
+
+    def solve_fn(self):
+        return C.cast(lib().Nfft4GPPrecondNysSolve, C.c_void_p)
+
+    def free(self):
+        if self.h:
+            lib().Nfft4GPPrecondNysFree(self.h)
+            self.h = None
+
+
+class FsaiPrecond:
+    def __init__(self):
+        self.h = lib().Nfft4GPPrecondFsaiCreate()
+
+    def set_factors(self, ia, ja, a):
+        ia = np.ascontiguousarray(ia, dtype=np.int32)
+        ja = np.ascontiguousarray(ja, dtype=np.int32)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if lib().Nfft4GPB200PrecondFsaiSetFactors(self.h, ia.size - 1, iptr(ia), iptr(ja), dptr(a)) != 0:
+            raise RuntimeError("Nfft4GPB200PrecondFsaiSetFactors failed")
+
+    def solve(self, rhs):
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        x = np.zeros_like(rhs)
+        if lib().Nfft4GPPrecondFsaiSolve(self.h, rhs.size, dptr(x), dptr(rhs)) != 0:
+            raise RuntimeError("Nfft4GPPrecondFsaiSolve failed")
+        return x
+
+    def solve_fn(self):
+        return C.cast(lib().Nfft4GPPrecondFsaiSolve, C.c_void_p)
+
+    def free(self):
+        if self.h:
+            lib().Nfft4GPPrecondFsaiFree(self.h)
+            self.h = None
+
+
+class AfnPrecond:
+    def __init__(self):
+        self.h = lib().Nfft4GPPrecondAFNCreate()
+
+    def set_factors(self, perm, L, K12, ia, ja, a):
+        k = L.shape[0]
+        n = perm.size
+        perm = np.ascontiguousarray(perm, dtype=np.int32)
+        Lf = np.asfortranarray(L, dtype=np.float64)
+        Kf = np.asfortranarray(K12, dtype=np.float64)
+        ia = np.ascontiguousarray(ia, dtype=np.int32)
+        ja = np.ascontiguousarray(ja, dtype=np.int32)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        rc = lib().Nfft4GPB200PrecondAFNSetFactors(self.h, n, k, iptr(perm), Lf.ctypes.data_as(c_double_p),
+                                                   Kf.ctypes.data_as(c_double_p), iptr(ia), iptr(ja), dptr(a))
+        if rc != 0:
+            raise RuntimeError("Nfft4GPB200PrecondAFNSetFactors failed")
+
+    def solve(self, rhs):
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        x = np.zeros_like(rhs)
+        if lib().Nfft4GPPrecondAFNSolve(self.h, rhs.size, dptr(x), dptr(rhs)) != 0:
+            raise RuntimeError("Nfft4GPPrecondAFNSolve failed")
+        return x
+
+    def solve_fn(self):
+        return C.cast(lib().Nfft4GPPrecondAFNSolve, C.c_void_p)
+
+    def free(self):
+        if self.h:
+            lib().Nfft4GPPrecondAFNFree(self.h)
+            self.h = None
+
+
+def solver_pcg(mat, n, matvec_fn, prec, solve_fn, x0, rhs, maxits, atol, tol, print_level=0):
+    """Nfft4GPSolverPcg with host vectors.  Returns (x, rel_res, rel_res_v, iters)."""
+    L = lib()
+    x = np.array(x0, dtype=np.float64)
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    rel = C.c_double(0.0)
+    relv = c_double_p()
+    it = C.c_int(0)
+    rc = L.Nfft4GPSolverPcg(mat, n, matvec_fn, prec, solve_fn, dptr(x), dptr(rhs), maxits, atol, tol,
+                            C.byref(rel), C.byref(relv), C.byref(it), print_level)
+    if rc != 0:
+        raise RuntimeError("Nfft4GPSolverPcg failed")
+    m = min(maxits, n) + 1
+    hist = np.ctypeslib.as_array(relv, shape=(m,)).copy() if relv else np.zeros(0)
+    if relv:
+        L.free(relv)
+    return x, rel.value, hist, it.value

@@ -1,0 +1,107 @@
+/* Thin C-ABI layer between the C host code (nfft_host.c, pcg_host.c, precond_host.c) and the
+ * hand-written sm_100a kernels (*.cu).  Plain pointers and sizes only; every function returns 0 on
+ * success and -1 after printing the CUDA error.  All launches go to ONE library stream. */
+#ifndef NFFT4GP_B200_DEV_H
+#define NFFT4GP_B200_DEV_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* fixed NFFT parameters of the reference (SRC/external/nfft_interface.c:18-27) */
+#define B200_NBAND 32 /* expansion degree N                  */
+#define B200_NOS 64   /* oversampled FFT length (sigma = 2)   */
+#define B200_MCUT 4   /* window cut-off m                     */
+#define B200_TAPS 10  /* 2m + 2                               */
+#define B200_SEG_MAX 512
+#define B200_JOBS 8   /* segments processed side by side by one CTA of the tiled 3-D kernels */
+
+/* device-side state of one feature window */
+typedef struct
+{
+   int d;        /* window dimension 1..3                                        */
+   int n;        /* number of points                                             */
+   int nseg;     /* number of (cell, point-range) segments, sorted by size desc  */
+   double *psi;  /* [n + pad][d*10] Kaiser-Bessel taps, cell-sorted point order  */
+   int *key;     /* [n] packed cell index ((c1+32)<<12 | (c2+32)<<6 | (c3+32))    */
+   int *perm;    /* [n] sorted position -> original point                        */
+   int *inv;     /* [n] original point -> sorted position                        */
+   int *seg_start, *seg_cnt, *seg_base; /* [nseg padded to a multiple of B200_JOBS] */
+   double *a;    /* [n + pad] (alpha/P) * x[perm], sorted order                  */
+   double *f;    /* [n] interpolation result, sorted order (kernel channel)      */
+   double *f2;   /* [n] derivative-kernel channel (gradient matvec only)         */
+   double *grid; /* [64^d] real oversampled grid (spread target, later Re h)     */
+   double *specA, *specB, *band; /* complex work arrays of the pruned FFT passes */
+   double *coef, *dcoef;         /* [32^d] complex  b_k / prod phi_hat(k_t)^2    */
+} b200_win_dev;
+
+/* ---- runtime ---- */
+int b200_init(int device);
+int b200_initialized(void);
+int b200_device_count(void);
+void *b200_malloc(size_t bytes);
+void b200_free(void *p);
+void *b200_host_alloc(size_t bytes);
+void b200_host_free(void *p);
+int b200_h2d(void *dst, const void *src, size_t bytes);
+int b200_d2h(void *dst, const void *src, size_t bytes);
+int b200_d2d(void *dst, const void *src, size_t bytes);
+int b200_memset(void *dst, int v, size_t bytes);
+int b200_sync(void);
+void *b200_event_create(void);
+void b200_event_destroy(void *ev);
+int b200_event_record(void *ev);
+float b200_event_elapsed_ms(void *a, void *b);
+long long b200_launch_count(void);
+void b200_launch_count_reset(void);
+void *b200_stream_handle(void); /* cudaStream_t, for NCCL */
+
+/* ---- NFFT window kernels (nfft_kernels.cu) ---- */
+int b200k_psi(const b200_win_dev *w, const double *d_xs /* [n][d] sorted scaled coords */);
+int b200k_prep(const b200_win_dev *w, const double *d_x, double scale);
+int b200k_spread(const b200_win_dev *w, int variant);
+int b200k_forward_fft(const b200_win_dev *w);                                   /* grid -> band (unscaled) */
+int b200k_backward_fft(const b200_win_dev *w, const double *d_coef);            /* band * coef -> grid (Re h) */
+int b200k_gather(const b200_win_dev *w, double *d_f, int variant);
+/* y = beta*y + sum_w c0*(f_w[inv_w] + mu*s*x)   (matvec epilogue, nfft_interface.c:428-494, 803-814) */
+int b200k_combine(int n, int P, const double *const *d_fptr, const int *const *d_invptr, const double *d_x,
+                  double s, double c0, double mu, double beta, double *d_y);
+/* gradient epilogue (nfft_interface.c:539-617, 826-837): y0 += f2*(f + mu a), y1 += c1*fd, y2 += ff*a */
+int b200k_combine_grad(int n, int P, const double *const *d_fptr, const double *const *d_f2ptr, const int *const *d_invptr,
+                       const double *d_x, double s, double f2, double ff, const double *d_c1w, double mu, double beta, double *d_y);
+
+/* ---- vector kernels for PCG (vec_kernels.cu) ---- */
+int b200k_dot(int n, const double *x, const double *y, double *d_out);          /* deterministic 2-stage */
+int b200k_dot2(int n, const double *x, const double *y, const double *u, const double *v, double *d_out2);
+int b200k_xpby(int n, const double *z, double beta, double *p);                 /* p = z + beta p */
+/* x += alpha p ; r -= alpha q ; out = r.r   (fused PCG update, pcg.c:165-169) */
+int b200k_pcg_update(int n, double alpha, const double *p, const double *q, double *x, double *r, double *d_out);
+int b200k_copy(int n, const double *src, double *dst);
+int b200k_fill(int n, double v, double *dst);
+int b200k_scale(int n, double a, double *x);
+int b200k_axpy(int n, double a, const double *x, double *y);
+
+/* ---- preconditioner kernels (precond_kernels.cu) ---- */
+/* Nystrom: y = rhs(perm); z = U'y; out(perm) = y/eta + U((s - 1/eta) .* z) -- two passes over U (n x k col-major) */
+int b200k_nys_apply(int n, int k, const int *perm, const double *U, const double *s, double eta,
+                    const double *rhs, double *x, double *work /* n + k + partial sums */, size_t work_doubles);
+size_t b200k_nys_work_doubles(int n, int k);
+/* CSR y = A x (one warp per row) */
+int b200k_csr_mv(int nrows, const int *ia, const int *ja, const double *a, const double *x, double *y);
+/* gather / scatter by permutation */
+int b200k_gather_perm(int n, const int *perm, const double *src, double *dst);  /* dst[i] = src[perm[i]] */
+int b200k_scatter_perm(int n, const int *perm, const double *src, double *dst); /* dst[perm[i]] = src[i] */
+/* dense column-major GEMV on device: y = alpha*op(A)x + beta*y, A m x n, lda = m */
+int b200k_gemv(char trans, int m, int n, double alpha, const double *A, const double *x, double beta, double *y);
+/* dense additive kernel block K(rows, cols) on device (kernels.c:3099-3494 call shapes):
+ * Xw: window-major feature copy [P][dw][n] (missing features of a short last window flagged by dims[w] < dw) */
+int b200k_dense_additive(const double *Xw, int n, int P, int dw, const int *d_dims, int kernel, double ff, double l,
+                         double noise_diag, const int *rows, int nr, const int *cols, int nc, int lower_only,
+                         double *K, int ldk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,82 @@
+/* Private host-side structures of libnfft4gp_b200 (C). */
+#ifndef NFFT4GP_B200_HOST_H
+#define NFFT4GP_B200_HOST_H
+
+#include <stddef.h>
+#include "b200_dev.h"
+
+#define B200_MAGIC_WINDOW 0x42323057   /* "B20W" */
+#define B200_MAGIC_SINGLE 0x42323053   /* "B20S" */
+#define B200_MAGIC_ADDITIVE 0x42323041 /* "B20A" */
+#define B200_MAGIC_NYS 0x4232304e      /* "B20N" */
+#define B200_MAGIC_FSAI 0x42323046     /* "B20F" */
+#define B200_MAGIC_AFN 0x42323058      /* "B20X" */
+#define B200_MAGIC_DENSE 0x42323044    /* "B20D" */
+
+/* One feature window: the analogue of the reference's str_adj (SRC/external/nfft_interface.h:35-57). */
+typedef struct b200_window
+{
+   int magic;
+   int kernel; /* 0 Gauss, 1 Matern-1/2 */
+   int d;
+   double sigma[2];
+   double mu;
+   int N, p, m;
+   double eps;
+   int n, max_n;
+   int NN;
+   double scale;        /* < 0 until the points have been scaled (first kernel build) */
+   double kernel_scale; /* f */
+   int built;
+   int *h_perm;         /* host copy of sorted -> original */
+   void *owner;         /* b200_single* for the single-window API, NULL inside an additive kernel */
+   b200_win_dev dev;
+} b200_window;
+
+/* Private state behind nfft4gp_kernel._external of an additive NFFT kernel handle. */
+typedef struct b200_additive
+{
+   int magic;
+   int n, P, dw, skip_last;
+   int kernel, built;
+   b200_window **win;
+   int *dims;
+   double *d_x, *d_y; /* staging for the host-pointer API (n, 3n) */
+   const double **d_fptr, **d_f2ptr;
+   const int **d_invptr;
+   double *d_c1w;
+   /* multi-GPU */
+   int shard_mode; /* 0 none, 1 by window, 2 by point block */
+   int nlocal;     /* windows owned by this rank under mode 1 */
+   const double **d_fptr_local;
+   const int **d_invptr_local;
+   double *d_ypart;
+} b200_additive;
+
+void *b200_xmalloc(size_t bytes);
+void *b200_xcalloc(size_t n, size_t sz);
+
+b200_additive *b200_additive_from_handle(void *data);
+int b200_additive_matvec_dev(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y);
+int b200_additive_grad_matvec_dev(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y);
+int b200_window_matvec_dev(b200_window *w, int n, double alpha, const double *d_x, double beta, double *d_y);
+int b200_window_grad_matvec_dev(b200_window *w, int n, double alpha, const double *d_x, double beta, double *d_y);
+
+/* comm_host.c */
+int b200_comm_rank(void);
+int b200_comm_size(void);
+int b200_comm_owns_window(const b200_additive *A, int w);
+int b200_comm_allreduce_sum(double *d_buf, size_t count);
+int b200_additive_epilogue(b200_additive *A, int n, const double *d_x, double s, double ff, double mu, double beta, double *d_y);
+
+/* precond_host.c: device-resident applies used by the device PCG */
+typedef int (*b200_dev_solve)(void *prec, int n, double *d_x, const double *d_rhs);
+typedef int (*b200_dev_matvec)(void *mat, int n, double alpha, const double *d_x, double beta, double *d_y);
+b200_dev_solve b200_lookup_dev_solve(void *host_fn);
+b200_dev_matvec b200_lookup_dev_matvec(void *host_fn, void *mat_data, void **dev_handle);
+
+/* pcg_host.c */
+int b200_pcg_device(void *mat, int n, b200_dev_matvec mv, void *prec, b200_dev_solve ps, double *d_x, const double *d_rhs,
+                    int maxits, int atol, double tol, double *prel_res, double **prel_res_v, int *piter, int print_level);
+
+#endif

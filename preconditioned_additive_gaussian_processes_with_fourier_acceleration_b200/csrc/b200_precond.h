@@ -1,0 +1,70 @@
+/* Private preconditioner structures of libnfft4gp_b200 (C host side). */
+#ifndef NFFT4GP_B200_PRECOND_H
+#define NFFT4GP_B200_PRECOND_H
+
+#include <stddef.h>
+
+/* Nystrom: fields follow precond_nys (INC/_preconds.h:320-351) where they have a meaning here. */
+typedef struct
+{
+   int magic;
+   int k_setup;  /* requested rank */
+   int own_perm;
+   int *perm;    /* caller's permutation (host), landmarks first */
+   int n, k;
+   double eta;   /* mu * f^2 (nys.c:641) */
+   int *d_perm;
+   double *d_U;  /* n x k column-major */
+   double *d_s;  /* 1 / (sigma_i^2 + eta) */
+   double *d_work;
+   size_t work_doubles;
+   double *d_x, *d_rhs; /* staging for the host-pointer solve */
+   int cap;
+   double tset;
+} b200_nys;
+
+/* FSAI: G lower-triangular CSR (diagonal last in each row, INC/_preconds.h:271) and its explicit transpose. */
+typedef struct
+{
+   int magic;
+   int lfil;
+   int n, nnz;
+   int *d_ia, *d_ja;
+   double *d_a;
+   int *d_iat, *d_jat;
+   double *d_at;
+   double *d_work;
+   double *d_x, *d_rhs;
+   int cap;
+   double tset;
+} b200_fsai;
+
+/* AFN (afn.h:27-58 design; MATLAB afn_setup.m / afn_solve.m). */
+typedef struct
+{
+   int magic;
+   int max_k, lfil;
+   int n, k;
+   int *d_perm;
+   double *d_Linv; /* k x k explicit inverse of chol(K11 + shift), lower, column-major */
+   double *d_K12;  /* k x (n-k) column-major */
+   b200_fsai schur;
+   void *nys;      /* set when the estimated rank is below max_k: Nystrom on the FPS ordering */
+   double *d_work; /* 2n + 2k */
+   double *d_x, *d_rhs;
+   int cap;
+   double tset;
+} b200_afn;
+
+int b200_nys_set_device_factors(b200_nys *s, int n, int k, const int *h_perm, double *d_U_owned, const double *h_s, double eta);
+int b200_fsai_set_host_factors(b200_fsai *s, int n, const int *ia, const int *ja, const double *a);
+int b200_afn_set_device_factors(b200_afn *s, int n, int k, const int *h_perm, const double *h_L, double *d_K12_owned,
+                                const int *ia, const int *ja, const double *a);
+void b200_fsai_release(b200_fsai *s);
+void b200_afn_release(b200_afn *s);
+void b200_tril_inverse(int k, const double *L, double *Linv);
+int b200_nys_solve_dev(void *vnys, int n, double *d_x, const double *d_rhs);
+int b200_fsai_solve_dev(void *vf, int n, double *d_x, const double *d_rhs);
+int b200_afn_solve_dev(void *va, int n, double *d_x, const double *d_rhs);
+
+#endif

@@ -1,0 +1,190 @@
+// Device runtime of libnfft4gp_b200: device selection, memory, one library stream, events, launch counter.
+// There is deliberately NO CPU fallback: every entry point fails loudly when no CUDA device is usable.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <atomic>
+
+#include "b200_dev.h"
+#include "b200_cuda_util.cuh"
+
+static int g_device = -1;
+static cudaStream_t g_stream = nullptr;
+std::atomic<long long> g_launches{0};
+
+cudaStream_t b200_stream() { return g_stream; }
+void b200_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+extern "C" {
+
+int b200_device_count(void)
+{
+   int c = 0;
+   if (cudaGetDeviceCount(&c) != cudaSuccess)
+   {
+      cudaGetLastError();
+      return 0;
+   }
+   return c;
+}
+
+int b200_initialized(void) { return g_device >= 0; }
+
+int b200_init(int device)
+{
+   if (g_device >= 0 && (device < 0 || device == g_device))
+      return 0;
+   int count = b200_device_count();
+   if (count <= 0)
+   {
+      fprintf(stderr, "nfft4gp_b200: FATAL: no CUDA device visible; this library has no CPU fallback.\n");
+      return -1;
+   }
+   if (device < 0)
+   {
+      const char *lr = getenv("LOCAL_RANK");
+      device = lr ? atoi(lr) % count : 0;
+   }
+   if (device >= count)
+   {
+      fprintf(stderr, "nfft4gp_b200: FATAL: device %d requested but only %d visible.\n", device, count);
+      return -1;
+   }
+   B200_CHECK(cudaSetDevice(device));
+   cudaDeviceProp prop;
+   B200_CHECK(cudaGetDeviceProperties(&prop, device));
+   if (prop.major < 10)
+   {
+      fprintf(stderr, "nfft4gp_b200: FATAL: device %d is sm_%d%d; kernels are built for sm_100a only.\n", device, prop.major, prop.minor);
+      return -1;
+   }
+   if (g_stream)
+      cudaStreamDestroy(g_stream);
+   B200_CHECK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+   g_device = device;
+   return 0;
+}
+
+static int ensure_init(void) { return g_device >= 0 ? 0 : b200_init(-1); }
+
+void *b200_malloc(size_t bytes)
+{
+   void *p = nullptr;
+   if (ensure_init())
+      return nullptr;
+   if (bytes == 0)
+      bytes = 8;
+   cudaError_t e = cudaMalloc(&p, bytes);
+   if (e != cudaSuccess)
+   {
+      fprintf(stderr, "nfft4gp_b200: cudaMalloc(%zu) failed: %s\n", bytes, cudaGetErrorString(e));
+      exit(EXIT_FAILURE); /* reference semantics: allocation failure terminates (SRC/utils/memory.h:85-95) */
+   }
+   return p;
+}
+
+void b200_free(void *p)
+{
+   if (p)
+      cudaFree(p);
+}
+
+void *b200_host_alloc(size_t bytes)
+{
+   void *p = nullptr;
+   if (ensure_init())
+      return nullptr;
+   if (bytes == 0)
+      bytes = 8;
+   if (cudaMallocHost(&p, bytes) != cudaSuccess)
+   {
+      fprintf(stderr, "nfft4gp_b200: cudaMallocHost(%zu) failed\n", bytes);
+      exit(EXIT_FAILURE);
+   }
+   return p;
+}
+
+void b200_host_free(void *p)
+{
+   if (p)
+      cudaFreeHost(p);
+}
+
+int b200_h2d(void *dst, const void *src, size_t bytes)
+{
+   if (ensure_init())
+      return -1;
+   B200_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream));
+   return 0;
+}
+
+int b200_d2h(void *dst, const void *src, size_t bytes)
+{
+   if (ensure_init())
+      return -1;
+   B200_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
+   B200_CHECK(cudaStreamSynchronize(g_stream));
+   return 0;
+}
+
+int b200_d2d(void *dst, const void *src, size_t bytes)
+{
+   if (ensure_init())
+      return -1;
+   B200_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream));
+   return 0;
+}
+
+int b200_memset(void *dst, int v, size_t bytes)
+{
+   if (ensure_init())
+      return -1;
+   B200_CHECK(cudaMemsetAsync(dst, v, bytes, g_stream));
+   return 0;
+}
+
+int b200_sync(void)
+{
+   if (ensure_init())
+      return -1;
+   B200_CHECK(cudaStreamSynchronize(g_stream));
+   return 0;
+}
+
+void *b200_event_create(void)
+{
+   cudaEvent_t ev;
+   if (ensure_init())
+      return nullptr;
+   if (cudaEventCreate(&ev) != cudaSuccess)
+      return nullptr;
+   return (void *)ev;
+}
+
+void b200_event_destroy(void *ev)
+{
+   if (ev)
+      cudaEventDestroy((cudaEvent_t)ev);
+}
+
+int b200_event_record(void *ev)
+{
+   B200_CHECK(cudaEventRecord((cudaEvent_t)ev, g_stream));
+   return 0;
+}
+
+float b200_event_elapsed_ms(void *a, void *b)
+{
+   float ms = -1.0f;
+   if (cudaEventSynchronize((cudaEvent_t)b) != cudaSuccess)
+      return -1.0f;
+   if (cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b) != cudaSuccess)
+      return -1.0f;
+   return ms;
+}
+
+long long b200_launch_count(void) { return g_launches.load(); }
+void b200_launch_count_reset(void) { g_launches.store(0); }
+void *b200_stream_handle(void) { return (void *)g_stream; }
+
+} // extern "C"

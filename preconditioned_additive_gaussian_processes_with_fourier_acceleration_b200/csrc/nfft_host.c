@@ -1,0 +1,1073 @@
+/* Host side (C) of the NFFT interface of libnfft4gp_b200: handle life cycle, per-window point scaling and
+ * cell sort, kernel Fourier coefficients, and the matvec drivers that sequence the CUDA kernels.
+ * Mirrors the operator interface of the reference's SRC/external/nfft_interface.c (same names, argument
+ * meaning, return codes) -- each function cites the lines it replaces.  The arithmetic of the hot path
+ * (NFFT3 fastsum in the reference) runs entirely on the GPU; there is no CPU fallback. */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nfft4gp_b200.h"
+#include "b200_dev.h"
+#include "b200_host.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846264338327950288
+#endif
+
+int g_variant_spread3 = 1, g_variant_gather3 = 1;
+
+/* ------------------------------------------------------------------ small host utilities */
+void *b200_xmalloc(size_t bytes)
+{
+   void *p = malloc(bytes ? bytes : 1);
+   if (!p)
+   {
+      printf("Error: nfft4gp_b200 host allocation of %zu bytes failed.\n", bytes);
+      exit(EXIT_FAILURE); /* SRC/utils/memory.h:85-95 */
+   }
+   return p;
+}
+
+void *b200_xcalloc(size_t n, size_t sz)
+{
+   void *p = calloc(n ? n : 1, sz ? sz : 1);
+   if (!p)
+   {
+      printf("Error: nfft4gp_b200 host allocation failed.\n");
+      exit(EXIT_FAILURE);
+   }
+   return p;
+}
+
+static size_t ipow(int b, int e)
+{
+   size_t r = 1;
+   while (e-- > 0)
+      r *= (size_t)b;
+   return r;
+}
+
+/* modified Bessel function I0, power series (all terms positive) */
+static double bessel_i0(double x)
+{
+   double q = 0.25 * x * x, term = 1.0, sum = 1.0;
+   int k;
+   for (k = 1; k < 1000; k++)
+   {
+      term *= q / ((double)k * (double)k);
+      sum += term;
+      if (term < 1e-20 * sum)
+         break;
+   }
+   return sum;
+}
+
+/* phi_hat(k) of the Kaiser-Bessel window, sigma = 2, b = pi (2 - 1/sigma) */
+static double kb_phi_hat(int k)
+{
+   double b = M_PI * (2.0 - 0.5);
+   double w = 2.0 * M_PI * (double)k / (double)B200_NOS;
+   return bessel_i0((double)B200_MCUT * sqrt(b * b - w * w));
+}
+
+/* in-place Stockham radix-2 DFT of length n (power of two) with stride, sign -1: e^{-2 pi i jk/n} */
+static void host_fft_strided(double *re, double *im, int n, size_t stride, int sign, double *wr, double *wi, double *tr, double *ti)
+{
+   int half = n / 2, l, m, j, k;
+   double *ar = wr + n, *ai = wi + n; /* scratch copies live after the twiddles */
+   for (j = 0; j < n; j++)
+   {
+      ar[j] = re[(size_t)j * stride];
+      ai[j] = im[(size_t)j * stride];
+   }
+   /* Stockham autosort: l = number of sub-transforms, m = their current length */
+   for (l = half, m = 1; l >= 1; l >>= 1, m <<= 1)
+   {
+      for (j = 0; j < l; j++)
+      {
+         double c = wr[j * m], s = sign * wi[j * m];
+         for (k = 0; k < m; k++)
+         {
+            double x0r = ar[k + j * m], x0i = ai[k + j * m];
+            double x1r = ar[k + j * m + l * m], x1i = ai[k + j * m + l * m];
+            double dr = x0r - x1r, di = x0i - x1i;
+            tr[k + 2 * j * m] = x0r + x1r;
+            ti[k + 2 * j * m] = x0i + x1i;
+            tr[k + 2 * j * m + m] = dr * c - di * s;
+            ti[k + 2 * j * m + m] = dr * s + di * c;
+         }
+      }
+      memcpy(ar, tr, sizeof(double) * (size_t)n);
+      memcpy(ai, ti, sizeof(double) * (size_t)n);
+   }
+   for (j = 0; j < n; j++)
+   {
+      re[(size_t)j * stride] = ar[j];
+      im[(size_t)j * stride] = ai[j];
+   }
+}
+
+/* d-dimensional unnormalised DFT of an n^d row-major array (split re / im), sign as above */
+static void host_fft_nd(double *re, double *im, int d, int n, int sign)
+{
+   size_t total = ipow(n, d), npencil = total / (size_t)n, p;
+   double *wr = (double *)b200_xmalloc(sizeof(double) * 2 * (size_t)n);
+   double *wi = (double *)b200_xmalloc(sizeof(double) * 2 * (size_t)n);
+   double *tr = (double *)b200_xmalloc(sizeof(double) * (size_t)n);
+   double *ti = (double *)b200_xmalloc(sizeof(double) * (size_t)n);
+   int t, j;
+   for (j = 0; j < n; j++)
+   {
+      long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n;
+      wr[j] = (double)cosl(a);
+      wi[j] = (double)sinl(a);
+   }
+   for (t = 0; t < d; t++)
+   {
+      size_t stride = ipow(n, d - 1 - t);
+      for (p = 0; p < npencil; p++)
+      {
+         size_t hi = p / stride, lo = p % stride;
+         size_t base = hi * stride * (size_t)n + lo;
+         host_fft_strided(re + base, im + base, n, stride, sign, wr, wi, tr, ti);
+      }
+   }
+   free(wr);
+   free(wi);
+   free(tr);
+   free(ti);
+}
+
+/* swap halves along every dimension (n even) */
+static void host_fftshift_nd(double *re, double *im, int d, int n)
+{
+   size_t total = ipow(n, d), idx;
+   double *r2 = (double *)b200_xmalloc(sizeof(double) * total);
+   double *i2 = (double *)b200_xmalloc(sizeof(double) * total);
+   int t;
+   for (idx = 0; idx < total; idx++)
+   {
+      size_t rem = idx, dst = 0, mul = 1;
+      for (t = d - 1; t >= 0; t--)
+      {
+         int c = (int)(rem % (size_t)n);
+         rem /= (size_t)n;
+         dst += (size_t)((c + n / 2) % n) * mul;
+         mul *= (size_t)n;
+      }
+      r2[dst] = re[idx];
+      i2[dst] = im[idx];
+   }
+   memcpy(re, r2, sizeof(double) * total);
+   memcpy(im, i2, sizeof(double) * total);
+   free(r2);
+   free(i2);
+}
+
+/* radial kernels of the reference's four fastsum plans (nfft_interface.c:227,230,363,366); which = 1: derivative kernel */
+static double radial_kernel(int kernel, int which, double r, double c)
+{
+   if (kernel == 0)
+   {
+      double q = r * r / (c * c);
+      return which ? q * exp(-q) : exp(-q);
+   }
+   else
+   {
+      double q = fabs(r) / c;
+      return which ? q * exp(-q) : exp(-q);
+   }
+}
+
+/* coef_k = b_k / prod_t phi_hat(k_t)^2 with b = fftshift(FFT_forward(fftshift(K(min(|j/N - 1/2|, 1/2)) / N^d)))
+ * (NFFT3 fastsum_precompute_kernel with eps_I = eps_B = 0).  Interleaved complex out. */
+static void build_coef(int d, int kernel, int which, double c, double *out)
+{
+   int N = B200_NBAND, t;
+   size_t total = ipow(N, d), j;
+   double *re = (double *)b200_xmalloc(sizeof(double) * total);
+   double *im = (double *)b200_xcalloc(total, sizeof(double));
+   double ph[B200_NBAND];
+   for (j = 0; j < total; j++)
+   {
+      double r;
+      if (d == 1)
+      {
+         r = -((double)j / (double)N - 0.5);
+         if (r < -0.5)
+            r = -0.5;
+         if (r > 0.5)
+            r = 0.5;
+      }
+      else
+      {
+         size_t kk = j;
+         double r2 = 0.0;
+         for (t = 0; t < d; t++)
+         {
+            double cc = (double)(kk % (size_t)N) / (double)N - 0.5;
+            r2 += cc * cc;
+            kk /= (size_t)N;
+         }
+         r = sqrt(r2);
+         if (r >= 0.5)
+            r = 0.5;
+      }
+      re[j] = radial_kernel(kernel, which, r, c) / (double)total;
+   }
+   host_fftshift_nd(re, im, d, N);
+   host_fft_nd(re, im, d, N, -1);
+   host_fftshift_nd(re, im, d, N);
+   for (t = 0; t < N; t++)
+      ph[t] = 1.0 / kb_phi_hat(t - N / 2);
+   for (j = 0; j < total; j++)
+   {
+      size_t rem = j;
+      double s = 1.0;
+      for (t = 0; t < d; t++)
+      {
+         s *= ph[rem % (size_t)N];
+         rem /= (size_t)N;
+      }
+      s *= s;
+      out[2 * j] = re[j] * s;
+      out[2 * j + 1] = im[j] * s;
+   }
+   free(re);
+   free(im);
+}
+
+/* ------------------------------------------------------------------ window (str_adj analogue) */
+static b200_window *window_create(int max_n, int dim)
+{
+   b200_window *w = (b200_window *)b200_xcalloc(1, sizeof(b200_window));
+   w->magic = B200_MAGIC_WINDOW;
+   w->d = dim;
+   w->N = B200_NBAND; /* nfft_interface.c:18-21 */
+   w->p = 1;
+   w->m = B200_MCUT;
+   w->eps = 0.0;
+   w->NN = B200_NOS; /* nfft_interface.c:25-27 */
+   w->scale = -1.0;
+   w->kernel_scale = 1.0;
+   w->max_n = max_n;
+   w->n = 0;
+   return w;
+}
+
+static void window_free_device(b200_window *w)
+{
+   b200_win_dev *v = &w->dev;
+   b200_free(v->psi);
+   b200_free(v->key);
+   b200_free(v->perm);
+   b200_free(v->inv);
+   b200_free(v->seg_start);
+   b200_free(v->seg_cnt);
+   b200_free(v->seg_base);
+   b200_free(v->a);
+   b200_free(v->f);
+   b200_free(v->f2);
+   b200_free(v->grid);
+   b200_free(v->specA);
+   b200_free(v->specB);
+   b200_free(v->band);
+   b200_free(v->coef);
+   b200_free(v->dcoef);
+   memset(v, 0, sizeof(*v));
+}
+
+static void window_free(b200_window *w)
+{
+   if (!w)
+      return;
+   window_free_device(w);
+   free(w->h_perm);
+   free(w);
+}
+
+typedef struct
+{
+   int start, cnt, base;
+} seg_t;
+
+static int seg_cmp(const void *a, const void *b)
+{
+   const seg_t *x = (const seg_t *)a, *y = (const seg_t *)b;
+   if (x->cnt != y->cnt)
+      return y->cnt - x->cnt;
+   return x->start - y->start;
+}
+
+/* First-call part of nfft_interface.c:150-213: centre every feature, r_max, scale to radius 0.25 (unless
+ * r_max is already in [0.125, 0.25]), point-major transpose -- same sequential fp64 arithmetic as the reference
+ * so that `scale` is bit-identical -- followed by this library's own bin sort by oversampled-grid cell.
+ * `cols` holds the window's d feature columns, n contiguous values each (feature-major, ldim = n). */
+static int window_setup_points(b200_window *w, const double *cols, int n)
+{
+   int d = w->d, i, j, t;
+   size_t nbins = ipow(B200_NOS, d);
+   double radius = 0.0;
+   double *tmp, *xs;
+   int *keys, *binstart, *perm, *inv;
+   b200_win_dev *v = &w->dev;
+
+   if (d < 1 || d > 3)
+   {
+      printf("Error: nfft4gp_b200 supports window dimensions 1..3, got %d.\n", d);
+      return -1;
+   }
+   if (b200_init(-1))
+      return -1;
+   tmp = (double *)b200_xmalloc(sizeof(double) * (size_t)n * d);
+   memcpy(tmp, cols, sizeof(double) * (size_t)n * d);
+   for (i = 0; i < d; i++)
+   {
+      double c = 0.0;
+      for (j = 0; j < n; j++)
+         c += tmp[(size_t)i * n + j];
+      c /= (double)n;
+      for (j = 0; j < n; j++)
+         tmp[(size_t)i * n + j] -= c;
+   }
+   for (j = 0; j < n; j++)
+   {
+      double r = 0.0;
+      for (i = 0; i < d; i++)
+         r += tmp[(size_t)i * n + j] * tmp[(size_t)i * n + j];
+      r = sqrt(r);
+      if (r > radius)
+         radius = r;
+   }
+   if (radius > 0.25 || radius < 0.125)
+   {
+      w->scale = 0.25 / radius;
+      for (j = 0; j < n * d; j++)
+         tmp[j] *= w->scale;
+   }
+   else
+      w->scale = 1.0;
+
+   /* cell keys, stable counting sort */
+   keys = (int *)b200_xmalloc(sizeof(int) * (size_t)n);
+   binstart = (int *)b200_xcalloc(nbins + 1, sizeof(int));
+   for (j = 0; j < n; j++)
+   {
+      int k = 0;
+      for (t = 0; t < d; t++)
+      {
+         int c = (int)floor(tmp[(size_t)t * n + j] * (double)B200_NOS);
+         k = (k << 6) | ((c + 32) & 63);
+      }
+      keys[j] = k;
+      binstart[k + 1]++;
+   }
+   for (i = 0; i < (int)nbins; i++)
+      binstart[i + 1] += binstart[i];
+   perm = (int *)b200_xmalloc(sizeof(int) * (size_t)n);
+   inv = (int *)b200_xmalloc(sizeof(int) * (size_t)n);
+   {
+      int *cursor = (int *)b200_xmalloc(sizeof(int) * nbins);
+      memcpy(cursor, binstart, sizeof(int) * nbins);
+      for (j = 0; j < n; j++)
+      {
+         int pos = cursor[keys[j]]++;
+         perm[pos] = j;
+         inv[j] = pos;
+      }
+      free(cursor);
+   }
+   /* sorted, point-major scaled coordinates */
+   xs = (double *)b200_xmalloc(sizeof(double) * (size_t)n * d);
+   for (j = 0; j < n; j++)
+      for (t = 0; t < d; t++)
+         xs[(size_t)j * d + t] = tmp[(size_t)t * n + perm[j]];
+   free(tmp);
+
+   /* device state */
+   window_free_device(w);
+   v->d = d;
+   v->n = n;
+   {
+      size_t pad = 16, gsz = ipow(B200_NOS, d), bsz = ipow(B200_NBAND, d);
+      double *d_xs = (double *)b200_malloc(sizeof(double) * (size_t)n * d);
+      v->psi = (double *)b200_malloc(sizeof(double) * ((size_t)n + pad) * d * B200_TAPS);
+      b200_memset(v->psi, 0, sizeof(double) * ((size_t)n + pad) * d * B200_TAPS);
+      v->key = (int *)b200_malloc(sizeof(int) * (size_t)n);
+      v->perm = (int *)b200_malloc(sizeof(int) * (size_t)n);
+      v->inv = (int *)b200_malloc(sizeof(int) * (size_t)n);
+      v->a = (double *)b200_malloc(sizeof(double) * ((size_t)n + pad));
+      b200_memset(v->a, 0, sizeof(double) * ((size_t)n + pad));
+      v->f = (double *)b200_malloc(sizeof(double) * (size_t)n);
+      v->f2 = NULL; /* allocated on the first gradient matvec */
+      v->grid = (double *)b200_malloc(sizeof(double) * gsz);
+      v->specA = (double *)b200_malloc(sizeof(double) * gsz); /* complex [64^(d-1)][32] */
+      v->specB = (double *)b200_malloc(sizeof(double) * gsz);
+      v->band = (double *)b200_malloc(sizeof(double) * 2 * bsz);
+      v->coef = (double *)b200_malloc(sizeof(double) * 2 * bsz);
+      v->dcoef = (double *)b200_malloc(sizeof(double) * 2 * bsz);
+      b200_h2d(d_xs, xs, sizeof(double) * (size_t)n * d);
+      b200_h2d(v->perm, perm, sizeof(int) * (size_t)n);
+      b200_h2d(v->inv, inv, sizeof(int) * (size_t)n);
+
+      /* segments: runs of one cell, split at B200_SEG_MAX, sorted by size (descending) so that the 8 jobs of a CTA
+       * of the tiled kernels carry similar work and the longest CTAs start first */
+      if (d == 3)
+      {
+         int nseg = 0, cap = 1024, b;
+         seg_t *segs = (seg_t *)b200_xmalloc(sizeof(seg_t) * (size_t)cap);
+         int *hs, *hc, *hb, npad;
+         for (b = 0; b < (int)nbins; b++)
+         {
+            int s = binstart[b], e = binstart[b + 1];
+            while (s < e)
+            {
+               int c = e - s > B200_SEG_MAX ? B200_SEG_MAX : e - s;
+               if (nseg == cap)
+               {
+                  cap *= 2;
+                  segs = (seg_t *)realloc(segs, sizeof(seg_t) * (size_t)cap);
+                  if (!segs)
+                     exit(EXIT_FAILURE);
+               }
+               segs[nseg].start = s;
+               segs[nseg].cnt = c;
+               segs[nseg].base = b;
+               nseg++;
+               s += c;
+            }
+         }
+         qsort(segs, (size_t)nseg, sizeof(seg_t), seg_cmp);
+         npad = (nseg + B200_JOBS - 1) / B200_JOBS * B200_JOBS;
+         if (npad == 0)
+            npad = B200_JOBS;
+         hs = (int *)b200_xcalloc((size_t)npad, sizeof(int));
+         hc = (int *)b200_xcalloc((size_t)npad, sizeof(int));
+         hb = (int *)b200_xcalloc((size_t)npad, sizeof(int));
+         for (i = 0; i < nseg; i++)
+         {
+            hs[i] = segs[i].start;
+            hc[i] = segs[i].cnt;
+            hb[i] = segs[i].base;
+         }
+         v->nseg = nseg;
+         v->seg_start = (int *)b200_malloc(sizeof(int) * (size_t)npad);
+         v->seg_cnt = (int *)b200_malloc(sizeof(int) * (size_t)npad);
+         v->seg_base = (int *)b200_malloc(sizeof(int) * (size_t)npad);
+         b200_h2d(v->seg_start, hs, sizeof(int) * (size_t)npad);
+         b200_h2d(v->seg_cnt, hc, sizeof(int) * (size_t)npad);
+         b200_h2d(v->seg_base, hb, sizeof(int) * (size_t)npad);
+         b200_sync();
+         free(hs);
+         free(hc);
+         free(hb);
+         free(segs);
+      }
+      if (b200k_psi(v, d_xs) || b200_sync())
+         return -1;
+      b200_free(d_xs);
+   }
+   free(w->h_perm);
+   w->h_perm = perm;
+   free(inv);
+   free(xs);
+   free(keys);
+   free(binstart);
+   w->n = n;
+   return 0;
+}
+
+/* Every-call part of nfft_interface.c:215-259 (Gauss) / 351-395 (Matern-1/2): new length scale -> new Fourier
+ * coefficient tables for the kernel and its derivative kernel.  The node-dependent tables are NOT rebuilt. */
+static int window_build(b200_window *w, int kernel, double f, double l, double mu)
+{
+   size_t bsz = ipow(B200_NBAND, w->d);
+   double *c = (double *)b200_xmalloc(sizeof(double) * 2 * bsz);
+   w->kernel = kernel;
+   w->sigma[0] = kernel == 0 ? l * w->scale * sqrt(2.0) : l * w->scale; /* :219 / :355 */
+   w->sigma[1] = w->sigma[0];
+   w->mu = mu;
+   build_coef(w->d, kernel, 0, w->sigma[0], c);
+   if (b200_h2d(w->dev.coef, c, sizeof(double) * 2 * bsz))
+      return -1;
+   build_coef(w->d, kernel, 1, w->sigma[1], c);
+   if (b200_h2d(w->dev.dcoef, c, sizeof(double) * 2 * bsz) || b200_sync())
+      return -1;
+   free(c);
+   w->kernel_scale = f; /* :256 */
+   w->built = 1;
+   return 0;
+}
+
+/* adjoint NFFT of (s * x) and interpolation with the kernel's coefficients -> dev.f (sorted order) */
+static int window_apply(b200_window *w, const double *d_x, double s, int with_derivative)
+{
+   b200_win_dev *v = &w->dev;
+   if (b200k_prep(v, d_x, s) || b200k_spread(v, g_variant_spread3) || b200k_forward_fft(v) ||
+       b200k_backward_fft(v, v->coef) || b200k_gather(v, v->f, g_variant_gather3))
+      return -1;
+   if (with_derivative)
+   {
+      if (!v->f2)
+         v->f2 = (double *)b200_malloc(sizeof(double) * (size_t)v->n);
+      /* the adjoint is shared between kernel and derivative kernel (the reference runs it twice, :533-534) */
+      if (b200k_backward_fft(v, v->dcoef) || b200k_gather(v, v->f2, g_variant_gather3))
+         return -1;
+   }
+   return 0;
+}
+
+/* gradient scale factor of nfft_interface.c:536-537 without the f^2 */
+static double window_grad_scale(const b200_window *w)
+{
+   return w->kernel == 0 ? 2.0 * w->scale * sqrt(2.0) / w->sigma[1] : w->scale / w->sigma[1];
+}
+
+/* ------------------------------------------------------------------ single-window API */
+static nfft4gp_kernel *kernel_shell(int max_n)
+{
+   nfft4gp_kernel *k = (nfft4gp_kernel *)b200_xcalloc(1, sizeof(nfft4gp_kernel));
+   k->_max_n = max_n;
+   k->_noise_level = 0.0;
+   return k;
+}
+
+typedef struct
+{
+   int magic;
+   b200_window *win;
+   double *d_x, *d_y;     /* staging for the host-pointer API: n and 3n */
+   const double **d_fptr; /* device arrays with one entry */
+   const double **d_f2ptr;
+   const int **d_invptr;
+   double *d_c1w;
+} b200_single;
+
+/* nfft_interface.c:3-42 */
+void *Nfft4GPNFFTKernelParamCreate(int max_n, int dim)
+{
+   nfft4gp_kernel *k = kernel_shell(max_n);
+   b200_single *s = (b200_single *)b200_xcalloc(1, sizeof(b200_single));
+   s->magic = B200_MAGIC_SINGLE;
+   s->win = window_create(max_n, dim);
+   s->win->owner = s;
+   k->_external = s;
+   printf("Initializing NFFT kernel with N = %d, p = %d, m = %d, eps = %4.2f\n", s->win->N, s->win->p, s->win->m, s->win->eps);
+   printf("Problem size: %d, problem dimension: %d\n", max_n, dim);
+   return k;
+}
+
+static void single_free_device(b200_single *s)
+{
+   b200_free(s->d_x);
+   b200_free(s->d_y);
+   b200_free((void *)s->d_fptr);
+   b200_free((void *)s->d_f2ptr);
+   b200_free((void *)s->d_invptr);
+   b200_free(s->d_c1w);
+   s->d_x = s->d_y = s->d_c1w = NULL;
+   s->d_fptr = s->d_f2ptr = NULL;
+   s->d_invptr = NULL;
+}
+
+/* nfft_interface.c:44-77 */
+void Nfft4GPNFFTKernelParamFree(void *kernel)
+{
+   nfft4gp_kernel *k = (nfft4gp_kernel *)kernel;
+   if (!k)
+      return;
+   b200_single *s = (b200_single *)k->_external;
+   if (s)
+   {
+      single_free_device(s);
+      window_free(s->win);
+      free(s);
+   }
+   free(k);
+}
+
+/* nfft_interface.c:79-82 */
+void Nfft4GPNFFTKernelFree(void *str) { (void)str; }
+
+static int single_kernel_build(void *str, int kernel, double *data, int n, int ldim, int d, double **Kp, double **dKp)
+{
+   nfft4gp_kernel *k = (nfft4gp_kernel *)str;
+   b200_single *s = (b200_single *)k->_external;
+   b200_window *w = s->win;
+   if (Kp == NULL || dKp == NULL)
+   {
+      printf("Error: NFFT kernel requires Kp and dKp to be not NULL.\n"); /* :136-140 */
+      return -1;
+   }
+   if (n != ldim)
+   {
+      printf("Error: NFFT kernel requires n == ldim.\n"); /* :142-146 */
+      return -1;
+   }
+   if (d != w->d)
+   {
+      printf("Error: NFFT kernel created for dimension %d, got %d.\n", w->d, d);
+      return -1;
+   }
+   if (w->scale < 0.0) /* :150 */
+   {
+      if (window_setup_points(w, data, n))
+         return -1;
+   }
+   if (window_build(w, kernel, k->_params[0], k->_params[1], k->_noise_level))
+      return -1;
+   *Kp = (double *)w; /* :258-259 */
+   *dKp = (double *)w;
+   return 0;
+}
+
+/* nfft_interface.c:129-263 */
+int Nfft4GPNFFTKernelGaussianKernel(void *str, double *data, int n, int ldim, int d, int *permr, int kr, int *permc, int kc,
+                                    double **Kp, double **dKp)
+{
+   (void)permr; (void)kr; (void)permc; (void)kc;
+   return single_kernel_build(str, 0, data, n, ldim, d, Kp, dKp);
+}
+
+/* nfft_interface.c:265-398 */
+int Nfft4GPNFFTKernelMatern12Kernel(void *str, double *data, int n, int ldim, int d, int *permr, int kr, int *permc, int kc,
+                                    double **Kp, double **dKp)
+{
+   (void)permr; (void)kr; (void)permc; (void)kc;
+   return single_kernel_build(str, 1, data, n, ldim, d, Kp, dKp);
+}
+
+static int single_ensure_staging(b200_single *s, int n)
+{
+   if (!s->d_x)
+   {
+      const double *fp;
+      const int *ip;
+      s->d_x = (double *)b200_malloc(sizeof(double) * (size_t)n);
+      s->d_y = (double *)b200_malloc(sizeof(double) * 3 * (size_t)n);
+      s->d_fptr = (const double **)b200_malloc(sizeof(double *));
+      s->d_f2ptr = (const double **)b200_malloc(sizeof(double *));
+      s->d_invptr = (const int **)b200_malloc(sizeof(int *));
+      s->d_c1w = (double *)b200_malloc(sizeof(double));
+      fp = s->win->dev.f;
+      ip = s->win->dev.inv;
+      if (b200_h2d((void *)s->d_fptr, &fp, sizeof(fp)) || b200_h2d((void *)s->d_invptr, &ip, sizeof(ip)) || b200_sync())
+         return -1;
+   }
+   return 0;
+}
+
+int b200_window_matvec_dev(b200_window *w, int n, double alpha, const double *d_x, double beta, double *d_y)
+{
+   b200_single *s = (b200_single *)w->owner;
+   double ff = w->kernel_scale * w->kernel_scale;
+   if (!w->built || n != w->n)
+   {
+      printf("Error: NFFT matvec on a kernel that was not built for n = %d.\n", n);
+      return -1;
+   }
+   if (!s || single_ensure_staging(s, n))
+      return -1;
+   if (window_apply(w, d_x, alpha, 0))
+      return -1;
+   return b200k_combine(n, 1, s->d_fptr, s->d_invptr, d_x, alpha, ff, w->mu, beta, d_y);
+}
+
+int b200_window_grad_matvec_dev(b200_window *w, int n, double alpha, const double *d_x, double beta, double *d_y)
+{
+   b200_single *s = (b200_single *)w->owner;
+   double ff = w->kernel_scale * w->kernel_scale, f2 = w->kernel_scale * 2.0, c1;
+   const double *fp;
+   if (!w->built || n != w->n)
+   {
+      printf("Error: NFFT matvec on a kernel that was not built for n = %d.\n", n);
+      return -1;
+   }
+   if (!s || single_ensure_staging(s, n))
+      return -1;
+   if (window_apply(w, d_x, alpha, 1))
+      return -1;
+   fp = w->dev.f2;
+   c1 = ff * window_grad_scale(w);
+   if (b200_h2d((void *)s->d_f2ptr, &fp, sizeof(fp)) || b200_h2d(s->d_c1w, &c1, sizeof(c1)) || b200_sync())
+      return -1;
+   return b200k_combine_grad(n, 1, s->d_fptr, s->d_f2ptr, s->d_invptr, d_x, alpha, f2, ff, s->d_c1w, w->mu, beta, d_y);
+}
+
+static int single_host_call(void *data, int n, double alpha, double *x, double beta, double *y, int grad)
+{
+   b200_window *w = (b200_window *)data;
+   b200_single *s;
+   size_t ny = grad ? 3 * (size_t)n : (size_t)n;
+   int rc;
+   if (!w || w->magic != B200_MAGIC_WINDOW)
+   {
+      printf("Error: Nfft4GPNFFTMatSymv needs the pointer returned by the NFFT kernel function.\n");
+      return -1;
+   }
+   s = (b200_single *)w->owner;
+   if (!s || single_ensure_staging(s, n))
+      return -1;
+   if (b200_h2d(s->d_x, x, sizeof(double) * (size_t)n))
+      return -1;
+   if (beta != 0.0 && b200_h2d(s->d_y, y, sizeof(double) * ny))
+      return -1;
+   rc = grad ? b200_window_grad_matvec_dev(w, n, alpha, s->d_x, beta, s->d_y) : b200_window_matvec_dev(w, n, alpha, s->d_x, beta, s->d_y);
+   if (rc)
+      return -1;
+   return b200_d2h(y, s->d_y, sizeof(double) * ny);
+}
+
+/* nfft_interface.c:400-497 */
+int Nfft4GPNFFTMatSymv(void *data, int n, double alpha, double *x, double beta, double *y)
+{
+   return single_host_call(data, n, alpha, x, beta, y, 0);
+}
+
+/* nfft_interface.c:499-620 */
+int Nfft4GPNFFTGradMatSymv(void *data, int n, double alpha, double *x, double beta, double *y)
+{
+   return single_host_call(data, n, alpha, x, beta, y, 1);
+}
+
+/* ------------------------------------------------------------------ additive (multi-window) API */
+
+/* nfft_interface.c:622-674 */
+void *Nfft4GPNFFTAdditiveKernelParamCreate(double *data, int n, int ldim, int d, int *windows, int nwindows, int dwindows)
+{
+   nfft4gp_kernel *k = kernel_shell(3 * n);
+   b200_additive *A = (b200_additive *)b200_xcalloc(1, sizeof(b200_additive));
+   int skip = 1, i, j;
+   int *fw = windows;
+   double *dst;
+   (void)d;
+   A->magic = B200_MAGIC_ADDITIVE;
+   A->n = n;
+   A->P = nwindows;
+   A->dw = dwindows;
+   k->_iparams[0] = nwindows;
+   k->_iparams[1] = dwindows;
+   k->_iparams[2] = 0;
+   while (skip < dwindows && windows[nwindows * dwindows - skip] < 0)
+   {
+      skip++;
+      k->_iparams[2]++;
+   }
+   A->skip_last = k->_iparams[2];
+   k->_ibufferp = (int **)b200_xmalloc(sizeof(int *));
+   k->_ibufferp[0] = windows; /* caller-owned, kept by pointer (:638-639) */
+   k->_buffer = (double *)b200_xmalloc(sizeof(double) * (size_t)n * nwindows * dwindows);
+   k->_own_buffer = 1;
+   A->win = (b200_window **)b200_xcalloc((size_t)nwindows, sizeof(b200_window *));
+   A->dims = (int *)b200_xcalloc((size_t)nwindows, sizeof(int));
+   dst = k->_buffer;
+   for (i = 0; i < nwindows; i++)
+   {
+      int actual = 0;
+      for (j = 0; j < dwindows; j++)
+      {
+         if (fw[0] >= 0)
+         {
+            memcpy(dst, data + (size_t)fw[0] * ldim, sizeof(double) * (size_t)n);
+            fw++;
+            dst += n;
+            actual++;
+         }
+      }
+      A->win[i] = window_create(n, actual);
+      A->dims[i] = actual;
+      printf("Initializing NFFT kernel with N = %d, p = %d, m = %d, eps = %4.2f\n", B200_NBAND, 1, B200_MCUT, 0.0);
+      printf("Problem size: %d, problem dimension: %d\n", n, actual);
+   }
+   k->_external = A;
+   return k;
+}
+
+static int additive_ensure_device(b200_additive *A)
+{
+   int P = A->P, i;
+   if (A->d_x)
+      return 0;
+   A->d_x = (double *)b200_malloc(sizeof(double) * (size_t)A->n);
+   A->d_y = (double *)b200_malloc(sizeof(double) * 3 * (size_t)A->n);
+   A->d_fptr = (const double **)b200_malloc(sizeof(double *) * (size_t)P);
+   A->d_f2ptr = (const double **)b200_malloc(sizeof(double *) * (size_t)P);
+   A->d_invptr = (const int **)b200_malloc(sizeof(int *) * (size_t)P);
+   A->d_c1w = (double *)b200_malloc(sizeof(double) * (size_t)P);
+   {
+      const double **fp = (const double **)b200_xmalloc(sizeof(double *) * (size_t)P);
+      const int **ip = (const int **)b200_xmalloc(sizeof(int *) * (size_t)P);
+      for (i = 0; i < P; i++)
+      {
+         fp[i] = A->win[i]->dev.f;
+         ip[i] = A->win[i]->dev.inv;
+      }
+      if (b200_h2d((void *)A->d_fptr, fp, sizeof(double *) * (size_t)P) ||
+          b200_h2d((void *)A->d_invptr, ip, sizeof(int *) * (size_t)P) || b200_sync())
+         return -1;
+      free(fp);
+      free(ip);
+   }
+   return 0;
+}
+
+static int additive_kernel_build(void *str, int kernel, double *data, int n, int ldim, int d, double **Kp, double **dKp)
+{
+   nfft4gp_kernel *k = (nfft4gp_kernel *)str;
+   b200_additive *A = (b200_additive *)k->_external;
+   double *cols = k->_buffer;
+   int i;
+   (void)data; (void)d;
+   if (Kp == NULL || dKp == NULL)
+   {
+      printf("Error: NFFT kernel requires Kp and dKp to be not NULL.\n");
+      return -1;
+   }
+   if (n != ldim || n != A->n)
+   {
+      printf("Error: NFFT kernel requires n == ldim.\n");
+      return -1;
+   }
+   for (i = 0; i < A->P; i++)
+   {
+      b200_window *w = A->win[i];
+      if (w->scale < 0.0)
+      {
+         if (window_setup_points(w, cols, n))
+            return -1;
+      }
+      /* hyper-parameters are read from the handle at build time (:697-699) */
+      if (window_build(w, kernel, k->_params[0], k->_params[1], k->_noise_level))
+         return -1;
+      cols += (size_t)n * A->dw; /* :703 -- the reference advances by dwindows columns per window */
+   }
+   A->kernel = kernel;
+   A->built = 1;
+   if (additive_ensure_device(A))
+      return -1;
+   *Kp = (double *)str; /* :730-731 */
+   *dKp = (double *)str;
+   return 0;
+}
+
+/* nfft_interface.c:676-734 */
+int Nfft4GPNFFTAdditiveKernelGaussianKernel(void *str, double *data, int n, int ldim, int d, int *permr, int kr, int *permc,
+                                            int kc, double **Kp, double **dKp)
+{
+   (void)permr; (void)kr; (void)permc; (void)kc;
+   return additive_kernel_build(str, 0, data, n, ldim, d, Kp, dKp);
+}
+
+/* nfft_interface.c:736-794 */
+int Nfft4GPNFFTAdditiveKernelMatern12Kernel(void *str, double *data, int n, int ldim, int d, int *permr, int kr, int *permc,
+                                            int kc, double **Kp, double **dKp)
+{
+   (void)permr; (void)kr; (void)permc; (void)kc;
+   return additive_kernel_build(str, 1, data, n, ldim, d, Kp, dKp);
+}
+
+b200_additive *b200_additive_from_handle(void *data)
+{
+   nfft4gp_kernel *k = (nfft4gp_kernel *)data;
+   b200_additive *A;
+   if (!k)
+      return NULL;
+   A = (b200_additive *)k->_external;
+   if (!A || A->magic != B200_MAGIC_ADDITIVE)
+      return NULL;
+   return A;
+}
+
+/* device-resident body of Nfft4GPAdditiveNFFTMatSymv (nfft_interface.c:796-817) */
+int b200_additive_matvec_dev(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y)
+{
+   double s = 1.0 / (double)A->P * alpha; /* :806 */
+   double f = A->win[0]->kernel_scale;
+   int i;
+   if (!A->built || n != A->n)
+   {
+      printf("Error: additive NFFT matvec on a kernel that was not built for n = %d.\n", n);
+      return -1;
+   }
+   for (i = 0; i < A->P; i++)
+   {
+      if (b200_comm_owns_window(A, i) == 0)
+         continue;
+      if (window_apply(A->win[i], d_x, s, 0))
+         return -1;
+   }
+   return b200_additive_epilogue(A, n, d_x, s, f * f, A->win[0]->mu, beta, d_y);
+}
+
+/* device-resident body of Nfft4GPAdditiveNFFTGradMatSymv (nfft_interface.c:819-840) */
+int b200_additive_grad_matvec_dev(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y)
+{
+   double s = 1.0 / (double)A->P * alpha;
+   double f = A->win[0]->kernel_scale, ff = f * f;
+   double *c1 = (double *)b200_xmalloc(sizeof(double) * (size_t)A->P);
+   const double **fp = (const double **)b200_xmalloc(sizeof(double *) * (size_t)A->P);
+   int i, rc;
+   if (!A->built || n != A->n)
+   {
+      printf("Error: additive NFFT matvec on a kernel that was not built for n = %d.\n", n);
+      return -1;
+   }
+   for (i = 0; i < A->P; i++)
+   {
+      if (window_apply(A->win[i], d_x, s, 1))
+         return -1;
+      c1[i] = ff * window_grad_scale(A->win[i]);
+      fp[i] = A->win[i]->dev.f2;
+   }
+   rc = b200_h2d((void *)A->d_f2ptr, fp, sizeof(double *) * (size_t)A->P) || b200_h2d(A->d_c1w, c1, sizeof(double) * (size_t)A->P) || b200_sync();
+   free(c1);
+   free(fp);
+   if (rc)
+      return -1;
+   return b200k_combine_grad(n, A->P, A->d_fptr, A->d_f2ptr, A->d_invptr, d_x, s, 2.0 * f, ff, A->d_c1w, A->win[0]->mu, beta, d_y);
+}
+
+static int additive_host_call(void *data, int n, double alpha, double *x, double beta, double *y, int grad)
+{
+   b200_additive *A = b200_additive_from_handle(data);
+   size_t ny = grad ? 3 * (size_t)n : (size_t)n;
+   int rc;
+   if (!A)
+   {
+      printf("Error: not an additive NFFT kernel handle.\n");
+      return -1;
+   }
+   if (additive_ensure_device(A))
+      return -1;
+   if (b200_h2d(A->d_x, x, sizeof(double) * (size_t)n))
+      return -1;
+   if (beta != 0.0 && b200_h2d(A->d_y, y, sizeof(double) * ny))
+      return -1;
+   rc = grad ? b200_additive_grad_matvec_dev(A, n, alpha, A->d_x, beta, A->d_y) : b200_additive_matvec_dev(A, n, alpha, A->d_x, beta, A->d_y);
+   if (rc)
+      return -1;
+   return b200_d2h(y, A->d_y, sizeof(double) * ny);
+}
+
+/* nfft_interface.c:796-817 */
+int Nfft4GPAdditiveNFFTMatSymv(void *data, int n, double alpha, double *x, double beta, double *y)
+{
+   return additive_host_call(data, n, alpha, x, beta, y, 0);
+}
+
+/* nfft_interface.c:819-840 */
+int Nfft4GPAdditiveNFFTGradMatSymv(void *data, int n, double alpha, double *x, double beta, double *y)
+{
+   return additive_host_call(data, n, alpha, x, beta, y, 1);
+}
+
+int Nfft4GPB200AdditiveNFFTMatSymvDevice(void *data, int n, double alpha, const double *d_x, double beta, double *d_y)
+{
+   b200_additive *A = b200_additive_from_handle(data);
+   if (!A)
+   {
+      printf("Error: not an additive NFFT kernel handle.\n");
+      return -1;
+   }
+   return b200_additive_matvec_dev(A, n, alpha, d_x, beta, d_y);
+}
+
+int Nfft4GPB200AdditiveNFFTGradMatSymvDevice(void *data, int n, double alpha, const double *d_x, double beta, double *d_y)
+{
+   b200_additive *A = b200_additive_from_handle(data);
+   if (!A)
+   {
+      printf("Error: not an additive NFFT kernel handle.\n");
+      return -1;
+   }
+   return b200_additive_grad_matvec_dev(A, n, alpha, d_x, beta, d_y);
+}
+
+/* nfft_interface.c:842-856 */
+void Nfft4GPAdditiveNFFTKernelFree(void *str)
+{
+   nfft4gp_kernel *k = (nfft4gp_kernel *)str;
+   b200_additive *A;
+   int i;
+   if (!k)
+      return;
+   A = (b200_additive *)k->_external;
+   if (A)
+   {
+      for (i = 0; i < A->P; i++)
+         window_free(A->win[i]);
+      free(A->win);
+      free(A->dims);
+      b200_free(A->d_x);
+      b200_free(A->d_y);
+      b200_free((void *)A->d_fptr);
+      b200_free((void *)A->d_f2ptr);
+      b200_free((void *)A->d_invptr);
+      b200_free(A->d_c1w);
+      b200_free(A->d_ypart);
+      free(A);
+   }
+   if (k->_own_buffer)
+      free(k->_buffer);
+   free(k->_ibufferp);
+   free(k);
+}
+
+/* ------------------------------------------------------------------ debug taps + knobs */
+int Nfft4GPB200DebugWindowInfo(void *h, int w, int *dim, double *scale, int *nseg)
+{
+   b200_additive *A = b200_additive_from_handle(h);
+   if (!A || w < 0 || w >= A->P)
+      return -1;
+   if (dim)
+      *dim = A->win[w]->d;
+   if (scale)
+      *scale = A->win[w]->scale;
+   if (nseg)
+      *nseg = A->win[w]->dev.nseg;
+   return 0;
+}
+
+static int debug_stage(void *h, int wi, double alpha, const double *x, double *out, int stage)
+{
+   b200_additive *A = b200_additive_from_handle(h);
+   b200_window *w;
+   b200_win_dev *v;
+   size_t gsz;
+   if (!A || wi < 0 || wi >= A->P || !A->built || additive_ensure_device(A))
+      return -1;
+   w = A->win[wi];
+   v = &w->dev;
+   gsz = ipow(B200_NOS, w->d);
+   if (b200_h2d(A->d_x, x, sizeof(double) * (size_t)A->n) || b200k_prep(v, A->d_x, alpha) || b200k_spread(v, g_variant_spread3))
+      return -1;
+   if (stage >= 1 && (b200k_forward_fft(v) || b200k_backward_fft(v, v->coef)))
+      return -1;
+   return b200_d2h(out, v->grid, sizeof(double) * gsz);
+}
+
+int Nfft4GPB200DebugSpread(void *h, int w, double alpha, const double *x, double *grid) { return debug_stage(h, w, alpha, x, grid, 0); }
+int Nfft4GPB200DebugGridAfterFFT(void *h, int w, double alpha, const double *x, double *g) { return debug_stage(h, w, alpha, x, g, 1); }
+
+int Nfft4GPB200DebugCoeff(void *h, int wi, int which, double *c)
+{
+   b200_additive *A = b200_additive_from_handle(h);
+   b200_window *w;
+   if (!A || wi < 0 || wi >= A->P || !A->built)
+      return -1;
+   w = A->win[wi];
+   return b200_d2h(c, which ? w->dev.dcoef : w->dev.coef, sizeof(double) * 2 * ipow(B200_NBAND, w->d));
+}
+
+int Nfft4GPB200SetVariant(const char *name, int variant)
+{
+   if (!strcmp(name, "spread3d"))
+      g_variant_spread3 = variant;
+   else if (!strcmp(name, "gather3d"))
+      g_variant_gather3 = variant;
+   else
+      return -1;
+   return 0;
+}

@@ -1,0 +1,279 @@
+/* Preconditioned conjugate gradients: host control flow (C) of the reference's Nfft4GPSolverPcg
+ * (SRC/solvers/pcg.c:3-206), with every vector operation on the GPU when the two plug points are this
+ * library's own device-capable operators.  The control flow is replicated statement by statement,
+ * including its quirks:
+ *   - *piter is only set on convergence CONFIRMED by the true-residual recheck (pcg.c:181-193); otherwise 0;
+ *   - rel_res_v[ii] is overwritten with the ABSOLUTE true residual at the recheck (pcg.c:187);
+ *   - maxits is clamped to n (pcg.c:54); early exits for ||b|| < eps (pcg.c:32) and ||r0|| < tolb (pcg.c:70);
+ *   - breakdown breaks rho == 0, beta == 0, pq <= 0 (pcg.c:119,136,155).
+ * Per iteration the device path runs: precond apply, one dot, one fused p-update, matvec, one dot and one
+ * fused x/r update + ||r||^2 -- four n-passes outside matvec/precond instead of the reference's nine. */
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nfft4gp_b200.h"
+#include "b200_dev.h"
+#include "b200_host.h"
+
+static double *g_scal_dev = NULL;  /* 2 doubles on the device */
+static double *g_scal_host = NULL; /* pinned mirror */
+
+static int scal_init(void)
+{
+   if (!g_scal_dev)
+   {
+      g_scal_dev = (double *)b200_malloc(sizeof(double) * 2);
+      g_scal_host = (double *)b200_host_alloc(sizeof(double) * 2);
+      if (!g_scal_dev || !g_scal_host)
+         return -1;
+   }
+   return 0;
+}
+
+static int dev_dot(int n, const double *x, const double *y, double *out)
+{
+   if (b200k_dot(n, x, y, g_scal_dev) || b200_d2h(g_scal_host, g_scal_dev, sizeof(double)))
+      return -1;
+   *out = g_scal_host[0];
+   return 0;
+}
+
+int b200_pcg_device(void *mat, int n, b200_dev_matvec mv, void *prec, b200_dev_solve ps, double *d_x, const double *d_rhs,
+                    int maxits, int atol, double tol, double *prel_res, double **prel_res_v, int *piter, int print_level)
+{
+   int iter = 0, ii, rc = -1;
+   double rho = 1.0, alpha, beta, normb, normr, normr2, tolb, t;
+   double *r = NULL, *z = NULL, *p = NULL, *q = NULL, *rel_res_v = NULL;
+   size_t bytes = sizeof(double) * (size_t)n;
+
+   if (scal_init())
+      return -1;
+   if (dev_dot(n, d_rhs, d_rhs, &t))
+      return -1;
+   normb = sqrt(t);
+   if (normb < DBL_EPSILON)
+   {
+      b200k_fill(n, 0.0, d_x);
+      *prel_res = 0.0;
+      *piter = 0;
+      *prel_res_v = (double *)b200_xcalloc(1, sizeof(double));
+      return b200_sync();
+   }
+   tolb = atol ? tol : tol * normb;
+   if (maxits > n)
+      maxits = n;
+   r = (double *)b200_malloc(bytes);
+   z = (double *)b200_malloc(bytes);
+   p = (double *)b200_malloc(bytes);
+   q = (double *)b200_malloc(bytes);
+
+   if (b200_d2d(r, d_rhs, bytes) || mv(mat, n, -1.0, d_x, 1.0, r) || dev_dot(n, r, r, &t))
+      goto done;
+   normr = sqrt(t);
+   if (normr < tolb)
+   {
+      *prel_res = normr / normb;
+      *piter = 0;
+      rel_res_v = (double *)b200_xmalloc(sizeof(double));
+      rel_res_v[0] = *prel_res;
+      *prel_res_v = rel_res_v;
+      rc = 0;
+      goto done;
+   }
+   normr2 = normr;
+   rel_res_v = (double *)b200_xcalloc((size_t)maxits + 1, sizeof(double));
+   rel_res_v[0] = normr / normb;
+   if (print_level > 0)
+   {
+      printf("--------------------------------------------------------------------------------\n");
+      printf("Start PCG\n");
+      printf("Residual Tol: %e\nMax number of iterations: %d\n", tolb, maxits);
+      printf("--------------------------------------------------------------------------------\n");
+      printf("Step    Residual norm  Relative res.  Convergence Rate\n");
+      printf("%5d   %8e   %8e   N/A\n", 0, normr, rel_res_v[0]);
+   }
+   for (ii = 1; ii <= maxits; ii++)
+   {
+      double rho1, pq, rr;
+      const double *zz = z;
+      if (prec)
+      {
+         if (ps(prec, n, z, r))
+            goto done;
+      }
+      else
+         zz = r; /* z = r: no copy needed on the device path */
+      rho1 = rho;
+      if (dev_dot(n, zz, r, &rho))
+         goto done;
+      if (rho == 0.0)
+      {
+         if (print_level > 1)
+            printf("rho = %.16e\n", rho);
+         break;
+      }
+      if (ii == 1)
+      {
+         if (b200_d2d(p, zz, bytes))
+            goto done;
+      }
+      else
+      {
+         beta = rho / rho1;
+         if (beta == 0.0)
+         {
+            if (print_level > 1)
+               printf("beta = %.16e\n", beta);
+            break;
+         }
+         if (b200k_xpby(n, zz, beta, p))
+            goto done;
+      }
+      if (mv(mat, n, 1.0, p, 0.0, q) || dev_dot(n, q, p, &pq))
+         goto done;
+      if (pq <= 0)
+      {
+         if (print_level > 1)
+            printf("pq = %.16e\n", pq);
+         break;
+      }
+      alpha = rho / pq;
+      if (b200k_pcg_update(n, alpha, p, q, d_x, r, g_scal_dev) || b200_d2h(g_scal_host, g_scal_dev, sizeof(double)))
+         goto done;
+      rr = g_scal_host[0];
+      normr = sqrt(rr);
+      normr2 = normr;
+      rel_res_v[ii] = normr / normb;
+      if (print_level > 0)
+         printf("%5d   %8e   %8e   %8.6f\n", ii, normr, rel_res_v[ii], rel_res_v[ii] / rel_res_v[ii - 1]);
+      if (normr <= tolb)
+      {
+         if (b200_d2d(r, d_rhs, bytes) || mv(mat, n, -1.0, d_x, 1.0, r) || dev_dot(n, r, r, &t))
+            goto done;
+         normr2 = sqrt(t);
+         rel_res_v[ii] = normr2;
+         if (normr2 <= tolb)
+         {
+            iter = ii;
+            break;
+         }
+      }
+   }
+   *prel_res = normr2 / normb;
+   *piter = iter;
+   *prel_res_v = rel_res_v;
+   rel_res_v = NULL;
+   rc = 0;
+done:
+   b200_sync();
+   b200_free(r);
+   b200_free(z);
+   b200_free(p);
+   b200_free(q);
+   if (rc)
+      free(rel_res_v);
+   return rc;
+}
+
+/* ---- FOREIGN function pointers (a caller's own CPU matvec / preconditioner, e.g. the reference's dense
+ * Nfft4GPDenseMatSymv): the iteration and all its vector operations still run on the GPU; only the foreign
+ * callback itself is given host copies of its operands. ---- */
+typedef struct
+{
+   func_symmatvec mv;
+   func_solve ps;
+   void *data;
+   double *hx, *hy;
+} foreign_ctx;
+
+static int foreign_matvec_dev(void *vctx, int n, double alpha, const double *d_x, double beta, double *d_y)
+{
+   foreign_ctx *c = (foreign_ctx *)vctx;
+   size_t bytes = sizeof(double) * (size_t)n;
+   if (b200_d2h(c->hx, d_x, bytes))
+      return -1;
+   if (beta != 0.0 && b200_d2h(c->hy, d_y, bytes))
+      return -1;
+   if (c->mv(c->data, n, alpha, c->hx, beta, c->hy))
+      return -1;
+   return b200_h2d(d_y, c->hy, bytes) || b200_sync();
+}
+
+static int foreign_solve_dev(void *vctx, int n, double *d_x, const double *d_rhs)
+{
+   foreign_ctx *c = (foreign_ctx *)vctx;
+   size_t bytes = sizeof(double) * (size_t)n;
+   if (b200_d2h(c->hx, d_rhs, bytes))
+      return -1;
+   if (c->ps(c->data, n, c->hy, c->hx))
+      return -1;
+   return b200_h2d(d_x, c->hy, bytes) || b200_sync();
+}
+
+/* SRC/solvers/pcg.c:3-206 */
+int Nfft4GPSolverPcg(void *mat_data, int n, func_symmatvec matvec, void *prec_data, func_solve precondfunc, double *x,
+                     double *rhs, int maxits, int atol, double tol, double *prel_res, double **prel_res_v, int *piter,
+                     int print_level)
+{
+   void *dev_mat = NULL;
+   b200_dev_matvec mv = b200_lookup_dev_matvec((void *)matvec, mat_data, &dev_mat);
+   b200_dev_solve ps = prec_data ? b200_lookup_dev_solve((void *)precondfunc) : NULL;
+   void *dev_prec = prec_data;
+   size_t bytes = sizeof(double) * (size_t)n;
+   foreign_ctx fmv, fps;
+   double *d_x, *d_rhs;
+   int rc = -1;
+   memset(&fmv, 0, sizeof(fmv));
+   memset(&fps, 0, sizeof(fps));
+   if (b200_init(-1))
+      return -1;
+   if (!mv)
+   {
+      fmv.mv = matvec;
+      fmv.data = mat_data;
+      fmv.hx = (double *)b200_host_alloc(bytes);
+      fmv.hy = (double *)b200_host_alloc(bytes);
+      mv = foreign_matvec_dev;
+      dev_mat = &fmv;
+   }
+   if (prec_data && !ps)
+   {
+      fps.ps = precondfunc;
+      fps.data = prec_data;
+      fps.hx = (double *)b200_host_alloc(bytes);
+      fps.hy = (double *)b200_host_alloc(bytes);
+      ps = foreign_solve_dev;
+      dev_prec = &fps;
+   }
+   d_x = (double *)b200_malloc(bytes);
+   d_rhs = (double *)b200_malloc(bytes);
+   if (!b200_h2d(d_x, x, bytes) && !b200_h2d(d_rhs, rhs, bytes))
+      rc = b200_pcg_device(dev_mat, n, mv, dev_prec, ps, d_x, d_rhs, maxits, atol, tol, prel_res, prel_res_v, piter, print_level);
+   if (!rc)
+      rc = b200_d2h(x, d_x, bytes);
+   b200_free(d_x);
+   b200_free(d_rhs);
+   b200_host_free(fmv.hx);
+   b200_host_free(fmv.hy);
+   b200_host_free(fps.hx);
+   b200_host_free(fps.hy);
+   return rc;
+}
+
+int Nfft4GPB200SolverPcgDevice(void *mat_data, int n, func_symmatvec matvec, void *prec_data, func_solve precondfunc,
+                               double *d_x, const double *d_rhs, int maxits, int atol, double tol, double *prel_res,
+                               double **prel_res_v, int *piter, int print_level)
+{
+   void *dev_mat = NULL;
+   b200_dev_matvec mv = b200_lookup_dev_matvec((void *)matvec, mat_data, &dev_mat);
+   b200_dev_solve ps = prec_data ? b200_lookup_dev_solve((void *)precondfunc) : NULL;
+   if (!mv || (prec_data && !ps))
+   {
+      printf("Error: Nfft4GPB200SolverPcgDevice needs this library's own matvec / preconditioner entry points.\n");
+      return -1;
+   }
+   return b200_pcg_device(dev_mat, n, mv, prec_data, ps, d_x, d_rhs, maxits, atol, tol, prel_res, prel_res_v, piter, print_level);
+}

@@ -1,0 +1,488 @@
+/* Preconditioner handles (C host side): Nystrom (NYS), FSAI and the AFN 2x2 block preconditioner.
+ * Factors live in HBM; the applies are sequences of the HBM-bound kernels of precond_kernels.cu.
+ *   NYS  apply  SRC/preconds/nys.c:115-173   M^{-1} r = U S U' r + (I - U U') r / eta     (2 passes over U here, 3 in the reference)
+ *   FSAI apply  SRC/preconds/fsai.c:106-123  M^{-1} r = G' (G r), G lower-triangular CSR   (G' stored explicitly: no scatter)
+ *   AFN  apply  SRC/preconds/afn.c:109-136 (uncompiled in the reference) = MATLAB afn_solve.m:39-69
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nfft4gp_b200.h"
+#include "b200_dev.h"
+#include "b200_host.h"
+#include "b200_precond.h"
+
+/* ------------------------------------------------------------------ staging for the host-pointer entry points */
+static int stage_vectors(double **d_x, double **d_rhs, int *cap, int n)
+{
+   if (*cap < n)
+   {
+      b200_free(*d_x);
+      b200_free(*d_rhs);
+      *d_x = (double *)b200_malloc(sizeof(double) * (size_t)n);
+      *d_rhs = (double *)b200_malloc(sizeof(double) * (size_t)n);
+      *cap = n;
+   }
+   return (*d_x && *d_rhs) ? 0 : -1;
+}
+
+/* ================================================================== NYS */
+void *Nfft4GPPrecondNysCreate(void)
+{
+   b200_nys *s = (b200_nys *)b200_xcalloc(1, sizeof(b200_nys));
+   s->magic = B200_MAGIC_NYS;
+   s->k_setup = 50; /* nys.c:8 */
+   s->eta = 1.0;
+   return s;
+}
+
+static void nys_release_factors(b200_nys *s)
+{
+   b200_free(s->d_perm);
+   b200_free(s->d_U);
+   b200_free(s->d_s);
+   b200_free(s->d_work);
+   s->d_perm = NULL;
+   s->d_U = s->d_s = s->d_work = NULL;
+   s->work_doubles = 0;
+   s->n = s->k = 0;
+}
+
+void Nfft4GPPrecondNysReset(void *str) /* nys.c:78-98: keep permutation */
+{
+   b200_nys *s = (b200_nys *)str;
+   if (s)
+      nys_release_factors(s);
+}
+
+void Nfft4GPPrecondNysFree(void *str)
+{
+   b200_nys *s = (b200_nys *)str;
+   if (!s)
+      return;
+   nys_release_factors(s);
+   b200_free(s->d_x);
+   b200_free(s->d_rhs);
+   if (s->own_perm)
+      free(s->perm);
+   free(s);
+}
+
+void Nfft4GPPrecondNysSetRank(void *str, int k) { ((b200_nys *)str)->k_setup = k; }
+
+void Nfft4GPPrecondNysSetPerm(void *str, int *perm, int own_perm)
+{
+   b200_nys *s = (b200_nys *)str;
+   s->perm = perm;
+   s->own_perm = own_perm;
+}
+
+int b200_nys_set_device_factors(b200_nys *s, int n, int k, const int *h_perm, double *d_U_owned, const double *h_s, double eta)
+{
+   nys_release_factors(s);
+   s->n = n;
+   s->k = k;
+   s->eta = eta;
+   s->d_U = d_U_owned;
+   s->d_s = (double *)b200_malloc(sizeof(double) * (size_t)k);
+   s->work_doubles = b200k_nys_work_doubles(n, k);
+   s->d_work = (double *)b200_malloc(sizeof(double) * s->work_doubles);
+   if (b200_h2d(s->d_s, h_s, sizeof(double) * (size_t)k))
+      return -1;
+   if (h_perm)
+   {
+      s->d_perm = (int *)b200_malloc(sizeof(int) * (size_t)n);
+      if (b200_h2d(s->d_perm, h_perm, sizeof(int) * (size_t)n))
+         return -1;
+   }
+   return b200_sync();
+}
+
+int Nfft4GPB200PrecondNysSetFactors(void *nys, int n, int k, const int *perm, const double *U, const double *sv, double eta)
+{
+   b200_nys *s = (b200_nys *)nys;
+   double *d_U;
+   if (!s || s->magic != B200_MAGIC_NYS || b200_init(-1))
+      return -1;
+   d_U = (double *)b200_malloc(sizeof(double) * (size_t)n * (size_t)k);
+   if (b200_h2d(d_U, U, sizeof(double) * (size_t)n * (size_t)k) || b200_sync())
+      return -1;
+   return b200_nys_set_device_factors(s, n, k, perm, d_U, sv, eta);
+}
+
+int Nfft4GPB200PrecondNysGetFactors(void *nys, int *n, int *k, int *perm, double *U, double *sv, double *eta)
+{
+   b200_nys *s = (b200_nys *)nys;
+   if (!s || s->magic != B200_MAGIC_NYS)
+      return -1;
+   if (n)
+      *n = s->n;
+   if (k)
+      *k = s->k;
+   if (eta)
+      *eta = s->eta;
+   if (perm && s->d_perm && b200_d2h(perm, s->d_perm, sizeof(int) * (size_t)s->n))
+      return -1;
+   if (U && s->d_U && b200_d2h(U, s->d_U, sizeof(double) * (size_t)s->n * (size_t)s->k))
+      return -1;
+   if (sv && s->d_s && b200_d2h(sv, s->d_s, sizeof(double) * (size_t)s->k))
+      return -1;
+   return 0;
+}
+
+int b200_nys_solve_dev(void *vnys, int n, double *d_x, const double *d_rhs)
+{
+   b200_nys *s = (b200_nys *)vnys;
+   if (!s || s->magic != B200_MAGIC_NYS || !s->d_U || n != s->n)
+   {
+      printf("Error: Nystrom preconditioner is not set up for n = %d.\n", n);
+      return -1;
+   }
+   return b200k_nys_apply(s->n, s->k, s->d_perm, s->d_U, s->d_s, s->eta, d_rhs, d_x, s->d_work, s->work_doubles);
+}
+
+int Nfft4GPPrecondNysSolve(void *vnys_mat, int n, double *x, double *rhs) /* nys.c:115-173 */
+{
+   b200_nys *s = (b200_nys *)vnys_mat;
+   if (!s || s->magic != B200_MAGIC_NYS || stage_vectors(&s->d_x, &s->d_rhs, &s->cap, n))
+      return -1;
+   if (b200_h2d(s->d_rhs, rhs, sizeof(double) * (size_t)n) || b200_nys_solve_dev(s, n, s->d_x, s->d_rhs))
+      return -1;
+   return b200_d2h(x, s->d_x, sizeof(double) * (size_t)n);
+}
+
+/* ================================================================== FSAI */
+void *Nfft4GPPrecondFsaiCreate(void)
+{
+   b200_fsai *s = (b200_fsai *)b200_xcalloc(1, sizeof(b200_fsai));
+   s->magic = B200_MAGIC_FSAI;
+   s->lfil = 50; /* fsai.c:12 */
+   return s;
+}
+
+void b200_fsai_release(b200_fsai *s)
+{
+   b200_free(s->d_ia);
+   b200_free(s->d_ja);
+   b200_free(s->d_a);
+   b200_free(s->d_iat);
+   b200_free(s->d_jat);
+   b200_free(s->d_at);
+   b200_free(s->d_work);
+   s->d_ia = s->d_ja = s->d_iat = s->d_jat = NULL;
+   s->d_a = s->d_at = s->d_work = NULL;
+   s->n = s->nnz = 0;
+}
+
+void Nfft4GPPrecondFsaiReset(void *str)
+{
+   b200_fsai *s = (b200_fsai *)str;
+   if (s)
+      b200_fsai_release(s);
+}
+
+void Nfft4GPPrecondFsaiFree(void *str)
+{
+   b200_fsai *s = (b200_fsai *)str;
+   if (!s)
+      return;
+   b200_fsai_release(s);
+   b200_free(s->d_x);
+   b200_free(s->d_rhs);
+   free(s);
+}
+
+void Nfft4GPPrecondFsaiSetLfil(void *str, int lfil) { ((b200_fsai *)str)->lfil = lfil; }
+
+/* upload G (CSR, rows sorted as given) and its explicit transpose */
+int b200_fsai_set_host_factors(b200_fsai *s, int n, const int *ia, const int *ja, const double *a)
+{
+   int nnz = ia[n], i, j;
+   int *iat = (int *)b200_xcalloc((size_t)n + 1, sizeof(int));
+   int *jat = (int *)b200_xmalloc(sizeof(int) * (size_t)(nnz ? nnz : 1));
+   double *at = (double *)b200_xmalloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
+   int *cur;
+   b200_fsai_release(s);
+   for (j = 0; j < nnz; j++)
+      iat[ja[j] + 1]++;
+   for (i = 0; i < n; i++)
+      iat[i + 1] += iat[i];
+   cur = (int *)b200_xmalloc(sizeof(int) * (size_t)(n ? n : 1));
+   memcpy(cur, iat, sizeof(int) * (size_t)n);
+   for (i = 0; i < n; i++)
+      for (j = ia[i]; j < ia[i + 1]; j++)
+      {
+         int pos = cur[ja[j]]++;
+         jat[pos] = i;
+         at[pos] = a[j];
+      }
+   free(cur);
+   s->n = n;
+   s->nnz = nnz;
+   s->d_ia = (int *)b200_malloc(sizeof(int) * ((size_t)n + 1));
+   s->d_ja = (int *)b200_malloc(sizeof(int) * (size_t)nnz);
+   s->d_a = (double *)b200_malloc(sizeof(double) * (size_t)nnz);
+   s->d_iat = (int *)b200_malloc(sizeof(int) * ((size_t)n + 1));
+   s->d_jat = (int *)b200_malloc(sizeof(int) * (size_t)nnz);
+   s->d_at = (double *)b200_malloc(sizeof(double) * (size_t)nnz);
+   s->d_work = (double *)b200_malloc(sizeof(double) * (size_t)n);
+   i = b200_h2d(s->d_ia, ia, sizeof(int) * ((size_t)n + 1)) || b200_h2d(s->d_ja, ja, sizeof(int) * (size_t)nnz) ||
+       b200_h2d(s->d_a, a, sizeof(double) * (size_t)nnz) || b200_h2d(s->d_iat, iat, sizeof(int) * ((size_t)n + 1)) ||
+       b200_h2d(s->d_jat, jat, sizeof(int) * (size_t)nnz) || b200_h2d(s->d_at, at, sizeof(double) * (size_t)nnz) || b200_sync();
+   free(iat);
+   free(jat);
+   free(at);
+   return i ? -1 : 0;
+}
+
+int Nfft4GPB200PrecondFsaiSetFactors(void *fsai, int n, const int *ia, const int *ja, const double *a)
+{
+   b200_fsai *s = (b200_fsai *)fsai;
+   if (!s || s->magic != B200_MAGIC_FSAI || b200_init(-1))
+      return -1;
+   return b200_fsai_set_host_factors(s, n, ia, ja, a);
+}
+
+int Nfft4GPB200PrecondFsaiGetFactors(void *fsai, int *n, int *nnz, int *ia, int *ja, double *a)
+{
+   b200_fsai *s = (b200_fsai *)fsai;
+   if (!s || s->magic != B200_MAGIC_FSAI)
+      return -1;
+   if (n)
+      *n = s->n;
+   if (nnz)
+      *nnz = s->nnz;
+   if (ia && s->d_ia && b200_d2h(ia, s->d_ia, sizeof(int) * ((size_t)s->n + 1)))
+      return -1;
+   if (ja && s->d_ja && b200_d2h(ja, s->d_ja, sizeof(int) * (size_t)s->nnz))
+      return -1;
+   if (a && s->d_a && b200_d2h(a, s->d_a, sizeof(double) * (size_t)s->nnz))
+      return -1;
+   return 0;
+}
+
+int b200_fsai_solve_dev(void *vf, int n, double *d_x, const double *d_rhs)
+{
+   b200_fsai *s = (b200_fsai *)vf;
+   if (!s || s->magic != B200_MAGIC_FSAI || !s->d_a || n != s->n)
+   {
+      printf("Error: FSAI preconditioner is not set up for n = %d.\n", n);
+      return -1;
+   }
+   /* INV = L' * L (fsai.c:112-116) */
+   if (b200k_csr_mv(n, s->d_ia, s->d_ja, s->d_a, d_rhs, s->d_work))
+      return -1;
+   return b200k_csr_mv(n, s->d_iat, s->d_jat, s->d_at, s->d_work, d_x);
+}
+
+int Nfft4GPPrecondFsaiSolve(void *vfsai_mat, int n, double *x, double *rhs) /* fsai.c:106-123 */
+{
+   b200_fsai *s = (b200_fsai *)vfsai_mat;
+   if (!s || s->magic != B200_MAGIC_FSAI || stage_vectors(&s->d_x, &s->d_rhs, &s->cap, n))
+      return -1;
+   if (b200_h2d(s->d_rhs, rhs, sizeof(double) * (size_t)n) || b200_fsai_solve_dev(s, n, s->d_x, s->d_rhs))
+      return -1;
+   return b200_d2h(x, s->d_x, sizeof(double) * (size_t)n);
+}
+
+/* ================================================================== AFN */
+void *Nfft4GPPrecondAFNCreate(void)
+{
+   b200_afn *s = (b200_afn *)b200_xcalloc(1, sizeof(b200_afn));
+   s->magic = B200_MAGIC_AFN;
+   s->max_k = 100; /* MATLAB test settings: maxrank 100-300, lfil 100 (test_solve_additive.m:35-40) */
+   s->lfil = 100;
+   s->schur.magic = B200_MAGIC_FSAI;
+   return s;
+}
+
+void b200_afn_release(b200_afn *s)
+{
+   b200_free(s->d_perm);
+   b200_free(s->d_Linv);
+   b200_free(s->d_K12);
+   b200_free(s->d_work);
+   s->d_perm = NULL;
+   s->d_Linv = s->d_K12 = s->d_work = NULL;
+   b200_fsai_release(&s->schur);
+   if (s->nys)
+   {
+      Nfft4GPPrecondNysFree(s->nys);
+      s->nys = NULL;
+   }
+   s->n = s->k = 0;
+}
+
+void Nfft4GPPrecondAFNFree(void *str)
+{
+   b200_afn *s = (b200_afn *)str;
+   if (!s)
+      return;
+   b200_afn_release(s);
+   b200_free(s->d_x);
+   b200_free(s->d_rhs);
+   free(s);
+}
+
+void Nfft4GPPrecondAFNSetRank(void *str, int max_k) { ((b200_afn *)str)->max_k = max_k; }
+void Nfft4GPPrecondAFNSetLfil(void *str, int lfil) { ((b200_afn *)str)->lfil = lfil; }
+
+/* explicit inverse of the k x k lower Cholesky factor (column-major), upper triangle zero */
+void b200_tril_inverse(int k, const double *L, double *Linv)
+{
+   int i, j, c;
+   memset(Linv, 0, sizeof(double) * (size_t)k * (size_t)k);
+   for (c = 0; c < k; c++)
+   {
+      /* solve L x = e_c by forward substitution */
+      double *x = Linv + (size_t)c * k;
+      x[c] = 1.0 / L[(size_t)c * k + c];
+      for (i = c + 1; i < k; i++)
+      {
+         double s = 0.0;
+         for (j = c; j < i; j++)
+            s -= L[(size_t)j * k + i] * x[j];
+         x[i] = s / L[(size_t)i * k + i];
+      }
+   }
+}
+
+int b200_afn_set_device_factors(b200_afn *s, int n, int k, const int *h_perm, const double *h_L, double *d_K12_owned,
+                                const int *ia, const int *ja, const double *a)
+{
+   double *Linv = (double *)b200_xmalloc(sizeof(double) * (size_t)k * (size_t)k);
+   int rc;
+   b200_afn_release(s);
+   s->n = n;
+   s->k = k;
+   b200_tril_inverse(k, h_L, Linv);
+   s->d_Linv = (double *)b200_malloc(sizeof(double) * (size_t)k * (size_t)k);
+   s->d_perm = (int *)b200_malloc(sizeof(int) * (size_t)n);
+   s->d_K12 = d_K12_owned;
+   s->d_work = (double *)b200_malloc(sizeof(double) * (2 * (size_t)n + 2 * (size_t)k));
+   rc = b200_h2d(s->d_Linv, Linv, sizeof(double) * (size_t)k * (size_t)k) || b200_h2d(s->d_perm, h_perm, sizeof(int) * (size_t)n) || b200_sync();
+   free(Linv);
+   if (rc)
+      return -1;
+   return b200_fsai_set_host_factors(&s->schur, n - k, ia, ja, a);
+}
+
+int Nfft4GPB200PrecondAFNSetFactors(void *afn, int n, int k, const int *perm, const double *L, const double *K12, const int *ia,
+                                    const int *ja, const double *a)
+{
+   b200_afn *s = (b200_afn *)afn;
+   double *d_K12;
+   size_t sz = sizeof(double) * (size_t)k * (size_t)(n - k);
+   if (!s || s->magic != B200_MAGIC_AFN || b200_init(-1))
+      return -1;
+   d_K12 = (double *)b200_malloc(sz);
+   if (b200_h2d(d_K12, K12, sz) || b200_sync())
+      return -1;
+   return b200_afn_set_device_factors(s, n, k, perm, L, d_K12, ia, ja, a);
+}
+
+int b200_afn_solve_dev(void *va, int n, double *d_x, const double *d_rhs)
+{
+   b200_afn *s = (b200_afn *)va;
+   int k, n2;
+   double *rp, *rp2, *y, *y2, *t;
+   if (!s || s->magic != B200_MAGIC_AFN)
+      return -1;
+   if (s->nys) /* rank < max rank: Nystrom on the FPS ordering (afn_setup.m:80-100, afn_solve.m:41-44) */
+      return b200_nys_solve_dev(s->nys, n, d_x, d_rhs);
+   if (!s->d_Linv || n != s->n)
+   {
+      printf("Error: AFN preconditioner is not set up for n = %d.\n", n);
+      return -1;
+   }
+   k = s->k;
+   n2 = n - k;
+   rp = s->d_work;
+   rp2 = rp + k;
+   y = s->d_work + n;
+   y2 = y + k;
+   t = s->d_work + 2 * (size_t)n; /* 2k scratch */
+   /* [rp; rp2] = rhs(perm) */
+   if (b200k_gather_perm(n, s->d_perm, d_rhs, rp))
+      return -1;
+   /* y = A11 \ rp = L^{-T} (L^{-1} rp) */
+   if (b200k_gemv('N', k, k, 1.0, s->d_Linv, rp, 0.0, t) || b200k_gemv('T', k, k, 1.0, s->d_Linv, t, 0.0, y))
+      return -1;
+   if (n2 > 0)
+   {
+      /* rp2 -= A21 y ; y2 = S^{-1} rp2 ; rp -= A12 y2 ; y = A11 \ rp */
+      if (b200k_gemv('T', k, n2, -1.0, s->d_K12, y, 1.0, rp2) || b200_fsai_solve_dev(&s->schur, n2, y2, rp2) ||
+          b200k_gemv('N', k, n2, -1.0, s->d_K12, y2, 1.0, rp) || b200k_gemv('N', k, k, 1.0, s->d_Linv, rp, 0.0, t) ||
+          b200k_gemv('T', k, k, 1.0, s->d_Linv, t, 0.0, y))
+         return -1;
+   }
+   return b200k_scatter_perm(n, s->d_perm, y, d_x);
+}
+
+int Nfft4GPPrecondAFNSolve(void *vafn_mat, int n, double *x, double *rhs)
+{
+   b200_afn *s = (b200_afn *)vafn_mat;
+   if (!s || s->magic != B200_MAGIC_AFN || stage_vectors(&s->d_x, &s->d_rhs, &s->cap, n))
+      return -1;
+   if (b200_h2d(s->d_rhs, rhs, sizeof(double) * (size_t)n) || b200_afn_solve_dev(s, n, s->d_x, s->d_rhs))
+      return -1;
+   return b200_d2h(x, s->d_x, sizeof(double) * (size_t)n);
+}
+
+/* ================================================================== plug-point lookup for the device PCG */
+static int additive_mv_dev(void *mat, int n, double alpha, const double *d_x, double beta, double *d_y)
+{
+   return b200_additive_matvec_dev((b200_additive *)mat, n, alpha, d_x, beta, d_y);
+}
+
+static int window_mv_dev(void *mat, int n, double alpha, const double *d_x, double beta, double *d_y)
+{
+   return b200_window_matvec_dev((b200_window *)mat, n, alpha, d_x, beta, d_y);
+}
+
+b200_dev_matvec b200_lookup_dev_matvec(void *host_fn, void *mat_data, void **dev_handle)
+{
+   if (host_fn == (void *)Nfft4GPAdditiveNFFTMatSymv)
+   {
+      b200_additive *A = b200_additive_from_handle(mat_data);
+      if (A)
+      {
+         *dev_handle = A;
+         return additive_mv_dev;
+      }
+   }
+   if (host_fn == (void *)Nfft4GPNFFTMatSymv)
+   {
+      b200_window *w = (b200_window *)mat_data;
+      if (w && w->magic == B200_MAGIC_WINDOW)
+      {
+         *dev_handle = w;
+         return window_mv_dev;
+      }
+   }
+   return NULL;
+}
+
+b200_dev_solve b200_lookup_dev_solve(void *host_fn)
+{
+   if (host_fn == (void *)Nfft4GPPrecondNysSolve)
+      return b200_nys_solve_dev;
+   if (host_fn == (void *)Nfft4GPPrecondFsaiSolve)
+      return b200_fsai_solve_dev;
+   if (host_fn == (void *)Nfft4GPPrecondAFNSolve)
+      return b200_afn_solve_dev;
+   return NULL;
+}
+
+int Nfft4GPB200PrecondSolveDevice(void *prec, func_solve which, int n, double *d_x, const double *d_rhs)
+{
+   b200_dev_solve f = b200_lookup_dev_solve((void *)which);
+   if (!f)
+   {
+      printf("Error: Nfft4GPB200PrecondSolveDevice needs one of this library's preconditioner solve functions.\n");
+      return -1;
+   }
+   return f(prec, n, d_x, d_rhs);
+}

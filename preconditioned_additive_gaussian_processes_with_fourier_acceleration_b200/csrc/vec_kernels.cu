@@ -1,0 +1,225 @@
+// Fused vector kernels of the device-resident PCG (replaces the nine unfused n-passes per iteration of
+// SRC/solvers/pcg.c:104-170 built on SRC/linearalg/vecops.c:3-155).  HBM-bound: every kernel streams its
+// operands once with 128-bit loads; reductions are two-stage with a fixed summation order (deterministic).
+#include <cuda_runtime.h>
+#include <cstdio>
+
+#include "b200_dev.h"
+#include "b200_cuda_util.cuh"
+
+#define RED_BLOCKS 1184 /* 148 SMs x 8 */
+#define RED_THREADS 256
+
+__device__ double g_partial[2 * RED_BLOCKS];
+
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+   v = b200_warp_sum(v);
+   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   __syncthreads();
+   if (lane == 0)
+      sh[wid] = v;
+   __syncthreads();
+   double r = 0.0;
+   if (threadIdx.x == 0)
+   {
+      for (int i = 0; i < (int)(blockDim.x >> 5); i++)
+         r += sh[i];
+   }
+   return r; // valid in thread 0
+}
+
+__global__ void __launch_bounds__(RED_THREADS) k_dot_stage1(int n, const double *__restrict__ x, const double *__restrict__ y)
+{
+   __shared__ double sh[32];
+   double s = 0.0;
+   int n2 = n >> 1;
+   const double2 *x2 = reinterpret_cast<const double2 *>(x), *y2 = reinterpret_cast<const double2 *>(y);
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
+   {
+      double2 a = x2[i], b = y2[i];
+      s = fma(a.x, b.x, s);
+      s = fma(a.y, b.y, s);
+   }
+   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+      s = fma(x[n - 1], y[n - 1], s);
+   double r = block_sum(s, sh);
+   if (threadIdx.x == 0)
+      g_partial[blockIdx.x] = r;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_dot2_stage1(int n, const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ u, const double *__restrict__ v)
+{
+   __shared__ double sh[32];
+   double s = 0.0, t = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+   {
+      s = fma(x[i], y[i], s);
+      t = fma(u[i], v[i], t);
+   }
+   double r = block_sum(s, sh);
+   double r2 = block_sum(t, sh);
+   if (threadIdx.x == 0)
+   {
+      g_partial[blockIdx.x] = r;
+      g_partial[RED_BLOCKS + blockIdx.x] = r2;
+   }
+}
+
+// x += alpha p ; r -= alpha q ; partial r.r
+__global__ void __launch_bounds__(RED_THREADS)
+k_pcg_update_stage1(int n, double alpha, const double *__restrict__ p, const double *__restrict__ q, double *__restrict__ x, double *__restrict__ r)
+{
+   __shared__ double sh[32];
+   double s = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+   {
+      x[i] += alpha * p[i];
+      double ri = r[i] - alpha * q[i];
+      r[i] = ri;
+      s = fma(ri, ri, s);
+   }
+   double t = block_sum(s, sh);
+   if (threadIdx.x == 0)
+      g_partial[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(RED_THREADS) k_reduce_stage2(int nblocks, int nvals, double *__restrict__ out)
+{
+   __shared__ double sh[32];
+   for (int v = 0; v < nvals; v++)
+   {
+      double s = 0.0;
+      for (int i = threadIdx.x; i < nblocks; i += blockDim.x)
+         s += g_partial[v * RED_BLOCKS + i];
+      double r = block_sum(s, sh);
+      if (threadIdx.x == 0)
+         out[v] = r;
+   }
+}
+
+__global__ void k_xpby(int n, const double *__restrict__ z, double beta, double *__restrict__ p)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n)
+      p[i] = z[i] + beta * p[i]; // pcg.c:145-146: p = beta*p ; p += z
+}
+
+__global__ void k_copy(int n, const double *__restrict__ s, double *__restrict__ d)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n)
+      d[i] = s[i];
+}
+
+__global__ void k_fill(int n, double v, double *__restrict__ d)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n)
+      d[i] = v;
+}
+
+__global__ void k_scale(int n, double a, double *__restrict__ x)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n)
+      x[i] *= a;
+}
+
+__global__ void k_axpy(int n, double a, const double *__restrict__ x, double *__restrict__ y)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n)
+      y[i] += a * x[i];
+}
+
+static int red_blocks(int n)
+{
+   int b = b200_cdiv(n, RED_THREADS * 4);
+   if (b < 1)
+      b = 1;
+   if (b > RED_BLOCKS)
+      b = RED_BLOCKS;
+   return b;
+}
+
+extern "C" {
+
+int b200k_dot(int n, const double *x, const double *y, double *d_out)
+{
+   int nb = red_blocks(n);
+   // the 128-bit path needs 16-byte aligned operands; fall back to the scalar two-vector kernel otherwise
+   if ((((size_t)x | (size_t)y) & 15) == 0)
+   {
+      k_dot_stage1<<<nb, RED_THREADS, 0, b200_stream()>>>(n, x, y);
+      B200_LAUNCHED();
+      k_reduce_stage2<<<1, RED_THREADS, 0, b200_stream()>>>(nb, 1, d_out);
+      B200_LAUNCHED();
+   }
+   else
+   {
+      k_dot2_stage1<<<nb, RED_THREADS, 0, b200_stream()>>>(n, x, y, x, y);
+      B200_LAUNCHED();
+      k_reduce_stage2<<<1, RED_THREADS, 0, b200_stream()>>>(nb, 1, d_out);
+      B200_LAUNCHED();
+   }
+   return 0;
+}
+
+int b200k_dot2(int n, const double *x, const double *y, const double *u, const double *v, double *d_out2)
+{
+   int nb = red_blocks(n);
+   k_dot2_stage1<<<nb, RED_THREADS, 0, b200_stream()>>>(n, x, y, u, v);
+   B200_LAUNCHED();
+   k_reduce_stage2<<<1, RED_THREADS, 0, b200_stream()>>>(nb, 2, d_out2);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_pcg_update(int n, double alpha, const double *p, const double *q, double *x, double *r, double *d_out)
+{
+   int nb = red_blocks(n);
+   k_pcg_update_stage1<<<nb, RED_THREADS, 0, b200_stream()>>>(n, alpha, p, q, x, r);
+   B200_LAUNCHED();
+   k_reduce_stage2<<<1, RED_THREADS, 0, b200_stream()>>>(nb, 1, d_out);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_xpby(int n, const double *z, double beta, double *p)
+{
+   k_xpby<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, z, beta, p);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_copy(int n, const double *src, double *dst)
+{
+   k_copy<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, src, dst);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_fill(int n, double v, double *dst)
+{
+   k_fill<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, v, dst);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_scale(int n, double a, double *x)
+{
+   k_scale<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, a, x);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_axpy(int n, double a, const double *x, double *y)
+{
+   k_axpy<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, a, x, y);
+   B200_LAUNCHED();
+   return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,122 @@
+"""GPU parity of the NFFT additive matvec (rows M1, M2, M3, S1, S2 of SURVEY.md section 8(a)) against the CPU oracle,
+called through the C ABI exactly like the reference drivers call nfft4gp (TESTS/TEST1/foo.cpp:216-251).
+Tolerance: north_star -- <= 1e-10 relative l2 in fp64 (we observe ~1e-14)."""
+import numpy as np
+import pytest
+
+from common import MATVEC_CASES, gaussian_cloud, rand_vec, rel_l2, uniform_cloud
+from oracle import oracle_api as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _pair(gpu, case, cloud=uniform_cloud):
+    name, n, d, win, nw, dw, kern, f, l, mu = case
+    X = cloud(n, d)
+    win = np.array(win, dtype=np.int32)
+    A = gpu.AdditiveNFFTKernel(X, win, nw, dw, kern).build(f, l, mu)
+    B = O.OracleAdditiveNFFT(X, win, nw, dw, kern).build(f, l, mu)
+    return A, B, n
+
+
+@pytest.mark.parametrize("case", MATVEC_CASES, ids=[c[0] for c in MATVEC_CASES])
+@pytest.mark.parametrize("variant", [1, 0], ids=["tiled", "generic"])
+def test_matvec_matches_oracle(gpu, case, variant):
+    L = gpu.lib()
+    L.Nfft4GPB200SetVariant(b"spread3d", variant)
+    L.Nfft4GPB200SetVariant(b"gather3d", variant)
+    try:
+        A, B, n = _pair(gpu, case)
+        x = rand_vec(n)
+        y0 = rand_vec(n, seed=5)
+        for alpha, beta in [(1.0, 0.0), (-1.0, 1.0), (0.7, 0.3)]:
+            yg = A.matvec(x, alpha, beta, y0)
+            yo = B.matvec(x, alpha, beta, y0)
+            assert rel_l2(yg, yo) <= TOL, (case[0], alpha, beta, rel_l2(yg, yo))
+        A.free()
+        B.free()
+    finally:
+        L.Nfft4GPB200SetVariant(b"spread3d", 1)
+        L.Nfft4GPB200SetVariant(b"gather3d", 1)
+
+
+@pytest.mark.parametrize("case", MATVEC_CASES[:7], ids=[c[0] for c in MATVEC_CASES[:7]])
+def test_grad_matvec_matches_oracle(gpu, case):
+    A, B, n = _pair(gpu, case)
+    x = rand_vec(n)
+    y0 = rand_vec(3 * n, seed=6)
+    for alpha, beta in [(1.0, 0.0), (0.5, 1.0), (-0.3, 0.4)]:
+        yg = A.grad_matvec(x, alpha, beta, y0)
+        yo = B.grad_matvec(x, alpha, beta, y0)
+        for blk in range(3):
+            sl = slice(blk * n, (blk + 1) * n)
+            assert rel_l2(yg[sl], yo[sl]) <= TOL, (case[0], blk, alpha, beta)
+    A.free()
+    B.free()
+
+
+def test_gaussian_cloud_and_rebuild(gpu):
+    """Clustered points (heavy cells -> split segments) and a hyper-parameter rebuild on the same handle."""
+    case = ("gauss_cloud", 20000, 9, list(range(9)), 3, 3, "gaussian", 1.0, 1.0, 0.01)
+    A, B, n = _pair(gpu, case, cloud=gaussian_cloud)
+    x = rand_vec(n)
+    assert rel_l2(A.matvec(x), B.matvec(x)) <= TOL
+    for (f, l, mu) in [(0.7, 0.5, 0.2), (1.5, 3.0, 1e-3)]:
+        A.build(f, l, mu)
+        B.build(f, l, mu)
+        assert rel_l2(A.matvec(x), B.matvec(x)) <= TOL
+    A.free()
+    B.free()
+
+
+def test_window_scale_is_bit_identical(gpu):
+    """The per-window scale factor (nfft_interface.c:162-196) is computed with the reference's arithmetic."""
+    case = MATVEC_CASES[2]
+    A, B, n = _pair(gpu, case)
+    for w in range(3):
+        dim, scale, nseg = A.window_info(w)
+        assert scale == B.window_scale(w)
+        assert dim == 3 and nseg > 0
+    A.free()
+    B.free()
+
+
+def test_stages_against_numpy(gpu):
+    """Stage taps: spread grid vs a direct numpy spread; Fourier coefficient table vs the oracle's b_k / phi_hat^2."""
+    n, d = 800, 3
+    X = uniform_cloud(n, d)
+    win = np.arange(3, dtype=np.int32)
+    A = gpu.AdditiveNFFTKernel(X, win, 1, 3, "gaussian").build(1.0, 1.0, 0.01)
+    B = O.OracleAdditiveNFFT(X, win, 1, 3, "gaussian").build(1.0, 1.0, 0.01)
+    x = rand_vec(n)
+    g = A.debug_spread(0, x)
+    pts = B.window_points(0)
+    L = O.lib()
+    ref = np.zeros((64, 64, 64))
+    for j in range(n):
+        c = np.floor(pts[j] * 64).astype(int)
+        psi = [[L.shim_kb_phi(pts[j, t] - (c[t] - 4 + lj) / 64.0, 64, 4) for lj in range(10)] for t in range(3)]
+        i0 = [(c[0] - 4 + lj) % 64 for lj in range(10)]
+        i1 = [(c[1] - 4 + lj) % 64 for lj in range(10)]
+        i2 = [(c[2] - 4 + lj) % 64 for lj in range(10)]
+        ref[np.ix_(i0, i1, i2)] += x[j] * np.einsum("a,b,c->abc", psi[0], psi[1], psi[2])
+    assert rel_l2(g, ref) <= 1e-12
+    # coefficient table
+    bh = B.window_bhat(0, 0)
+    ph = np.array([1.0 / L.shim_kb_phi_hut(k - 16, 64, 4) for k in range(32)])
+    scale = np.einsum("a,b,c->abc", ph, ph, ph) ** 2
+    assert rel_l2(A.debug_coeff(0, 0), bh * scale) <= 1e-12
+    # grid after scaling + inverse FFT vs numpy FFTs of the device's own spread grid
+    h = A.debug_grid_after_fft(0, x)
+    G = np.fft.ifftn(g) * g.size  # e^{+}
+    k = np.r_[0:16, 48:64]
+    kk = np.r_[16:32, 0:16]
+    band = G[np.ix_(k, k, k)]
+    coef = A.debug_coeff(0, 0)[np.ix_(kk, kk, kk)]
+    Hh = np.zeros((64, 64, 64), dtype=complex)
+    Hh[np.ix_(k, k, k)] = band * coef
+    href = np.real(np.fft.fftn(Hh))
+    assert rel_l2(h, href) <= 1e-12
+    A.free()
+    B.free()
