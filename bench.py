@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of nfft4gp_b200 (contract: see the task statement / DESIGN.md section "Measurement").
+
+Metric  : NFFT additive-kernel matvecs/s (BASELINE.json), config C2: n = 10^6 synthetic points, d = 9 split into three
+          3-feature windows, Gaussian kernel, fp64.  A "step" = one full additive matvec  y <- K x.
+value   : device-resident vectors (inputs already in HBM), CUDA events on the library stream, max over ranks.
+e2e     : the same metric through the reference-facing C-ABI call Nfft4GPAdditiveNFFTMatSymv with HOST (pinned) vectors,
+          host->device and device->host copies inside the timed region.
+roofline: dominant kernel class of the step, per-launch duration measured with CUDA events on the launching stream
+          inside this run; algorithmic bytes per launch from SURVEY.md 8(d).
+cpu_baseline / --impl reference: the reference's own CPU implementation of the path (reference wrapper
+          nfft_interface.c on the NFFT3 fastsum restatement, oracle/_ref; or the self-contained oracle port) on the box's
+          host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "nfft_additive_matvecs_per_s"
+UNIT = "matvecs/s"
+PROF_CLASSES = ["prep", "spread", "fft_fwd", "fft_inv", "gather", "combine", "vec", "nys", "csr", "gemv", "other"]
+
+
+def synthetic_problem(n, d=9, seed=906):
+    """Reference-style synthetic cloud (Nfft4GPDatasetUniformRandom, SRC/utils/utils.c:266-286): n^(1/d) U(0,1),
+    feature-major; x = U(0,1) - 0.5 (TESTS/TEST1/foo.cpp:243-247); l resolved by N = 32."""
+    rng = np.random.default_rng(seed)
+    X = rng.random((d, n)) * n ** (1.0 / d)
+    x = rng.random(n) - 0.5
+    windows = np.arange(d, dtype=np.int32)
+    side = n ** (1.0 / d)
+    l = 0.25 * side  # resolved by the 32 Fourier modes: NFFT vs dense ~3e-8 rel. (tests/test_oracle.py)
+    return X, x, windows, dict(f=1.0, l=l, mu=0.01)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_handle(X, windows, hp):
+    """The reference's CPU implementation of the path: oracle/_ref (reference wrapper, unmodified, on the fastsum
+    restatement) when it was built here, else the self-contained oracle port."""
+    from oracle import refapi
+    if refapi.available():
+        try:
+            A = refapi.RefAdditiveNFFT(X, windows, 3, 3, "gaussian").build(hp["f"], hp["l"], hp["mu"])
+            return A, "reference"
+        except Exception:
+            pass
+    from oracle import oracle_api
+    A = oracle_api.OracleAdditiveNFFT(X, windows, 3, 3, "gaussian").build(hp["f"], hp["l"], hp["mu"])
+    return A, "port"
+
+
+def time_cpu(A, x, steps, warmup):
+    for _ in range(warmup):
+        A.matvec(x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        y = A.matvec(x)
+    dt = time.perf_counter() - t0
+    return steps / dt, y
+
+
+def cpu_cores():
+    from oracle import oracle_api
+    return int(oracle_api.lib().oracle_num_threads())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.n
+    X, x, windows, hp = synthetic_problem(n)
+    A, kind = cpu_reference_handle(X, windows, hp)
+    val, _ = time_cpu(A, x, args.steps, args.warmup)
+    cores = cpu_cores()
+    sample = f"{args.steps} full additive matvecs at n={n}, d=9 (3x3-D windows) after {args.warmup} warm-up, {cores} OpenMP threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C2: additive Gaussian NFFT matvec n={n} d=9 three 3-D windows N=32 n_os=64 m=4"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch  # plumbing only: torch.distributed rendezvous + barrier
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import preconditioned_additive_gaussian_processes_with_fourier_acceleration_b200 as pkg
+    L = pkg.lib()
+    if L.Nfft4GPB200Init(local_rank) != 0:
+        raise SystemExit("nfft4gp_b200: no usable CUDA device (no CPU fallback)")
+
+    n = args.n
+    X, x, windows, hp = synthetic_problem(n)
+    A = pkg.AdditiveNFFTKernel(X, windows, 3, 3, "gaussian").build(hp["f"], hp["l"], hp["mu"])
+
+    scaling = "strong"
+    parallelism = "single"
+    if world > 1:
+        # one NCCL communicator for the library; the unique id travels through torch.distributed
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            assert L.Nfft4GPB200CommGetUniqueId(buf) == 0
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        raw = bytes(uid.cpu().numpy().tobytes())
+        assert L.Nfft4GPB200CommInit(rank, world, raw) == 0
+        mode = int(os.environ.get("NFFT4GP_SHARD_MODE", "2"))
+        assert L.Nfft4GPB200SetSharding(A.h, mode) == 0
+        parallelism = {1: f"window-sharded x{world} + 1 allreduce(y)", 2: f"point-block-sharded x{world} + 1 allreduce(grids)"}[mode]
+
+    dx = L.Nfft4GPB200DeviceAlloc(8 * n)
+    dy = L.Nfft4GPB200DeviceAlloc(8 * n)
+    L.Nfft4GPB200MemcpyH2D(dx, x.ctypes.data, 8 * n)
+    e0, e1 = L.Nfft4GPB200EventCreate(), L.Nfft4GPB200EventCreate()
+
+    def barrier():
+        L.Nfft4GPB200DeviceSynchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        L.Nfft4GPB200DeviceSynchronize()
+
+    def timed_region(steps, fn):
+        barrier()
+        L.Nfft4GPB200EventRecord(e0)
+        for _ in range(steps):
+            fn()
+        L.Nfft4GPB200EventRecord(e1)
+        ms = L.Nfft4GPB200EventElapsedMs(e0, e1)
+        barrier()
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    step_dev = lambda: A.matvec_device(dx, dy)
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.Nfft4GPB200LaunchCountReset()
+    ms_total = timed_region(args.steps, step_dev)
+    launches = int(L.Nfft4GPB200LaunchCount())
+    # second pass of the same K steps with per-launch CUDA events on the library stream: kernel durations for the roofline
+    L.Nfft4GPB200ProfileStart()
+    ms_prof_total = timed_region(args.steps, step_dev)
+    sums = (C.c_double * len(PROF_CLASSES))()
+    counts = (C.c_longlong * len(PROF_CLASSES))()
+    L.Nfft4GPB200ProfileStop(sums, counts, len(PROF_CLASSES))
+    clocks = sampler.stop() if rank == 0 else None
+
+    ms_per_step = ms_total / args.steps
+    value = 1000.0 / ms_per_step
+
+    # ---- e2e through the reference-facing host-pointer call, pinned host vectors
+    hx = L.Nfft4GPB200HostAlloc(8 * n)
+    hy = L.Nfft4GPB200HostAlloc(8 * n)
+    C.memmove(hx, x.ctypes.data, 8 * n)
+    hxp = C.cast(hx, C.POINTER(C.c_double))
+    hyp = C.cast(hy, C.POINTER(C.c_double))
+
+    def step_host():
+        assert L.Nfft4GPAdditiveNFFTMatSymv(A.K, n, 1.0, hxp, 0.0, hyp) == 0
+
+    for _ in range(3):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    L.Nfft4GPB200DeviceSynchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = args.steps / e2e_s
+    y_host = np.ctypeslib.as_array(hyp, shape=(n,)).copy()
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            L.Nfft4GPB200CommFinalize()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel class
+    pk, pk_kind = peaks()
+    per_class = {PROF_CLASSES[i]: {"ms_per_step": sums[i] / args.steps, "launches_per_step": counts[i] / args.steps}
+                 for i in range(len(PROF_CLASSES)) if counts[i] > 0}
+    dom = max(per_class, key=lambda k: per_class[k]["ms_per_step"])
+    dom_launch_ms = per_class[dom]["ms_per_step"] / per_class[dom]["launches_per_step"]
+    # algorithmic bytes per launch: one window, one direction: coordinates 8*d_w*n + vector 8*n
+    n_loc = n // world if (world > 1 and os.environ.get("NFFT4GP_SHARD_MODE", "2") == "2") else n
+    alg_bytes = {"spread": 32.0 * n_loc, "gather": 32.0 * n_loc}.get(dom, 16.0 * n)
+    achieved = alg_bytes / (dom_launch_ms * 1e-3) / 1e9
+    peak = float(pk["hbm_gbs"])
+    # fp64 view of the same launch: 2 * 10^3 flop per point (1000 FMAs), B200 fp64 FMA pipe = 64 lanes/SM/clk
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp64_peak = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
+    fp64_ach = 2000.0 * n_loc / (dom_launch_ms * 1e-3) / 1e12
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({pk_kind})", "traffic": None,
+                "launch_ms": dom_launch_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "3-D windows are fp64-pipe-bound (62 flop/B, SURVEY.md finding 4): see fp64",
+                "fp64": {"achieved_tflops": fp64_ach, "peak_tflops": fp64_peak, "frac": fp64_ach / fp64_peak,
+                         "peak_source": f"148 SM x 64 DFMA/clk x {sm_mhz:.0f} MHz (median SM clock under load)"},
+                "step_share": per_class[dom]["ms_per_step"] / (ms_prof_total / args.steps),
+                "per_class_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in per_class.items()},
+                "profiled_ms_per_step": ms_prof_total / args.steps}
+
+    # ---- CPU baseline on the host cores (bounded sample) + parity of this very run against it
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        Aref, kind = cpu_reference_handle(X, windows, hp)
+        cval, y_cpu = time_cpu(Aref, x, args.cpu_steps, 1)
+        cores = cpu_cores()
+        rel = float(np.linalg.norm(y_host - y_cpu) / np.linalg.norm(y_cpu))
+        cpu = {"value": cval, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{args.cpu_steps} full additive matvecs at n={n} (same workload) after 1 warm-up, {cores} OpenMP threads",
+               "rel_l2_gpu_vs_cpu": rel}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"C2: additive Gaussian NFFT matvec n={n} d=9 three 3-D windows N=32 n_os=64 m=4 (BASELINE.json configs[1])",
+                   "parallelism": parallelism, "l": hp["l"], "f": hp["f"], "mu": hp["mu"],
+                   "l2_policy": "inputs larger than L2: window tables streamed per step = 2 x 3 x 240 MB >> 126 MB"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+                "api": "Nfft4GPAdditiveNFFTMatSymv(host x, host y), pinned host memory"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        L.Nfft4GPB200CommFinalize()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

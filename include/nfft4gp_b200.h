@@ -188,6 +188,12 @@ void Nfft4GPB200EventDestroy(void *ev);
 int Nfft4GPB200EventRecord(void *ev);
 float Nfft4GPB200EventElapsedMs(void *start, void *stop); /* synchronises on `stop` */
 
+/* Per-kernel-class timing with CUDA events recorded on the library stream around every launch (bench.py roofline).
+ * classes: 0 prep, 1 spread, 2 fft forward, 3 fft inverse(+scale), 4 gather, 5 combine, 6 vector ops, 7 Nystrom,
+ * 8 CSR SpMV, 9 GEMV, 10 other.  Stop synchronises, fills sums_ms[ncls] / counts[ncls], returns the region count. */
+void Nfft4GPB200ProfileStart(void);
+int Nfft4GPB200ProfileStop(double *sums_ms, long long *counts, int ncls);
+
 /* Device-resident variants of the plug points: same semantics, x / y / rhs are DEVICE pointers. */
 int Nfft4GPB200AdditiveNFFTMatSymvDevice(void *data, int n, double alpha, const double *d_x, double beta, double *d_y);
 int Nfft4GPB200AdditiveNFFTGradMatSymvDevice(void *data, int n, double alpha, const double *d_x, double beta, double *d_y);

@@ -103,6 +103,8 @@ def lib():
         "Nfft4GPB200DebugCoeff": (i, [vp, i, i, c_double_p]),
         "Nfft4GPB200DebugGridAfterFFT": (i, [vp, i, d, c_double_p, c_double_p]),
         "Nfft4GPB200SetVariant": (i, [C.c_char_p, i]),
+        "Nfft4GPB200ProfileStart": (None, []),
+        "Nfft4GPB200ProfileStop": (i, [c_double_p, C.POINTER(C.c_longlong), i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export what the header declares

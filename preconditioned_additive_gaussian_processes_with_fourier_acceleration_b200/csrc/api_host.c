@@ -24,3 +24,7 @@ void *Nfft4GPB200EventCreate(void) { return b200_event_create(); }
 void Nfft4GPB200EventDestroy(void *ev) { b200_event_destroy(ev); }
 int Nfft4GPB200EventRecord(void *ev) { return b200_event_record(ev); }
 float Nfft4GPB200EventElapsedMs(void *start, void *stop) { return b200_event_elapsed_ms(start, stop); }
+
+/* per-kernel-class CUDA-event timing on the library stream (bench.py roofline) */
+void Nfft4GPB200ProfileStart(void) { b200_prof_start(); }
+int Nfft4GPB200ProfileStop(double *sums_ms, long long *counts, int ncls) { return b200_prof_stop(sums_ms, counts, ncls); }

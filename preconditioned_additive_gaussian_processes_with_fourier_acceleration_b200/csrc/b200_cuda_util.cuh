@@ -5,6 +5,11 @@
 
 cudaStream_t b200_stream();
 void b200_count_launch();
+void b200_prof_begin(int cls);
+void b200_prof_end();
+// kernel classes of the profiling facility (keep in sync with bench.py)
+enum { PC_PREP = 0, PC_SPREAD = 1, PC_FFT_FWD = 2, PC_FFT_INV = 3, PC_GATHER = 4, PC_COMBINE = 5, PC_VEC = 6, PC_NYS = 7, PC_CSR = 8, PC_GEMV = 9, PC_OTHER = 10, PC_COUNT = 11 };
+struct B200ProfScope { B200ProfScope(int c) { b200_prof_begin(c); } ~B200ProfScope() { b200_prof_end(); } };
 
 #define B200_CHECK(call)                                                                                  \
    do                                                                                                     \

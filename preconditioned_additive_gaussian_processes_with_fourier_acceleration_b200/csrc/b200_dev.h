@@ -57,6 +57,8 @@ float b200_event_elapsed_ms(void *a, void *b);
 long long b200_launch_count(void);
 void b200_launch_count_reset(void);
 void *b200_stream_handle(void); /* cudaStream_t, for NCCL */
+void b200_prof_start(void);
+int b200_prof_stop(double *sums_ms, long long *counts, int ncls);
 
 /* ---- NFFT window kernels (nfft_kernels.cu) ---- */
 int b200k_psi(const b200_win_dev *w, const double *d_xs /* [n][d] sorted scaled coords */);

@@ -15,7 +15,68 @@ std::atomic<long long> g_launches{0};
 cudaStream_t b200_stream() { return g_stream; }
 void b200_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// ---- per-kernel-class event timing (bench.py roofline): events are recorded on the library stream around every
+// launch-layer call while profiling is on; elapsed times are summed per class after a synchronize.
+#define B200_PROF_MAX 16384
+static bool g_prof_on = false;
+static int g_prof_n = 0;
+static cudaEvent_t g_prof_a[B200_PROF_MAX], g_prof_b[B200_PROF_MAX];
+static int g_prof_cls[B200_PROF_MAX];
+static int g_prof_created = 0;
+
+void b200_prof_begin(int cls)
+{
+   if (!g_prof_on || g_prof_n >= B200_PROF_MAX)
+      return;
+   if (g_prof_n >= g_prof_created)
+   {
+      cudaEventCreate(&g_prof_a[g_prof_created]);
+      cudaEventCreate(&g_prof_b[g_prof_created]);
+      g_prof_created++;
+   }
+   g_prof_cls[g_prof_n] = cls;
+   cudaEventRecord(g_prof_a[g_prof_n], g_stream);
+}
+
+void b200_prof_end()
+{
+   if (!g_prof_on || g_prof_n >= B200_PROF_MAX)
+      return;
+   cudaEventRecord(g_prof_b[g_prof_n], g_stream);
+   g_prof_n++;
+}
+
 extern "C" {
+
+void b200_prof_start(void)
+{
+   g_prof_n = 0;
+   g_prof_on = true;
+}
+
+// sums[c] = total ms of class c, counts[c] = number of timed regions; returns number of regions
+int b200_prof_stop(double *sums, long long *counts, int ncls)
+{
+   g_prof_on = false;
+   cudaStreamSynchronize(g_stream);
+   for (int c = 0; c < ncls; c++)
+   {
+      sums[c] = 0.0;
+      counts[c] = 0;
+   }
+   for (int i = 0; i < g_prof_n; i++)
+   {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, g_prof_a[i], g_prof_b[i]) == cudaSuccess && g_prof_cls[i] < ncls)
+      {
+         sums[g_prof_cls[i]] += ms;
+         counts[g_prof_cls[i]]++;
+      }
+   }
+   int n = g_prof_n;
+   g_prof_n = 0;
+   return n;
+}
 
 int b200_device_count(void)
 {

@@ -723,6 +723,7 @@ extern "C" {
 
 int b200k_psi(const b200_win_dev *w, const double *d_xs)
 {
+   B200ProfScope prof_scope_(PC_OTHER);
    if (w->n <= 0)
       return 0;
    int grid = b200_cdiv(w->n, 128);
@@ -738,6 +739,7 @@ int b200k_psi(const b200_win_dev *w, const double *d_xs)
 
 int b200k_prep(const b200_win_dev *w, const double *d_x, double scale)
 {
+   B200ProfScope prof_scope_(PC_PREP);
    k_prep<<<b200_cdiv(w->n, 256), 256, 0, b200_stream()>>>(d_x, w->perm, scale, w->a, w->n);
    B200_LAUNCHED();
    return 0;
@@ -747,6 +749,7 @@ static size_t grid_elems(int d) { return d == 1 ? 64 : (d == 2 ? 64 * 64 : 64 * 
 
 int b200k_spread(const b200_win_dev *w, int variant)
 {
+   B200ProfScope prof_scope_(PC_SPREAD);
    B200_CHECK(cudaMemsetAsync(w->grid, 0, sizeof(double) * grid_elems(w->d), b200_stream()));
    if (w->d == 3 && variant == 1)
    {
@@ -771,6 +774,7 @@ int b200k_spread(const b200_win_dev *w, int variant)
 
 int b200k_gather(const b200_win_dev *w, double *d_f, int variant)
 {
+   B200ProfScope prof_scope_(PC_GATHER);
    if (w->d == 3 && variant == 1)
    {
       int nblk = (w->nseg + B200_JOBS - 1) / B200_JOBS;
@@ -795,6 +799,7 @@ int b200k_gather(const b200_win_dev *w, double *d_f, int variant)
 // grid (real 64^d) -> band (complex 32^d), unscaled, e^{+}
 int b200k_forward_fft(const b200_win_dev *w)
 {
+   B200ProfScope prof_scope_(PC_FFT_FWD);
    if (ensure_twiddles())
       return -1;
    cudaStream_t s = b200_stream();
@@ -826,6 +831,7 @@ int b200k_forward_fft(const b200_win_dev *w)
 // band * coef -> grid (real part of the zero-padded e^{-} transform)
 int b200k_backward_fft(const b200_win_dev *w, const double *d_coef)
 {
+   B200ProfScope prof_scope_(PC_FFT_INV);
    if (ensure_twiddles())
       return -1;
    cudaStream_t s = b200_stream();
@@ -858,6 +864,7 @@ int b200k_backward_fft(const b200_win_dev *w, const double *d_coef)
 int b200k_combine(int n, int P, const double *const *d_fptr, const int *const *d_invptr, const double *d_x, double s,
                   double c0, double mu, double beta, double *d_y)
 {
+   B200ProfScope prof_scope_(PC_COMBINE);
    k_combine<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, P, d_fptr, d_invptr, d_x, s, c0, mu, beta, d_y);
    B200_LAUNCHED();
    return 0;
@@ -866,6 +873,7 @@ int b200k_combine(int n, int P, const double *const *d_fptr, const int *const *d
 int b200k_combine_grad(int n, int P, const double *const *d_fptr, const double *const *d_f2ptr, const int *const *d_invptr,
                        const double *d_x, double s, double f2, double ff, const double *d_c1w, double mu, double beta, double *d_y)
 {
+   B200ProfScope prof_scope_(PC_COMBINE);
    k_combine_grad<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, P, d_fptr, d_f2ptr, d_invptr, d_x, s, f2, ff, d_c1w, mu, beta, d_y);
    B200_LAUNCHED();
    return 0;

@@ -281,6 +281,7 @@ size_t b200k_nys_work_doubles(int n, int k)
 int b200k_nys_apply(int n, int k, const int *perm, const double *U, const double *s, double eta, const double *rhs,
                     double *x, double *work, size_t work_doubles)
 {
+   B200ProfScope prof_scope_(PC_NYS);
    int nchunks = b200_cdiv(n, NYS_ROWS);
    if (work_doubles < b200k_nys_work_doubles(n, k))
    {
@@ -300,6 +301,7 @@ int b200k_nys_apply(int n, int k, const int *perm, const double *U, const double
 
 int b200k_csr_mv(int nrows, const int *ia, const int *ja, const double *a, const double *x, double *y)
 {
+   B200ProfScope prof_scope_(PC_CSR);
    k_csr_mv<<<b200_cdiv((long long)nrows * 32, 256), 256, 0, b200_stream()>>>(nrows, ia, ja, a, x, y);
    B200_LAUNCHED();
    return 0;
@@ -307,6 +309,7 @@ int b200k_csr_mv(int nrows, const int *ia, const int *ja, const double *a, const
 
 int b200k_gather_perm(int n, const int *perm, const double *src, double *dst)
 {
+   B200ProfScope prof_scope_(PC_OTHER);
    k_gather_perm<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, perm, src, dst);
    B200_LAUNCHED();
    return 0;
@@ -314,6 +317,7 @@ int b200k_gather_perm(int n, const int *perm, const double *src, double *dst)
 
 int b200k_scatter_perm(int n, const int *perm, const double *src, double *dst)
 {
+   B200ProfScope prof_scope_(PC_OTHER);
    k_scatter_perm<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, perm, src, dst);
    B200_LAUNCHED();
    return 0;
@@ -321,6 +325,7 @@ int b200k_scatter_perm(int n, const int *perm, const double *src, double *dst)
 
 int b200k_gemv(char trans, int m, int n, double alpha, const double *A, const double *x, double beta, double *y)
 {
+   B200ProfScope prof_scope_(PC_GEMV);
    cudaStream_t st = b200_stream();
    if (trans == 'T' || trans == 't')
    {
@@ -344,6 +349,7 @@ int b200k_gemv(char trans, int m, int n, double alpha, const double *A, const do
 int b200k_dense_additive(const double *Xw, int n, int P, int dw, const int *d_dims, int kernel, double ff, double l,
                          double noise_diag, const int *rows, int nr, const int *cols, int nc, int lower_only, double *K, int ldk)
 {
+   B200ProfScope prof_scope_(PC_OTHER);
    // gridDim.y is limited to 65535: walk the columns in blocks
    for (int c0 = 0; c0 < nc; c0 += 65535)
    {

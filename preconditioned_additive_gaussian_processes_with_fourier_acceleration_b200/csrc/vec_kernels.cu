@@ -148,6 +148,7 @@ extern "C" {
 
 int b200k_dot(int n, const double *x, const double *y, double *d_out)
 {
+   B200ProfScope prof_scope_(PC_VEC);
    int nb = red_blocks(n);
    // the 128-bit path needs 16-byte aligned operands; fall back to the scalar two-vector kernel otherwise
    if ((((size_t)x | (size_t)y) & 15) == 0)
@@ -169,6 +170,7 @@ int b200k_dot(int n, const double *x, const double *y, double *d_out)
 
 int b200k_dot2(int n, const double *x, const double *y, const double *u, const double *v, double *d_out2)
 {
+   B200ProfScope prof_scope_(PC_VEC);
    int nb = red_blocks(n);
    k_dot2_stage1<<<nb, RED_THREADS, 0, b200_stream()>>>(n, x, y, u, v);
    B200_LAUNCHED();
@@ -179,6 +181,7 @@ int b200k_dot2(int n, const double *x, const double *y, const double *u, const d
 
 int b200k_pcg_update(int n, double alpha, const double *p, const double *q, double *x, double *r, double *d_out)
 {
+   B200ProfScope prof_scope_(PC_VEC);
    int nb = red_blocks(n);
    k_pcg_update_stage1<<<nb, RED_THREADS, 0, b200_stream()>>>(n, alpha, p, q, x, r);
    B200_LAUNCHED();
@@ -189,6 +192,7 @@ int b200k_pcg_update(int n, double alpha, const double *p, const double *q, doub
 
 int b200k_xpby(int n, const double *z, double beta, double *p)
 {
+   B200ProfScope prof_scope_(PC_VEC);
    k_xpby<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, z, beta, p);
    B200_LAUNCHED();
    return 0;
@@ -196,6 +200,7 @@ int b200k_xpby(int n, const double *z, double beta, double *p)
 
 int b200k_copy(int n, const double *src, double *dst)
 {
+   B200ProfScope prof_scope_(PC_VEC);
    k_copy<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, src, dst);
    B200_LAUNCHED();
    return 0;
@@ -203,6 +208,7 @@ int b200k_copy(int n, const double *src, double *dst)
 
 int b200k_fill(int n, double v, double *dst)
 {
+   B200ProfScope prof_scope_(PC_VEC);
    k_fill<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, v, dst);
    B200_LAUNCHED();
    return 0;
@@ -210,6 +216,7 @@ int b200k_fill(int n, double v, double *dst)
 
 int b200k_scale(int n, double a, double *x)
 {
+   B200ProfScope prof_scope_(PC_VEC);
    k_scale<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, a, x);
    B200_LAUNCHED();
    return 0;
@@ -217,6 +224,7 @@ int b200k_scale(int n, double a, double *x)
 
 int b200k_axpy(int n, double a, const double *x, double *y)
 {
+   B200ProfScope prof_scope_(PC_VEC);
    k_axpy<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, a, x, y);
    B200_LAUNCHED();
    return 0;

@@ -5,9 +5,9 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, ".")
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import preconditioned_additive_gaussian_processes_with_fourier_acceleration_b200 as pkg
-from tests.common import uniform_cloud, gaussian_cloud, rand_vec
+from common import uniform_cloud, gaussian_cloud, rand_vec
 
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1000000
 cloud = gaussian_cloud if (len(sys.argv) > 2 and sys.argv[2] == "gauss") else uniform_cloud
