@@ -15,20 +15,21 @@ extern "C" {
 #define B200_NOS 64   /* oversampled FFT length (sigma = 2)   */
 #define B200_MCUT 4   /* window cut-off m                     */
 #define B200_TAPS 10  /* 2m + 2                               */
-#define B200_SEG_MAX 512
-#define B200_JOBS 8   /* segments processed side by side by one CTA of the tiled 3-D kernels */
 
 /* device-side state of one feature window */
 typedef struct
 {
    int d;        /* window dimension 1..3                                        */
    int n;        /* number of points                                             */
-   int nseg;     /* number of (cell, point-range) segments, sorted by size desc  */
+   int nseg;     /* number of (cell, warp-range) segments (information only)     */
    double *psi;  /* [n + pad][d*10] Kaiser-Bessel taps, cell-sorted point order  */
    int *key;     /* [n] packed cell index ((c1+32)<<12 | (c2+32)<<6 | (c3+32))    */
    int *perm;    /* [n] sorted position -> original point                        */
    int *inv;     /* [n] original point -> sorted position                        */
-   int *seg_start, *seg_cnt, *seg_base; /* [nseg padded to a multiple of B200_JOBS] */
+   int nchunk;   /* 3-D windows: number of chunk descriptors                      */
+   int *chunks;  /* [nchunk + pad] int4 {first point, count <= 8, packed cell key, 0}: <= 8 consecutive points of ONE cell */
+   int nwr;      /* number of warp ranges (= resident warps of the 3-D kernels, one persistent wave) */
+   int *cfirst;  /* [nwr + 1] warp r owns chunks [cfirst[r], cfirst[r+1]): equal point counts per warp */
    double *a;    /* [n + pad] (alpha/P) * x[perm], sorted order                  */
    double *f;    /* [n] interpolation result, sorted order (kernel channel)      */
    double *f2;   /* [n] derivative-kernel channel (gradient matvec only)         */
@@ -67,6 +68,10 @@ int b200k_spread(const b200_win_dev *w, int variant);
 int b200k_forward_fft(const b200_win_dev *w);                                   /* grid -> band (unscaled) */
 int b200k_backward_fft(const b200_win_dev *w, const double *d_coef);            /* band * coef -> grid (Re h) */
 int b200k_gather(const b200_win_dev *w, double *d_f, int variant);
+/* nfft3d_warp.cu: warp-per-segment 3-D kernels */
+int b200k_warp_ranges(void);
+int b200k_spread3_warp(const b200_win_dev *w);
+int b200k_gather3_warp(const b200_win_dev *w, double *d_f);
 /* y = beta*y + sum_w c0*(f_w[inv_w] + mu*s*x)   (matvec epilogue, nfft_interface.c:428-494, 803-814) */
 int b200k_combine(int n, int P, const double *const *d_fptr, const int *const *d_invptr, const double *d_x,
                   double s, double c0, double mu, double beta, double *d_y);

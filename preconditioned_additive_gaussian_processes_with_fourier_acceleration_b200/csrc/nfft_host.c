@@ -264,9 +264,8 @@ static void window_free_device(b200_window *w)
    b200_free(v->key);
    b200_free(v->perm);
    b200_free(v->inv);
-   b200_free(v->seg_start);
-   b200_free(v->seg_cnt);
-   b200_free(v->seg_base);
+   b200_free(v->chunks);
+   b200_free(v->cfirst);
    b200_free(v->a);
    b200_free(v->f);
    b200_free(v->f2);
@@ -286,19 +285,6 @@ static void window_free(b200_window *w)
    window_free_device(w);
    free(w->h_perm);
    free(w);
-}
-
-typedef struct
-{
-   int start, cnt, base;
-} seg_t;
-
-static int seg_cmp(const void *a, const void *b)
-{
-   const seg_t *x = (const seg_t *)a, *y = (const seg_t *)b;
-   if (x->cnt != y->cnt)
-      return y->cnt - x->cnt;
-   return x->start - y->start;
 }
 
 /* First-call part of nfft_interface.c:150-213: centre every feature, r_max, scale to radius 0.25 (unless
@@ -416,54 +402,86 @@ static int window_setup_points(b200_window *w, const double *cols, int n)
        * of the tiled kernels carry similar work and the longest CTAs start first */
       if (d == 3)
       {
-         int nseg = 0, cap = 1024, b;
-         seg_t *segs = (seg_t *)b200_xmalloc(sizeof(seg_t) * (size_t)cap);
-         int *hs, *hc, *hb, npad;
+         /* Work decomposition of the streaming 3-D kernels: the cell-sorted point array is cut into nwr CONTIGUOUS
+          * ranges of (almost) equal point count, one per resident warp of one persistent wave; each range is cut at cell
+          * boundaries and then into CHUNKS of <= 8 consecutive points of one cell -- the unit the device pipeline
+          * stages and computes without any data-dependent branch.  Equal point counts give equal fp64 work per warp
+          * whatever the density of the cloud (a heavy cell is simply shared by several warps). */
+         int nwr = b200k_warp_ranges();
+         int nseg = 0, nch = 0, cap = 4096, r = 0, b, prev = -1;
+         int *hc = (int *)b200_xmalloc(sizeof(int) * 4 * (size_t)cap);
+         int *hw = (int *)b200_xcalloc((size_t)nwr + 1, sizeof(int));
+         /* cost model in point-equivalents of the fp64 pipe: 1 per point, 1 per chunk (ring bookkeeping), and per cell
+          * change 2 per plane shifted in the same (c1,c2) row or 24 for a full footprint flush / reload */
+         double total = 0.0, acc_cost = 0.0, target;
+         for (b = 0; b < (int)nbins; b++)
+         {
+            int cnt = binstart[b + 1] - binstart[b];
+            if (cnt == 0)
+               continue;
+            total += (double)cnt + (double)((cnt + 7) / 8);
+            total += (prev >= 0 && (prev >> 6) == (b >> 6) && b - prev < B200_TAPS) ? 2.0 * (b - prev) : 24.0;
+            prev = b;
+         }
+         target = total / (double)nwr;
+         prev = -1;
+         hw[0] = 0;
          for (b = 0; b < (int)nbins; b++)
          {
             int s = binstart[b], e = binstart[b + 1];
+            if (s == e)
+               continue;
+            nseg++;
+            acc_cost += (prev >= 0 && (prev >> 6) == (b >> 6) && b - prev < B200_TAPS) ? 2.0 * (b - prev) : 24.0;
+            prev = b;
             while (s < e)
             {
-               int c = e - s > B200_SEG_MAX ? B200_SEG_MAX : e - s;
-               if (nseg == cap)
+               int c = e - s > 8 ? 8 : e - s;
+               /* open the next warp range when this one has its share of the cost */
+               while (r + 1 < nwr && acc_cost >= target * (double)(r + 1))
+               {
+                  r++;
+                  hw[r] = nch;
+               }
+               if (nch + 8 >= cap)
                {
                   cap *= 2;
-                  segs = (seg_t *)realloc(segs, sizeof(seg_t) * (size_t)cap);
-                  if (!segs)
+                  hc = (int *)realloc(hc, sizeof(int) * 4 * (size_t)cap);
+                  if (!hc)
                      exit(EXIT_FAILURE);
                }
-               segs[nseg].start = s;
-               segs[nseg].cnt = c;
-               segs[nseg].base = b;
-               nseg++;
+               hc[4 * nch + 0] = s;
+               hc[4 * nch + 1] = c;
+               hc[4 * nch + 2] = b;
+               hc[4 * nch + 3] = 0;
+               nch++;
                s += c;
+               acc_cost += (double)c + 1.0;
             }
          }
-         qsort(segs, (size_t)nseg, sizeof(seg_t), seg_cmp);
-         npad = (nseg + B200_JOBS - 1) / B200_JOBS * B200_JOBS;
-         if (npad == 0)
-            npad = B200_JOBS;
-         hs = (int *)b200_xcalloc((size_t)npad, sizeof(int));
-         hc = (int *)b200_xcalloc((size_t)npad, sizeof(int));
-         hb = (int *)b200_xcalloc((size_t)npad, sizeof(int));
-         for (i = 0; i < nseg; i++)
+         while (r + 1 < nwr)
          {
-            hs[i] = segs[i].start;
-            hc[i] = segs[i].cnt;
-            hb[i] = segs[i].base;
+            r++;
+            hw[r] = nch;
+         }
+         hw[nwr] = nch;
+         for (i = 0; i < 4; i++) /* padding descriptors (count 0) so that look-ahead loads stay in bounds */
+         {
+            hc[4 * (nch + i) + 0] = 0;
+            hc[4 * (nch + i) + 1] = 0;
+            hc[4 * (nch + i) + 2] = 0;
+            hc[4 * (nch + i) + 3] = 0;
          }
          v->nseg = nseg;
-         v->seg_start = (int *)b200_malloc(sizeof(int) * (size_t)npad);
-         v->seg_cnt = (int *)b200_malloc(sizeof(int) * (size_t)npad);
-         v->seg_base = (int *)b200_malloc(sizeof(int) * (size_t)npad);
-         b200_h2d(v->seg_start, hs, sizeof(int) * (size_t)npad);
-         b200_h2d(v->seg_cnt, hc, sizeof(int) * (size_t)npad);
-         b200_h2d(v->seg_base, hb, sizeof(int) * (size_t)npad);
+         v->nchunk = nch;
+         v->nwr = nwr;
+         v->chunks = (int *)b200_malloc(sizeof(int) * 4 * ((size_t)nch + 4));
+         v->cfirst = (int *)b200_malloc(sizeof(int) * ((size_t)nwr + 1));
+         b200_h2d(v->chunks, hc, sizeof(int) * 4 * ((size_t)nch + 4));
+         b200_h2d(v->cfirst, hw, sizeof(int) * ((size_t)nwr + 1));
          b200_sync();
-         free(hs);
          free(hc);
-         free(hb);
-         free(segs);
+         free(hw);
       }
       if (b200k_psi(v, d_xs) || b200_sync())
          return -1;

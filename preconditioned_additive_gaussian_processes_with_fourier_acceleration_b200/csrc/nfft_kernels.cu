@@ -8,11 +8,10 @@
 //   gather    f_j = sum_taps h[l] psi_1 psi_2 psi_3    NFFT trafo, B
 //   combine   y = beta y + f^2 ( sum_w f_w + mu a )                       (nfft_interface.c:428-494, 803-814)
 //
-// Points are bin-sorted by oversampled-grid cell at setup.  For 3-D windows the hot kernels are register-tiled:
-// the 10x10x10 footprint of a cell is owned by 20 threads (5x2x5 outputs each), the points of the cell stream
-// through shared memory (cp.async double buffering), and only the finished footprint touches the L2-resident
-// grid (one RED per output per segment) -- no per-point global atomics.  1-D / 2-D windows use the generic
-// warp-aggregated kernels.  No cuFFT, no CPU fallback.
+// Points are bin-sorted by oversampled-grid cell at setup.  The hot 3-D spread / gather kernels live in
+// nfft3d_warp.cu (warp-per-segment, register-tiled); this file holds the generic warp-aggregated kernels used for
+// 1-D / 2-D windows (and as the on-device cross-check of the 3-D kernels, variant 0), the shared-memory FFT passes and
+// the epilogues.  No cuFFT, no CPU fallback.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <cstdint>
@@ -226,241 +225,6 @@ __global__ void k_gather_generic(const double *__restrict__ psi, const int *__re
       }
    }
    f[j] = acc;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// register-tiled 3-D spread / gather.
-// CTA = 160 threads = B200_JOBS (8) jobs x 20 threads; a job = one segment (a run of <= B200_SEG_MAX
-// cell-sorted points of ONE grid cell).  Thread (i1,i2,i3) of a job owns the 5x2x5 block
-// l1 in [5 i1, 5 i1+5), l2 in [2 i2, 2 i2+2), l3 in [5 i3, 5 i3+5) of the cell's 10^3 footprint.
-// Per point and thread: 12 operands from shared memory, 12 DMUL + 50 DFMA (spread) -- 5 fp64 ops per
-// operand, above the 4 ops/operand that shared-memory bandwidth (128 B/clk/SM) can feed the fp64 pipe.
-// ---------------------------------------------------------------------------------------------------
-#define T3_S 8                               /* points per job per stage                    */
-#define T3_JS (T3_S * 3 * TAPS + 2)          /* job stride in doubles (+2: bank skew)       */
-#define T3_THREADS (B200_JOBS * 20)
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8_zfill(void *smem, const void *gmem, bool valid)
-{
-   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-   int sz = valid ? 8 : 0;
-   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
-{
-   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
-// stage the psi rows (and optionally the coefficients a) of points [start+c, start+c+S) of one job
-__device__ __forceinline__ void t3_stage(double *st, double *ast, const double *__restrict__ psi, const double *__restrict__ a,
-                                         int start, int cnt, int c, int jb, int lt)
-{
-   if (c < cnt)
-   {
-      const double *src = psi + (size_t)(start + c) * (3 * TAPS);
-      double *dst = st + jb * T3_JS;
-#pragma unroll
-      for (int k = 0; k < 6; k++) // 8 points * 240 B = 120 x 16 B over 20 threads
-      {
-         int idx = lt + 20 * k;
-         cp_async16(dst + 2 * idx, src + 2 * idx);
-      }
-      if (a != nullptr && lt < T3_S)
-      {
-         bool ok = (c + lt) < cnt;
-         cp_async8_zfill(ast + jb * T3_S + lt, a + start + (ok ? c + lt : 0), ok);
-      }
-   }
-}
-
-__global__ void __launch_bounds__(T3_THREADS, 2)
-k_spread3_tiled(const double *__restrict__ psi, const double *__restrict__ a, const int *__restrict__ seg_start,
-                const int *__restrict__ seg_cnt, const int *__restrict__ seg_base, double *__restrict__ grid)
-{
-   __shared__ __align__(16) double st[2][B200_JOBS * T3_JS];
-   __shared__ __align__(16) double ast[2][B200_JOBS * T3_S];
-
-   const int tid = threadIdx.x;
-   const int jb = tid / 20, lt = tid % 20;
-   const int i1 = lt / 10, i2 = (lt % 10) >> 1, i3 = lt & 1;
-   const int seg = blockIdx.x * B200_JOBS + jb;
-   const int start = seg_start[seg], cnt = seg_cnt[seg];
-   const int maxcnt = seg_cnt[blockIdx.x * B200_JOBS]; // segments are sorted by size, descending
-   const int nch = (maxcnt + T3_S - 1) / T3_S;
-
-   double acc[5][2][5];
-#pragma unroll
-   for (int x = 0; x < 5; x++)
-#pragma unroll
-      for (int y = 0; y < 2; y++)
-#pragma unroll
-         for (int z = 0; z < 5; z++)
-            acc[x][y][z] = 0.0;
-
-   t3_stage(st[0], ast[0], psi, a, start, cnt, 0, jb, lt);
-   cp_async_commit();
-   for (int ch = 0; ch < nch; ch++)
-   {
-      const int buf = ch & 1;
-      if (ch + 1 < nch)
-         t3_stage(st[buf ^ 1], ast[buf ^ 1], psi, a, start, cnt, (ch + 1) * T3_S, jb, lt);
-      cp_async_commit();
-      cp_async_wait<1>();
-      __syncthreads();
-      if (ch * T3_S < cnt)
-      {
-         const double *row = st[buf] + jb * T3_JS;
-         const double *av = ast[buf] + jb * T3_S;
-#pragma unroll
-         for (int p = 0; p < T3_S; p++)
-         {
-            const double *r = row + p * (3 * TAPS);
-            const double aj = av[p];
-            const double2 p2 = *reinterpret_cast<const double2 *>(r + TAPS + 2 * i2);
-            double p1[5], p3[5];
-#pragma unroll
-            for (int x = 0; x < 5; x++)
-               p1[x] = r[5 * i1 + x];
-#pragma unroll
-            for (int z = 0; z < 5; z++)
-               p3[z] = r[2 * TAPS + 5 * i3 + z];
-            const double q0 = aj * p2.x, q1 = aj * p2.y;
-#pragma unroll
-            for (int x = 0; x < 5; x++)
-            {
-               const double qa0 = p1[x] * q0, qa1 = p1[x] * q1;
-#pragma unroll
-               for (int z = 0; z < 5; z++)
-               {
-                  acc[x][0][z] = fma(qa0, p3[z], acc[x][0][z]);
-                  acc[x][1][z] = fma(qa1, p3[z], acc[x][1][z]);
-               }
-            }
-         }
-      }
-      __syncthreads();
-   }
-   if (cnt > 0)
-   {
-      const int kb = seg_base[seg];
-      const int c1 = (kb >> 12) & 63, c2 = (kb >> 6) & 63, c3 = kb & 63;
-#pragma unroll
-      for (int x = 0; x < 5; x++)
-      {
-         const int g1 = tap_index(c1, 5 * i1 + x);
-#pragma unroll
-         for (int y = 0; y < 2; y++)
-         {
-            const int g2 = tap_index(c2, 2 * i2 + y);
-            double *gr = grid + (size_t)(g1 * NOS + g2) * NOS;
-#pragma unroll
-            for (int z = 0; z < 5; z++)
-               atomicAdd(gr + tap_index(c3, 5 * i3 + z), acc[x][y][z]);
-         }
-      }
-   }
-}
-
-__global__ void __launch_bounds__(T3_THREADS, 2)
-k_gather3_tiled(const double *__restrict__ psi, const int *__restrict__ seg_start, const int *__restrict__ seg_cnt,
-                const int *__restrict__ seg_base, const double *__restrict__ h, double *__restrict__ f)
-{
-   __shared__ __align__(16) double st[2][B200_JOBS * T3_JS];
-   __shared__ double part[B200_JOBS][T3_S][21];
-
-   const int tid = threadIdx.x;
-   const int jb = tid / 20, lt = tid % 20;
-   const int i1 = lt / 10, i2 = (lt % 10) >> 1, i3 = lt & 1;
-   const int seg = blockIdx.x * B200_JOBS + jb;
-   const int start = seg_start[seg], cnt = seg_cnt[seg];
-   const int maxcnt = seg_cnt[blockIdx.x * B200_JOBS];
-   const int nch = (maxcnt + T3_S - 1) / T3_S;
-
-   t3_stage(st[0], nullptr, psi, nullptr, start, cnt, 0, jb, lt);
-   cp_async_commit();
-
-   double hr[5][2][5];
-   {
-      const int kb = seg_base[seg];
-      const int c1 = (kb >> 12) & 63, c2 = (kb >> 6) & 63, c3 = kb & 63;
-#pragma unroll
-      for (int x = 0; x < 5; x++)
-      {
-         const int g1 = tap_index(c1, 5 * i1 + x);
-#pragma unroll
-         for (int y = 0; y < 2; y++)
-         {
-            const int g2 = tap_index(c2, 2 * i2 + y);
-            const double *gr = h + (size_t)(g1 * NOS + g2) * NOS;
-#pragma unroll
-            for (int z = 0; z < 5; z++)
-               hr[x][y][z] = (cnt > 0) ? __ldg(gr + tap_index(c3, 5 * i3 + z)) : 0.0;
-         }
-      }
-   }
-
-   for (int ch = 0; ch < nch; ch++)
-   {
-      const int buf = ch & 1;
-      if (ch + 1 < nch)
-         t3_stage(st[buf ^ 1], nullptr, psi, nullptr, start, cnt, (ch + 1) * T3_S, jb, lt);
-      cp_async_commit();
-      cp_async_wait<1>();
-      __syncthreads();
-      const bool active = ch * T3_S < cnt;
-      if (active)
-      {
-         const double *row = st[buf] + jb * T3_JS;
-#pragma unroll
-         for (int p = 0; p < T3_S; p++)
-         {
-            const double *r = row + p * (3 * TAPS);
-            const double2 p2 = *reinterpret_cast<const double2 *>(r + TAPS + 2 * i2);
-            double p1[5], p3[5];
-#pragma unroll
-            for (int x = 0; x < 5; x++)
-               p1[x] = r[5 * i1 + x];
-#pragma unroll
-            for (int z = 0; z < 5; z++)
-               p3[z] = r[2 * TAPS + 5 * i3 + z];
-            double tot = 0.0;
-#pragma unroll
-            for (int x = 0; x < 5; x++)
-            {
-               double s0 = hr[x][0][0] * p3[0], s1 = hr[x][1][0] * p3[0];
-#pragma unroll
-               for (int z = 1; z < 5; z++)
-               {
-                  s0 = fma(hr[x][0][z], p3[z], s0);
-                  s1 = fma(hr[x][1][z], p3[z], s1);
-               }
-               double tx = fma(s1, p2.y, s0 * p2.x);
-               tot = fma(tx, p1[x], tot);
-            }
-            part[jb][p][lt] = tot;
-         }
-      }
-      __syncthreads();
-      if (active && lt < T3_S)
-      {
-         const int pj = ch * T3_S + lt;
-         if (pj < cnt)
-         {
-            double s = 0.0;
-#pragma unroll
-            for (int q = 0; q < 20; q++)
-               s += part[jb][lt][q];
-            f[start + pj] = s;
-         }
-      }
-   }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -751,16 +515,8 @@ int b200k_spread(const b200_win_dev *w, int variant)
 {
    B200ProfScope prof_scope_(PC_SPREAD);
    B200_CHECK(cudaMemsetAsync(w->grid, 0, sizeof(double) * grid_elems(w->d), b200_stream()));
-   if (w->d == 3 && variant == 1)
-   {
-      int nblk = (w->nseg + B200_JOBS - 1) / B200_JOBS;
-      if (nblk > 0)
-      {
-         k_spread3_tiled<<<nblk, T3_THREADS, 0, b200_stream()>>>(w->psi, w->a, w->seg_start, w->seg_cnt, w->seg_base, w->grid);
-         B200_LAUNCHED();
-      }
-      return 0;
-   }
+   if (w->d == 3 && variant != 0) // variant 0 = generic kernel (cross-check)
+      return b200k_spread3_warp(w);
    int grid = b200_cdiv(w->n, 128);
    if (w->d == 1)
       k_spread_generic<1><<<grid, 128, 0, b200_stream()>>>(w->psi, w->key, w->a, w->grid, w->n);
@@ -775,16 +531,8 @@ int b200k_spread(const b200_win_dev *w, int variant)
 int b200k_gather(const b200_win_dev *w, double *d_f, int variant)
 {
    B200ProfScope prof_scope_(PC_GATHER);
-   if (w->d == 3 && variant == 1)
-   {
-      int nblk = (w->nseg + B200_JOBS - 1) / B200_JOBS;
-      if (nblk > 0)
-      {
-         k_gather3_tiled<<<nblk, T3_THREADS, 0, b200_stream()>>>(w->psi, w->seg_start, w->seg_cnt, w->seg_base, w->grid, d_f);
-         B200_LAUNCHED();
-      }
-      return 0;
-   }
+   if (w->d == 3 && variant != 0)
+      return b200k_gather3_warp(w, d_f);
    int grid = b200_cdiv(w->n, 128);
    if (w->d == 1)
       k_gather_generic<1><<<grid, 128, 0, b200_stream()>>>(w->psi, w->key, w->grid, d_f, w->n);
