@@ -316,6 +316,8 @@ def solver_pcg(mat, n, matvec_fn, prec, solve_fn, x0, rhs, maxits, atol, tol, pr
     if rc != 0:
         raise RuntimeError("Nfft4GPSolverPcg failed")
     m = min(maxits, n) + 1
+    if it.value == 0 and not atol and rel.value <= tol:
+        m = 1  # early exits of pcg.c:32-41 / 70-84 allocate a single entry
     hist = np.ctypeslib.as_array(relv, shape=(m,)).copy() if relv else np.zeros(0)
     if relv:
         L.free(relv)
