@@ -1,0 +1,137 @@
+"""Generate the golden fixtures of tests/golden/ by running the REFERENCE'S OWN C sources (oracle/_ref =
+/root/reference/SRC compiled unmodified on the NFFT3 fastsum shim) in this container.  The fixtures travel to the GPU box;
+/root/reference does not.  Run:  make -C oracle ref && python scripts/make_golden.py
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import refapi as R  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+L = R.lib()
+
+
+def cloud(n, d, seed):
+    rng = np.random.default_rng(seed)
+    return rng.random((d, n)) * n ** (1.0 / d)
+
+
+def nfft_case(name, n, d, win, nw, dw, kern, f, l, mu, seed):
+    X = cloud(n, d, seed)
+    win = np.array(win, dtype=np.int32)
+    rng = np.random.default_rng(seed + 1)
+    x = rng.random(n) - 0.5
+    y0 = rng.random(n) - 0.5
+    g0 = rng.random(3 * n) - 0.5
+    A = R.RefAdditiveNFFT(X, win, nw, dw, "gaussian" if kern == "gaussian" else "matern").build(f, l, mu)
+    out = {"X": X, "windows": win, "nw": nw, "dw": dw, "kernel": kern, "f": f, "l": l, "mu": mu, "x": x, "y0": y0, "g0": g0}
+    for tag, (al, be) in {"a1b0": (1.0, 0.0), "am1b1": (-1.0, 1.0), "a07b03": (0.7, 0.3)}.items():
+        out["y_" + tag] = A.matvec(x, al, be, y0)
+        out["g_" + tag] = A.grad_matvec(x, al, be, g0)
+    # dense arbiter (unpadded windows only: the reference's dense skip-window detection is broken for padded ones)
+    if -1 not in win.tolist():
+        D = R.RefAdditiveDense(X, win, nw, dw, "gaussian" if kern == "gaussian" else "matern").build(f, l, mu)
+        out["y_dense"] = D.matvec(x)
+        out["g_dense"] = D.grad_matvec(x)
+    np.savez_compressed(os.path.join(OUT, f"nfft_{name}.npz"), **out)
+    A.free()
+    print("wrote", name)
+
+
+def solver_case():
+    """Reference PCG / Nystrom / FSAI on the reference's dense additive kernel."""
+    n, d = 300, 9
+    X = cloud(n, d, 41)
+    win = np.arange(9, dtype=np.int32)
+    f, l, mu = 1.1, 0.5, 0.05
+    D = R.RefAdditiveDense(X, win, 3, 3, "gaussian").build(f, l, mu, grad=False)
+    rng = np.random.default_rng(42)
+    rhs = rng.random(n) - 0.5
+    mv = L.Nfft4GPDenseMatSymv
+    out = {"X": X, "windows": win, "f": f, "l": l, "mu": mu, "rhs": rhs, "K": D.matrix()}
+    x, rel, hist, it = R.ref_pcg(D.K, n, mv, None, None, np.zeros(n), rhs, 400, 0, 1e-8)
+    out.update(pcg_x=x, pcg_rel=rel, pcg_hist=hist, pcg_it=it)
+    x2, rel2, hist2, it2 = R.ref_pcg(D.K, n, mv, None, None, np.zeros(n), rhs, 7, 0, 1e-12)  # non-convergence: iter = 0
+    out.update(pcg7_x=x2, pcg7_rel=rel2, pcg7_hist=hist2, pcg7_it=it2)
+    # Nystrom with a fixed permutation, rank 40
+    perm = np.random.default_rng(43).permutation(n).astype(np.int32)
+    nys = L.Nfft4GPPrecondNysCreate()
+    L.Nfft4GPPrecondNysSetRank(nys, 40)
+    L.Nfft4GPPrecondNysSetPerm(nys, R.iptr(perm), 0)
+    assert L.Nfft4GPPrecondNysSetupWithKernel(R.dptr(D.X), n, n, d, C.cast(L.Nfft4GPKernelAdditiveKernel, C.c_void_p), D.h, 0, nys) == 0
+    z = np.zeros(n)
+    L.Nfft4GPPrecondNysSolve(nys, n, R.dptr(z), R.dptr(rhs))
+    xn, reln, histn, itn = R.ref_pcg(D.K, n, mv, nys, L.Nfft4GPPrecondNysSolve, np.zeros(n), rhs, 400, 0, 1e-8)
+    out.update(nys_perm=perm, nys_k=40, nys_z=z, nys_pcg_it=itn, nys_pcg_rel=reln, nys_pcg_hist=histn)
+
+    # read the factors back from the reference struct (INC/_preconds.h:320-351)
+    class PNys(C.Structure):
+        _fields_ = [("_k_setup", C.c_int), ("_own_perm", C.c_int), ("_perm", C.c_void_p), ("_n", C.c_int), ("_tits", C.c_int),
+                    ("_titt", C.c_double), ("_tset", C.c_double), ("_tlogdet", C.c_double), ("_tdvp", C.c_double),
+                    ("_nys_opt", C.c_int), ("_k", C.c_int), ("_eta", C.c_double), ("_f2", C.c_double),
+                    ("_U", R.c_double_p), ("_s", R.c_double_p), ("_work", R.c_double_p)]
+
+    ps = PNys.from_address(nys)
+    out["nys_U"] = np.ctypeslib.as_array(ps._U, shape=(40, n)).T.copy()  # column-major n x k
+    out["nys_s"] = np.ctypeslib.as_array(ps._s, shape=(40,)).copy()
+    out["nys_eta"] = ps._eta
+    np.savez_compressed(os.path.join(OUT, "solver_dense300.npz"), **out)
+    print("wrote solver case: pcg it", it, "nys-pcg it", itn)
+
+
+def fsai_case():
+    """Reference FSAI on the reference's plain dense Gaussian kernel (3 features).  NB: Nfft4GPPrecondFsaiSetupWithKernel
+    segfaults in the reference when it is handed the dense ADDITIVE kernel (observed here, gcc 13.3, also single-threaded),
+    so the golden vector for the FSAI row uses the kernel the reference's own drivers combine it with."""
+    n, d = 300, 3
+    X = cloud(n, d, 51)
+    f, l, mu = 1.0, 0.8, 0.05
+    L.Nfft4GPKernelParamCreate.restype = C.c_void_p
+    L.Nfft4GPKernelParamCreate.argtypes = [C.c_int, C.c_int]
+    kh = L.Nfft4GPKernelParamCreate(n, 1)
+    R.set_hyper(kh, f, l, mu)
+    K = C.c_void_p()
+    assert L.Nfft4GPKernelGaussianKernel(kh, R.dptr(X), n, n, d, None, 0, None, 0, C.byref(K), None) == 0
+    Km = np.ctypeslib.as_array(C.cast(K, R.c_double_p), shape=(n, n)).T.copy()
+    Km = np.tril(Km) + np.tril(Km, -1).T
+    rng = np.random.default_rng(52)
+    rhs = rng.random(n) - 0.5
+    out = {"X": X, "f": f, "l": l, "mu": mu, "rhs": rhs, "K": Km}
+    fs = L.Nfft4GPPrecondFsaiCreate()
+    L.Nfft4GPPrecondFsaiSetLfil(fs, 12)
+    assert L.Nfft4GPPrecondFsaiSetupWithKernel(R.dptr(X), n, n, d, C.cast(L.Nfft4GPKernelGaussianKernel, C.c_void_p), kh, 0, fs) == 0
+    zf = np.zeros(n)
+    L.Nfft4GPPrecondFsaiSolve(fs, n, R.dptr(zf), R.dptr(rhs))
+
+    class PFsai(C.Structure):
+        _fields_ = [("_lfil", C.c_int), ("_n", C.c_int), ("_tits", C.c_int), ("_titt", C.c_double), ("_tset", C.c_double),
+                    ("_tlogdet", C.c_double), ("_tdvp", C.c_double), ("_L_i", R.c_int_p), ("_L_j", R.c_int_p),
+                    ("_L_a", R.c_double_p), ("_dL_a", R.c_double_p), ("_work", R.c_double_p)]
+
+    pf = PFsai.from_address(fs)
+    ia = np.ctypeslib.as_array(pf._L_i, shape=(n + 1,)).copy()
+    nnz = int(ia[-1])
+    out.update(fsai_lfil=12, fsai_z=zf, fsai_ia=ia, fsai_ja=np.ctypeslib.as_array(pf._L_j, shape=(nnz,)).copy(),
+               fsai_a=np.ctypeslib.as_array(pf._L_a, shape=(nnz,)).copy())
+    xf, relf, histf, itf = R.ref_pcg(K, n, L.Nfft4GPDenseMatSymv, fs, L.Nfft4GPPrecondFsaiSolve, np.zeros(n), rhs, 400, 0, 1e-8)
+    x0, rel0, hist0, it0 = R.ref_pcg(K, n, L.Nfft4GPDenseMatSymv, None, None, np.zeros(n), rhs, 400, 0, 1e-8)
+    out.update(fsai_pcg_it=itf, fsai_pcg_rel=relf, fsai_pcg_x=xf, pcg_it=it0)
+    np.savez_compressed(os.path.join(OUT, "fsai_gauss300.npz"), **out)
+    print("wrote fsai case: nnz", nnz, "fsai-pcg it", itf, "plain pcg it", it0)
+
+
+if __name__ == "__main__":
+    nfft_case("gauss_3x3d", 400, 9, list(range(9)), 3, 3, "gaussian", 1.2, 0.5, 0.01, 11)
+    nfft_case("bike_pattern", 350, 13, [1, 8, 6, 9, 4, 2, 5, 3, 11], 3, 3, "gaussian", 0.9, 0.45, 0.02, 12)
+    nfft_case("padded_last", 300, 5, [0, 1, 3, 2, 4, -1], 2, 3, "gaussian", 1.0, 0.6, 0.01, 13)
+    nfft_case("matern_2d", 300, 4, [0, 1, 2, 3], 2, 2, "matern12", 1.1, 1.5, 0.05, 14)
+    nfft_case("gauss_1d", 250, 3, [0, 1, 2], 3, 1, "gaussian", 1.3, 1.2, 0.01, 15)
+    solver_case()
+    fsai_case()
