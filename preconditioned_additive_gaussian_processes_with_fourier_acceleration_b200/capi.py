@@ -170,9 +170,10 @@ class AdditiveNFFTKernel:
             raise RuntimeError("Nfft4GPAdditiveNFFTGradMatSymv failed")
         return y
 
-    def matvec_device(self, d_x, d_y, alpha=1.0, beta=0.0):
-        """x, y are raw device pointers (ints), e.g. torch_tensor.data_ptr()."""
-        if lib().Nfft4GPB200AdditiveNFFTMatSymvDevice(self.K, self.n, alpha, d_x, beta, d_y) != 0:
+    def matvec_device(self, d_x, d_y, alpha=1.0, beta=0.0, n_local=None):
+        """x, y are raw device pointers (ints), e.g. torch_tensor.data_ptr(); n_local = length of this rank's block under
+        point-block sharding."""
+        if lib().Nfft4GPB200AdditiveNFFTMatSymvDevice(self.K, self.n if n_local is None else n_local, alpha, d_x, beta, d_y) != 0:
             raise RuntimeError("Nfft4GPB200AdditiveNFFTMatSymvDevice failed")
 
     def window_info(self, w):

@@ -23,13 +23,15 @@ typedef struct b200_window
    double mu;
    int N, p, m;
    double eps;
-   int n, max_n;
+   int n, max_n;     /* n = number of points this rank tabulates (local block under point-block sharding) */
+   int n_global;     /* number of points of the window on all ranks */
    int NN;
    double scale;        /* < 0 until the points have been scaled (first kernel build) */
    double kernel_scale; /* f */
    int built;
    int *h_perm;         /* host copy of sorted -> original */
    void *owner;         /* b200_single* for the single-window API, NULL inside an additive kernel */
+   double *ext_grid;    /* grid storage owned by the additive handle (all windows contiguous), or NULL */
    b200_win_dev dev;
 } b200_window;
 
@@ -47,6 +49,9 @@ typedef struct b200_additive
    double *d_c1w;
    /* multi-GPU */
    int shard_mode; /* 0 none, 1 by window, 2 by point block */
+   int blk_lo, blk_hi;   /* mode 2: this rank's block of points [blk_lo, blk_hi); otherwise [0, n) */
+   double *d_grids;      /* all windows' oversampled grids, contiguous: the ONE allreduce buffer of mode 2 */
+   size_t grids_doubles;
    int nlocal;     /* windows owned by this rank under mode 1 */
    const double **d_fptr_local;
    const int **d_invptr_local;
@@ -67,6 +72,7 @@ int b200_comm_rank(void);
 int b200_comm_size(void);
 int b200_comm_owns_window(const b200_additive *A, int w);
 int b200_comm_allreduce_sum(double *d_buf, size_t count);
+int b200_comm_build_local_windows(b200_additive *A);
 int b200_additive_epilogue(b200_additive *A, int n, const double *d_x, double s, double ff, double mu, double beta, double *d_y);
 
 /* precond_host.c: device-resident applies used by the device PCG */

@@ -132,53 +132,50 @@ int b200_comm_owns_window(const b200_additive *A, int w)
    return (w % g_size) == g_rank;
 }
 
+/* local pointer arrays of the windows this rank owns (mode 1); called once the windows exist on the device */
+int b200_comm_build_local_windows(b200_additive *A)
+{
+   int P = A->P, i, nl = 0, rc;
+   const double **fp;
+   const int **ip;
+   if (A->shard_mode != 1 || g_size == 1 || A->d_fptr_local)
+      return 0;
+   fp = (const double **)b200_xmalloc(sizeof(double *) * (size_t)P);
+   ip = (const int **)b200_xmalloc(sizeof(int *) * (size_t)P);
+   for (i = 0; i < P; i++)
+      if (b200_comm_owns_window(A, i))
+      {
+         fp[nl] = A->win[i]->dev.f;
+         ip[nl] = A->win[i]->dev.inv;
+         nl++;
+      }
+   A->nlocal = nl;
+   A->d_fptr_local = (const double **)b200_malloc(sizeof(double *) * (size_t)(nl ? nl : 1));
+   A->d_invptr_local = (const int **)b200_malloc(sizeof(int *) * (size_t)(nl ? nl : 1));
+   if (!A->d_ypart)
+      A->d_ypart = (double *)b200_malloc(sizeof(double) * (size_t)A->n);
+   rc = b200_h2d((void *)A->d_fptr_local, fp, sizeof(double *) * (size_t)nl) ||
+        b200_h2d((void *)A->d_invptr_local, ip, sizeof(int *) * (size_t)nl) || b200_sync();
+   free(fp);
+   free(ip);
+   return rc ? -1 : 0;
+}
+
+/* Must be called BEFORE the first kernel build of the handle (the point tables are built per shard). */
 int Nfft4GPB200SetSharding(void *handle, int mode)
 {
    b200_additive *A = b200_additive_from_handle(handle);
-   int P, i, nl = 0;
-   if (!A || mode < 0 || mode > 1)
+   if (!A || mode < 0 || mode > 2)
    {
-      printf("Error: Nfft4GPB200SetSharding: bad handle or unsupported mode %d.\n", mode);
+      printf("Error: Nfft4GPB200SetSharding: bad handle or unknown mode %d.\n", mode);
+      return -1;
+   }
+   if (A->built)
+   {
+      printf("Error: Nfft4GPB200SetSharding must precede the first kernel build of the handle.\n");
       return -1;
    }
    A->shard_mode = mode;
-   b200_free((void *)A->d_fptr_local);
-   b200_free((void *)A->d_invptr_local);
-   A->d_fptr_local = NULL;
-   A->d_invptr_local = NULL;
-   A->nlocal = 0;
-   if (mode == 1 && g_size > 1)
-   {
-      const double **fp;
-      const int **ip;
-      int rc;
-      P = A->P;
-      if (!A->built)
-      {
-         printf("Error: Nfft4GPB200SetSharding must follow the first kernel build.\n");
-         return -1;
-      }
-      fp = (const double **)b200_xmalloc(sizeof(double *) * (size_t)P);
-      ip = (const int **)b200_xmalloc(sizeof(int *) * (size_t)P);
-      for (i = 0; i < P; i++)
-         if (b200_comm_owns_window(A, i))
-         {
-            fp[nl] = A->win[i]->dev.f;
-            ip[nl] = A->win[i]->dev.inv;
-            nl++;
-         }
-      A->nlocal = nl;
-      A->d_fptr_local = (const double **)b200_malloc(sizeof(double *) * (size_t)(nl ? nl : 1));
-      A->d_invptr_local = (const int **)b200_malloc(sizeof(int *) * (size_t)(nl ? nl : 1));
-      if (!A->d_ypart)
-         A->d_ypart = (double *)b200_malloc(sizeof(double) * (size_t)A->n);
-      rc = b200_h2d((void *)A->d_fptr_local, fp, sizeof(double *) * (size_t)nl) ||
-           b200_h2d((void *)A->d_invptr_local, ip, sizeof(int *) * (size_t)nl) || b200_sync();
-      free(fp);
-      free(ip);
-      if (rc)
-         return -1;
-   }
    return 0;
 }
 

@@ -269,7 +269,8 @@ static void window_free_device(b200_window *w)
    b200_free(v->a);
    b200_free(v->f);
    b200_free(v->f2);
-   b200_free(v->grid);
+   if (v->grid != w->ext_grid)
+      b200_free(v->grid);
    b200_free(v->specA);
    b200_free(v->specB);
    b200_free(v->band);
@@ -291,8 +292,11 @@ static void window_free(b200_window *w)
  * r_max is already in [0.125, 0.25]), point-major transpose -- same sequential fp64 arithmetic as the reference
  * so that `scale` is bit-identical -- followed by this library's own bin sort by oversampled-grid cell.
  * `cols` holds the window's d feature columns, n contiguous values each (feature-major, ldim = n). */
-static int window_setup_points(b200_window *w, const double *cols, int n)
+static int window_setup_points(b200_window *w, const double *cols, int n_all, int lo, int hi)
 {
+   /* n_all points define centre and scale (identical on every rank); this rank tabulates the block [lo, hi) only
+    * (the whole range unless the handle is sharded by point block) */
+   const int n = hi - lo;
    int d = w->d, i, j, t;
    size_t nbins = ipow(B200_NOS, d);
    double radius = 0.0;
@@ -307,22 +311,22 @@ static int window_setup_points(b200_window *w, const double *cols, int n)
    }
    if (b200_init(-1))
       return -1;
-   tmp = (double *)b200_xmalloc(sizeof(double) * (size_t)n * d);
-   memcpy(tmp, cols, sizeof(double) * (size_t)n * d);
+   tmp = (double *)b200_xmalloc(sizeof(double) * (size_t)n_all * d);
+   memcpy(tmp, cols, sizeof(double) * (size_t)n_all * d);
    for (i = 0; i < d; i++)
    {
       double c = 0.0;
-      for (j = 0; j < n; j++)
-         c += tmp[(size_t)i * n + j];
-      c /= (double)n;
-      for (j = 0; j < n; j++)
-         tmp[(size_t)i * n + j] -= c;
+      for (j = 0; j < n_all; j++)
+         c += tmp[(size_t)i * n_all + j];
+      c /= (double)n_all;
+      for (j = 0; j < n_all; j++)
+         tmp[(size_t)i * n_all + j] -= c;
    }
-   for (j = 0; j < n; j++)
+   for (j = 0; j < n_all; j++)
    {
       double r = 0.0;
       for (i = 0; i < d; i++)
-         r += tmp[(size_t)i * n + j] * tmp[(size_t)i * n + j];
+         r += tmp[(size_t)i * n_all + j] * tmp[(size_t)i * n_all + j];
       r = sqrt(r);
       if (r > radius)
          radius = r;
@@ -330,7 +334,7 @@ static int window_setup_points(b200_window *w, const double *cols, int n)
    if (radius > 0.25 || radius < 0.125)
    {
       w->scale = 0.25 / radius;
-      for (j = 0; j < n * d; j++)
+      for (j = 0; j < n_all * d; j++)
          tmp[j] *= w->scale;
    }
    else
@@ -344,7 +348,7 @@ static int window_setup_points(b200_window *w, const double *cols, int n)
       int k = 0;
       for (t = 0; t < d; t++)
       {
-         int c = (int)floor(tmp[(size_t)t * n + j] * (double)B200_NOS);
+         int c = (int)floor(tmp[(size_t)t * n_all + lo + j] * (double)B200_NOS);
          k = (k << 6) | ((c + 32) & 63);
       }
       keys[j] = k;
@@ -369,7 +373,7 @@ static int window_setup_points(b200_window *w, const double *cols, int n)
    xs = (double *)b200_xmalloc(sizeof(double) * (size_t)n * d);
    for (j = 0; j < n; j++)
       for (t = 0; t < d; t++)
-         xs[(size_t)j * d + t] = tmp[(size_t)t * n + perm[j]];
+         xs[(size_t)j * d + t] = tmp[(size_t)t * n_all + lo + perm[j]];
    free(tmp);
 
    /* device state */
@@ -388,7 +392,7 @@ static int window_setup_points(b200_window *w, const double *cols, int n)
       b200_memset(v->a, 0, sizeof(double) * ((size_t)n + pad));
       v->f = (double *)b200_malloc(sizeof(double) * (size_t)n);
       v->f2 = NULL; /* allocated on the first gradient matvec */
-      v->grid = (double *)b200_malloc(sizeof(double) * gsz);
+      v->grid = w->ext_grid ? w->ext_grid : (double *)b200_malloc(sizeof(double) * gsz);
       v->specA = (double *)b200_malloc(sizeof(double) * gsz); /* complex [64^(d-1)][32] */
       v->specB = (double *)b200_malloc(sizeof(double) * gsz);
       v->band = (double *)b200_malloc(sizeof(double) * 2 * bsz);
@@ -494,6 +498,7 @@ static int window_setup_points(b200_window *w, const double *cols, int n)
    free(keys);
    free(binstart);
    w->n = n;
+   w->n_global = n_all;
    return 0;
 }
 
@@ -519,22 +524,33 @@ static int window_build(b200_window *w, int kernel, double f, double l, double m
    return 0;
 }
 
-/* adjoint NFFT of (s * x) and interpolation with the kernel's coefficients -> dev.f (sorted order) */
-static int window_apply(b200_window *w, const double *d_x, double s, int with_derivative)
+/* first half of a window's matvec: a = s * x[perm], adjoint-NFFT spread onto the oversampled grid */
+static int window_spread(b200_window *w, const double *d_x, double s)
 {
    b200_win_dev *v = &w->dev;
-   if (b200k_prep(v, d_x, s) || b200k_spread(v, g_variant_spread3) || b200k_forward_fft(v) ||
-       b200k_backward_fft(v, v->coef) || b200k_gather(v, v->f, g_variant_gather3))
+   return (b200k_prep(v, d_x, s) || b200k_spread(v, g_variant_spread3)) ? -1 : 0;
+}
+
+/* second half: FFT, multiplication by the kernel's Fourier coefficients, inverse FFT, interpolation -> dev.f (sorted order) */
+static int window_finish(b200_window *w, int with_derivative)
+{
+   b200_win_dev *v = &w->dev;
+   if (b200k_forward_fft(v) || b200k_backward_fft(v, v->coef) || b200k_gather(v, v->f, g_variant_gather3))
       return -1;
    if (with_derivative)
    {
       if (!v->f2)
-         v->f2 = (double *)b200_malloc(sizeof(double) * (size_t)v->n);
+         v->f2 = (double *)b200_malloc(sizeof(double) * (size_t)(v->n ? v->n : 1));
       /* the adjoint is shared between kernel and derivative kernel (the reference runs it twice, :533-534) */
       if (b200k_backward_fft(v, v->dcoef) || b200k_gather(v, v->f2, g_variant_gather3))
          return -1;
    }
    return 0;
+}
+
+static int window_apply(b200_window *w, const double *d_x, double s, int with_derivative)
+{
+   return (window_spread(w, d_x, s) || window_finish(w, with_derivative)) ? -1 : 0;
 }
 
 /* gradient scale factor of nfft_interface.c:536-537 without the f^2 */
@@ -631,7 +647,7 @@ static int single_kernel_build(void *str, int kernel, double *data, int n, int l
    }
    if (w->scale < 0.0) /* :150 */
    {
-      if (window_setup_points(w, data, n))
+      if (window_setup_points(w, data, n, 0, n))
          return -1;
    }
    if (window_build(w, kernel, k->_params[0], k->_params[1], k->_noise_level))
@@ -848,12 +864,36 @@ static int additive_kernel_build(void *str, int kernel, double *data, int n, int
       printf("Error: NFFT kernel requires n == ldim.\n");
       return -1;
    }
+   if (!A->d_grids)
+   {
+      /* one contiguous buffer for the oversampled grids of all windows (the allreduce buffer of point-block sharding) */
+      size_t off = 0;
+      for (i = 0; i < A->P; i++)
+         off += ipow(B200_NOS, A->win[i]->d);
+      if (b200_init(-1))
+         return -1;
+      A->grids_doubles = off;
+      A->d_grids = (double *)b200_malloc(sizeof(double) * off);
+      off = 0;
+      for (i = 0; i < A->P; i++)
+      {
+         A->win[i]->ext_grid = A->d_grids + off;
+         off += ipow(B200_NOS, A->win[i]->d);
+      }
+      A->blk_lo = 0;
+      A->blk_hi = n;
+      if (A->shard_mode == 2 && b200_comm_size() > 1)
+      {
+         A->blk_lo = (int)((long long)n * b200_comm_rank() / b200_comm_size());
+         A->blk_hi = (int)((long long)n * (b200_comm_rank() + 1) / b200_comm_size());
+      }
+   }
    for (i = 0; i < A->P; i++)
    {
       b200_window *w = A->win[i];
       if (w->scale < 0.0)
       {
-         if (window_setup_points(w, cols, n))
+         if (window_setup_points(w, cols, n, A->blk_lo, A->blk_hi))
             return -1;
       }
       /* hyper-parameters are read from the handle at build time (:697-699) */
@@ -863,7 +903,7 @@ static int additive_kernel_build(void *str, int kernel, double *data, int n, int
    }
    A->kernel = kernel;
    A->built = 1;
-   if (additive_ensure_device(A))
+   if (additive_ensure_device(A) || b200_comm_build_local_windows(A))
       return -1;
    *Kp = (double *)str; /* :730-731 */
    *dKp = (double *)str;
@@ -898,24 +938,37 @@ b200_additive *b200_additive_from_handle(void *data)
    return A;
 }
 
-/* device-resident body of Nfft4GPAdditiveNFFTMatSymv (nfft_interface.c:796-817) */
+/* number of vector entries this rank owns: n, or its point block under point-block sharding (mode 2) */
+static int additive_local_n(const b200_additive *A) { return A->blk_hi - A->blk_lo; }
+
+/* spread of all windows, then (mode 2) the ONE collective of the matvec, then FFT / scale / inverse FFT / gather */
+static int additive_apply_windows(b200_additive *A, const double *d_x, double s, int with_derivative)
+{
+   int i;
+   for (i = 0; i < A->P; i++)
+      if (b200_comm_owns_window(A, i) && window_spread(A->win[i], d_x, s))
+         return -1;
+   if (A->shard_mode == 2 && b200_comm_size() > 1 && b200_comm_allreduce_sum(A->d_grids, A->grids_doubles))
+      return -1;
+   for (i = 0; i < A->P; i++)
+      if (b200_comm_owns_window(A, i) && window_finish(A->win[i], with_derivative))
+         return -1;
+   return 0;
+}
+
+/* device-resident body of Nfft4GPAdditiveNFFTMatSymv (nfft_interface.c:796-817).
+ * n = length of d_x / d_y = the rank's block under point-block sharding, the full n otherwise. */
 int b200_additive_matvec_dev(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y)
 {
    double s = 1.0 / (double)A->P * alpha; /* :806 */
    double f = A->win[0]->kernel_scale;
-   int i;
-   if (!A->built || n != A->n)
+   if (!A->built || n != additive_local_n(A))
    {
       printf("Error: additive NFFT matvec on a kernel that was not built for n = %d.\n", n);
       return -1;
    }
-   for (i = 0; i < A->P; i++)
-   {
-      if (b200_comm_owns_window(A, i) == 0)
-         continue;
-      if (window_apply(A->win[i], d_x, s, 0))
-         return -1;
-   }
+   if (additive_apply_windows(A, d_x, s, 0))
+      return -1;
    return b200_additive_epilogue(A, n, d_x, s, f * f, A->win[0]->mu, beta, d_y);
 }
 
@@ -924,18 +977,25 @@ int b200_additive_grad_matvec_dev(b200_additive *A, int n, double alpha, const d
 {
    double s = 1.0 / (double)A->P * alpha;
    double f = A->win[0]->kernel_scale, ff = f * f;
-   double *c1 = (double *)b200_xmalloc(sizeof(double) * (size_t)A->P);
-   const double **fp = (const double **)b200_xmalloc(sizeof(double *) * (size_t)A->P);
+   double *c1;
+   const double **fp;
    int i, rc;
-   if (!A->built || n != A->n)
+   if (!A->built || n != additive_local_n(A))
    {
       printf("Error: additive NFFT matvec on a kernel that was not built for n = %d.\n", n);
       return -1;
    }
+   if (A->shard_mode == 1 && b200_comm_size() > 1)
+   {
+      printf("Error: the gradient matvec is not available under window sharding; use point-block sharding (mode 2).\n");
+      return -1;
+   }
+   if (additive_apply_windows(A, d_x, s, 1))
+      return -1;
+   c1 = (double *)b200_xmalloc(sizeof(double) * (size_t)A->P);
+   fp = (const double **)b200_xmalloc(sizeof(double *) * (size_t)A->P);
    for (i = 0; i < A->P; i++)
    {
-      if (window_apply(A->win[i], d_x, s, 1))
-         return -1;
       c1[i] = ff * window_grad_scale(A->win[i]);
       fp[i] = A->win[i]->dev.f2;
    }
@@ -947,26 +1007,34 @@ int b200_additive_grad_matvec_dev(b200_additive *A, int n, double alpha, const d
    return b200k_combine_grad(n, A->P, A->d_fptr, A->d_f2ptr, A->d_invptr, d_x, s, 2.0 * f, ff, A->d_c1w, A->win[0]->mu, beta, d_y);
 }
 
+/* reference-facing host-pointer call: x, y are FULL host vectors of length n (3n for the gradient); under point-block
+ * sharding every rank moves and computes only its own block [blk_lo, blk_hi) of them */
 static int additive_host_call(void *data, int n, double alpha, double *x, double beta, double *y, int grad)
 {
    b200_additive *A = b200_additive_from_handle(data);
-   size_t ny = grad ? 3 * (size_t)n : (size_t)n;
-   int rc;
+   int rc, nl, lo, b, nblk = grad ? 3 : 1;
    if (!A)
    {
       printf("Error: not an additive NFFT kernel handle.\n");
       return -1;
    }
-   if (additive_ensure_device(A))
+   if (n != A->n || additive_ensure_device(A))
       return -1;
-   if (b200_h2d(A->d_x, x, sizeof(double) * (size_t)n))
+   nl = additive_local_n(A);
+   lo = A->blk_lo;
+   if (b200_h2d(A->d_x, x + lo, sizeof(double) * (size_t)nl))
       return -1;
-   if (beta != 0.0 && b200_h2d(A->d_y, y, sizeof(double) * ny))
-      return -1;
-   rc = grad ? b200_additive_grad_matvec_dev(A, n, alpha, A->d_x, beta, A->d_y) : b200_additive_matvec_dev(A, n, alpha, A->d_x, beta, A->d_y);
+   if (beta != 0.0)
+      for (b = 0; b < nblk; b++)
+         if (b200_h2d(A->d_y + (size_t)b * nl, y + (size_t)b * n + lo, sizeof(double) * (size_t)nl))
+            return -1;
+   rc = grad ? b200_additive_grad_matvec_dev(A, nl, alpha, A->d_x, beta, A->d_y) : b200_additive_matvec_dev(A, nl, alpha, A->d_x, beta, A->d_y);
    if (rc)
       return -1;
-   return b200_d2h(y, A->d_y, sizeof(double) * ny);
+   for (b = 0; b < nblk; b++)
+      if (b200_d2h(y + (size_t)b * n + lo, A->d_y + (size_t)b * nl, sizeof(double) * (size_t)nl))
+         return -1;
+   return 0;
 }
 
 /* nfft_interface.c:796-817 */
@@ -1025,6 +1093,9 @@ void Nfft4GPAdditiveNFFTKernelFree(void *str)
       b200_free((void *)A->d_invptr);
       b200_free(A->d_c1w);
       b200_free(A->d_ypart);
+      b200_free(A->d_grids);
+      b200_free((void *)A->d_fptr_local);
+      b200_free((void *)A->d_invptr_local);
       free(A);
    }
    if (k->_own_buffer)

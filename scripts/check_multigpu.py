@@ -1,0 +1,59 @@
+"""Multi-GPU parity check (run under torchrun on N GPUs): window sharding (mode 1) and point-block sharding (mode 2) of the
+additive NFFT matvec against the CPU oracle.  python -m torch.distributed.run --nproc-per-node N scripts/check_multigpu.py"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import preconditioned_additive_gaussian_processes_with_fourier_acceleration_b200 as pkg  # noqa: E402
+from oracle import oracle_api as O  # noqa: E402
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+L = pkg.lib()
+assert L.Nfft4GPB200Init(lr) == 0
+uid = torch.zeros(128, dtype=torch.uint8)
+if rank == 0:
+    buf = (C.c_char * 128)()
+    assert L.Nfft4GPB200CommGetUniqueId(buf) == 0
+    uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+uid = uid.cuda()
+dist.broadcast(uid, 0)
+assert L.Nfft4GPB200CommInit(rank, world, bytes(uid.cpu().numpy().tobytes())) == 0
+
+rng = np.random.default_rng(5)
+n, d = 20000, 9
+X = rng.random((d, n)) * n ** (1.0 / d)
+x = rng.random(n) - 0.5
+y0 = rng.random(n) - 0.5
+win = np.arange(9, dtype=np.int32)
+f, l, mu = 1.1, 0.25 * n ** (1 / 9), 0.02
+ref = O.OracleAdditiveNFFT(X, win, 3, 3, "gaussian").build(f, l, mu).matvec(x, 0.7, 0.3, y0) if rank == 0 else None
+ok = True
+for mode in (1, 2):
+    A = pkg.AdditiveNFFTKernel(X, win, 3, 3, "gaussian")
+    assert L.Nfft4GPB200SetSharding(A.h, mode) == 0
+    A.build(f, l, mu)
+    y = A.matvec(x, 0.7, 0.3, y0)  # host-pointer API: every rank fills the entries it owns
+    if mode == 2:  # assemble the blocks for the check
+        t = torch.zeros(n, dtype=torch.float64, device="cuda")
+        lo, hi = rank * n // world, (rank + 1) * n // world
+        t[lo:hi] = torch.from_numpy(y[lo:hi]).cuda()
+        dist.all_reduce(t)
+        y = t.cpu().numpy()
+    if rank == 0:
+        err = float(np.linalg.norm(y - ref) / np.linalg.norm(ref))
+        print(f"mode {mode} on {world} GPUs: rel l2 vs oracle {err:.2e}")
+        ok = ok and err <= 1e-10
+    A.free()
+dist.barrier()
+L.Nfft4GPB200CommFinalize()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
