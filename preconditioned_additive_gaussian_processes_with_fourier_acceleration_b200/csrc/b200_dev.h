@@ -68,6 +68,9 @@ int b200k_spread(const b200_win_dev *w, int variant);
 int b200k_forward_fft(const b200_win_dev *w);                                   /* grid -> band (unscaled) */
 int b200k_backward_fft(const b200_win_dev *w, const double *d_coef);            /* band * coef -> grid (Re h) */
 int b200k_gather(const b200_win_dev *w, double *d_f, int variant);
+/* nb equally shaped windows whose work arrays are stored contiguously (slot = the size for dimension w->d) */
+int b200k_forward_fft_batch(const b200_win_dev *w, int nb);
+int b200k_backward_fft_batch(const b200_win_dev *w, int nb, int which);
 /* nfft3d_warp.cu: warp-per-segment 3-D kernels */
 int b200k_warp_ranges(void);
 int b200k_spread3_warp(const b200_win_dev *w);

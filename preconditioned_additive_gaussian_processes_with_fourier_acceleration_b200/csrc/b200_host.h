@@ -31,7 +31,9 @@ typedef struct b200_window
    int built;
    int *h_perm;         /* host copy of sorted -> original */
    void *owner;         /* b200_single* for the single-window API, NULL inside an additive kernel */
-   double *ext_grid;    /* grid storage owned by the additive handle (all windows contiguous), or NULL */
+   /* work arrays owned by the additive handle (all windows contiguous, so that FFT passes can be batched over windows and
+    * the grids form ONE allreduce buffer); NULL = owned by the window */
+   double *ext_grid, *ext_specA, *ext_specB, *ext_band, *ext_coef, *ext_dcoef;
    b200_win_dev dev;
 } b200_window;
 
@@ -52,6 +54,8 @@ typedef struct b200_additive
    int blk_lo, blk_hi;   /* mode 2: this rank's block of points [blk_lo, blk_hi); otherwise [0, n) */
    double *d_grids;      /* all windows' oversampled grids, contiguous: the ONE allreduce buffer of mode 2 */
    size_t grids_doubles;
+   double *d_specA, *d_specB, *d_band, *d_coef, *d_dcoef; /* contiguous slots of the leading equally shaped windows */
+   int nbatch;           /* number of leading windows with the dimension of window 0 (batched FFT passes) */
    int nlocal;     /* windows owned by this rank under mode 1 */
    const double **d_fptr_local;
    const int **d_invptr_local;

@@ -271,11 +271,16 @@ static void window_free_device(b200_window *w)
    b200_free(v->f2);
    if (v->grid != w->ext_grid)
       b200_free(v->grid);
-   b200_free(v->specA);
-   b200_free(v->specB);
-   b200_free(v->band);
-   b200_free(v->coef);
-   b200_free(v->dcoef);
+   if (v->specA != w->ext_specA)
+      b200_free(v->specA);
+   if (v->specB != w->ext_specB)
+      b200_free(v->specB);
+   if (v->band != w->ext_band)
+      b200_free(v->band);
+   if (v->coef != w->ext_coef)
+      b200_free(v->coef);
+   if (v->dcoef != w->ext_dcoef)
+      b200_free(v->dcoef);
    memset(v, 0, sizeof(*v));
 }
 
@@ -393,11 +398,11 @@ static int window_setup_points(b200_window *w, const double *cols, int n_all, in
       v->f = (double *)b200_malloc(sizeof(double) * (size_t)n);
       v->f2 = NULL; /* allocated on the first gradient matvec */
       v->grid = w->ext_grid ? w->ext_grid : (double *)b200_malloc(sizeof(double) * gsz);
-      v->specA = (double *)b200_malloc(sizeof(double) * gsz); /* complex [64^(d-1)][32] */
-      v->specB = (double *)b200_malloc(sizeof(double) * gsz);
-      v->band = (double *)b200_malloc(sizeof(double) * 2 * bsz);
-      v->coef = (double *)b200_malloc(sizeof(double) * 2 * bsz);
-      v->dcoef = (double *)b200_malloc(sizeof(double) * 2 * bsz);
+      v->specA = w->ext_specA ? w->ext_specA : (double *)b200_malloc(sizeof(double) * gsz); /* complex [64^(d-1)][32] */
+      v->specB = w->ext_specB ? w->ext_specB : (double *)b200_malloc(sizeof(double) * gsz);
+      v->band = w->ext_band ? w->ext_band : (double *)b200_malloc(sizeof(double) * 2 * bsz);
+      v->coef = w->ext_coef ? w->ext_coef : (double *)b200_malloc(sizeof(double) * 2 * bsz);
+      v->dcoef = w->ext_dcoef ? w->ext_dcoef : (double *)b200_malloc(sizeof(double) * 2 * bsz);
       b200_h2d(d_xs, xs, sizeof(double) * (size_t)n * d);
       b200_h2d(v->perm, perm, sizeof(int) * (size_t)n);
       b200_h2d(v->inv, inv, sizeof(int) * (size_t)n);
@@ -880,6 +885,27 @@ static int additive_kernel_build(void *str, int kernel, double *data, int n, int
          A->win[i]->ext_grid = A->d_grids + off;
          off += ipow(B200_NOS, A->win[i]->d);
       }
+      {
+         /* the leading windows of equal dimension share contiguous work arrays: their FFT passes run as one batch */
+         int d0 = A->win[0]->d, nb = 0;
+         size_t gsz = ipow(B200_NOS, d0), bsz = ipow(B200_NBAND, d0);
+         while (nb < A->P && A->win[nb]->d == d0)
+            nb++;
+         A->nbatch = nb;
+         A->d_specA = (double *)b200_malloc(sizeof(double) * gsz * (size_t)nb);
+         A->d_specB = (double *)b200_malloc(sizeof(double) * gsz * (size_t)nb);
+         A->d_band = (double *)b200_malloc(sizeof(double) * 2 * bsz * (size_t)nb);
+         A->d_coef = (double *)b200_malloc(sizeof(double) * 2 * bsz * (size_t)nb);
+         A->d_dcoef = (double *)b200_malloc(sizeof(double) * 2 * bsz * (size_t)nb);
+         for (i = 0; i < nb; i++)
+         {
+            A->win[i]->ext_specA = A->d_specA + gsz * (size_t)i;
+            A->win[i]->ext_specB = A->d_specB + gsz * (size_t)i;
+            A->win[i]->ext_band = A->d_band + 2 * bsz * (size_t)i;
+            A->win[i]->ext_coef = A->d_coef + 2 * bsz * (size_t)i;
+            A->win[i]->ext_dcoef = A->d_dcoef + 2 * bsz * (size_t)i;
+         }
+      }
       A->blk_lo = 0;
       A->blk_hi = n;
       if (A->shard_mode == 2 && b200_comm_size() > 1)
@@ -950,6 +976,31 @@ static int additive_apply_windows(b200_additive *A, const double *d_x, double s,
          return -1;
    if (A->shard_mode == 2 && b200_comm_size() > 1 && b200_comm_allreduce_sum(A->d_grids, A->grids_doubles))
       return -1;
+   if (!(A->shard_mode == 1 && b200_comm_size() > 1) && A->nbatch > 1)
+   {
+      /* equally shaped leading windows: every FFT pass is ONE launch over the batch */
+      b200_win_dev *v0 = &A->win[0]->dev;
+      if (b200k_forward_fft_batch(v0, A->nbatch) || b200k_backward_fft_batch(v0, A->nbatch, 0))
+         return -1;
+      for (i = 0; i < A->nbatch; i++)
+         if (b200k_gather(&A->win[i]->dev, A->win[i]->dev.f, g_variant_gather3))
+            return -1;
+      if (with_derivative)
+      {
+         for (i = 0; i < A->nbatch; i++)
+            if (!A->win[i]->dev.f2)
+               A->win[i]->dev.f2 = (double *)b200_malloc(sizeof(double) * (size_t)(A->win[i]->dev.n ? A->win[i]->dev.n : 1));
+         if (b200k_backward_fft_batch(v0, A->nbatch, 1))
+            return -1;
+         for (i = 0; i < A->nbatch; i++)
+            if (b200k_gather(&A->win[i]->dev, A->win[i]->dev.f2, g_variant_gather3))
+               return -1;
+      }
+      for (i = A->nbatch; i < A->P; i++)
+         if (window_finish(A->win[i], with_derivative))
+            return -1;
+      return 0;
+   }
    for (i = 0; i < A->P; i++)
       if (b200_comm_owns_window(A, i) && window_finish(A->win[i], with_derivative))
          return -1;
@@ -1094,6 +1145,11 @@ void Nfft4GPAdditiveNFFTKernelFree(void *str)
       b200_free(A->d_c1w);
       b200_free(A->d_ypart);
       b200_free(A->d_grids);
+      b200_free(A->d_specA);
+      b200_free(A->d_specB);
+      b200_free(A->d_band);
+      b200_free(A->d_coef);
+      b200_free(A->d_dcoef);
       b200_free((void *)A->d_fptr_local);
       b200_free((void *)A->d_invptr_local);
       free(A);

@@ -305,10 +305,14 @@ __device__ __forceinline__ void fft64(double2 v[8], int t, double2 *ex, int sr, 
 }
 
 // contiguous-axis forward pass: real rows [rows][64] -> complex band [rows][32]   (sign +)
-__global__ void __launch_bounds__(256) k_fft_rows_fwd(const double *__restrict__ in, double2 *__restrict__ out, int rows)
+// blockIdx.y = window of a batch of equally shaped windows stored with strides in_ws / out_ws (elements)
+__global__ void __launch_bounds__(256)
+k_fft_rows_fwd(const double *__restrict__ in, double2 *__restrict__ out, int rows, size_t in_ws, size_t out_ws)
 {
    __shared__ double2 ex[32 * 8 * 9];
    const int p = threadIdx.x >> 3, t = threadIdx.x & 7;
+   in += blockIdx.y * in_ws;
+   out += blockIdx.y * out_ws;
    const int row = blockIdx.x * 32 + p;
    const bool ok = row < rows;
    double2 v[8];
@@ -328,10 +332,15 @@ __global__ void __launch_bounds__(256) k_fft_rows_fwd(const double *__restrict__
 
 // contiguous-axis inverse pass: complex band [rows][32] (optionally * coef) -> real rows [rows][64]   (sign -)
 __global__ void __launch_bounds__(256)
-k_fft_rows_inv(const double2 *__restrict__ in, const double2 *__restrict__ coef, double *__restrict__ out, int rows)
+k_fft_rows_inv(const double2 *__restrict__ in, const double2 *__restrict__ coef, double *__restrict__ out, int rows, size_t in_ws,
+               size_t coef_ws, size_t out_ws)
 {
    __shared__ double2 ex[32 * 8 * 9];
    const int p = threadIdx.x >> 3, t = threadIdx.x & 7;
+   in += blockIdx.y * in_ws;
+   out += blockIdx.y * out_ws;
+   if (coef)
+      coef += blockIdx.y * coef_ws;
    const int row = blockIdx.x * 32 + p;
    const bool ok = row < rows;
    double2 v[8];
@@ -370,10 +379,14 @@ k_fft_rows_inv(const double2 *__restrict__ in, const double2 *__restrict__ coef,
 template <bool FWD>
 __global__ void __launch_bounds__(256)
 k_fft_cols(const double2 *__restrict__ in, const double2 *__restrict__ coef, double2 *__restrict__ out,
-           int in_slab, int in_row, int out_slab, int out_row)
+           int in_slab, int in_row, int out_slab, int out_row, size_t in_ws, size_t coef_ws, size_t out_ws)
 {
    __shared__ double2 ex[8 * 8 * 32];
    const int c = threadIdx.x & 31, t = threadIdx.x >> 5;
+   in += blockIdx.y * in_ws;
+   out += blockIdx.y * out_ws;
+   if (coef)
+      coef += blockIdx.y * coef_ws;
    const double2 *i_ = in + (size_t)blockIdx.x * in_slab + c;
    double2 *o = out + (size_t)blockIdx.x * out_slab + c;
    double2 v[8];
@@ -544,69 +557,86 @@ int b200k_gather(const b200_win_dev *w, double *d_f, int variant)
    return 0;
 }
 
-// grid (real 64^d) -> band (complex 32^d), unscaled, e^{+}
-int b200k_forward_fft(const b200_win_dev *w)
+// strides (in elements of the respective type) between consecutive windows of a batch; see nfft_host.c (the additive
+// handle stores the work arrays of all windows contiguously with the slot size of the common window dimension)
+static size_t ws_grid(int d) { return grid_elems(d); }                     // double
+static size_t ws_spec(int d) { return grid_elems(d) / 2; }                 // double2 (specA / specB slots hold 64^d doubles)
+static size_t ws_band(int d) { return d == 1 ? 32 : (d == 2 ? 32 * 32 : 32 * 32 * 32); } // double2
+
+// grid (real 64^d) -> band (complex 32^d), unscaled, e^{+}; nb equally shaped windows starting at w
+int b200k_forward_fft_batch(const b200_win_dev *w, int nb)
 {
    B200ProfScope prof_scope_(PC_FFT_FWD);
    if (ensure_twiddles())
       return -1;
    cudaStream_t s = b200_stream();
+   const int d = w->d;
    double2 *A = (double2 *)w->specA, *B = (double2 *)w->specB, *band = (double2 *)w->band;
-   if (w->d == 1)
+   const size_t gs = ws_grid(d), ss = ws_spec(d), bs = ws_band(d);
+   if (d == 1)
    {
-      k_fft_rows_fwd<<<1, 256, 0, s>>>(w->grid, band, 1);
+      k_fft_rows_fwd<<<dim3(1, nb), 256, 0, s>>>(w->grid, band, 1, gs, bs);
       B200_LAUNCHED();
    }
-   else if (w->d == 2)
+   else if (d == 2)
    {
-      k_fft_rows_fwd<<<2, 256, 0, s>>>(w->grid, A, 64); // [64 l1][32 k2]
+      k_fft_rows_fwd<<<dim3(2, nb), 256, 0, s>>>(w->grid, A, 64, gs, ss); // [64 l1][32 k2]
       B200_LAUNCHED();
-      k_fft_cols<true><<<1, 256, 0, s>>>(A, nullptr, band, 0, 32, 0, 32); // along l1 -> [32 k1][32 k2]
+      k_fft_cols<true><<<dim3(1, nb), 256, 0, s>>>(A, nullptr, band, 0, 32, 0, 32, ss, 0, bs); // along l1 -> [32 k1][32 k2]
       B200_LAUNCHED();
    }
    else
    {
-      k_fft_rows_fwd<<<128, 256, 0, s>>>(w->grid, A, 4096); // [64 l1][64 l2][32 k3]
+      k_fft_rows_fwd<<<dim3(128, nb), 256, 0, s>>>(w->grid, A, 4096, gs, ss); // [64 l1][64 l2][32 k3]
       B200_LAUNCHED();
-      k_fft_cols<true><<<64, 256, 0, s>>>(A, nullptr, B, 64 * 32, 32, 32 * 32, 32); // along l2 -> [64 l1][32 k2][32 k3]
+      k_fft_cols<true><<<dim3(64, nb), 256, 0, s>>>(A, nullptr, B, 64 * 32, 32, 32 * 32, 32, ss, 0, ss); // along l2 -> [64 l1][32 k2][32 k3]
       B200_LAUNCHED();
-      k_fft_cols<true><<<32, 256, 0, s>>>(B, nullptr, band, 32, 32 * 32, 32, 32 * 32); // along l1 -> [32 k1][32 k2][32 k3]
+      k_fft_cols<true><<<dim3(32, nb), 256, 0, s>>>(B, nullptr, band, 32, 32 * 32, 32, 32 * 32, ss, 0, bs); // along l1 -> [32 k1][32 k2][32 k3]
       B200_LAUNCHED();
    }
    return 0;
 }
 
-// band * coef -> grid (real part of the zero-padded e^{-} transform)
-int b200k_backward_fft(const b200_win_dev *w, const double *d_coef)
+// band * coef -> grid (real part of the zero-padded e^{-} transform); which = 0 kernel, 1 derivative-kernel coefficients
+int b200k_backward_fft_batch(const b200_win_dev *w, int nb, int which)
 {
    B200ProfScope prof_scope_(PC_FFT_INV);
    if (ensure_twiddles())
       return -1;
    cudaStream_t s = b200_stream();
+   const int d = w->d;
    double2 *A = (double2 *)w->specA, *B = (double2 *)w->specB, *band = (double2 *)w->band;
-   const double2 *coef = (const double2 *)d_coef;
-   if (w->d == 1)
+   const double2 *coef = (const double2 *)(which ? w->dcoef : w->coef);
+   const size_t gs = ws_grid(d), ss = ws_spec(d), bs = ws_band(d);
+   if (d == 1)
    {
-      k_fft_rows_inv<<<1, 256, 0, s>>>(band, coef, w->grid, 1);
+      k_fft_rows_inv<<<dim3(1, nb), 256, 0, s>>>(band, coef, w->grid, 1, bs, bs, gs);
       B200_LAUNCHED();
    }
-   else if (w->d == 2)
+   else if (d == 2)
    {
-      k_fft_cols<false><<<1, 256, 0, s>>>(band, coef, A, 0, 32, 0, 32); // along k1 -> [64 l1][32 k2]
+      k_fft_cols<false><<<dim3(1, nb), 256, 0, s>>>(band, coef, A, 0, 32, 0, 32, bs, bs, ss); // along k1 -> [64 l1][32 k2]
       B200_LAUNCHED();
-      k_fft_rows_inv<<<2, 256, 0, s>>>(A, nullptr, w->grid, 64);
+      k_fft_rows_inv<<<dim3(2, nb), 256, 0, s>>>(A, nullptr, w->grid, 64, ss, 0, gs);
       B200_LAUNCHED();
    }
    else
    {
-      k_fft_cols<false><<<32, 256, 0, s>>>(band, coef, B, 32, 32 * 32, 32, 32 * 32); // along k1 -> [64 l1][32 k2][32 k3]
+      k_fft_cols<false><<<dim3(32, nb), 256, 0, s>>>(band, coef, B, 32, 32 * 32, 32, 32 * 32, bs, bs, ss); // along k1 -> [64 l1][32 k2][32 k3]
       B200_LAUNCHED();
-      k_fft_cols<false><<<64, 256, 0, s>>>(B, nullptr, A, 32 * 32, 32, 64 * 32, 32); // along k2 -> [64 l1][64 l2][32 k3]
+      k_fft_cols<false><<<dim3(64, nb), 256, 0, s>>>(B, nullptr, A, 32 * 32, 32, 64 * 32, 32, ss, 0, ss); // along k2 -> [64 l1][64 l2][32 k3]
       B200_LAUNCHED();
-      k_fft_rows_inv<<<128, 256, 0, s>>>(A, nullptr, w->grid, 4096);
+      k_fft_rows_inv<<<dim3(128, nb), 256, 0, s>>>(A, nullptr, w->grid, 4096, ss, 0, gs);
       B200_LAUNCHED();
    }
    return 0;
+}
+
+int b200k_forward_fft(const b200_win_dev *w) { return b200k_forward_fft_batch(w, 1); }
+
+int b200k_backward_fft(const b200_win_dev *w, const double *d_coef)
+{
+   return b200k_backward_fft_batch(w, 1, d_coef == w->dcoef ? 1 : 0);
 }
 
 int b200k_combine(int n, int P, const double *const *d_fptr, const int *const *d_invptr, const double *d_x, double s,
