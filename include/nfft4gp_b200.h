@@ -159,7 +159,9 @@ int Nfft4GPKernelGaussianKernel(void *str, NFFT4GP_DOUBLE *data, int n, int ldim
                                 int *permc, int kc, NFFT4GP_DOUBLE **Kp, NFFT4GP_DOUBLE **dKp);   /* kernels.c:680  */
 int Nfft4GPKernelMatern12Kernel(void *str, NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *permr, int kr,
                                 int *permc, int kc, NFFT4GP_DOUBLE **Kp, NFFT4GP_DOUBLE **dKp);   /* kernels.c:2390 */
-void Nfft4GPKernelParamFree(void *str);                                                           /* kernels.c (_linearalg.h:458) */
+void *Nfft4GPKernelParamCreate(int max_n, int omp);                                               /* kernels.c:404 (_linearalg.h:459) */
+void Nfft4GPKernelParamFree(void *str);                                                           /* kernels.c:443 (_linearalg.h:467) */
+void Nfft4GPKernelFree(void *str);                                                                /* func_free of *Kp (_linearalg.h:475) */
 
 /* ------------------------------------------------------------------------------------------
  * Part 2: B200 extensions
@@ -212,6 +214,18 @@ int Nfft4GPB200PrecondAFNSetFactors(void *afn, int n, int k, const int *perm, co
 /* read factors back (parity tests of the setups); any output pointer may be NULL */
 int Nfft4GPB200PrecondNysGetFactors(void *nys, int *n, int *k, int *perm, double *U, double *s, double *eta);
 int Nfft4GPB200PrecondFsaiGetFactors(void *fsai, int *n, int *nnz, int *ia, int *ja, double *a);
+int Nfft4GPB200PrecondAFNGetFactors(void *afn, int *n, int *k, int *k_est, int *is_nys, int *perm, double *Linv /* k x k */,
+                                    double *K12 /* k x (n-k) */, int *nnz, int *ia, int *ja, double *a);
+/* AFN rank estimation (afn_setup.m:111-293): m sampled points (default 500), numests repetitions (default 5; 0 = skip the
+ * estimation and use the maximum rank), noran != 0 = never switch to the Nystrom form, seed of the sub-sampling generator */
+int Nfft4GPB200PrecondAFNSetRankEstimation(void *afn, int m, int numests, int noran, unsigned long long seed);
+/* setup building blocks, exposed for the parity tests (host in / host out; the device ones need a GPU) */
+int Nfft4GPB200HostPotrf(int n, double *A /* lower, column-major, in place */);
+int Nfft4GPB200HostSyev(int n, double *A /* in: symmetric; out: eigenvectors */, double *w /* ascending */, int want_vectors);
+int Nfft4GPB200Dgemm(char transa, char transb, int M, int N, int K, double alpha, const double *A, int lda, const double *B, int ldb,
+                     double beta, double *C, int ldc);
+int Nfft4GPB200Fps(const double *data, int n, int ldim, int d, int k, int *perm_out /* k */);
+int Nfft4GPB200KnnPattern(const double *data, int n, int ldim, int d, int lfil, int *ia /* n+1 */, int *ja /* nnz */);
 
 /* Multi-GPU (one process per GPU).  The NCCL communicator is created from a unique id that the caller
  * broadcasts (128 bytes).  mode 0: replicate; 1: shard by feature window, allreduce(sum) of y per matvec;

@@ -9,6 +9,8 @@ from .capi import (  # noqa: F401
     LIB_PATH,
     AdditiveNFFTKernel,
     AfnPrecond,
+    DenseAdditiveKernel,
+    DensePlainKernel,
     FsaiPrecond,
     NysPrecond,
     build_library,
@@ -16,4 +18,4 @@ from .capi import (  # noqa: F401
     solver_pcg,
 )
 
-__all__ = ["LIB_PATH", "AdditiveNFFTKernel", "NysPrecond", "FsaiPrecond", "AfnPrecond", "build_library", "lib", "solver_pcg"]
+__all__ = ["LIB_PATH", "AdditiveNFFTKernel", "DenseAdditiveKernel", "DensePlainKernel", "NysPrecond", "FsaiPrecond", "AfnPrecond", "build_library", "lib", "solver_pcg"]

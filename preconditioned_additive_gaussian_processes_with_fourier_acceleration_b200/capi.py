@@ -79,6 +79,14 @@ def lib():
         "Nfft4GPKernelAdditiveKernelParamCreate": (vp, [c_double_p, i, i, i, c_int_p, i, i, vp]),
         "Nfft4GPKernelAdditiveKernel": (i, kargs), "Nfft4GPKernelGaussianKernel": (i, kargs),
         "Nfft4GPKernelMatern12Kernel": (i, kargs), "Nfft4GPKernelParamFree": (None, [vp]),
+        "Nfft4GPKernelParamCreate": (vp, [i, i]), "Nfft4GPKernelFree": (None, [vp]),
+        "Nfft4GPB200PrecondAFNGetFactors": (i, [vp, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_double_p, c_double_p, c_int_p,
+                                                c_int_p, c_int_p, c_double_p]),
+        "Nfft4GPB200PrecondAFNSetRankEstimation": (i, [vp, i, i, i, C.c_ulonglong]),
+        "Nfft4GPB200HostPotrf": (i, [i, c_double_p]), "Nfft4GPB200HostSyev": (i, [i, c_double_p, c_double_p, i]),
+        "Nfft4GPB200Dgemm": (i, [C.c_char, C.c_char, i, i, i, d, c_double_p, i, c_double_p, i, d, c_double_p, i]),
+        "Nfft4GPB200Fps": (i, [c_double_p, i, i, i, i, c_int_p]),
+        "Nfft4GPB200KnnPattern": (i, [c_double_p, i, i, i, i, c_int_p, c_int_p]),
         "Nfft4GPB200Init": (i, [i]), "Nfft4GPB200DeviceCount": (i, []), "Nfft4GPB200Version": (C.c_char_p, []),
         "Nfft4GPB200LaunchCount": (C.c_longlong, []), "Nfft4GPB200LaunchCountReset": (None, []),
         "Nfft4GPB200HostAlloc": (vp, [C.c_size_t]), "Nfft4GPB200HostFree": (None, [vp]),
@@ -211,10 +219,114 @@ class AdditiveNFFTKernel:
             self.h = None
 
 
+def _set_hyper(handle, f, l, mu):
+    k = Nfft4GPKernel.from_address(handle)
+    k._params[0] = f
+    k._params[1] = l
+    k._noise_level = mu
+
+
+class DenseAdditiveKernel:
+    """Dense additive kernel handle (reference call sequence TESTS/TEST3/foo3.cpp:251-256): the func_kernel the
+    preconditioner setups are given.  X feature-major (d, n)."""
+
+    def __init__(self, X, windows, nwindows, dwindows, kernel="gaussian"):
+        L = lib()
+        self.X = np.ascontiguousarray(X, dtype=np.float64)
+        self.d, self.n = self.X.shape
+        self.windows = np.ascontiguousarray(windows, dtype=np.int32)
+        base = L.Nfft4GPKernelGaussianKernel if kernel == "gaussian" else L.Nfft4GPKernelMatern12Kernel
+        self.h = L.Nfft4GPKernelAdditiveKernelParamCreate(dptr(self.X), self.n, self.n, self.d, iptr(self.windows), nwindows, dwindows,
+                                                         C.cast(base, C.c_void_p))
+        if not self.h:
+            raise RuntimeError("Nfft4GPKernelAdditiveKernelParamCreate failed")
+
+    def set_hyper(self, f, l, mu):
+        _set_hyper(self.h, f, l, mu)
+        return self
+
+    def fn(self):
+        return C.cast(lib().Nfft4GPKernelAdditiveKernel, C.c_void_p)
+
+    def block(self, permr=None, permc=None):
+        return _kernel_block(lib().Nfft4GPKernelAdditiveKernel, self.h, self.X, permr, permc)
+
+    def free(self):
+        if self.h:
+            lib().Nfft4GPKernelParamFree(self.h)
+            self.h = None
+
+
+class DensePlainKernel:
+    """Plain Gaussian / Matern-1/2 kernel over all features of X (kernels.c:680 / 2390)."""
+
+    def __init__(self, X, kernel="gaussian"):
+        L = lib()
+        self.X = np.ascontiguousarray(X, dtype=np.float64)
+        self.d, self.n = self.X.shape
+        self._fn = L.Nfft4GPKernelGaussianKernel if kernel == "gaussian" else L.Nfft4GPKernelMatern12Kernel
+        self.h = L.Nfft4GPKernelParamCreate(self.n, 1)
+
+    def set_hyper(self, f, l, mu):
+        _set_hyper(self.h, f, l, mu)
+        return self
+
+    def fn(self):
+        return C.cast(self._fn, C.c_void_p)
+
+    def block(self, permr=None, permc=None):
+        return _kernel_block(self._fn, self.h, self.X, permr, permc)
+
+    def free(self):
+        if self.h:
+            lib().Nfft4GPKernelParamFree(self.h)
+            self.h = None
+
+
+def _kernel_block(fn, h, X, permr, permc):
+    """func_kernel call shapes of kernels.c:701-991; returns the column-major block as an (nr, nc) array."""
+    d, n = X.shape
+    K = C.c_void_p()
+    pr = None if permr is None else np.ascontiguousarray(permr, dtype=np.int32)
+    pc = None if permc is None else np.ascontiguousarray(permc, dtype=np.int32)
+    rc = fn(h, dptr(X), n, n, d, iptr(pr) if pr is not None else None, 0 if pr is None else pr.size,
+            iptr(pc) if pc is not None else None, 0 if pc is None else pc.size, C.byref(K), None)
+    if rc != 0:
+        raise RuntimeError("dense kernel evaluation failed")
+    nr = n if pr is None else pr.size
+    nc = nr if pc is None else pc.size
+    out = np.ctypeslib.as_array(C.cast(K, c_double_p), shape=(nc, nr)).T.copy()
+    lib().Nfft4GPKernelFree(K)
+    return out
+
+
 class NysPrecond:
     def __init__(self):
         self.h = lib().Nfft4GPPrecondNysCreate()
         self._keep = []
+
+    def setup(self, kernel, perm, k):
+        """Nfft4GPPrecondNysSetPerm / SetRank / SetupWithKernel (TESTS/TEST3/foo3.cpp:262-265, nys.c:518-660)."""
+        L = lib()
+        self._perm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
+        if self._perm is not None:
+            L.Nfft4GPPrecondNysSetPerm(self.h, iptr(self._perm), 0)
+        L.Nfft4GPPrecondNysSetRank(self.h, k)
+        rc = L.Nfft4GPPrecondNysSetupWithKernel(dptr(kernel.X), kernel.n, kernel.n, kernel.d, kernel.fn(), kernel.h, 0, self.h)
+        if rc != 0:
+            raise RuntimeError("Nfft4GPPrecondNysSetupWithKernel failed")
+        self.n = kernel.n
+        return self
+
+    def get_factors(self):
+        L = lib()
+        n, k, eta = C.c_int(), C.c_int(), C.c_double()
+        assert L.Nfft4GPB200PrecondNysGetFactors(self.h, C.byref(n), C.byref(k), None, None, None, C.byref(eta)) == 0
+        perm = np.zeros(n.value, dtype=np.int32)
+        U = np.zeros((k.value, n.value))
+        s = np.zeros(k.value)
+        assert L.Nfft4GPB200PrecondNysGetFactors(self.h, None, None, iptr(perm), dptr(U), dptr(s), None) == 0
+        return perm, U.T.copy(), s, eta.value
 
     def set_factors(self, perm, U, s, eta):
         n, k = U.shape
@@ -247,6 +359,25 @@ class FsaiPrecond:
     def __init__(self):
         self.h = lib().Nfft4GPPrecondFsaiCreate()
 
+    def setup(self, kernel, lfil):
+        """Nfft4GPPrecondFsaiSetLfil / SetupWithKernel (fsai.c:100-104, 302-673)."""
+        L = lib()
+        L.Nfft4GPPrecondFsaiSetLfil(self.h, lfil)
+        rc = L.Nfft4GPPrecondFsaiSetupWithKernel(dptr(kernel.X), kernel.n, kernel.n, kernel.d, kernel.fn(), kernel.h, 0, self.h)
+        if rc != 0:
+            raise RuntimeError("Nfft4GPPrecondFsaiSetupWithKernel failed")
+        return self
+
+    def get_factors(self):
+        L = lib()
+        n, nnz = C.c_int(), C.c_int()
+        assert L.Nfft4GPB200PrecondFsaiGetFactors(self.h, C.byref(n), C.byref(nnz), None, None, None) == 0
+        ia = np.zeros(n.value + 1, dtype=np.int32)
+        ja = np.zeros(nnz.value, dtype=np.int32)
+        a = np.zeros(nnz.value)
+        assert L.Nfft4GPB200PrecondFsaiGetFactors(self.h, None, None, iptr(ia), iptr(ja), dptr(a)) == 0
+        return ia, ja, a
+
     def set_factors(self, ia, ja, a):
         ia = np.ascontiguousarray(ia, dtype=np.int32)
         ja = np.ascontiguousarray(ja, dtype=np.int32)
@@ -273,6 +404,40 @@ class FsaiPrecond:
 class AfnPrecond:
     def __init__(self):
         self.h = lib().Nfft4GPPrecondAFNCreate()
+
+    def setup(self, kernel, max_k, lfil, est_m=500, numests=5, noran=0, seed=906):
+        """Nfft4GPPrecondAFNSetRank / SetLfil / SetupWithKernel (afn.h:65-132; MATLAB afn_setup.m:30-109)."""
+        L = lib()
+        L.Nfft4GPPrecondAFNSetRank(self.h, max_k)
+        L.Nfft4GPPrecondAFNSetLfil(self.h, lfil)
+        assert L.Nfft4GPB200PrecondAFNSetRankEstimation(self.h, est_m, numests, noran, seed) == 0
+        rc = L.Nfft4GPPrecondAFNSetupWithKernel(dptr(kernel.X), kernel.n, kernel.n, kernel.d, kernel.fn(), kernel.h, 0, self.h)
+        if rc != 0:
+            raise RuntimeError("Nfft4GPPrecondAFNSetupWithKernel failed")
+        return self
+
+    def get_factors(self):
+        """dict(n, k, k_est, is_nys, perm[, Linv, K12, ia, ja, a])"""
+        L = lib()
+        n, k, ke, isn, nnz = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        assert L.Nfft4GPB200PrecondAFNGetFactors(self.h, C.byref(n), C.byref(k), C.byref(ke), C.byref(isn), None, None, None,
+                                                 C.byref(nnz), None, None, None) == 0
+        out = dict(n=n.value, k=k.value, k_est=ke.value, is_nys=bool(isn.value))
+        perm = np.zeros(n.value, dtype=np.int32)
+        if isn.value:
+            assert L.Nfft4GPB200PrecondAFNGetFactors(self.h, None, None, None, None, iptr(perm), None, None, None, None, None, None) == 0
+            out["perm"] = perm
+            return out
+        n2 = n.value - k.value
+        Linv = np.zeros((k.value, k.value))
+        K12 = np.zeros((n2, k.value))
+        ia = np.zeros(n2 + 1, dtype=np.int32)
+        ja = np.zeros(nnz.value, dtype=np.int32)
+        a = np.zeros(nnz.value)
+        assert L.Nfft4GPB200PrecondAFNGetFactors(self.h, None, None, None, None, iptr(perm), dptr(Linv), dptr(K12), None,
+                                                 iptr(ia), iptr(ja), dptr(a)) == 0
+        out.update(perm=perm, Linv=Linv.T.copy(), K12=K12.T.copy(), ia=ia, ja=ja, a=a)
+        return out
 
     def set_factors(self, perm, L, K12, ia, ja, a):
         k = L.shape[0]

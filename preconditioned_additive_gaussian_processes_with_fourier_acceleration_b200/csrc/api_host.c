@@ -5,6 +5,7 @@
 #include "nfft4gp_b200.h"
 #include "b200_dev.h"
 #include "b200_host.h"
+#include "b200_precond.h"
 
 int Nfft4GPB200Init(int device) { return b200_init(device); }
 int Nfft4GPB200DeviceCount(void) { return b200_device_count(); }
@@ -28,3 +29,81 @@ float Nfft4GPB200EventElapsedMs(void *start, void *stop) { return b200_event_ela
 /* per-kernel-class CUDA-event timing on the library stream (bench.py roofline) */
 void Nfft4GPB200ProfileStart(void) { b200_prof_start(); }
 int Nfft4GPB200ProfileStop(double *sums_ms, long long *counts, int ncls) { return b200_prof_stop(sums_ms, counts, ncls); }
+
+/* ------------------------------------------------------------------ setup building blocks for the parity tests */
+int Nfft4GPB200HostPotrf(int n, double *A) { return b200_potrf_lower(n, A, n); }
+int Nfft4GPB200HostSyev(int n, double *A, double *w, int want_vectors) { return want_vectors ? b200_syev(n, A, w) : b200_syev_values(n, A, w); }
+
+int Nfft4GPB200Dgemm(char transa, char transb, int M, int N, int K, double alpha, const double *A, int lda, const double *B, int ldb,
+                     double beta, double *C, int ldc)
+{
+   size_t ca = (size_t)lda * (size_t)(transa == 'N' ? K : M), cb = (size_t)ldb * (size_t)(transb == 'N' ? N : K), cc = (size_t)ldc * (size_t)N;
+   double *dA, *dB, *dC;
+   int rc;
+   if (b200_init(-1))
+      return -1;
+   dA = (double *)b200_malloc(sizeof(double) * ca);
+   dB = (double *)b200_malloc(sizeof(double) * cb);
+   dC = (double *)b200_malloc(sizeof(double) * cc);
+   rc = !dA || !dB || !dC || b200_h2d(dA, A, sizeof(double) * ca) || b200_h2d(dB, B, sizeof(double) * cb) || b200_h2d(dC, C, sizeof(double) * cc) ||
+        b200k_dgemm(transa, transb, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc) || b200_d2h(C, dC, sizeof(double) * cc);
+   b200_free(dA);
+   b200_free(dB);
+   b200_free(dC);
+   return rc ? -1 : 0;
+}
+
+static double *upload_compact(const double *data, int n, int ldim, int d)
+{
+   double *d_X = (double *)b200_malloc(sizeof(double) * (size_t)n * d);
+   int t;
+   for (t = 0; d_X && t < d; t++)
+      if (b200_h2d(d_X + (size_t)t * n, data + (size_t)t * ldim, sizeof(double) * (size_t)n))
+      {
+         b200_free(d_X);
+         return NULL;
+      }
+   return d_X;
+}
+
+int Nfft4GPB200Fps(const double *data, int n, int ldim, int d, int k, int *perm_out)
+{
+   double c[64], *d_X, *d_c;
+   int t, i, rc, *d_p;
+   if (b200_init(-1) || d > 64 || k > n)
+      return -1;
+   for (t = 0; t < d; t++)
+   {
+      double s = 0.0;
+      for (i = 0; i < n; i++)
+         s += data[(size_t)t * ldim + i] / n;
+      c[t] = s;
+   }
+   d_X = upload_compact(data, n, ldim, d);
+   d_c = (double *)b200_malloc(sizeof(double) * 64);
+   d_p = (int *)b200_malloc(sizeof(int) * (size_t)k);
+   rc = !d_X || !d_c || !d_p || b200_h2d(d_c, c, sizeof(double) * (size_t)d) || b200k_fps(d_X, n, n, d, d_c, k, d_p) ||
+        b200_d2h(perm_out, d_p, sizeof(int) * (size_t)k);
+   b200_free(d_X);
+   b200_free(d_c);
+   b200_free(d_p);
+   return rc ? -1 : 0;
+}
+
+int Nfft4GPB200KnnPattern(const double *data, int n, int ldim, int d, int lfil, int *ia, int *ja)
+{
+   long long nnz = b200k_knn_nnz(n, lfil);
+   double *d_X;
+   int rc, *d_ia, *d_ja;
+   if (b200_init(-1))
+      return -1;
+   d_X = upload_compact(data, n, ldim, d);
+   d_ia = (int *)b200_malloc(sizeof(int) * ((size_t)n + 1));
+   d_ja = (int *)b200_malloc(sizeof(int) * (size_t)nnz);
+   rc = !d_X || !d_ia || !d_ja || b200k_knn_pattern(d_X, n, n, d, lfil, d_ia, d_ja) || b200_d2h(ia, d_ia, sizeof(int) * ((size_t)n + 1)) ||
+        b200_d2h(ja, d_ja, sizeof(int) * (size_t)nnz);
+   b200_free(d_X);
+   b200_free(d_ia);
+   b200_free(d_ja);
+   return rc ? -1 : 0;
+}

@@ -111,6 +111,24 @@ int b200k_dense_additive(const double *Xw, int n, int P, int dw, const int *d_di
                          double noise_diag, const int *rows, int nr, const int *cols, int nc, int lower_only,
                          double *K, int ldk);
 
+/* ---- setup-side kernels (setup_kernels.cu) ---- */
+/* column-major fp64 GEMM on the tensor cores (DMMA): C = alpha op(A) op(B) + beta C, op = 'N' | 'T' */
+int b200k_dgemm(char transa, char transb, int M, int N, int K, double alpha, const double *A, int lda, const double *B, int ldb,
+                double beta, double *C, int ldc);
+/* farthest point sampling of k points (first = nearest to d_center); X feature-major with leading dimension ld */
+int b200k_fps(const double *d_X, int n, int ld, int d, const double *d_center, int k, int *d_perm_out);
+/* KNN pattern of the FSAI: row i = its lfil-1 nearest earlier points + the diagonal (last); d_ia[n+1], d_ja[b200k_knn_nnz] */
+long long b200k_knn_nnz(int n, int lfil);
+int b200k_knn_pattern(const double *d_X, int n, int ld, int d, int lfil, int *d_ia, int *d_ja);
+/* FSAI values for every row of a pattern (one small Cholesky solve per row); see setup_kernels.cu */
+int b200k_fsai_rows(const double *d_Xw, const int *d_dims, int n_points, int P, int dw, int kernel, double ff, double l,
+                    double noise_diag, int nrows, const int *d_ia, const int *d_ja, const int *d_rowmap, const double *d_Z, int kz,
+                    int kmax, double *d_a, int *breakdown_out);
+int b200k_csr_transpose(int nrows, int ncols, int nnz, const int *d_ia, const int *d_ja, const double *d_a, int *d_iat, int *d_jat,
+                        double *d_at);
+int b200k_gather_rows(int n, int ncol, const int *d_perm, const double *d_src, int lds, double *d_dst, int ldd);
+int b200k_scale_columns(int n, int k, const double *d_scale, double *d_U);
+
 #ifdef __cplusplus
 }
 #endif

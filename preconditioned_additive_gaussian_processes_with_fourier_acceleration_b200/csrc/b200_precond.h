@@ -3,6 +3,7 @@
 #define NFFT4GP_B200_PRECOND_H
 
 #include <stddef.h>
+#include "nfft4gp_b200.h"
 
 /* Nystrom: fields follow precond_nys (INC/_preconds.h:320-351) where they have a meaning here. */
 typedef struct
@@ -44,6 +45,9 @@ typedef struct
 {
    int magic;
    int max_k, lfil;
+   int est_m, est_num, noran; /* rank estimation: sample size (500), repetitions (5; 0 = use max_k), never switch to Nystrom */
+   unsigned long long est_seed;
+   int k_est;                 /* last estimated rank (before the cap), -1 when the estimation was skipped */
    int n, k;
    int *d_perm;
    double *d_Linv; /* k x k explicit inverse of chol(K11 + shift), lower, column-major */
@@ -58,6 +62,8 @@ typedef struct
 
 int b200_nys_set_device_factors(b200_nys *s, int n, int k, const int *h_perm, double *d_U_owned, const double *h_s, double eta);
 int b200_fsai_set_host_factors(b200_fsai *s, int n, const int *ia, const int *ja, const double *a);
+/* takes ownership of the device CSR arrays and builds the explicit transpose on the device */
+int b200_fsai_set_device_factors(b200_fsai *s, int n, int nnz, int *d_ia, int *d_ja, double *d_a);
 int b200_afn_set_device_factors(b200_afn *s, int n, int k, const int *h_perm, const double *h_L, double *d_K12_owned,
                                 const int *ia, const int *ja, const double *a);
 void b200_fsai_release(b200_fsai *s);
@@ -66,5 +72,31 @@ void b200_tril_inverse(int k, const double *L, double *Linv);
 int b200_nys_solve_dev(void *vnys, int n, double *d_x, const double *d_rhs);
 int b200_fsai_solve_dev(void *vf, int n, double *d_x, const double *d_rhs);
 int b200_afn_solve_dev(void *va, int n, double *d_x, const double *d_rhs);
+
+/* dense_small.c: O(k^3) host factorizations of the k x k landmark block */
+double b200_sym_fro_lower(int n, const double *A, int lda);
+double b200_chol_shift(int n, double fro);
+int b200_potrf_lower(int n, double *A, int lda);
+int b200_syev(int n, double *A, double *w);
+int b200_syev_values(int n, double *A, double *w);
+double b200_spd_norm2(int m, const double *S, int lds, double *work);
+
+/* dense_host.c: device view of a dense kernel handle that this library can evaluate on the GPU */
+typedef struct
+{
+   const double *d_Xw; /* window-major features [P * dw][n] on the device */
+   const int *d_dims;  /* [P] actual dimension of every window */
+   int n, P, dw;
+   int kernel;         /* 0 Gauss, 1 Matern-1/2 */
+   double f, l, mu;    /* hyper-parameters read from the handle at call time */
+   int d_all;          /* number of feature columns of the caller's data (KNN / FPS use all of them) */
+   int owns;           /* temporary upload (plain kernels): release with b200_dense_view_release */
+} b200_dense_view;
+/* returns 0 and fills *v when fkernel is one of this library's dense kernels; 1 when it is a foreign function */
+int b200_dense_view_acquire(func_kernel fkernel, void *fkernel_params, const double *data, int n, int ldim, int d, b200_dense_view *v);
+void b200_dense_view_release(b200_dense_view *v);
+/* K(rows, cols) on the device: rows/cols device index arrays (NULL = 0..), column-major with leading dimension ldk */
+int b200_dense_view_block(const b200_dense_view *v, double noise_diag, const int *d_rows, int nr, const int *d_cols, int nc,
+                          int lower_only, double *d_K, int ldk);
 
 #endif

@@ -196,45 +196,40 @@ void Nfft4GPPrecondFsaiFree(void *str)
 
 void Nfft4GPPrecondFsaiSetLfil(void *str, int lfil) { ((b200_fsai *)str)->lfil = lfil; }
 
-/* upload G (CSR, rows sorted as given) and its explicit transpose */
-int b200_fsai_set_host_factors(b200_fsai *s, int n, const int *ia, const int *ja, const double *a)
+/* takes ownership of the device CSR arrays of G and builds the explicit transpose (columns ordered by row) on the device */
+int b200_fsai_set_device_factors(b200_fsai *s, int n, int nnz, int *d_ia, int *d_ja, double *d_a)
 {
-   int nnz = ia[n], i, j;
-   int *iat = (int *)b200_xcalloc((size_t)n + 1, sizeof(int));
-   int *jat = (int *)b200_xmalloc(sizeof(int) * (size_t)(nnz ? nnz : 1));
-   double *at = (double *)b200_xmalloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
-   int *cur;
    b200_fsai_release(s);
-   for (j = 0; j < nnz; j++)
-      iat[ja[j] + 1]++;
-   for (i = 0; i < n; i++)
-      iat[i + 1] += iat[i];
-   cur = (int *)b200_xmalloc(sizeof(int) * (size_t)(n ? n : 1));
-   memcpy(cur, iat, sizeof(int) * (size_t)n);
-   for (i = 0; i < n; i++)
-      for (j = ia[i]; j < ia[i + 1]; j++)
-      {
-         int pos = cur[ja[j]]++;
-         jat[pos] = i;
-         at[pos] = a[j];
-      }
-   free(cur);
    s->n = n;
    s->nnz = nnz;
-   s->d_ia = (int *)b200_malloc(sizeof(int) * ((size_t)n + 1));
-   s->d_ja = (int *)b200_malloc(sizeof(int) * (size_t)nnz);
-   s->d_a = (double *)b200_malloc(sizeof(double) * (size_t)nnz);
+   s->d_ia = d_ia;
+   s->d_ja = d_ja;
+   s->d_a = d_a;
    s->d_iat = (int *)b200_malloc(sizeof(int) * ((size_t)n + 1));
-   s->d_jat = (int *)b200_malloc(sizeof(int) * (size_t)nnz);
-   s->d_at = (double *)b200_malloc(sizeof(double) * (size_t)nnz);
-   s->d_work = (double *)b200_malloc(sizeof(double) * (size_t)n);
-   i = b200_h2d(s->d_ia, ia, sizeof(int) * ((size_t)n + 1)) || b200_h2d(s->d_ja, ja, sizeof(int) * (size_t)nnz) ||
-       b200_h2d(s->d_a, a, sizeof(double) * (size_t)nnz) || b200_h2d(s->d_iat, iat, sizeof(int) * ((size_t)n + 1)) ||
-       b200_h2d(s->d_jat, jat, sizeof(int) * (size_t)nnz) || b200_h2d(s->d_at, at, sizeof(double) * (size_t)nnz) || b200_sync();
-   free(iat);
-   free(jat);
-   free(at);
-   return i ? -1 : 0;
+   s->d_jat = (int *)b200_malloc(sizeof(int) * (size_t)(nnz ? nnz : 1));
+   s->d_at = (double *)b200_malloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
+   s->d_work = (double *)b200_malloc(sizeof(double) * (size_t)(n ? n : 1));
+   if (!s->d_iat || !s->d_jat || !s->d_at || !s->d_work)
+      return -1;
+   return b200k_csr_transpose(n, n, nnz, d_ia, d_ja, d_a, s->d_iat, s->d_jat, s->d_at) || b200_sync();
+}
+
+/* upload G (CSR, rows as given) */
+int b200_fsai_set_host_factors(b200_fsai *s, int n, const int *ia, const int *ja, const double *a)
+{
+   int nnz = ia[n];
+   int *d_ia = (int *)b200_malloc(sizeof(int) * ((size_t)n + 1));
+   int *d_ja = (int *)b200_malloc(sizeof(int) * (size_t)(nnz ? nnz : 1));
+   double *d_a = (double *)b200_malloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
+   if (!d_ia || !d_ja || !d_a || b200_h2d(d_ia, ia, sizeof(int) * ((size_t)n + 1)) || b200_h2d(d_ja, ja, sizeof(int) * (size_t)nnz) ||
+       b200_h2d(d_a, a, sizeof(double) * (size_t)nnz) || b200_sync())
+   {
+      b200_free(d_ia);
+      b200_free(d_ja);
+      b200_free(d_a);
+      return -1;
+   }
+   return b200_fsai_set_device_factors(s, n, nnz, d_ia, d_ja, d_a);
 }
 
 int Nfft4GPB200PrecondFsaiSetFactors(void *fsai, int n, const int *ia, const int *ja, const double *a)
@@ -292,8 +287,12 @@ void *Nfft4GPPrecondAFNCreate(void)
 {
    b200_afn *s = (b200_afn *)b200_xcalloc(1, sizeof(b200_afn));
    s->magic = B200_MAGIC_AFN;
-   s->max_k = 100; /* MATLAB test settings: maxrank 100-300, lfil 100 (test_solve_additive.m:35-40) */
+   s->max_k = 100; /* MATLAB test settings: maxrank 100-300, lfil 100, m 500, 5 estimates (test_solve_additive.m:35-40) */
    s->lfil = 100;
+   s->est_m = 500;
+   s->est_num = 5;
+   s->est_seed = 906ULL;
+   s->k_est = -1;
    s->schur.magic = B200_MAGIC_FSAI;
    return s;
 }
@@ -329,24 +328,41 @@ void Nfft4GPPrecondAFNFree(void *str)
 void Nfft4GPPrecondAFNSetRank(void *str, int max_k) { ((b200_afn *)str)->max_k = max_k; }
 void Nfft4GPPrecondAFNSetLfil(void *str, int lfil) { ((b200_afn *)str)->lfil = lfil; }
 
-/* explicit inverse of the k x k lower Cholesky factor (column-major), upper triangle zero */
-void b200_tril_inverse(int k, const double *L, double *Linv)
+int Nfft4GPB200PrecondAFNSetRankEstimation(void *str, int m, int numests, int noran, unsigned long long seed)
 {
-   int i, j, c;
-   memset(Linv, 0, sizeof(double) * (size_t)k * (size_t)k);
-   for (c = 0; c < k; c++)
-   {
-      /* solve L x = e_c by forward substitution */
-      double *x = Linv + (size_t)c * k;
-      x[c] = 1.0 / L[(size_t)c * k + c];
-      for (i = c + 1; i < k; i++)
-      {
-         double s = 0.0;
-         for (j = c; j < i; j++)
-            s -= L[(size_t)j * k + i] * x[j];
-         x[i] = s / L[(size_t)i * k + i];
-      }
-   }
+   b200_afn *s = (b200_afn *)str;
+   if (!s || s->magic != B200_MAGIC_AFN)
+      return -1;
+   s->est_m = m > 1 ? m : 2;
+   s->est_num = numests;
+   s->noran = noran;
+   s->est_seed = seed;
+   return 0;
+}
+
+int Nfft4GPB200PrecondAFNGetFactors(void *afn, int *n, int *k, int *k_est, int *is_nys, int *perm, double *Linv, double *K12, int *nnz,
+                                    int *ia, int *ja, double *a)
+{
+   b200_afn *s = (b200_afn *)afn;
+   if (!s || s->magic != B200_MAGIC_AFN)
+      return -1;
+   if (n)
+      *n = s->n;
+   if (k)
+      *k = s->k;
+   if (k_est)
+      *k_est = s->k_est;
+   if (is_nys)
+      *is_nys = s->nys != NULL;
+   if (s->nys)
+      return perm ? Nfft4GPB200PrecondNysGetFactors(s->nys, NULL, NULL, perm, NULL, NULL, NULL) : 0;
+   if (perm && s->d_perm && b200_d2h(perm, s->d_perm, sizeof(int) * (size_t)s->n))
+      return -1;
+   if (Linv && s->d_Linv && b200_d2h(Linv, s->d_Linv, sizeof(double) * (size_t)s->k * (size_t)s->k))
+      return -1;
+   if (K12 && s->d_K12 && b200_d2h(K12, s->d_K12, sizeof(double) * (size_t)s->k * (size_t)(s->n - s->k)))
+      return -1;
+   return Nfft4GPB200PrecondFsaiGetFactors(&s->schur, NULL, nnz, ia, ja, a);
 }
 
 int b200_afn_set_device_factors(b200_afn *s, int n, int k, const int *h_perm, const double *h_L, double *d_K12_owned,

@@ -1,25 +1,737 @@
-/* Preconditioner setups (C host side).  See DESIGN.md for the status of each. */
+/* Preconditioner setups (C host side, rows N2 / G2 / A2 of SURVEY.md 8(a)).
+ *   Nystrom  SRC/preconds/nys.c:518-660       K11 Cholesky + shift (chol.c:439-466), G = L^{-1}, U = K1 G', SVD through eig(U'U)
+ *   FSAI     SRC/preconds/fsai.c:302-673      KNN pattern (kernels.c:121-277) + one k x k Cholesky solve per row
+ *   AFN      MATLAB afn_setup.m:30-109 (SRC/preconds/afn.c is not compiled by the reference): rank estimate, farthest
+ *            point sampling, Cholesky of K11, K12, L^{-1} K12, FSAI of the Schur complement; Nystrom when the rank is low
+ * Everything O(n) and above runs on the GPU (setup_kernels.cu, precond_kernels.cu); the O(k^3) factorizations of the
+ * landmark block run here (dense_small.c).  A dense kernel of this library (Nfft4GPKernel{Additive,Gaussian,Matern12}Kernel)
+ * is evaluated on the device; a foreign func_kernel is honoured by the Nystrom setup only (two host calls, as the
+ * reference makes them).  require_grad != 0 (preconditioner derivatives for the GP loss gradient) is SURVEY.md 8(f) "next". */
+#include <math.h>
+#include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+
 #include "nfft4gp_b200.h"
 #include "b200_dev.h"
 #include "b200_host.h"
 #include "b200_precond.h"
 
-int Nfft4GPPrecondNysSetupWithKernel(double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params, int require_grad, void *vnys_mat)
+static double wtime(void)
 {
-   (void)data; (void)n; (void)ldim; (void)d; (void)fkernel; (void)fkernel_params; (void)require_grad; (void)vnys_mat;
-   printf("Error: nfft4gp_b200: Nystrom setup not built yet.\n");
-   return -1;
+   struct timeval t;
+   gettimeofday(&t, NULL);
+   return (double)t.tv_sec + 1e-6 * (double)t.tv_usec;
 }
-int Nfft4GPPrecondFsaiSetupWithKernel(double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params, int require_grad, void *vfsai_mat)
+
+static int *identity_perm(int n)
 {
-   (void)data; (void)n; (void)ldim; (void)d; (void)fkernel; (void)fkernel_params; (void)require_grad; (void)vfsai_mat;
-   printf("Error: nfft4gp_b200: FSAI setup not built yet.\n");
-   return -1;
+   int *p = (int *)b200_xmalloc(sizeof(int) * (size_t)(n ? n : 1)), i;
+   for (i = 0; i < n; i++)
+      p[i] = i;
+   return p;
 }
-int Nfft4GPPrecondAFNSetupWithKernel(double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params, int require_grad, void *vafn_mat)
+
+/* feature-major n x d copy of the caller's data on the device, leading dimension n */
+static double *upload_features(const double *data, int n, int ldim, int d)
 {
-   (void)data; (void)n; (void)ldim; (void)d; (void)fkernel; (void)fkernel_params; (void)require_grad; (void)vafn_mat;
-   printf("Error: nfft4gp_b200: AFN setup not built yet.\n");
-   return -1;
+   double *d_X = (double *)b200_malloc(sizeof(double) * (size_t)n * d);
+   int t;
+   if (!d_X)
+      return NULL;
+   for (t = 0; t < d; t++)
+      if (b200_h2d(d_X + (size_t)t * n, data + (size_t)t * ldim, sizeof(double) * (size_t)n))
+      {
+         b200_free(d_X);
+         return NULL;
+      }
+   if (b200_sync())
+   {
+      b200_free(d_X);
+      return NULL;
+   }
+   return d_X;
+}
+
+static int *upload_ints(const int *h, size_t count)
+{
+   int *d = (int *)b200_malloc(sizeof(int) * (count ? count : 1));
+   if (d && count && (b200_h2d(d, h, sizeof(int) * count) || b200_sync()))
+   {
+      b200_free(d);
+      return NULL;
+   }
+   return d;
+}
+
+/* shifted Cholesky of the k x k landmark block held on the host (lower triangle), chol.c:439-466; L overwrites K11 */
+static int landmark_cholesky(int k, double *K11)
+{
+   double fro = b200_sym_fro_lower(k, K11, k), nu = b200_chol_shift(k, fro);
+   int i, info;
+   for (i = 0; i < k; i++)
+      K11[(size_t)i * k + i] += nu;
+   info = b200_potrf_lower(k, K11, k);
+   if (info)
+      printf("Error: Cholesky of the %d x %d landmark block failed at pivot %d.\n", k, k, info);
+   return info;
+}
+
+/* ================================================================== Nystrom (nys.c:518-660) */
+static int nys_setup_perm(b200_nys *s, double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params,
+                          const int *perm_in, int k)
+{
+   nfft4gp_kernel *pk = (nfft4gp_kernel *)fkernel_params;
+   b200_dense_view v;
+   int own, rc = -1, i, j, *perm = NULL, *d_perm = NULL;
+   double *K11 = NULL, *G = NULL, *AA = NULL, *w = NULL, *sv = NULL, *Vs = NULL;
+   double *d_K1 = NULL, *d_U = NULL, *d_small = NULL, *d_small2 = NULL;
+   double noise_level, f2, eta;
+   size_t kk;
+   if (b200_init(-1))
+      return -1;
+   if (k > n)
+      k = n;
+   if (k <= 0)
+   {
+      printf("Error: Nystrom setup needs a positive rank.\n");
+      return -1;
+   }
+   kk = (size_t)k * (size_t)k;
+   own = b200_dense_view_acquire(fkernel, fkernel_params, data, n, ldim, d, &v);
+   if (own < 0)
+      return -1;
+   noise_level = pk->_noise_level;
+   f2 = pk->_params[0] * pk->_params[0];
+   eta = noise_level * f2; /* nys.c:641 */
+   perm = (int *)b200_xmalloc(sizeof(int) * (size_t)n);
+   if (perm_in)
+      memcpy(perm, perm_in, sizeof(int) * (size_t)n);
+   else
+      for (i = 0; i < n; i++)
+         perm[i] = i;
+   K11 = (double *)b200_xcalloc(kk, sizeof(double));
+   d_K1 = (double *)b200_malloc(sizeof(double) * (size_t)n * k);
+   d_U = (double *)b200_malloc(sizeof(double) * (size_t)n * k);
+   d_small = (double *)b200_malloc(sizeof(double) * kk);
+   d_small2 = (double *)b200_malloc(sizeof(double) * kk);
+   if (!d_K1 || !d_U || !d_small || !d_small2)
+      goto done;
+   if (own == 0)
+   {
+      /* K1 = K(perm, perm[0:k]) (n x k, no noise: nys.c:597) and K11 = its leading block (noise 0: nys.c:562) */
+      d_perm = upload_ints(perm, (size_t)n);
+      if (!d_perm || b200_dense_view_block(&v, 0.0, d_perm, n, d_perm, k, 0, d_K1, n) ||
+          b200_dense_view_block(&v, 0.0, d_perm, k, d_perm, k, 1, d_small, k) || b200_d2h(K11, d_small, sizeof(double) * kk))
+         goto done;
+   }
+   else
+   {
+      /* foreign kernel: the reference's own two host calls, then upload */
+      double *K1h = NULL;
+      pk->_noise_level = 0.0;
+      i = fkernel(fkernel_params, data, n, ldim, d, perm, n, perm, k, &K1h, NULL);
+      pk->_noise_level = noise_level;
+      if (i || !K1h)
+      {
+         printf("Error: the kernel function failed in the Nystrom setup.\n");
+         free(K1h);
+         goto done;
+      }
+      for (j = 0; j < k; j++)
+         for (i = j; i < k; i++)
+            K11[(size_t)j * k + i] = K1h[(size_t)j * n + i];
+      i = b200_h2d(d_K1, K1h, sizeof(double) * (size_t)n * k) || b200_sync();
+      free(K1h);
+      if (i)
+         goto done;
+   }
+   if (landmark_cholesky(k, K11))
+      goto done;
+   /* G = L^{-1} (nys.c:576), U = K1 G' (dtrmm R,L,T: nys.c:602) */
+   G = (double *)b200_xmalloc(sizeof(double) * kk);
+   b200_tril_inverse(k, K11, G);
+   if (b200_h2d(d_small, G, sizeof(double) * kk) || b200k_dgemm('N', 'T', n, k, k, 1.0, d_K1, n, d_small, k, 0.0, d_U, n))
+      goto done;
+   /* SVD of U through the eigen-decomposition of U'U (matops.c:65-137): U = W S V'  =>  W = U V S^{-1} */
+   AA = (double *)b200_xmalloc(sizeof(double) * kk);
+   w = (double *)b200_xmalloc(sizeof(double) * (size_t)k);
+   sv = (double *)b200_xmalloc(sizeof(double) * (size_t)k);
+   Vs = (double *)b200_xmalloc(sizeof(double) * kk);
+   if (b200k_dgemm('T', 'N', k, k, n, 1.0, d_U, n, d_U, n, 0.0, d_small2, k) || b200_d2h(AA, d_small2, sizeof(double) * kk))
+      goto done;
+   for (j = 0; j < k; j++) /* exact symmetry for the eigensolver */
+      for (i = j + 1; i < k; i++)
+      {
+         double m = 0.5 * (AA[(size_t)j * k + i] + AA[(size_t)i * k + j]);
+         AA[(size_t)j * k + i] = AA[(size_t)i * k + j] = m;
+      }
+   if (b200_syev(k, AA, w))
+   {
+      printf("Error: the eigensolver did not converge in the Nystrom setup.\n");
+      goto done;
+   }
+   /* descending singular values; column c of W = U * V(:, k-1-c) / sigma_c.  The reference takes sqrt of a possibly
+    * negative eigenvalue (NaN) and mis-steps for sigma < 1e-12 (matops.c:114-129); here: clamp at 0, scale by 1e12. */
+   for (j = 0; j < k; j++)
+   {
+      double ev = w[k - 1 - j], sig = sqrt(ev > 0.0 ? ev : 0.0), sc = sig < 1e-12 ? 1e12 : 1.0 / sig;
+      double val;
+      for (i = 0; i < k; i++)
+         Vs[(size_t)j * k + i] = AA[(size_t)(k - 1 - j) * k + i] * sc;
+      val = 1.0 / (sig * sig + eta); /* nys.c:643-647 */
+      sv[j] = val > 0.0 ? val : 0.0;
+   }
+   if (b200_h2d(d_small, Vs, sizeof(double) * kk) || b200k_dgemm('N', 'N', n, k, k, 1.0, d_U, n, d_small, k, 0.0, d_K1, n) || b200_sync())
+      goto done;
+   /* the handle takes ownership of d_K1 (= W) */
+   rc = b200_nys_set_device_factors(s, n, k, perm, d_K1, sv, eta);
+   d_K1 = NULL;
+done:
+   b200_free(d_K1);
+   b200_free(d_U);
+   b200_free(d_small);
+   b200_free(d_small2);
+   b200_free(d_perm);
+   free(perm);
+   free(K11);
+   free(G);
+   free(AA);
+   free(w);
+   free(sv);
+   free(Vs);
+   if (own == 0)
+      b200_dense_view_release(&v);
+   return rc;
+}
+
+int Nfft4GPPrecondNysSetupWithKernel(double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params, int require_grad,
+                                     void *vnys_mat)
+{
+   b200_nys *s = (b200_nys *)vnys_mat;
+   double t0 = wtime();
+   int rc;
+   if (!s || s->magic != B200_MAGIC_NYS || !fkernel || !fkernel_params)
+      return -1;
+   if (require_grad)
+   {
+      printf("Error: nfft4gp_b200 builds the Nystrom preconditioner without derivative terms (require_grad must be 0).\n");
+      return -1;
+   }
+   rc = nys_setup_perm(s, data, n, ldim, d, fkernel, fkernel_params, s->perm, s->k_setup);
+   s->tset = wtime() - t0;
+   return rc;
+}
+
+/* ================================================================== FSAI (fsai.c:302-673) */
+int Nfft4GPPrecondFsaiSetupWithKernel(double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params, int require_grad,
+                                      void *vfsai_mat)
+{
+   b200_fsai *s = (b200_fsai *)vfsai_mat;
+   b200_dense_view v;
+   double t0 = wtime(), *d_X = NULL, *d_a = NULL;
+   int own, rc = -1, lfil, kmax, bad = 0, *d_ia = NULL, *d_ja = NULL;
+   long long nnz;
+   if (!s || s->magic != B200_MAGIC_FSAI || !fkernel || !fkernel_params || b200_init(-1))
+      return -1;
+   if (require_grad)
+   {
+      printf("Error: nfft4gp_b200 builds the FSAI preconditioner without derivative terms (require_grad must be 0).\n");
+      return -1;
+   }
+   own = b200_dense_view_acquire(fkernel, fkernel_params, data, n, ldim, d, &v);
+   if (own)
+   {
+      if (own > 0)
+         printf("Error: the FSAI setup needs one of this library's dense kernels (Nfft4GPKernel{Additive,Gaussian,Matern12}Kernel).\n");
+      return -1;
+   }
+   lfil = s->lfil < 1 ? 1 : s->lfil;
+   kmax = lfil < n ? lfil : n;
+   nnz = b200k_knn_nnz(n, lfil);
+   if (nnz > 2147483647LL)
+   {
+      printf("Error: FSAI pattern with %lld entries exceeds the 32-bit index range of the reference's CSR format.\n", nnz);
+      goto done;
+   }
+   d_X = upload_features(data, n, ldim, d);
+   d_ia = (int *)b200_malloc(sizeof(int) * ((size_t)n + 1));
+   d_ja = (int *)b200_malloc(sizeof(int) * (size_t)nnz);
+   d_a = (double *)b200_malloc(sizeof(double) * (size_t)nnz);
+   if (!d_X || !d_ia || !d_ja || !d_a)
+      goto done;
+   if (b200k_knn_pattern(d_X, n, n, d, lfil, d_ia, d_ja) ||
+       b200k_fsai_rows(v.d_Xw, v.d_dims, v.n, v.P, v.dw, v.kernel, v.f * v.f, v.l, v.mu * v.f * v.f, n, d_ia, d_ja, NULL, NULL, 0, kmax, d_a,
+                       &bad))
+      goto done;
+   if (bad)
+   {
+      printf("Error: FSAI breakdown: %d rows have a kernel block that is not positive definite.\n", bad);
+      goto done;
+   }
+   rc = b200_fsai_set_device_factors(s, n, (int)nnz, d_ia, d_ja, d_a);
+   d_ia = d_ja = NULL;
+   d_a = NULL;
+done:
+   b200_free(d_X);
+   b200_free(d_ia);
+   b200_free(d_ja);
+   b200_free(d_a);
+   b200_dense_view_release(&v);
+   s->tset = wtime() - t0;
+   return rc;
+}
+
+/* ================================================================== AFN (afn_setup.m:30-109) */
+
+/* counter-based generator for the sub-samples of the rank estimation (the reference uses rand(); MATLAB randsample) */
+static uint64_t splitmix64(uint64_t *st)
+{
+   uint64_t z = (*st += 0x9e3779b97f4a7c15ULL);
+   z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+   z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+   return z ^ (z >> 31);
+}
+
+/* first m entries of a Fisher-Yates shuffle of pool[0:n) */
+static void sample_without_replacement(int *pool, int n, int m, uint64_t *st)
+{
+   int i;
+   for (i = 0; i < m; i++)
+   {
+      int j = i + (int)(splitmix64(st) % (uint64_t)(n - i)), t = pool[i];
+      pool[i] = pool[j];
+      pool[j] = t;
+   }
+}
+
+/* Upload a scaled sub-sample as its own small problem: window features (for the kernel) and all features (for FPS). */
+typedef struct
+{
+   double *d_Xw, *d_X;
+   int m;
+} rank_sample;
+
+static int rank_sample_upload(const b200_dense_view *v, const double *h_Xw, size_t h_ldw, const double *data, int ldim, int d,
+                              const int *rows, int m, double scale, rank_sample *rs)
+{
+   int nf = v->P * v->dw, t, i;
+   double *tmp = (double *)b200_xmalloc(sizeof(double) * (size_t)m * (size_t)(nf > d ? nf : d));
+   rs->m = m;
+   rs->d_Xw = (double *)b200_malloc(sizeof(double) * (size_t)m * nf);
+   rs->d_X = (double *)b200_malloc(sizeof(double) * (size_t)m * d);
+   if (!rs->d_Xw || !rs->d_X)
+   {
+      free(tmp);
+      return -1;
+   }
+   for (t = 0; t < nf; t++)
+      for (i = 0; i < m; i++)
+         tmp[(size_t)t * m + i] = h_Xw[(size_t)t * h_ldw + rows[i]] * scale;
+   if (b200_h2d(rs->d_Xw, tmp, sizeof(double) * (size_t)m * nf) || b200_sync())
+   {
+      free(tmp);
+      return -1;
+   }
+   for (t = 0; t < d; t++)
+      for (i = 0; i < m; i++)
+         tmp[(size_t)t * m + i] = data[(size_t)t * ldim + rows[i]] * scale;
+   i = b200_h2d(rs->d_X, tmp, sizeof(double) * (size_t)m * d) || b200_sync();
+   free(tmp);
+   return i ? -1 : 0;
+}
+
+static void rank_sample_free(rank_sample *rs)
+{
+   b200_free(rs->d_Xw);
+   b200_free(rs->d_X);
+   rs->d_Xw = rs->d_X = NULL;
+}
+
+/* host features behind a dense view: window-major for the additive kernel, the caller's data otherwise */
+static const double *view_host_features(func_kernel fkernel, void *fkernel_params, const double *data, int n, int ldim, size_t *ld)
+{
+   if (fkernel == Nfft4GPKernelAdditiveKernel)
+   {
+      *ld = (size_t)n;
+      return ((nfft4gp_kernel *)fkernel_params)->_buffer;
+   }
+   *ld = (size_t)ldim;
+   return data;
+}
+
+static int centroid_to_device(const double *data, int n, int ldim, int d, const int *rows, double scale, double **d_c)
+{
+   double c[64];
+   int t, i;
+   for (t = 0; t < d; t++)
+   {
+      double s = 0.0;
+      for (i = 0; i < n; i++)
+         s += data[(size_t)t * ldim + (rows ? rows[i] : i)] * scale / n; /* ordering.c:470-474: x_mean += x / n */
+      c[t] = s;
+   }
+   *d_c = (double *)b200_malloc(sizeof(double) * 64);
+   if (!*d_c || b200_h2d(*d_c, c, sizeof(double) * (size_t)d) || b200_sync())
+      return -1;
+   return 0;
+}
+
+/* smallest r such that || K - K(:,1:r) K(1:r,1:r)^{-1} K(1:r,:) ||_2 / nrm < tol, K symmetric positive definite (full
+ * storage, destroyed).  MATLAB bisects over r (afn_setup.m:196-207); the error is monotone in r, so one right-looking
+ * Cholesky sweep that watches the trailing Schur complement finds the same r: max diag <= ||S||_2 <= trace bracket the
+ * norm, the power iteration runs only when the bracket straddles the threshold. */
+static int nystrom_error_rank(int m, double *K, double nrm, double tol, double *work /* 2m */)
+{
+   int r, i, j;
+   for (r = 1; r < m; r++)
+   {
+      /* eliminate column r-1 */
+      int c = r - 1;
+      double piv = K[(size_t)c * m + c], tr = 0.0, mx = 0.0;
+      if (!(piv > 0.0))
+         return r; /* numerically rank deficient: the Nystrom error is at rounding level */
+      for (j = r; j < m; j++)
+      {
+         double f = K[(size_t)c * m + j] / piv;
+         double *cj = K + (size_t)j * m;
+         const double *cc = K + (size_t)c * m;
+         for (i = j; i < m; i++)
+            cj[i] -= cc[i] * f;
+      }
+      for (j = r; j < m; j++)
+      {
+         double dj = K[(size_t)j * m + j];
+         tr += dj;
+         if (dj > mx)
+            mx = dj;
+      }
+      if (mx / nrm >= tol)
+         continue;
+      if (tr / nrm < tol)
+         return r;
+      {
+         /* symmetrise the trailing block (only its lower triangle is maintained) and take its 2-norm */
+         int ms = m - r;
+         double *S = (double *)b200_xmalloc(sizeof(double) * (size_t)ms * ms), nrm2;
+         for (j = 0; j < ms; j++)
+            for (i = j; i < ms; i++)
+               S[(size_t)j * ms + i] = S[(size_t)i * ms + j] = K[(size_t)(j + r) * m + (i + r)];
+         nrm2 = b200_spd_norm2(ms, S, ms, work);
+         free(S);
+         if (nrm2 / nrm < tol)
+            return r;
+      }
+   }
+   return m;
+}
+
+/* afn_setup.m:111-293.  Returns the estimated rank (>= 0) or -1 on error. */
+static int afn_rank_estimate(b200_afn *s, const b200_dense_view *v, func_kernel fkernel, void *fkernel_params, const double *data, int n,
+                             int ldim, int d, int max_k)
+{
+   size_t h_ld;
+   const double *h_Xw = view_host_features(fkernel, fkernel_params, data, n, ldim, &h_ld);
+   int m = s->est_m < n ? s->est_m : n, numests = s->est_num, e, i, j, r = 0, k_scaled, rc = -1;
+   int *pool = identity_perm(n), *permf = (int *)b200_xmalloc(sizeof(int) * (size_t)(m > max_k ? m : max_k));
+   int *d_permf = (int *)b200_malloc(sizeof(int) * (size_t)m);
+   double *Km = (double *)b200_xmalloc(sizeof(double) * (size_t)m * m), *work = (double *)b200_xmalloc(sizeof(double) * 2 * (size_t)m);
+   double *d_K = (double *)b200_malloc(sizeof(double) * (size_t)m * m), *d_c = NULL;
+   uint64_t st = s->est_seed;
+   b200_dense_view sv = *v;
+   rank_sample rs = {NULL, NULL, 0};
+   if (!d_permf || !d_K)
+      goto done;
+   /* ---- scaled Nystrom-error estimate (afn_setup.m:163-228) */
+   for (e = 0; e < numests; e++)
+   {
+      double nu, fro, n2;
+      for (i = 0; i < n; i++)
+         pool[i] = i;
+      sample_without_replacement(pool, n, m, &st);
+      if (rank_sample_upload(v, h_Xw, h_ld, data, ldim, d, pool, m, pow((double)m / n, 1.0 / d), &rs) ||
+          centroid_to_device(data, m, ldim, d, pool, pow((double)m / n, 1.0 / d), &d_c) || b200k_fps(rs.d_X, m, m, d, d_c, m, d_permf))
+         goto done;
+      /* Km = K(permfps, permfps) without noise, f = 1 */
+      sv.d_Xw = rs.d_Xw;
+      sv.n = m;
+      sv.f = 1.0;
+      if (b200_dense_view_block(&sv, 0.0, d_permf, m, d_permf, m, 0, d_K, m) || b200_d2h(Km, d_K, sizeof(double) * (size_t)m * m))
+         goto done;
+      n2 = b200_spd_norm2(m, Km, m, work);
+      nu = sqrt((double)m) * (nextafter(n2, n2 + 1.0) - n2); /* sqrt(m) * eps(norm(Km, 2)) */
+      fro = 0.0;
+      for (j = 0; j < m; j++)
+      {
+         Km[(size_t)j * m + j] += nu;
+         for (i = 0; i < m; i++)
+            fro += Km[(size_t)j * m + i] * Km[(size_t)j * m + i];
+      }
+      fro = sqrt(fro);
+      i = nystrom_error_rank(m, Km, fro, 0.1, work);
+      if (i > r)
+         r = i;
+      rank_sample_free(&rs);
+      b200_free(d_c);
+      d_c = NULL;
+   }
+   k_scaled = (int)ceil((double)r * n / m);
+   if (k_scaled > max_k)
+   {
+      rc = k_scaled;
+      goto done;
+   }
+   /* ---- numerical rank of sub-sampled kernel matrices (afn_setup.m:230-292) */
+   {
+      int mk = max_k < n ? max_k : n;
+      double thr = 1.1 * v->mu / (v->f * v->f);
+      if (mk < m)
+         mk = m;
+      r = 0;
+      for (e = 0; e < numests; e++)
+      {
+         double scale = 1.0;
+         int cnt = 0;
+         for (i = 0; i < n; i++)
+            pool[i] = i;
+         sample_without_replacement(pool, n, mk, &st);
+         if (mk > m)
+         {
+            /* sub-sample again: m of the mk points, scaled */
+            for (i = 0; i < mk; i++)
+               permf[i] = pool[i];
+            sample_without_replacement(permf, mk, m, &st);
+            scale = pow((double)m / mk, 1.0 / d);
+         }
+         else
+            for (i = 0; i < m; i++)
+               permf[i] = pool[i];
+         if (rank_sample_upload(v, h_Xw, h_ld, data, ldim, d, permf, m, scale, &rs))
+            goto done;
+         sv = *v;
+         sv.d_Xw = rs.d_Xw;
+         sv.n = m;
+         if (b200_dense_view_block(&sv, v->mu * v->f * v->f, NULL, m, NULL, m, 0, d_K, m) || b200_d2h(Km, d_K, sizeof(double) * (size_t)m * m))
+            goto done;
+         if (b200_syev_values(m, Km, work))
+            goto done;
+         for (i = 0; i < m; i++)
+            cnt += (work[i] > thr);
+         if (cnt > r)
+            r = cnt;
+         rank_sample_free(&rs);
+      }
+      rc = (int)floor((double)r * mk / m);
+   }
+done:
+   rank_sample_free(&rs);
+   b200_free(d_c);
+   b200_free(d_permf);
+   b200_free(d_K);
+   free(pool);
+   free(permf);
+   free(Km);
+   free(work);
+   return rc;
+}
+
+/* Nfft4GPExpandPerm (utils.c:208): the k selected indices first, the remaining ones in ascending order */
+static int *expand_perm(const int *sel, int k, int n)
+{
+   int *perm = (int *)b200_xmalloc(sizeof(int) * (size_t)n), i, pos = k;
+   char *mark = (char *)b200_xcalloc((size_t)n, 1);
+   for (i = 0; i < k; i++)
+   {
+      perm[i] = sel[i];
+      mark[sel[i]] = 1;
+   }
+   for (i = 0; i < n; i++)
+      if (!mark[i])
+         perm[pos++] = i;
+   free(mark);
+   return perm;
+}
+
+static int afn_use_nystrom(b200_afn *s, double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params, int *perm, int k)
+{
+   void *nys = Nfft4GPPrecondNysCreate();
+   int rc = nys_setup_perm((b200_nys *)nys, data, n, ldim, d, fkernel, fkernel_params, perm, k);
+   if (rc)
+   {
+      Nfft4GPPrecondNysFree(nys);
+      return -1;
+   }
+   s->nys = nys;
+   s->n = n;
+   s->k = k;
+   return 0;
+}
+
+int Nfft4GPPrecondAFNSetupWithKernel(double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params, int require_grad,
+                                     void *vafn_mat)
+{
+   b200_afn *s = (b200_afn *)vafn_mat;
+   b200_dense_view v;
+   double t0 = wtime();
+   int own, rc = -1, k, max_k, n2, lfil, kmax, bad = 0, i;
+   int *sel = NULL, *perm = NULL, *d_sel = NULL, *d_perm = NULL, *d_ia = NULL, *d_ja = NULL;
+   double *d_X = NULL, *d_X2 = NULL, *d_c = NULL, *d_K11 = NULL, *d_Linv = NULL, *d_K12 = NULL, *d_GK12 = NULL, *d_a = NULL;
+   double *K11 = NULL, *Linv = NULL;
+   long long nnz;
+   if (!s || s->magic != B200_MAGIC_AFN || !fkernel || !fkernel_params || b200_init(-1))
+      return -1;
+   if (require_grad)
+   {
+      printf("Error: nfft4gp_b200 builds the AFN preconditioner without derivative terms (require_grad must be 0).\n");
+      return -1;
+   }
+   if (d > 64)
+   {
+      printf("Error: the AFN setup supports at most 64 features.\n");
+      return -1;
+   }
+   own = b200_dense_view_acquire(fkernel, fkernel_params, data, n, ldim, d, &v);
+   if (own)
+   {
+      if (own > 0)
+         printf("Error: the AFN setup needs one of this library's dense kernels (Nfft4GPKernel{Additive,Gaussian,Matern12}Kernel).\n");
+      return -1;
+   }
+   b200_afn_release(s);
+   max_k = s->max_k < n ? s->max_k : n;
+   if (max_k < 1)
+      max_k = 1;
+   /* 1. rank estimation (afn_setup.m:55-58) */
+   if (s->est_num > 0)
+   {
+      k = afn_rank_estimate(s, &v, fkernel, fkernel_params, data, n, ldim, d, max_k);
+      if (k < 0)
+         goto done;
+      s->k_est = k;
+      if (k > max_k)
+         k = max_k;
+   }
+   else
+   {
+      k = max_k;
+      s->k_est = -1;
+   }
+   if (k < 1)
+      k = 1;
+   /* 2. landmarks = farthest point sampling on all features (afn_setup.m:61-63) */
+   d_X = upload_features(data, n, ldim, d);
+   d_sel = (int *)b200_malloc(sizeof(int) * (size_t)k);
+   sel = (int *)b200_xmalloc(sizeof(int) * (size_t)k);
+   if (!d_X || !d_sel || centroid_to_device(data, n, ldim, d, NULL, 1.0, &d_c) || b200k_fps(d_X, n, n, d, d_c, k, d_sel) ||
+       b200_d2h(sel, d_sel, sizeof(int) * (size_t)k))
+      goto done;
+   perm = expand_perm(sel, k, n);
+   /* 3. low rank: Nystrom on the FPS ordering (afn_setup.m:80-84, afn.c:294-304) */
+   if (k < max_k && !s->noran)
+   {
+      rc = afn_use_nystrom(s, data, n, ldim, d, fkernel, fkernel_params, perm, k);
+      goto done;
+   }
+   /* 4. K11 = L L' (with the noise term and the stabilising shift, chol_setup.m:52-56 / chol.c:439-466) */
+   n2 = n - k;
+   d_perm = upload_ints(perm, (size_t)n);
+   K11 = (double *)b200_xcalloc((size_t)k * k, sizeof(double));
+   Linv = (double *)b200_xmalloc(sizeof(double) * (size_t)k * k);
+   d_K11 = (double *)b200_malloc(sizeof(double) * (size_t)k * k);
+   d_Linv = (double *)b200_malloc(sizeof(double) * (size_t)k * k);
+   if (!d_perm || !d_K11 || !d_Linv || b200_dense_view_block(&v, v.mu * v.f * v.f, d_perm, k, d_perm, k, 1, d_K11, k) ||
+       b200_d2h(K11, d_K11, sizeof(double) * (size_t)k * k) || landmark_cholesky(k, K11))
+      goto done;
+   b200_tril_inverse(k, K11, Linv);
+   if (b200_h2d(d_Linv, Linv, sizeof(double) * (size_t)k * k) || b200_sync())
+      goto done;
+   if (n2 > 0)
+   {
+      /* 5. K12 = K(perm1, perm2), GK12 = L^{-1} K12 (schurCombinedKernel.m; kernels.c:3510-3523) */
+      lfil = s->lfil < 1 ? 1 : s->lfil;
+      kmax = lfil < n2 ? lfil : n2;
+      nnz = b200k_knn_nnz(n2, lfil);
+      if (nnz > 2147483647LL)
+      {
+         printf("Error: FSAI pattern with %lld entries exceeds the 32-bit index range of the reference's CSR format.\n", nnz);
+         goto done;
+      }
+      d_K12 = (double *)b200_malloc(sizeof(double) * (size_t)k * n2);
+      d_GK12 = (double *)b200_malloc(sizeof(double) * (size_t)k * n2);
+      d_X2 = (double *)b200_malloc(sizeof(double) * (size_t)n2 * d);
+      d_ia = (int *)b200_malloc(sizeof(int) * ((size_t)n2 + 1));
+      d_ja = (int *)b200_malloc(sizeof(int) * (size_t)nnz);
+      d_a = (double *)b200_malloc(sizeof(double) * (size_t)nnz);
+      if (!d_K12 || !d_GK12 || !d_X2 || !d_ia || !d_ja || !d_a)
+         goto done;
+      if (b200_dense_view_block(&v, 0.0, d_perm, k, d_perm + k, n2, 0, d_K12, k) ||
+          b200k_dgemm('N', 'N', k, n2, k, 1.0, d_Linv, k, d_K12, k, 0.0, d_GK12, k))
+         goto done;
+      /* 6. FSAI of the Schur complement S = K22 - GK12' GK12 on the non-landmark points in their order
+       *    (fsai_setup.m:42-88 with the pattern size of the compiled C code: lfil entries per row incl. the diagonal) */
+      if (b200k_gather_rows(n2, d, d_perm + k, d_X, n, d_X2, n2) || b200k_knn_pattern(d_X2, n2, n2, d, lfil, d_ia, d_ja) ||
+          b200k_fsai_rows(v.d_Xw, v.d_dims, v.n, v.P, v.dw, v.kernel, v.f * v.f, v.l, v.mu * v.f * v.f, n2, d_ia, d_ja, d_perm + k, d_GK12, k,
+                          kmax, d_a, &bad))
+         goto done;
+      if (bad)
+      {
+         /* afn_setup.m:93-98: FSAI broke down -> Nystrom with the maximum rank */
+         printf("Warning: FSAI of the Schur complement broke down in %d rows; switching to the Nystrom preconditioner of rank %d.\n", bad, max_k);
+         if (k < max_k)
+         {
+            /* landmarks for the larger rank */
+            b200_free(d_sel);
+            free(sel);
+            free(perm);
+            perm = NULL;
+            d_sel = (int *)b200_malloc(sizeof(int) * (size_t)max_k);
+            sel = (int *)b200_xmalloc(sizeof(int) * (size_t)max_k);
+            if (!d_sel || b200k_fps(d_X, n, n, d, d_c, max_k, d_sel) || b200_d2h(sel, d_sel, sizeof(int) * (size_t)max_k))
+               goto done;
+            perm = expand_perm(sel, max_k, n);
+         }
+         rc = afn_use_nystrom(s, data, n, ldim, d, fkernel, fkernel_params, perm, max_k);
+         goto done;
+      }
+      if (b200_fsai_set_device_factors(&s->schur, n2, (int)nnz, d_ia, d_ja, d_a))
+      {
+         d_ia = d_ja = NULL;
+         d_a = NULL;
+         goto done;
+      }
+      d_ia = d_ja = NULL;
+      d_a = NULL;
+   }
+   s->n = n;
+   s->k = k;
+   s->d_perm = d_perm;
+   s->d_Linv = d_Linv;
+   s->d_K12 = d_K12;
+   s->d_work = (double *)b200_malloc(sizeof(double) * (2 * (size_t)n + 2 * (size_t)k));
+   d_perm = NULL;
+   d_Linv = d_K12 = NULL;
+   rc = s->d_work ? 0 : -1;
+done:
+   i = rc;
+   b200_free(d_X);
+   b200_free(d_X2);
+   b200_free(d_c);
+   b200_free(d_K11);
+   b200_free(d_Linv);
+   b200_free(d_K12);
+   b200_free(d_GK12);
+   b200_free(d_a);
+   b200_free(d_sel);
+   b200_free(d_perm);
+   b200_free(d_ia);
+   b200_free(d_ja);
+   free(sel);
+   free(perm);
+   free(K11);
+   free(Linv);
+   b200_dense_view_release(&v);
+   s->tset = wtime() - t0;
+   return i;
 }

@@ -127,7 +127,50 @@ def fsai_case():
     print("wrote fsai case: nnz", nnz, "fsai-pcg it", itf, "plain pcg it", it0)
 
 
+def nys_plain_case():
+    """Reference Nystrom setup + apply on the reference's PLAIN Gaussian kernel (9 features).  With the dense ADDITIVE kernel
+    the reference's setup reads the wrong entries of the handle's feature copy (kernels.c:3160 indexes it with the caller's
+    n = k while nys.c:549 passes sub-sampled data), so the setup row is pinned on the kernel where the reference is right."""
+    n, d, k = 300, 9, 40
+    X = cloud(n, d, 61)
+    f, l, mu = 1.1, 1.4, 0.05
+    L.Nfft4GPKernelParamCreate.restype = C.c_void_p
+    L.Nfft4GPKernelParamCreate.argtypes = [C.c_int, C.c_int]
+    kh = L.Nfft4GPKernelParamCreate(n, 1)
+    R.set_hyper(kh, f, l, mu)
+    K = C.c_void_p()
+    assert L.Nfft4GPKernelGaussianKernel(kh, R.dptr(X), n, n, d, None, 0, None, 0, C.byref(K), None) == 0
+    Km = np.ctypeslib.as_array(C.cast(K, R.c_double_p), shape=(n, n)).T.copy()
+    Km = np.tril(Km) + np.tril(Km, -1).T
+    rhs = np.random.default_rng(62).random(n) - 0.5
+    perm = np.random.default_rng(63).permutation(n).astype(np.int32)
+    nys = L.Nfft4GPPrecondNysCreate()
+    L.Nfft4GPPrecondNysSetRank(nys, k)
+    L.Nfft4GPPrecondNysSetPerm(nys, R.iptr(perm), 0)
+    assert L.Nfft4GPPrecondNysSetupWithKernel(R.dptr(X), n, n, d, C.cast(L.Nfft4GPKernelGaussianKernel, C.c_void_p), kh, 0, nys) == 0
+    z = np.zeros(n)
+    L.Nfft4GPPrecondNysSolve(nys, n, R.dptr(z), R.dptr(rhs))
+    xn, reln, histn, itn = R.ref_pcg(K, n, L.Nfft4GPDenseMatSymv, nys, L.Nfft4GPPrecondNysSolve, np.zeros(n), rhs, 400, 0, 1e-8)
+    x0, rel0, hist0, it0 = R.ref_pcg(K, n, L.Nfft4GPDenseMatSymv, None, None, np.zeros(n), rhs, 400, 0, 1e-8)
+
+    class PNys(C.Structure):
+        _fields_ = [("_k_setup", C.c_int), ("_own_perm", C.c_int), ("_perm", C.c_void_p), ("_n", C.c_int), ("_tits", C.c_int),
+                    ("_titt", C.c_double), ("_tset", C.c_double), ("_tlogdet", C.c_double), ("_tdvp", C.c_double),
+                    ("_nys_opt", C.c_int), ("_k", C.c_int), ("_eta", C.c_double), ("_f2", C.c_double),
+                    ("_U", R.c_double_p), ("_s", R.c_double_p), ("_work", R.c_double_p)]
+
+    ps = PNys.from_address(nys)
+    out = {"X": X, "f": f, "l": l, "mu": mu, "rhs": rhs, "K": Km, "perm": perm, "k": k, "z": z,
+           "U": np.ctypeslib.as_array(ps._U, shape=(k, n)).T.copy(), "s": np.ctypeslib.as_array(ps._s, shape=(k,)).copy(),
+           "eta": ps._eta, "nys_pcg_it": itn, "nys_pcg_x": xn, "pcg_it": it0}
+    np.savez_compressed(os.path.join(OUT, "nys_gauss300.npz"), **out)
+    print("wrote nys plain case: nys-pcg it", itn, "plain pcg it", it0)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "nys":
+        nys_plain_case()
+        sys.exit(0)
     nfft_case("gauss_3x3d", 400, 9, list(range(9)), 3, 3, "gaussian", 1.2, 0.5, 0.01, 11)
     nfft_case("bike_pattern", 350, 13, [1, 8, 6, 9, 4, 2, 5, 3, 11], 3, 3, "gaussian", 0.9, 0.45, 0.02, 12)
     nfft_case("padded_last", 300, 5, [0, 1, 3, 2, 4, -1], 2, 3, "gaussian", 1.0, 0.6, 0.01, 13)
@@ -135,3 +178,4 @@ if __name__ == "__main__":
     nfft_case("gauss_1d", 250, 3, [0, 1, 2], 3, 1, "gaussian", 1.3, 1.2, 0.01, 15)
     solver_case()
     fsai_case()
+    nys_plain_case()
