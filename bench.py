@@ -153,6 +153,53 @@ def run_reference(args):
     return 0
 
 
+def run_pcg_section(pkg, L, A, X, rhs, windows, hp, args, hbm_peak):
+    """Second half of BASELINE.json's metric: AFN-preconditioned CG on the NFFT additive matvec to 1e-6 relative residual
+    (config C3, n = 10^6, d = 9, Gaussian).  Two landmark ranks: the one BASELINE.json names (500; too small for n = 10^6 at
+    mu = 0.01 -- reported with an iteration cap) and one that converges.  Setup (GPU: KNN pattern, FSAI rows, landmark GEMMs
+    on the fp64 tensor cores) and solve are timed separately with a device synchronise on both sides; a second, profiled
+    pass of 50 iterations gives the per-class kernel times of one iteration and the HBM fraction of the AFN apply."""
+    n = X.shape[1]
+    mu = args.pcg_mu
+    A.build(hp["f"], hp["l"], mu)
+    D = pkg.DenseAdditiveKernel(X, windows, 3, 3, "gaussian").set_hyper(hp["f"], hp["l"], mu)
+    out = {"config": f"C3: AFN-PCG to 1e-6 rel. residual, n={n}, d=9, Gaussian, f={hp['f']}, l={hp['l']:.4f}, mu={mu}, lfil=100, rhs=U(0,1)-0.5",
+           "unit": "s", "runs": []}
+    for rank, maxits in ((500, 300), (args.pcg_rank, 3000)):
+        t0 = time.perf_counter()
+        P = pkg.AfnPrecond().setup(D, rank, 100, numests=0, noran=1)
+        L.Nfft4GPB200DeviceSynchronize()
+        setup_s = time.perf_counter() - t0
+        L.Nfft4GPB200LaunchCountReset()
+        t0 = time.perf_counter()
+        xs, rel, hist, its = pkg.solver_pcg(A.K, n, A.matvec_fn(), P.h, P.solve_fn(), np.zeros(n), rhs, maxits, 0, 1e-6)
+        L.Nfft4GPB200DeviceSynchronize()
+        solve_s = time.perf_counter() - t0
+        launches = int(L.Nfft4GPB200LaunchCount())
+        done = its if its > 0 else maxits
+        # profiled pass: 50 iterations with per-launch events
+        L.Nfft4GPB200ProfileStart()
+        pkg.solver_pcg(A.K, n, A.matvec_fn(), P.h, P.solve_fn(), np.zeros(n), rhs, 50, 0, 1e-30)
+        sums = (C.c_double * len(PROF_CLASSES))()
+        counts = (C.c_longlong * len(PROF_CLASSES))()
+        L.Nfft4GPB200ProfileStop(sums, counts, len(PROF_CLASSES))
+        per_it = {PROF_CLASSES[i]: round(sums[i] / 51.0, 5) for i in range(len(PROF_CLASSES)) if counts[i] > 0}
+        n2 = n - rank
+        gemv_bytes = 2.0 * 8.0 * rank * n2          # two passes over K12 per apply
+        csr_bytes = 2.0 * 12.0 * 100.0 * n2         # G and G' (value + column index) per apply
+        run = {"precond": f"AFN rank {rank} + FSAI(lfil 100) of the Schur complement", "setup_s": setup_s, "solve_s": solve_s,
+               "iters": its, "converged": bool(its > 0), "rel_res": rel, "ms_per_iter": 1000.0 * solve_s / max(done, 1),
+               "gpu_launches": launches, "per_class_ms_per_iter": per_it,
+               "afn_apply_hbm": {"gemv_GBs": gemv_bytes / (per_it.get("gemv", float("nan")) * 1e-3) / 1e9,
+                                 "spmv_GBs": csr_bytes / (per_it.get("csr", float("nan")) * 1e-3) / 1e9, "peak_GBs": hbm_peak}}
+        out["runs"].append(run)
+        P.free()
+    out["value"] = out["runs"][-1]["solve_s"] if out["runs"][-1]["converged"] else None
+    D.free()
+    A.build(hp["f"], hp["l"], hp["mu"])
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -162,6 +209,9 @@ def main():
     ap.add_argument("--n", type=int, default=1000000)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pcg", action="store_true", help="skip the C3 AFN-PCG solve section")
+    ap.add_argument("--pcg-rank", type=int, default=4000, help="landmark rank of the converging AFN configuration")
+    ap.add_argument("--pcg-mu", type=float, default=0.01)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -324,6 +374,10 @@ def main():
                "sample": f"{args.cpu_steps} full additive matvecs at n={n} (same workload) after 1 warm-up, {cores} OpenMP threads",
                "rel_l2_gpu_vs_cpu": rel}
 
+    pcg = None
+    if world == 1 and not args.no_pcg:
+        pcg = run_pcg_section(pkg, L, A, X, x, windows, hp, args, peak)
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
@@ -337,6 +391,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "pcg": pcg,
     }
     print(json.dumps(line))
     if dist is not None:

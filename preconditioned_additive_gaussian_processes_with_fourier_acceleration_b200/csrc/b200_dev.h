@@ -128,6 +128,9 @@ int b200k_csr_transpose(int nrows, int ncols, int nnz, const int *d_ia, const in
                         double *d_at);
 int b200k_gather_rows(int n, int ncol, const int *d_perm, const double *d_src, int lds, double *d_dst, int ldd);
 int b200k_scale_columns(int n, int k, const double *d_scale, double *d_U);
+/* blocked Cholesky of an SPD matrix (lower, ld n) on the device; d_Linv = explicit inverse of the factor (upper zero) */
+int b200k_potrf_inverse(int n, double *d_A, double *d_Linv, int *info);
+int b200k_add_diag(int n, double *d_A, int lda, double v);
 
 #ifdef __cplusplus
 }

@@ -66,14 +66,23 @@ static int *upload_ints(const int *h, size_t count)
    return d;
 }
 
-/* shifted Cholesky of the k x k landmark block held on the host (lower triangle), chol.c:439-466; L overwrites K11 */
-static int landmark_cholesky(int k, double *K11)
+/* Shifted Cholesky of the k x k landmark block (device, lower triangle, ld k), chol.c:439-466: the stabilising shift
+ * sqrt(k) ulp(||K11||_F) is derived on the host from a copy of the block, the blocked factorisation and the explicit
+ * inverse of the factor (dtrtri, matops.c:40-48) run on the device.  d_K11 <- L, d_Linv <- L^{-1}. */
+static int landmark_cholesky(int k, double *d_K11, double *d_Linv)
 {
-   double fro = b200_sym_fro_lower(k, K11, k), nu = b200_chol_shift(k, fro);
-   int i, info;
-   for (i = 0; i < k; i++)
-      K11[(size_t)i * k + i] += nu;
-   info = b200_potrf_lower(k, K11, k);
+   double *h = (double *)b200_xmalloc(sizeof(double) * (size_t)k * k), fro, nu;
+   int info = 0;
+   if (b200_d2h(h, d_K11, sizeof(double) * (size_t)k * k))
+   {
+      free(h);
+      return -1;
+   }
+   fro = b200_sym_fro_lower(k, h, k);
+   nu = b200_chol_shift(k, fro);
+   free(h);
+   if (b200k_add_diag(k, d_K11, k, nu) || b200k_potrf_inverse(k, d_K11, d_Linv, &info))
+      return -1;
    if (info)
       printf("Error: Cholesky of the %d x %d landmark block failed at pivot %d.\n", k, k, info);
    return info;
@@ -86,7 +95,7 @@ static int nys_setup_perm(b200_nys *s, double *data, int n, int ldim, int d, fun
    nfft4gp_kernel *pk = (nfft4gp_kernel *)fkernel_params;
    b200_dense_view v;
    int own, rc = -1, i, j, *perm = NULL, *d_perm = NULL;
-   double *K11 = NULL, *G = NULL, *AA = NULL, *w = NULL, *sv = NULL, *Vs = NULL;
+   double *K11 = NULL, *AA = NULL, *w = NULL, *sv = NULL, *Vs = NULL;
    double *d_K1 = NULL, *d_U = NULL, *d_small = NULL, *d_small2 = NULL;
    double noise_level, f2, eta;
    size_t kk;
@@ -124,7 +133,7 @@ static int nys_setup_perm(b200_nys *s, double *data, int n, int ldim, int d, fun
       /* K1 = K(perm, perm[0:k]) (n x k, no noise: nys.c:597) and K11 = its leading block (noise 0: nys.c:562) */
       d_perm = upload_ints(perm, (size_t)n);
       if (!d_perm || b200_dense_view_block(&v, 0.0, d_perm, n, d_perm, k, 0, d_K1, n) ||
-          b200_dense_view_block(&v, 0.0, d_perm, k, d_perm, k, 1, d_small, k) || b200_d2h(K11, d_small, sizeof(double) * kk))
+          b200_dense_view_block(&v, 0.0, d_perm, k, d_perm, k, 1, d_small2, k))
          goto done;
    }
    else
@@ -143,17 +152,13 @@ static int nys_setup_perm(b200_nys *s, double *data, int n, int ldim, int d, fun
       for (j = 0; j < k; j++)
          for (i = j; i < k; i++)
             K11[(size_t)j * k + i] = K1h[(size_t)j * n + i];
-      i = b200_h2d(d_K1, K1h, sizeof(double) * (size_t)n * k) || b200_sync();
+      i = b200_h2d(d_K1, K1h, sizeof(double) * (size_t)n * k) || b200_h2d(d_small2, K11, sizeof(double) * kk) || b200_sync();
       free(K1h);
       if (i)
          goto done;
    }
-   if (landmark_cholesky(k, K11))
-      goto done;
-   /* G = L^{-1} (nys.c:576), U = K1 G' (dtrmm R,L,T: nys.c:602) */
-   G = (double *)b200_xmalloc(sizeof(double) * kk);
-   b200_tril_inverse(k, K11, G);
-   if (b200_h2d(d_small, G, sizeof(double) * kk) || b200k_dgemm('N', 'T', n, k, k, 1.0, d_K1, n, d_small, k, 0.0, d_U, n))
+   /* K11 + shift = L L' (chol.c:439-466), G = L^{-1} (nys.c:576), U = K1 G' (dtrmm R,L,T: nys.c:602) */
+   if (landmark_cholesky(k, d_small2, d_small) || b200k_dgemm('N', 'T', n, k, k, 1.0, d_K1, n, d_small, k, 0.0, d_U, n))
       goto done;
    /* SVD of U through the eigen-decomposition of U'U (matops.c:65-137): U = W S V'  =>  W = U V S^{-1} */
    AA = (double *)b200_xmalloc(sizeof(double) * kk);
@@ -197,7 +202,6 @@ done:
    b200_free(d_perm);
    free(perm);
    free(K11);
-   free(G);
    free(AA);
    free(w);
    free(sv);
@@ -578,7 +582,6 @@ int Nfft4GPPrecondAFNSetupWithKernel(double *data, int n, int ldim, int d, func_
    int own, rc = -1, k, max_k, n2, lfil, kmax, bad = 0, i;
    int *sel = NULL, *perm = NULL, *d_sel = NULL, *d_perm = NULL, *d_ia = NULL, *d_ja = NULL;
    double *d_X = NULL, *d_X2 = NULL, *d_c = NULL, *d_K11 = NULL, *d_Linv = NULL, *d_K12 = NULL, *d_GK12 = NULL, *d_a = NULL;
-   double *K11 = NULL, *Linv = NULL;
    long long nnz;
    if (!s || s->magic != B200_MAGIC_AFN || !fkernel || !fkernel_params || b200_init(-1))
       return -1;
@@ -637,15 +640,10 @@ int Nfft4GPPrecondAFNSetupWithKernel(double *data, int n, int ldim, int d, func_
    /* 4. K11 = L L' (with the noise term and the stabilising shift, chol_setup.m:52-56 / chol.c:439-466) */
    n2 = n - k;
    d_perm = upload_ints(perm, (size_t)n);
-   K11 = (double *)b200_xcalloc((size_t)k * k, sizeof(double));
-   Linv = (double *)b200_xmalloc(sizeof(double) * (size_t)k * k);
    d_K11 = (double *)b200_malloc(sizeof(double) * (size_t)k * k);
    d_Linv = (double *)b200_malloc(sizeof(double) * (size_t)k * k);
    if (!d_perm || !d_K11 || !d_Linv || b200_dense_view_block(&v, v.mu * v.f * v.f, d_perm, k, d_perm, k, 1, d_K11, k) ||
-       b200_d2h(K11, d_K11, sizeof(double) * (size_t)k * k) || landmark_cholesky(k, K11))
-      goto done;
-   b200_tril_inverse(k, K11, Linv);
-   if (b200_h2d(d_Linv, Linv, sizeof(double) * (size_t)k * k) || b200_sync())
+       landmark_cholesky(k, d_K11, d_Linv))
       goto done;
    if (n2 > 0)
    {
@@ -729,8 +727,6 @@ done:
    b200_free(d_ja);
    free(sel);
    free(perm);
-   free(K11);
-   free(Linv);
    b200_dense_view_release(&v);
    s->tset = wtime() - t0;
    return i;

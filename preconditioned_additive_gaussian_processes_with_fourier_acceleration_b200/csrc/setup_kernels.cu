@@ -845,6 +845,96 @@ __global__ void k_scale_columns(int n, int k, const double *__restrict__ scale, 
    U[e] *= scale[e / n];
 }
 
+
+// =====================================================================================================================
+// Blocked Cholesky of the k x k landmark block and the explicit inverse of its factor, on the device (k up to a few
+// thousand: the O(k^3) work is GEMM-shaped and goes through k_dgemm_dmma; the 64 x 64 diagonal blocks are factored and
+// inverted by one CTA in shared memory).
+// =====================================================================================================================
+#define CH_NB 64
+
+// A: nb x nb diagonal block (lower, leading dimension lda) -> L11 in place; W (nb x nb, ld nb, upper zero) = inv(L11)
+__global__ void __launch_bounds__(256)
+k_chol_diag_block(double *__restrict__ A, int lda, int nb, double *__restrict__ W, int ldw, int *__restrict__ info, int j0)
+{
+   extern __shared__ double chs[];
+   double (*S)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(chs);
+   double (*X)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(chs + CH_NB * (CH_NB + 1));
+   __shared__ int bad;
+   const int tid = threadIdx.x;
+   if (tid == 0)
+      bad = 0;
+   for (int e = tid; e < nb * nb; e += 256)
+   {
+      int r = e % nb, c = e / nb;
+      S[c][r] = (r >= c) ? A[(size_t)c * lda + r] : 0.0;
+      X[c][r] = 0.0;
+   }
+   __syncthreads();
+   for (int j = 0; j < nb; j++)
+   {
+      double piv = S[j][j];
+      if (!(piv > 0.0))
+      {
+         if (tid == 0 && !bad)
+            bad = j0 + j + 1;
+         piv = 1.0;
+      }
+      double dj = sqrt(piv);
+      __syncthreads();
+      for (int r = j + tid; r < nb; r += 256)
+         S[j][r] = (r == j) ? dj : S[j][r] / dj;
+      __syncthreads();
+      const int m = nb - j - 1;
+      for (int e = tid; e < m * m; e += 256)
+      {
+         int r = j + 1 + e % m, c = j + 1 + e / m;
+         if (r >= c)
+            S[c][r] -= S[j][r] * S[j][c];
+      }
+      __syncthreads();
+   }
+   // inverse: thread c solves L x = e_c by forward substitution
+   if (tid < nb)
+   {
+      int c = tid;
+      X[c][c] = 1.0 / S[c][c];
+      for (int i = c + 1; i < nb; i++)
+      {
+         double s = 0.0;
+         for (int j = c; j < i; j++)
+            s -= S[j][i] * X[c][j];
+         X[c][i] = s / S[i][i];
+      }
+   }
+   __syncthreads();
+   for (int e = tid; e < nb * nb; e += 256)
+   {
+      int r = e % nb, c = e / nb;
+      if (r >= c)
+         A[(size_t)c * lda + r] = S[c][r];
+      W[(size_t)c * ldw + r] = X[c][r];
+   }
+   if (tid == 0 && bad)
+      atomicCAS(info, 0, bad);
+}
+
+__global__ void k_add_diag(int n, double *__restrict__ A, int lda, double v)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n)
+      A[(size_t)i * lda + i] += v;
+}
+
+__global__ void k_copy_block(int m, int n, const double *__restrict__ src, int lds, double *__restrict__ dst, int ldd)
+{
+   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= (size_t)m * n)
+      return;
+   int r = (int)(e % m), c = (int)(e / m);
+   dst[(size_t)c * ldd + r] = src[(size_t)c * lds + r];
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 static double *g_part = nullptr;
 static size_t g_part_doubles = 0;
@@ -1092,6 +1182,65 @@ int b200k_scale_columns(int n, int k, const double *d_scale, double *d_U)
    B200ProfScope prof_scope_(PC_OTHER);
    k_scale_columns<<<b200_cdiv((long long)n * k, 256), 256, 0, b200_stream()>>>(n, k, d_scale, d_U);
    B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_add_diag(int n, double *d_A, int lda, double v)
+{
+   k_add_diag<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, d_A, lda, v);
+   B200_LAUNCHED();
+   return 0;
+}
+
+// In: d_A lower triangle of an SPD n x n matrix (ld n).  Out: d_A = its Cholesky factor L (lower), d_Linv = inv(L) (full
+// storage, upper zero).  *info = 0 or the 1-based index of the first non-positive pivot (dpotrf convention).
+int b200k_potrf_inverse(int n, double *d_A, double *d_Linv, int *info)
+{
+   B200ProfScope prof_scope_(PC_OTHER);
+   cudaStream_t st = b200_stream();
+   double *panel = nullptr, *T = nullptr;
+   int *d_info = nullptr;
+   *info = 0;
+   B200_CHECK(cudaMalloc(&panel, sizeof(double) * (size_t)n * CH_NB));
+   B200_CHECK(cudaMalloc(&T, sizeof(double) * (size_t)n * CH_NB));
+   B200_CHECK(cudaMalloc(&d_info, sizeof(int)));
+   B200_CHECK(cudaMemsetAsync(d_info, 0, sizeof(int), st));
+   B200_CHECK(cudaMemsetAsync(d_Linv, 0, sizeof(double) * (size_t)n * n, st));
+   const size_t chsm = sizeof(double) * 2 * CH_NB * (CH_NB + 1);
+   B200_CHECK(cudaFuncSetAttribute(k_chol_diag_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chsm));
+   for (int j0 = 0; j0 < n; j0 += CH_NB)
+   {
+      int nb = n - j0 < CH_NB ? n - j0 : CH_NB;
+      int m = n - j0 - nb;
+      double *Ajj = d_A + (size_t)j0 * n + j0;
+      double *Wjj = d_Linv + (size_t)j0 * n + j0; // inv(L_jj) lands directly in the diagonal block of Linv
+      k_chol_diag_block<<<1, 256, chsm, st>>>(Ajj, n, nb, Wjj, n, d_info, j0);
+      B200_LAUNCHED();
+      if (m > 0)
+      {
+         double *A21 = Ajj + nb;
+         // panel = A21 * inv(L_jj)'  ;  A21 <- panel  ;  A22 -= panel * panel'
+         if (b200k_dgemm('N', 'T', m, nb, nb, 1.0, A21, n, Wjj, n, 0.0, panel, m))
+            return -1;
+         k_copy_block<<<b200_cdiv((long long)m * nb, 256), 256, 0, st>>>(m, nb, panel, m, A21, n);
+         B200_LAUNCHED();
+         if (b200k_dgemm('N', 'T', m, m, nb, -1.0, panel, m, panel, m, 1.0, Ajj + (size_t)nb * n + nb, n))
+            return -1;
+      }
+   }
+   // inv(L) by block rows: X(i, 0:i0) = -inv(L_ii) * ( L(i, 0:i0) * X(0:i0, 0:i0) )
+   for (int i0 = CH_NB; i0 < n; i0 += CH_NB)
+   {
+      int nb = n - i0 < CH_NB ? n - i0 : CH_NB;
+      if (b200k_dgemm('N', 'N', nb, i0, i0, 1.0, d_A + i0, n, d_Linv, n, 0.0, T, nb) ||
+          b200k_dgemm('N', 'N', nb, i0, nb, -1.0, d_Linv + (size_t)i0 * n + i0, n, T, nb, 0.0, d_Linv + i0, n))
+         return -1;
+   }
+   B200_CHECK(cudaMemcpyAsync(info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+   B200_CHECK(cudaStreamSynchronize(st));
+   cudaFree(panel);
+   cudaFree(T);
+   cudaFree(d_info);
    return 0;
 }
 
