@@ -240,7 +240,8 @@ int Nfft4GPB200DebugWindowInfo(void *additive_handle, int w, int *dim, double *s
 int Nfft4GPB200DebugSpread(void *additive_handle, int w, double alpha, const double *x, double *grid /* 64^dim */);
 int Nfft4GPB200DebugCoeff(void *additive_handle, int w, int which, double *c /* 2 * 32^dim: b_k/phi_hat^2 interleaved */);
 int Nfft4GPB200DebugGridAfterFFT(void *additive_handle, int w, double alpha, const double *x, double *h /* 64^dim */);
-/* tuning knobs (bench / A-B tests): name in {"spread3d","gather3d"}; variant 0 = generic, 1 = tiled (default) */
+/* tuning knobs (bench / A-B tests): name in {"spread3d","gather3d"}; variant -1 = automatic (default), 0 = generic
+ * thread-per-point, 1 = DFMA warp-per-range with register-tile shifting, 5 = fp64 tensor-core (DMMA) warp-per-range */
 int Nfft4GPB200SetVariant(const char *name, int variant);
 
 #ifdef __cplusplus

@@ -15,6 +15,9 @@ extern "C" {
 #define B200_NOS 64   /* oversampled FFT length (sigma = 2)   */
 #define B200_MCUT 4   /* window cut-off m                     */
 #define B200_TAPS 10  /* 2m + 2                               */
+/* 3-D windows: average points per occupied cell from which the tensor-core spread / gather (full footprint flush per
+ * cell change) beats the DFMA kernels (register-tile shift along l3): measured cross-over, see profiles/README.md */
+#define B200_MMA_MIN_POINTS_PER_CELL 24
 
 /* device-side state of one feature window */
 typedef struct
@@ -75,6 +78,9 @@ int b200k_backward_fft_batch(const b200_win_dev *w, int nb, int which);
 int b200k_warp_ranges(void);
 int b200k_spread3_warp(const b200_win_dev *w);
 int b200k_gather3_warp(const b200_win_dev *w, double *d_f);
+/* nfft3d_mma.cu: the same streaming decomposition on the fp64 tensor cores (DMMA) */
+int b200k_spread3_mma(const b200_win_dev *w);
+int b200k_gather3_mma(const b200_win_dev *w, double *d_f);
 /* y = beta*y + sum_w c0*(f_w[inv_w] + mu*s*x)   (matvec epilogue, nfft_interface.c:428-494, 803-814) */
 int b200k_combine(int n, int P, const double *const *d_fptr, const int *const *d_invptr, const double *d_x,
                   double s, double c0, double mu, double beta, double *d_y);

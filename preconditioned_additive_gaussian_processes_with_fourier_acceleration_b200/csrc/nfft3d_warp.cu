@@ -30,9 +30,15 @@
 #define NOS B200_NOS
 #define ROW (3 * TAPS)
 #define WS 8                       /* points per stage = max points per chunk */
+#ifndef WNS
 #define WNS 3                      /* ring depth                              */
+#endif
+#ifndef WARPS_PER_CTA
 #define WARPS_PER_CTA 4
+#endif
+#ifndef CTAS_PER_SM
 #define CTAS_PER_SM 3
+#endif
 #define STAGE_D (WS * ROW + WS)    /* doubles per stage: tap rows + a-values  */
 #define CP16_PER_STAGE (WS * ROW * 8 / 16)
 

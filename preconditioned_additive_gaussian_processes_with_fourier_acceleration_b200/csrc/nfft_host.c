@@ -16,7 +16,7 @@
 #define M_PI 3.14159265358979323846264338327950288
 #endif
 
-int g_variant_spread3 = 1, g_variant_gather3 = 1;
+int g_variant_spread3 = -1, g_variant_gather3 = -1; /* -1 = automatic (b200k_spread / b200k_gather) */
 
 /* ------------------------------------------------------------------ small host utilities */
 void *b200_xmalloc(size_t bytes)

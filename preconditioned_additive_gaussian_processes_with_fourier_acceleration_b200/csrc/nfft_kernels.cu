@@ -528,7 +528,11 @@ int b200k_spread(const b200_win_dev *w, int variant)
 {
    B200ProfScope prof_scope_(PC_SPREAD);
    B200_CHECK(cudaMemsetAsync(w->grid, 0, sizeof(double) * grid_elems(w->d), b200_stream()));
-   if (w->d == 3 && variant != 0) // variant 0 = generic kernel (cross-check)
+   if (variant < 0) // automatic: tensor-core kernels for dense cells, DFMA kernels with register-tile shifting for sparse ones
+      variant = (w->nseg > 0 && w->n / w->nseg >= B200_MMA_MIN_POINTS_PER_CELL) ? 5 : 1;
+   if (w->d == 3 && variant == 5) // fp64 tensor-core kernels (nfft3d_mma.cu)
+      return b200k_spread3_mma(w);
+   if (w->d == 3 && variant != 0) // DFMA kernels (nfft3d_warp.cu); variant 0 = generic kernel (cross-check)
       return b200k_spread3_warp(w);
    int grid = b200_cdiv(w->n, 128);
    if (w->d == 1)
@@ -544,6 +548,10 @@ int b200k_spread(const b200_win_dev *w, int variant)
 int b200k_gather(const b200_win_dev *w, double *d_f, int variant)
 {
    B200ProfScope prof_scope_(PC_GATHER);
+   if (variant < 0)
+      variant = (w->nseg > 0 && w->n / w->nseg >= B200_MMA_MIN_POINTS_PER_CELL) ? 5 : 1;
+   if (w->d == 3 && variant == 5)
+      return b200k_gather3_mma(w, d_f);
    if (w->d == 3 && variant != 0)
       return b200k_gather3_warp(w, d_f);
    int grid = b200_cdiv(w->n, 128);
