@@ -81,6 +81,27 @@ int b200k_gather3_warp(const b200_win_dev *w, double *d_f);
 /* nfft3d_mma.cu: the same streaming decomposition on the fp64 tensor cores (DMMA) */
 int b200k_spread3_mma(const b200_win_dev *w);
 int b200k_gather3_mma(const b200_win_dev *w, double *d_f);
+/* all (equally shaped, dense) 3-D windows of an additive kernel in one launch: per-window pointers and the window's own
+ * partition of its chunk list into `nwarps` warp ranges (cfirst has nwarps + 1 entries); warp_begin = prefix sum of nwarps */
+typedef struct
+{
+   const double *psi;
+   const double *a;
+   const int *chunks;
+   const int *cfirst;
+   double *grid;
+   double *f;
+   int warp_begin;
+   int nwarps;
+} b200_mma_win;
+int b200k_spread3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps);
+int b200k_gather3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps);
+int b200k_spread_batch_begin(double *d_grids, size_t doubles);
+int b200k_spread_batch_end(void);
+int b200k_gather_batch_begin(void);
+int b200k_gather_batch_end(void);
+/* a_w = s * x[perm_w] for nb windows in one launch (device arrays of per-window pointers / sizes) */
+int b200k_prep_batch(int nb, const int *const *d_perm, double *const *d_a, const int *d_n, int nmax, const double *d_x, double s);
 /* y = beta*y + sum_w c0*(f_w[inv_w] + mu*s*x)   (matvec epilogue, nfft_interface.c:428-494, 803-814) */
 int b200k_combine(int n, int P, const double *const *d_fptr, const int *const *d_invptr, const double *d_x,
                   double s, double c0, double mu, double beta, double *d_y);

@@ -30,6 +30,8 @@ typedef struct b200_window
    double kernel_scale; /* f */
    int built;
    int *h_perm;         /* host copy of sorted -> original */
+   int *h_chunks;       /* host copy of the 3-D chunk descriptors (int4 each), kept to re-partition them for fused launches */
+   int h_nchunk;
    void *owner;         /* b200_single* for the single-window API, NULL inside an additive kernel */
    /* work arrays owned by the additive handle (all windows contiguous, so that FFT passes can be batched over windows and
     * the grids form ONE allreduce buffer); NULL = owned by the window */
@@ -56,6 +58,15 @@ typedef struct b200_additive
    size_t grids_doubles;
    double *d_specA, *d_specB, *d_band, *d_coef, *d_dcoef; /* contiguous slots of the leading equally shaped windows */
    int nbatch;           /* number of leading windows with the dimension of window 0 (batched FFT passes) */
+   /* fused spread / gather of the leading nbatch dense 3-D windows in one launch (nfft3d_mma.cu) */
+   int fused_ready;      /* 0 = not examined, 1 = descriptors built, -1 = not applicable */
+   int fused_warps;
+   void *d_fused[2];     /* b200_mma_win[nbatch] for the kernel channel (f) and the derivative channel (f2) */
+   int **d_fused_cfirst; /* host array of nbatch device pointers (owned) */
+   const int **d_prep_perm;
+   double **d_prep_a;
+   int *d_prep_n;
+   int prep_nmax;
    int nlocal;     /* windows owned by this rank under mode 1 */
    const double **d_fptr_local;
    const int **d_invptr_local;

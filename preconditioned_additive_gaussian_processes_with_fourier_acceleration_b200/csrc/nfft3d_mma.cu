@@ -6,8 +6,14 @@
 // Both run on mma.sync.m8n8k4.f64 (DMMA.8x8x4 in SASS): measured on this pool's B200 (scripts/fp64_dmma.cu) the fp64
 // tensor path and the DFMA pipe are ONE unit (36-37 vs 33 TFLOP/s, no overlap), but a DMMA carries 256 FMAs per warp
 // instruction instead of 32, which removes the issue-slot and operand-delivery limits of the DFMA kernels
-// (nfft3d_warp.cu: 57 % fp64-pipe activity at best).  Tiling: M = the 100 (x,y) pairs -> 13 tiles of 8 (96 % filled),
-// N = z -> 2 tiles of 8 (10 of 16 columns used), K = points (4 per instruction).
+// (nfft3d_warp.cu: 57 % fp64-pipe activity at best).  The footprint is tiled in two parts so that the awkward extent 10 = 8 + 2
+// does not waste half of the instructions:
+//   main  z in 0..7 : M = the 100 (x,y) pairs -> 13 tiles of 8 (96 % filled), N = z (one tile), K = points (4 per instruction);
+//                     tiles 0..9 hold (x = i, y = 0..7), tiles 10..12 the pairs with y in {8, 9}: a thread's operand factors are
+//                     then psi2[g] (one load per 4 points) and psi1[0..9] (warp-broadcast loads), which keeps the shared-memory
+//                     pipe (128 B/clk per SM, shared by the 4 tensor pipes) off the critical path
+//   edge  z in 8..9 : M = x -> 2 tiles, N = the 20 (y, z) pairs -> 3 tiles, K = points   (spread; 6 instead of 13 instructions)
+//                     M = points, N = (y, z) -> 3 tiles, K = x -> 3 steps                (gather; 9 instead of 25 instructions)
 //
 // Streaming, work decomposition and the per-warp cp.async ring are those of nfft3d_warp.cu: one warp per contiguous range
 // of cell-sorted points, chunks of <= 8 points of one cell, 240 B of taps per point read from HBM exactly once.
@@ -85,59 +91,58 @@ __device__ __forceinline__ void m_stage_issue(double *st, const double *__restri
 }
 
 // ---------------------------------------------------------------------------------------------------- spread
-// C fragment of m-tile i, n-tile nt: rows m = 8 i + g <-> (x, y) = (m / 10, m % 10); columns z = 8 nt + 2 t + {0, 1}
-__device__ __forceinline__ void m_spread_flush(double *__restrict__ grid, int key, int g, int t, double acc[MT][2][2])
+// main accumulators: tile i < 10: rows y = g, x = i; tile 10 + i': rows (x = 4 i' + g / 2, y = 8 + (g & 1)); columns z = 2 t + {0, 1}
+// edge accumulators: tile (i, j): rows x = 8 i + g; columns 8 j + 2 t + {0, 1} <-> y = 4 j + t, z = 8 + {0, 1}
+__device__ __forceinline__ void m_spread_flush(double *__restrict__ grid, int key, int g, int t, double acc[MT][2], double ace[2][3][2])
 {
    const int c1 = (key >> 12) & 63, c2 = (key >> 6) & 63, c3 = key & 63;
+   const int z0 = m_tap_idx(c3, 2 * t), z1 = m_tap_idx(c3, 2 * t + 1);
 #pragma unroll
    for (int i = 0; i < MT; i++)
    {
-      const int m = 8 * i + g;
-      if (m < 100)
+      const int x = i < 10 ? i : 4 * (i - 10) + (g >> 1);
+      const int y = i < 10 ? g : 8 + (g & 1);
+      if (x < TAPS)
       {
-         const int x = m / 10, y = m - 10 * x;
          double *rowp = grid + (size_t)(m_tap_idx(c1, x) * NOS + m_tap_idx(c2, y)) * NOS;
-         atomicAdd(rowp + m_tap_idx(c3, 2 * t), acc[i][0][0]);
-         atomicAdd(rowp + m_tap_idx(c3, 2 * t + 1), acc[i][0][1]);
-         if (t == 0)
-         {
-            atomicAdd(rowp + m_tap_idx(c3, 8), acc[i][1][0]);
-            atomicAdd(rowp + m_tap_idx(c3, 9), acc[i][1][1]);
-         }
+         atomicAdd(rowp + z0, acc[i][0]);
+         atomicAdd(rowp + z1, acc[i][1]);
       }
-      acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+      acc[i][0] = acc[i][1] = 0.0;
    }
+#pragma unroll
+   for (int i = 0; i < 2; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+      {
+         const int x = 8 * i + g, y = 4 * j + t;
+         if (x < TAPS && y < TAPS)
+         {
+            double *rowp = grid + (size_t)(m_tap_idx(c1, x) * NOS + m_tap_idx(c2, y)) * NOS;
+            atomicAdd(rowp + m_tap_idx(c3, 8), ace[i][j][0]);
+            atomicAdd(rowp + m_tap_idx(c3, 9), ace[i][j][1]);
+         }
+         ace[i][j][0] = ace[i][j][1] = 0.0;
+      }
 }
 
-__global__ void __launch_bounds__(MWARPS_PER_CTA * 32, MCTAS_PER_SM)
-k_spread3_mma(const double *__restrict__ psi, const double *__restrict__ a, const int4 *__restrict__ chunks,
-              const int *__restrict__ cfirst, double *__restrict__ grid)
+// one warp streams the chunks [c0, c1) of one window
+__device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, const double *__restrict__ a, const int4 *__restrict__ chunks,
+                                               int c0, int c1, double *__restrict__ grid, double (*st)[STAGE_D], int lane)
 {
-   __shared__ __align__(16) double smem[MWARPS_PER_CTA][MWNS][STAGE_D];
-   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-   const int gw = blockIdx.x * MWARPS_PER_CTA + wid;
    const int g = lane >> 2, t = lane & 3;
-   double(*st)[STAGE_D] = smem[wid];
-   const int c0 = cfirst[gw], c1 = cfirst[gw + 1];
    if (c0 >= c1)
       return;
 
-   // shared-memory offsets of this thread's A-operand factors: psi1[x(m)] and psi2[y(m)], m = 8 i + g (clamped for padding rows)
-   int offx[MT], offy[MT];
+   double acc[MT][2], ace[2][3][2];
 #pragma unroll
    for (int i = 0; i < MT; i++)
-   {
-      int m = 8 * i + g;
-      m = m < 100 ? m : 99;
-      offx[i] = m / 10;
-      offy[i] = TAPS + (m - 10 * (m / 10));
-   }
-   const double pad12 = (8 * (MT - 1) + g) < 100 ? 1.0 : 0.0; // tile 12 holds the pairs 96..99 in rows g < 4 only
-
-   double acc[MT][2][2];
+      acc[i][0] = acc[i][1] = 0.0;
 #pragma unroll
-   for (int i = 0; i < MT; i++)
-      acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+   for (int i = 0; i < 2; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+         ace[i][j][0] = ace[i][j][1] = 0.0;
 
    int4 dcur = chunks[c0];
    int key = dcur.z;
@@ -161,7 +166,7 @@ k_spread3_mma(const double *__restrict__ psi, const double *__restrict__ a, cons
 
       if (dcur.z != key) // warp-uniform: the stream enters another cell -> write the footprint out
       {
-         m_spread_flush(grid, key, g, t, acc);
+         m_spread_flush(grid, key, g, t, acc, ace);
          key = dcur.z;
       }
 
@@ -171,54 +176,103 @@ k_spread3_mma(const double *__restrict__ psi, const double *__restrict__ a, cons
       {
          if (kk == 1 && dcur.y <= 4) // warp-uniform: the second k-step holds only zero-weight points
             break;
-         const double *row = stage + (4 * kk + t) * RS;   // B row k = t: the point of this thread
+         const double *row = stage + (4 * kk + t) * RS;   // operand column / row k = t: the point of this thread
          const double aj = stage[WS * RS + 4 * kk + t];    // zero past the end of the chunk
+         // main part: B(k, n = g) = a psi3[g];  A(m, k) = psi1[x] psi2[y] with (x, y) = (i, g) for the tiles i < 10 and
+         // (4 i' + g / 2, 8 + (g & 1)) for the tiles 10 + i'
          const double b0 = aj * row[2 * TAPS + g];
-         const double b1 = (g < 2) ? aj * row[2 * TAPS + 8 + g] : 0.0;
+         const double p2 = row[TAPS + g];
+         const double p2e = row[TAPS + 8 + (g & 1)];
 #pragma unroll
-         for (int i = 0; i < MT; i++)
+         for (int i = 0; i < 10; i += 2)
          {
-            double af = row[offx[i]] * row[offy[i]];
-            if (i == MT - 1)
-               af *= pad12;
-            m_dmma(acc[i][0][0], acc[i][0][1], af, b0);
-            m_dmma(acc[i][1][0], acc[i][1][1], af, b1);
+            const double2 p1 = *reinterpret_cast<const double2 *>(row + i);
+            m_dmma(acc[i][0], acc[i][1], p1.x * p2, b0);
+            m_dmma(acc[i + 1][0], acc[i + 1][1], p1.y * p2, b0);
+         }
+#pragma unroll
+         for (int i = 0; i < 3; i++)
+         {
+            const int x = 4 * i + (g >> 1);
+            const double af = (i < 2 || g < 4) ? row[x < TAPS ? x : TAPS - 1] * p2e : 0.0;
+            m_dmma(acc[10 + i][0], acc[10 + i][1], af, b0);
+         }
+         // edge part: A(x, k) = a psi1[x], B(k, n = g of tile j) = psi2[4 j + g / 2] psi3[8 + (g & 1)]
+         const double p3 = row[2 * TAPS + 8 + (g & 1)];
+         const double ae0 = aj * row[g];
+         const double ae1 = (g < 2) ? aj * row[8 + g] : 0.0;
+#pragma unroll
+         for (int j = 0; j < 3; j++)
+         {
+            const int y = 4 * j + (g >> 1);
+            const double be = (j < 2 || g < 4) ? row[TAPS + (y < TAPS ? y : TAPS - 1)] * p3 : 0.0;
+            m_dmma(ace[0][j][0], ace[0][j][1], ae0, be);
+            m_dmma(ace[1][j][0], ace[1][j][1], ae1, be);
          }
       }
       dcur = dnext;
       dissue = dissue_next;
    }
-   m_spread_flush(grid, key, g, t, acc);
+   m_spread_flush(grid, key, g, t, acc, ace);
+}
+
+__global__ void __launch_bounds__(MWARPS_PER_CTA * 32, MCTAS_PER_SM)
+k_spread3_mma(const double *__restrict__ psi, const double *__restrict__ a, const int4 *__restrict__ chunks,
+              const int *__restrict__ cfirst, double *__restrict__ grid)
+{
+   __shared__ __align__(16) double smem[MWARPS_PER_CTA][MWNS][STAGE_D];
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   const int gw = blockIdx.x * MWARPS_PER_CTA + wid;
+   m_spread_range(psi, a, chunks, cfirst[gw], cfirst[gw + 1], grid, smem[wid], lane);
+}
+
+// all windows of an additive kernel in ONE persistent wave: warp gw belongs to the window w with
+// wbeg[w] <= gw < wbeg[w + 1] and streams range gw - wbeg[w] of that window's own partition
+__global__ void __launch_bounds__(MWARPS_PER_CTA * 32, MCTAS_PER_SM)
+k_spread3_mma_batch(const b200_mma_win *__restrict__ W, int P)
+{
+   __shared__ __align__(16) double smem[MWARPS_PER_CTA][MWNS][STAGE_D];
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   const int gw = blockIdx.x * MWARPS_PER_CTA + wid;
+   int w = 0;
+   while (w + 1 < P && gw >= W[w + 1].warp_begin)
+      w++;
+   const int r = gw - W[w].warp_begin;
+   if (r >= W[w].nwarps)
+      return;
+   m_spread_range(W[w].psi, W[w].a, (const int4 *)W[w].chunks, W[w].cfirst[r], W[w].cfirst[r + 1], W[w].grid, smem[wid], lane);
 }
 
 // ---------------------------------------------------------------------------------------------------- gather
-// B operand (constant per cell): k-step s, row k = t <-> pair m = 4 s + t; column n = g <-> z = g (n-tile 0), 8 + g (n-tile 1, g < 2)
-__device__ __forceinline__ void m_gather_load(const double *__restrict__ h, int key, int g, int t, double hb[KS][2])
+// B operands (constant per cell).  main k-steps: s < 20: row k = t <-> (x = s / 2, y = 4 (s & 1) + t); s = 20 + s':
+// (x = 2 s' + t / 2, y = 8 + (t & 1)); column n = g <-> z = g.
+// edge: k-step s (3), row k = t <-> x = 4 s + t; tile j (3), column n = g <-> y = 4 j + g / 2, z = 8 + (g & 1).
+__device__ __forceinline__ void m_gather_load(const double *__restrict__ h, int key, int g, int t, double hb[KS], double he[3][3])
 {
    const int c1 = (key >> 12) & 63, c2 = (key >> 6) & 63, c3 = key & 63;
    const int z0 = m_tap_idx(c3, g), z1 = m_tap_idx(c3, 8 + (g & 1));
 #pragma unroll
    for (int s = 0; s < KS; s++)
    {
-      const int m = 4 * s + t;
-      const int x = m / 10, y = m - 10 * x;
-      const double *rowp = h + (size_t)(m_tap_idx(c1, x) * NOS + m_tap_idx(c2, y)) * NOS;
-      hb[s][0] = __ldg(rowp + z0);
-      hb[s][1] = (g < 2) ? __ldg(rowp + z1) : 0.0;
+      const int x = s < 20 ? (s >> 1) : 2 * (s - 20) + (t >> 1);
+      const int y = s < 20 ? 4 * (s & 1) + t : 8 + (t & 1);
+      hb[s] = __ldg(h + (size_t)(m_tap_idx(c1, x) * NOS + m_tap_idx(c2, y)) * NOS + z0);
    }
+#pragma unroll
+   for (int s = 0; s < 3; s++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+      {
+         const int x = 4 * s + t, y = 4 * j + (g >> 1);
+         he[s][j] = (x < TAPS && y < TAPS) ? __ldg(h + (size_t)(m_tap_idx(c1, x) * NOS + m_tap_idx(c2, y)) * NOS + z1) : 0.0;
+      }
 }
 
-__global__ void __launch_bounds__(MWARPS_PER_CTA * 32, MCTAS_PER_SM)
-k_gather3_mma(const double *__restrict__ psi, const int4 *__restrict__ chunks, const int *__restrict__ cfirst,
-              const double *__restrict__ h, double *__restrict__ f)
+__device__ __forceinline__ void m_gather_range(const double *__restrict__ psi, const int4 *__restrict__ chunks, int c0, int c1,
+                                               const double *__restrict__ h, double *__restrict__ f, double (*st)[STAGE_D], int lane)
 {
-   __shared__ __align__(16) double smem[MWARPS_PER_CTA][MWNS][STAGE_D];
-   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-   const int gw = blockIdx.x * MWARPS_PER_CTA + wid;
    const int g = lane >> 2, t = lane & 3;
-   double(*st)[STAGE_D] = smem[wid];
    const unsigned full = 0xffffffffu;
-   const int c0 = cfirst[gw], c1 = cfirst[gw + 1];
    if (c0 >= c1)
       return;
 
@@ -233,8 +287,8 @@ k_gather3_mma(const double *__restrict__ psi, const int4 *__restrict__ chunks, c
    }
    int4 dissue = chunks[c0 + MWNS - 1];
 
-   double hb[KS][2];
-   m_gather_load(h, key, g, t, hb);
+   double hb[KS], he[3][3];
+   m_gather_load(h, key, g, t, hb, he);
 
    for (int c = c0; c < c1; c++)
    {
@@ -249,36 +303,59 @@ k_gather3_mma(const double *__restrict__ psi, const int4 *__restrict__ chunks, c
       if (dcur.z != key) // warp-uniform
       {
          key = dcur.z;
-         m_gather_load(h, key, g, t, hb);
+         m_gather_load(h, key, g, t, hb, he);
       }
 
       // A operand: row = point g of the chunk, column k = t <-> pair m = 4 s + t
       const double *row = st[(c - c0) % MWNS] + g * RS;
-      double ca[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, cb[2][2] = {{0.0, 0.0}, {0.0, 0.0}}; // two chains per n-tile (even / odd s)
+      // main part, four dependency chains.  A(point g, k = t) = psi1[x] psi2[y] with the pair of k-step s (see m_gather_load)
+      double ca[2] = {0.0, 0.0}, cb[2] = {0.0, 0.0}, cc[2] = {0.0, 0.0}, cd[2] = {0.0, 0.0};
+      {
+         const double q0 = row[TAPS + t], q1 = row[TAPS + 4 + t], q2 = row[TAPS + 8 + (t & 1)];
 #pragma unroll
-      for (int s = 0; s < KS; s++)
-      {
-         const int m = 4 * s + t;
-         const int x = m / 10, y = m - 10 * x;
-         const double af = row[x] * row[TAPS + y];
-         if (s & 1)
+         for (int x = 0; x < 10; x += 2)
          {
-            m_dmma(cb[0][0], cb[0][1], af, hb[s][0]);
-            m_dmma(cb[1][0], cb[1][1], af, hb[s][1]);
+            const double2 p1 = *reinterpret_cast<const double2 *>(row + x);
+            m_dmma(ca[0], ca[1], p1.x * q0, hb[2 * x]);
+            m_dmma(cb[0], cb[1], p1.x * q1, hb[2 * x + 1]);
+            m_dmma(cc[0], cc[1], p1.y * q0, hb[2 * x + 2]);
+            m_dmma(cd[0], cd[1], p1.y * q1, hb[2 * x + 3]);
          }
-         else
+#pragma unroll
+         for (int s = 0; s < 5; s++)
          {
-            m_dmma(ca[0][0], ca[0][1], af, hb[s][0]);
-            m_dmma(ca[1][0], ca[1][1], af, hb[s][1]);
+            const double af = row[2 * s + (t >> 1)] * q2;
+            if (s & 1)
+               m_dmma(cb[0], cb[1], af, hb[20 + s]);
+            else
+               m_dmma(ca[0], ca[1], af, hb[20 + s]);
          }
+         ca[0] += cb[0] + (cc[0] + cd[0]);
+         ca[1] += cb[1] + (cc[1] + cd[1]);
       }
-      // C: row = point g; columns z = 2 t, 2 t + 1 (n-tile 0) and 8 + 2 t, 9 + 2 t (n-tile 1: only t = 0 is inside the footprint)
-      double v = (ca[0][0] + cb[0][0]) * row[2 * TAPS + 2 * t];
-      v = fma(ca[0][1] + cb[0][1], row[2 * TAPS + 2 * t + 1], v);
-      if (t == 0)
+      // edge part: T'(point, (y, z)) = sum_x psi1[x] H[x, y, z], z in {8, 9}
+      double ce[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+      for (int s = 0; s < 3; s++)
       {
-         v = fma(ca[1][0] + cb[1][0], row[2 * TAPS + 8], v);
-         v = fma(ca[1][1] + cb[1][1], row[2 * TAPS + 9], v);
+         const int x = 4 * s + t;
+         const double ax = (x < TAPS) ? row[x] : 0.0;
+#pragma unroll
+         for (int j = 0; j < 3; j++)
+            m_dmma(ce[j][0], ce[j][1], ax, he[s][j]);
+      }
+      // main C: row = point g; columns z = 2 t, 2 t + 1.  edge C: columns 8 j + 2 t + {0, 1} <-> y = 4 j + t, z = 8 + {0, 1}
+      double v = ca[0] * row[2 * TAPS + 2 * t];
+      v = fma(ca[1], row[2 * TAPS + 2 * t + 1], v);
+      {
+         const double p8 = row[2 * TAPS + 8], p9 = row[2 * TAPS + 9];
+#pragma unroll
+         for (int j = 0; j < 3; j++)
+         {
+            const int y = 4 * j + t;
+            if (y < TAPS)
+               v = fma(row[TAPS + y], fma(ce[j][1], p9, ce[j][0] * p8), v);
+         }
       }
       v += __shfl_xor_sync(full, v, 1);
       v += __shfl_xor_sync(full, v, 2);
@@ -288,6 +365,31 @@ k_gather3_mma(const double *__restrict__ psi, const int4 *__restrict__ chunks, c
       dissue = dissue_next;
    }
    m_wait<0>();
+}
+
+__global__ void __launch_bounds__(MWARPS_PER_CTA * 32, MCTAS_PER_SM)
+k_gather3_mma(const double *__restrict__ psi, const int4 *__restrict__ chunks, const int *__restrict__ cfirst,
+              const double *__restrict__ h, double *__restrict__ f)
+{
+   __shared__ __align__(16) double smem[MWARPS_PER_CTA][MWNS][STAGE_D];
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   const int gw = blockIdx.x * MWARPS_PER_CTA + wid;
+   m_gather_range(psi, chunks, cfirst[gw], cfirst[gw + 1], h, f, smem[wid], lane);
+}
+
+__global__ void __launch_bounds__(MWARPS_PER_CTA * 32, MCTAS_PER_SM)
+k_gather3_mma_batch(const b200_mma_win *__restrict__ W, int P)
+{
+   __shared__ __align__(16) double smem[MWARPS_PER_CTA][MWNS][STAGE_D];
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   const int gw = blockIdx.x * MWARPS_PER_CTA + wid;
+   int w = 0;
+   while (w + 1 < P && gw >= W[w + 1].warp_begin)
+      w++;
+   const int r = gw - W[w].warp_begin;
+   if (r >= W[w].nwarps)
+      return;
+   m_gather_range(W[w].psi, (const int4 *)W[w].chunks, W[w].cfirst[r], W[w].cfirst[r + 1], W[w].grid, W[w].f, smem[wid], lane);
 }
 
 // ---------------------------------------------------------------------------------------------------- launch layer
@@ -310,6 +412,21 @@ int b200k_gather3_mma(const b200_win_dev *w, double *d_f)
    if (w->nchunk <= 0)
       return 0;
    k_gather3_mma<<<w->nwr / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, 0, b200_stream()>>>(w->psi, (const int4 *)w->chunks, w->cfirst, w->grid, d_f);
+   B200_LAUNCHED();
+   return 0;
+}
+
+// fused launches over the P windows described by d_batch (device array); total_warps = sum of nwarps, a multiple of the CTA size
+int b200k_spread3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps)
+{
+   k_spread3_mma_batch<<<total_warps / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, 0, b200_stream()>>>(d_batch, P);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_gather3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps)
+{
+   k_gather3_mma_batch<<<total_warps / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, 0, b200_stream()>>>(d_batch, P);
    B200_LAUNCHED();
    return 0;
 }

@@ -290,6 +290,7 @@ static void window_free(b200_window *w)
       return;
    window_free_device(w);
    free(w->h_perm);
+   free(w->h_chunks);
    free(w);
 }
 
@@ -489,7 +490,9 @@ static int window_setup_points(b200_window *w, const double *cols, int n_all, in
          b200_h2d(v->chunks, hc, sizeof(int) * 4 * ((size_t)nch + 4));
          b200_h2d(v->cfirst, hw, sizeof(int) * ((size_t)nwr + 1));
          b200_sync();
-         free(hc);
+         free(w->h_chunks);
+         w->h_chunks = hc; /* kept: fused launches cut the same chunk list into a different number of ranges */
+         w->h_nchunk = nch;
          free(hw);
       }
       if (b200k_psi(v, d_xs) || b200_sync())
@@ -967,13 +970,225 @@ b200_additive *b200_additive_from_handle(void *data)
 /* number of vector entries this rank owns: n, or its point block under point-block sharding (mode 2) */
 static int additive_local_n(const b200_additive *A) { return A->blk_hi - A->blk_lo; }
 
+
+/* ------------------------------------------------------------------ fused launches over the windows of an additive kernel
+ * The streaming 3-D kernels run as ONE persistent wave.  Launching them once per window costs a fixed 20-30 us each time
+ * (ramp-up, the final footprint flush / first footprint load of every warp, the tail of the wave); with all windows in one
+ * launch that is paid once: the wave's warps are divided among the windows in proportion to their cost and every window's
+ * chunk list is re-cut into that many ranges of equal cost. */
+static double chunk_cost(const int *hc, int c, int prev_key)
+{
+   /* point-equivalents of the tensor pipe: 1 per point, 1 per chunk, 24 per footprint flush / reload */
+   return (double)hc[4 * c + 1] + 1.0 + (hc[4 * c + 2] != prev_key ? 24.0 : 0.0);
+}
+
+static void additive_fused_release(b200_additive *A)
+{
+   int i;
+   b200_free(A->d_fused[0]);
+   b200_free(A->d_fused[1]);
+   A->d_fused[0] = A->d_fused[1] = NULL;
+   if (A->d_fused_cfirst)
+      for (i = 0; i < A->nbatch; i++)
+         b200_free(A->d_fused_cfirst[i]);
+   free(A->d_fused_cfirst);
+   A->d_fused_cfirst = NULL;
+   b200_free((void *)A->d_prep_perm);
+   b200_free(A->d_prep_a);
+   b200_free(A->d_prep_n);
+   A->d_prep_perm = NULL;
+   A->d_prep_a = NULL;
+   A->d_prep_n = NULL;
+   A->fused_ready = 0;
+}
+
+static int additive_fused_upload(b200_additive *A, int channel, const int *wbeg, const int *wcnt)
+{
+   int nb = A->nbatch, i, rc;
+   b200_mma_win *hw = (b200_mma_win *)b200_xcalloc((size_t)nb, sizeof(b200_mma_win));
+   for (i = 0; i < nb; i++)
+   {
+      b200_win_dev *v = &A->win[i]->dev;
+      hw[i].psi = v->psi;
+      hw[i].a = v->a;
+      hw[i].chunks = v->chunks;
+      hw[i].cfirst = A->d_fused_cfirst[i];
+      hw[i].grid = v->grid;
+      hw[i].f = channel ? v->f2 : v->f;
+      hw[i].warp_begin = wbeg[i];
+      hw[i].nwarps = wcnt[i];
+   }
+   if (!A->d_fused[channel])
+      A->d_fused[channel] = b200_malloc(sizeof(b200_mma_win) * (size_t)nb);
+   rc = !A->d_fused[channel] || b200_h2d(A->d_fused[channel], hw, sizeof(b200_mma_win) * (size_t)nb) || b200_sync();
+   free(hw);
+   return rc ? -1 : 0;
+}
+
+/* returns 1 when the fused path is available */
+static int additive_fused_prepare(b200_additive *A)
+{
+   int nb = A->nbatch, i, c, total_warps = b200k_warp_ranges();
+   int *wbeg, *wcnt, *hn;
+   const int **hperm;
+   double **ha, *cost, total = 0.0;
+   if (g_variant_spread3 >= 0 || g_variant_gather3 >= 0)
+      return 0; /* an explicit kernel variant was requested (A/B runs): per-window launches */
+   if (A->fused_ready)
+      return A->fused_ready > 0;
+   A->fused_ready = -1;
+   if (nb < 2 || A->win[0]->d != 3 || (A->shard_mode == 1 && b200_comm_size() > 1))
+      return 0;
+   for (i = 0; i < nb; i++)
+   {
+      b200_win_dev *v = &A->win[i]->dev;
+      if (!A->win[i]->h_chunks || v->nchunk <= 0 || v->nseg <= 0 || v->n / v->nseg < B200_MMA_MIN_POINTS_PER_CELL)
+         return 0; /* a sparse or empty window: per-window launches (DFMA kernels with register-tile shifting) */
+   }
+   cost = (double *)b200_xcalloc((size_t)nb, sizeof(double));
+   wbeg = (int *)b200_xcalloc((size_t)nb + 1, sizeof(int));
+   wcnt = (int *)b200_xcalloc((size_t)nb, sizeof(int));
+   for (i = 0; i < nb; i++)
+   {
+      const int *hc = A->win[i]->h_chunks;
+      int prev = -1;
+      for (c = 0; c < A->win[i]->h_nchunk; c++)
+      {
+         cost[i] += chunk_cost(hc, c, prev);
+         prev = hc[4 * c + 2];
+      }
+      total += cost[i];
+   }
+   /* warps per window in proportion to cost (at least one), summing to the size of the wave */
+   {
+      int assigned = 0, big = 0;
+      for (i = 0; i < nb; i++)
+      {
+         wcnt[i] = (int)(total_warps * cost[i] / total);
+         if (wcnt[i] < 1)
+            wcnt[i] = 1;
+         assigned += wcnt[i];
+         if (cost[i] > cost[big])
+            big = i;
+      }
+      wcnt[big] += total_warps - assigned;
+      if (wcnt[big] < 1)
+      {
+         free(cost);
+         free(wbeg);
+         free(wcnt);
+         return 0;
+      }
+      for (i = 0; i < nb; i++)
+         wbeg[i + 1] = wbeg[i] + wcnt[i];
+   }
+   A->d_fused_cfirst = (int **)b200_xcalloc((size_t)nb, sizeof(int *));
+   for (i = 0; i < nb; i++)
+   {
+      const int *hc = A->win[i]->h_chunks;
+      int nch = A->win[i]->h_nchunk, r = 0, prev = -1, *hw = (int *)b200_xcalloc((size_t)wcnt[i] + 1, sizeof(int));
+      double acc = 0.0, target = cost[i] / (double)wcnt[i];
+      for (c = 0; c < nch; c++)
+      {
+         while (r + 1 < wcnt[i] && acc >= target * (double)(r + 1))
+            hw[++r] = c;
+         acc += chunk_cost(hc, c, prev);
+         prev = hc[4 * c + 2];
+      }
+      while (r + 1 < wcnt[i])
+         hw[++r] = nch;
+      hw[wcnt[i]] = nch;
+      A->d_fused_cfirst[i] = (int *)b200_malloc(sizeof(int) * ((size_t)wcnt[i] + 1));
+      if (!A->d_fused_cfirst[i] || b200_h2d(A->d_fused_cfirst[i], hw, sizeof(int) * ((size_t)wcnt[i] + 1)) || b200_sync())
+      {
+         free(hw);
+         free(cost);
+         free(wbeg);
+         free(wcnt);
+         additive_fused_release(A);
+         A->fused_ready = -1;
+         return 0;
+      }
+      free(hw);
+   }
+   A->fused_warps = total_warps;
+   /* per-window pointers of the batched prep kernel */
+   hperm = (const int **)b200_xcalloc((size_t)nb, sizeof(int *));
+   ha = (double **)b200_xcalloc((size_t)nb, sizeof(double *));
+   hn = (int *)b200_xcalloc((size_t)nb, sizeof(int));
+   A->prep_nmax = 0;
+   for (i = 0; i < nb; i++)
+   {
+      hperm[i] = A->win[i]->dev.perm;
+      ha[i] = A->win[i]->dev.a;
+      hn[i] = A->win[i]->dev.n;
+      if (hn[i] > A->prep_nmax)
+         A->prep_nmax = hn[i];
+   }
+   A->d_prep_perm = (const int **)b200_malloc(sizeof(int *) * (size_t)nb);
+   A->d_prep_a = (double **)b200_malloc(sizeof(double *) * (size_t)nb);
+   A->d_prep_n = (int *)b200_malloc(sizeof(int) * (size_t)nb);
+   c = b200_h2d((void *)A->d_prep_perm, hperm, sizeof(int *) * (size_t)nb) || b200_h2d(A->d_prep_a, ha, sizeof(double *) * (size_t)nb) ||
+       b200_h2d(A->d_prep_n, hn, sizeof(int) * (size_t)nb) || additive_fused_upload(A, 0, wbeg, wcnt);
+   free(hperm);
+   free(ha);
+   free(hn);
+   free(cost);
+   if (c)
+   {
+      free(wbeg);
+      free(wcnt);
+      additive_fused_release(A);
+      A->fused_ready = -1;
+      return 0;
+   }
+   free(wbeg);
+   free(wcnt);
+   A->fused_ready = 1;
+   return 1;
+}
+
+/* derivative channel: same descriptors with f2 as the output */
+static int additive_fused_channel1(b200_additive *A)
+{
+   int nb = A->nbatch, i, rc;
+   b200_mma_win *hw;
+   if (A->d_fused[1])
+      return 0;
+   hw = (b200_mma_win *)b200_xcalloc((size_t)nb, sizeof(b200_mma_win));
+   if (b200_d2h(hw, A->d_fused[0], sizeof(b200_mma_win) * (size_t)nb))
+   {
+      free(hw);
+      return -1;
+   }
+   for (i = 0; i < nb; i++)
+      hw[i].f = A->win[i]->dev.f2;
+   A->d_fused[1] = b200_malloc(sizeof(b200_mma_win) * (size_t)nb);
+   rc = !A->d_fused[1] || b200_h2d(A->d_fused[1], hw, sizeof(b200_mma_win) * (size_t)nb) || b200_sync();
+   free(hw);
+   return rc ? -1 : 0;
+}
+
 /* spread of all windows, then (mode 2) the ONE collective of the matvec, then FFT / scale / inverse FFT / gather */
 static int additive_apply_windows(b200_additive *A, const double *d_x, double s, int with_derivative)
 {
-   int i;
-   for (i = 0; i < A->P; i++)
-      if (b200_comm_owns_window(A, i) && window_spread(A->win[i], d_x, s))
+   int i, fused = additive_fused_prepare(A);
+   if (fused)
+   {
+      /* batched prep, one memset of the contiguous grids, one persistent wave for the spread of all batch windows */
+      size_t gsz = ipow(B200_NOS, 3) * (size_t)A->nbatch;
+      if (b200k_prep_batch(A->nbatch, A->d_prep_perm, A->d_prep_a, A->d_prep_n, A->prep_nmax, d_x, s) ||
+          b200k_spread_batch_begin(A->d_grids, gsz) || b200k_spread3_mma_batch((const b200_mma_win *)A->d_fused[0], A->nbatch, A->fused_warps) ||
+          b200k_spread_batch_end())
          return -1;
+      for (i = A->nbatch; i < A->P; i++)
+         if (window_spread(A->win[i], d_x, s))
+            return -1;
+   }
+   else
+      for (i = 0; i < A->P; i++)
+         if (b200_comm_owns_window(A, i) && window_spread(A->win[i], d_x, s))
+            return -1;
    if (A->shard_mode == 2 && b200_comm_size() > 1 && b200_comm_allreduce_sum(A->d_grids, A->grids_doubles))
       return -1;
    if (!(A->shard_mode == 1 && b200_comm_size() > 1) && A->nbatch > 1)
@@ -982,9 +1197,16 @@ static int additive_apply_windows(b200_additive *A, const double *d_x, double s,
       b200_win_dev *v0 = &A->win[0]->dev;
       if (b200k_forward_fft_batch(v0, A->nbatch) || b200k_backward_fft_batch(v0, A->nbatch, 0))
          return -1;
-      for (i = 0; i < A->nbatch; i++)
-         if (b200k_gather(&A->win[i]->dev, A->win[i]->dev.f, g_variant_gather3))
+      if (fused)
+      {
+         if (b200k_gather_batch_begin() || b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[0], A->nbatch, A->fused_warps) ||
+             b200k_gather_batch_end())
             return -1;
+      }
+      else
+         for (i = 0; i < A->nbatch; i++)
+            if (b200k_gather(&A->win[i]->dev, A->win[i]->dev.f, g_variant_gather3))
+               return -1;
       if (with_derivative)
       {
          for (i = 0; i < A->nbatch; i++)
@@ -992,9 +1214,16 @@ static int additive_apply_windows(b200_additive *A, const double *d_x, double s,
                A->win[i]->dev.f2 = (double *)b200_malloc(sizeof(double) * (size_t)(A->win[i]->dev.n ? A->win[i]->dev.n : 1));
          if (b200k_backward_fft_batch(v0, A->nbatch, 1))
             return -1;
-         for (i = 0; i < A->nbatch; i++)
-            if (b200k_gather(&A->win[i]->dev, A->win[i]->dev.f2, g_variant_gather3))
+         if (fused)
+         {
+            if (additive_fused_channel1(A) || b200k_gather_batch_begin() ||
+                b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[1], A->nbatch, A->fused_warps) || b200k_gather_batch_end())
                return -1;
+         }
+         else
+            for (i = 0; i < A->nbatch; i++)
+               if (b200k_gather(&A->win[i]->dev, A->win[i]->dev.f2, g_variant_gather3))
+                  return -1;
       }
       for (i = A->nbatch; i < A->P; i++)
          if (window_finish(A->win[i], with_derivative))
@@ -1152,6 +1381,7 @@ void Nfft4GPAdditiveNFFTKernelFree(void *str)
       b200_free(A->d_dcoef);
       b200_free((void *)A->d_fptr_local);
       b200_free((void *)A->d_invptr_local);
+      additive_fused_release(A);
       free(A);
    }
    if (k->_own_buffer)
