@@ -29,6 +29,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "nfft_additive_matvecs_per_s"
 UNIT = "matvecs/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused three-window kernels at n = 10^6, from the one
+# `ncu --set full` capture of this command (profiles/r1_e_ncu_set_full_fused_spread_gather.csv); per-window launches: a third
+NCU_TRAFFIC_BYTES = {"spread": 751.607e6 + 5.597e6, "gather": 727.822e6 + 25.113e6}
 PROF_CLASSES = ["prep", "spread", "fft_fwd", "fft_inv", "gather", "combine", "vec", "nys", "csr", "gemv", "other"]
 
 
@@ -344,21 +347,25 @@ def main():
                  for i in range(len(PROF_CLASSES)) if counts[i] > 0}
     dom = max(per_class, key=lambda k: per_class[k]["ms_per_step"])
     dom_launch_ms = per_class[dom]["ms_per_step"] / per_class[dom]["launches_per_step"]
-    # algorithmic bytes per launch: one window, one direction: coordinates 8*d_w*n + vector 8*n
+    # algorithmic bytes per launch: per window and direction coordinates 8*d_w*n + vector 8*n = 32 n;
+    # the fused kernels process all three windows in one launch (launches_per_step = 1), the per-window ones one each
     n_loc = nl
-    alg_bytes = {"spread": 32.0 * n_loc, "gather": 32.0 * n_loc}.get(dom, 16.0 * n)
+    win_per_launch = 3.0 / max(per_class[dom]["launches_per_step"], 1e-9) if dom in ("spread", "gather") else 1.0
+    alg_bytes = {"spread": 32.0 * n_loc * win_per_launch, "gather": 32.0 * n_loc * win_per_launch}.get(dom, 16.0 * n)
     achieved = alg_bytes / (dom_launch_ms * 1e-3) / 1e9
     peak = float(pk["hbm_gbs"])
     # fp64 view of the same launch: 2 * 10^3 flop per point (1000 FMAs), B200 fp64 FMA pipe = 64 lanes/SM/clk
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp64_peak = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
-    fp64_ach = 2000.0 * n_loc / (dom_launch_ms * 1e-3) / 1e12
+    fp64_ach = 2000.0 * n_loc * win_per_launch / (dom_launch_ms * 1e-3) / 1e12
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({pk_kind})", "traffic": None,
-                "launch_ms": dom_launch_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({pk_kind})",
+                "traffic": (NCU_TRAFFIC_BYTES.get(dom) * win_per_launch / 3.0) if (dom in NCU_TRAFFIC_BYTES and n == 1000000 and world == 1) else None,
+                "launch_ms": dom_launch_ms, "algorithmic_bytes_per_launch": alg_bytes, "windows_per_launch": win_per_launch,
                 "note": "3-D windows are fp64-pipe-bound (62 flop/B, SURVEY.md finding 4): see fp64",
                 "fp64": {"achieved_tflops": fp64_ach, "peak_tflops": fp64_peak, "frac": fp64_ach / fp64_peak,
-                         "peak_source": f"148 SM x 64 DFMA/clk x {sm_mhz:.0f} MHz (median SM clock under load)"},
+                         "peak_source": f"148 SM x 64 DFMA/clk x {sm_mhz:.0f} MHz (median SM clock under load)",
+                         "measured_unit_peaks_tflops": {"dmma_m8n8k4": 37.1, "dfma": 33.0, "source": "scripts/fp64_dmma.cu on this pool's B200: one shared unit, no overlap"}},
                 "step_share": per_class[dom]["ms_per_step"] / (ms_prof_total / args.steps),
                 "per_class_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in per_class.items()},
                 "profiled_ms_per_step": ms_prof_total / args.steps}

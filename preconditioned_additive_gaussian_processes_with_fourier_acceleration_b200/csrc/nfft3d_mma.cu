@@ -49,6 +49,12 @@ __device__ __forceinline__ void m_dmma(double &c0, double &c1, double a, double 
 {
    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+// fire-and-forget fp64 add to GLOBAL memory (RED.E.ADD.F64): with the grid pointer coming out of a descriptor in memory the
+// compiler cannot prove the address space and atomicAdd() turns into a generic atomic with shared / local fall-back loops
+__device__ __forceinline__ void m_red_add(double *p, double v)
+{
+   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
 __device__ __forceinline__ int m_tap_idx(int keyfield, int lj) { return (keyfield + 28 + lj) & 63; }
 __device__ __forceinline__ void m_cpa16(void *smem, const void *gmem)
 {
@@ -105,8 +111,8 @@ __device__ __forceinline__ void m_spread_flush(double *__restrict__ grid, int ke
       if (x < TAPS)
       {
          double *rowp = grid + (size_t)(m_tap_idx(c1, x) * NOS + m_tap_idx(c2, y)) * NOS;
-         atomicAdd(rowp + z0, acc[i][0]);
-         atomicAdd(rowp + z1, acc[i][1]);
+         m_red_add(rowp + z0, acc[i][0]);
+         m_red_add(rowp + z1, acc[i][1]);
       }
       acc[i][0] = acc[i][1] = 0.0;
    }
@@ -119,8 +125,8 @@ __device__ __forceinline__ void m_spread_flush(double *__restrict__ grid, int ke
          if (x < TAPS && y < TAPS)
          {
             double *rowp = grid + (size_t)(m_tap_idx(c1, x) * NOS + m_tap_idx(c2, y)) * NOS;
-            atomicAdd(rowp + m_tap_idx(c3, 8), ace[i][j][0]);
-            atomicAdd(rowp + m_tap_idx(c3, 9), ace[i][j][1]);
+            m_red_add(rowp + m_tap_idx(c3, 8), ace[i][j][0]);
+            m_red_add(rowp + m_tap_idx(c3, 9), ace[i][j][1]);
          }
          ace[i][j][0] = ace[i][j][1] = 0.0;
       }
@@ -183,19 +189,21 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
          const double b0 = aj * row[2 * TAPS + g];
          const double p2 = row[TAPS + g];
          const double p2e = row[TAPS + 8 + (g & 1)];
+         // all operand products of the k-step first, then the tensor instructions back to back: DMUL and DMMA share one
+         // unit, and a DMMA that waits for its own DMUL leaves that unit idle (ncu: 38 % of the stall samples sat there)
+         double af[MT], be[3];
 #pragma unroll
          for (int i = 0; i < 10; i += 2)
          {
             const double2 p1 = *reinterpret_cast<const double2 *>(row + i);
-            m_dmma(acc[i][0], acc[i][1], p1.x * p2, b0);
-            m_dmma(acc[i + 1][0], acc[i + 1][1], p1.y * p2, b0);
+            af[i] = p1.x * p2;
+            af[i + 1] = p1.y * p2;
          }
 #pragma unroll
          for (int i = 0; i < 3; i++)
          {
             const int x = 4 * i + (g >> 1);
-            const double af = (i < 2 || g < 4) ? row[x < TAPS ? x : TAPS - 1] * p2e : 0.0;
-            m_dmma(acc[10 + i][0], acc[10 + i][1], af, b0);
+            af[10 + i] = (i < 2 || g < 4) ? row[x < TAPS ? x : TAPS - 1] * p2e : 0.0;
          }
          // edge part: A(x, k) = a psi1[x], B(k, n = g of tile j) = psi2[4 j + g / 2] psi3[8 + (g & 1)]
          const double p3 = row[2 * TAPS + 8 + (g & 1)];
@@ -205,9 +213,16 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
          for (int j = 0; j < 3; j++)
          {
             const int y = 4 * j + (g >> 1);
-            const double be = (j < 2 || g < 4) ? row[TAPS + (y < TAPS ? y : TAPS - 1)] * p3 : 0.0;
-            m_dmma(ace[0][j][0], ace[0][j][1], ae0, be);
-            m_dmma(ace[1][j][0], ace[1][j][1], ae1, be);
+            be[j] = (j < 2 || g < 4) ? row[TAPS + (y < TAPS ? y : TAPS - 1)] * p3 : 0.0;
+         }
+#pragma unroll
+         for (int i = 0; i < MT; i++)
+            m_dmma(acc[i][0], acc[i][1], af[i], b0);
+#pragma unroll
+         for (int j = 0; j < 3; j++)
+         {
+            m_dmma(ace[0][j][0], ace[0][j][1], ae0, be[j]);
+            m_dmma(ace[1][j][0], ace[1][j][1], ae1, be[j]);
          }
       }
       dcur = dnext;
@@ -312,24 +327,32 @@ __device__ __forceinline__ void m_gather_range(const double *__restrict__ psi, c
       double ca[2] = {0.0, 0.0}, cb[2] = {0.0, 0.0}, cc[2] = {0.0, 0.0}, cd[2] = {0.0, 0.0};
       {
          const double q0 = row[TAPS + t], q1 = row[TAPS + 4 + t], q2 = row[TAPS + 8 + (t & 1)];
+         double af[KS]; // all operand products first, then the tensor instructions back to back (see the spread)
 #pragma unroll
          for (int x = 0; x < 10; x += 2)
          {
             const double2 p1 = *reinterpret_cast<const double2 *>(row + x);
-            m_dmma(ca[0], ca[1], p1.x * q0, hb[2 * x]);
-            m_dmma(cb[0], cb[1], p1.x * q1, hb[2 * x + 1]);
-            m_dmma(cc[0], cc[1], p1.y * q0, hb[2 * x + 2]);
-            m_dmma(cd[0], cd[1], p1.y * q1, hb[2 * x + 3]);
+            af[2 * x] = p1.x * q0;
+            af[2 * x + 1] = p1.x * q1;
+            af[2 * x + 2] = p1.y * q0;
+            af[2 * x + 3] = p1.y * q1;
          }
 #pragma unroll
          for (int s = 0; s < 5; s++)
+            af[20 + s] = row[2 * s + (t >> 1)] * q2;
+#pragma unroll
+         for (int s = 0; s < 20; s += 4)
          {
-            const double af = row[2 * s + (t >> 1)] * q2;
-            if (s & 1)
-               m_dmma(cb[0], cb[1], af, hb[20 + s]);
-            else
-               m_dmma(ca[0], ca[1], af, hb[20 + s]);
+            m_dmma(ca[0], ca[1], af[s], hb[s]);
+            m_dmma(cb[0], cb[1], af[s + 1], hb[s + 1]);
+            m_dmma(cc[0], cc[1], af[s + 2], hb[s + 2]);
+            m_dmma(cd[0], cd[1], af[s + 3], hb[s + 3]);
          }
+         m_dmma(ca[0], ca[1], af[20], hb[20]);
+         m_dmma(cb[0], cb[1], af[21], hb[21]);
+         m_dmma(cc[0], cc[1], af[22], hb[22]);
+         m_dmma(cd[0], cd[1], af[23], hb[23]);
+         m_dmma(ca[0], ca[1], af[24], hb[24]);
          ca[0] += cb[0] + (cc[0] + cd[0]);
          ca[1] += cb[1] + (cc[1] + cd[1]);
       }

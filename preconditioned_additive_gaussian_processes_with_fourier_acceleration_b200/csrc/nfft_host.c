@@ -976,23 +976,32 @@ static int additive_local_n(const b200_additive *A) { return A->blk_hi - A->blk_
  * (ramp-up, the final footprint flush / first footprint load of every warp, the tail of the wave); with all windows in one
  * launch that is paid once: the wave's warps are divided among the windows in proportion to their cost and every window's
  * chunk list is re-cut into that many ranges of equal cost. */
-static double chunk_cost(const int *hc, int c, int prev_key)
+/* point-equivalents of the tensor pipe: 1 per point, 1 per chunk, `flush` per cell change (spread: the footprint is written
+ * out with 1216 fp64 REDs; gather: it is re-read from the L2-resident grid) -- measured optima on a Gaussian cloud, where
+ * the sparse periphery makes the difference (profiles/README.md); uniform clouds are insensitive */
+#define FUSED_FLUSH_COST_SPREAD 60.0
+#define FUSED_FLUSH_COST_GATHER 24.0
+static double chunk_cost(const int *hc, int c, int prev_key, double flush)
 {
-   /* point-equivalents of the tensor pipe: 1 per point, 1 per chunk, 24 per footprint flush / reload */
-   return (double)hc[4 * c + 1] + 1.0 + (hc[4 * c + 2] != prev_key ? 24.0 : 0.0);
+   return (double)hc[4 * c + 1] + 1.0 + (hc[4 * c + 2] != prev_key ? flush : 0.0);
 }
 
 static void additive_fused_release(b200_additive *A)
 {
-   int i;
-   b200_free(A->d_fused[0]);
-   b200_free(A->d_fused[1]);
-   A->d_fused[0] = A->d_fused[1] = NULL;
-   if (A->d_fused_cfirst)
-      for (i = 0; i < A->nbatch; i++)
-         b200_free(A->d_fused_cfirst[i]);
-   free(A->d_fused_cfirst);
-   A->d_fused_cfirst = NULL;
+   int i, k;
+   for (k = 0; k < 3; k++)
+   {
+      b200_free(A->d_fused[k]);
+      A->d_fused[k] = NULL;
+   }
+   for (k = 0; k < 2; k++)
+   {
+      if (A->d_fused_cfirst[k])
+         for (i = 0; i < A->nbatch; i++)
+            b200_free(A->d_fused_cfirst[k][i]);
+      free(A->d_fused_cfirst[k]);
+      A->d_fused_cfirst[k] = NULL;
+   }
    b200_free((void *)A->d_prep_perm);
    b200_free(A->d_prep_a);
    b200_free(A->d_prep_n);
@@ -1002,36 +1011,88 @@ static void additive_fused_release(b200_additive *A)
    A->fused_ready = 0;
 }
 
-static int additive_fused_upload(b200_additive *A, int channel, const int *wbeg, const int *wcnt)
+/* cut every batch window's chunk list into ranges of equal cost; the warps of the wave are divided among the windows in
+ * proportion to their cost.  dir 0 = spread, 1 = gather.  Fills d_fused[dir] (gather: output f) and d_fused_cfirst[dir]. */
+static int additive_fused_partition(b200_additive *A, int dir, int total_warps)
 {
-   int nb = A->nbatch, i, rc;
+   const double flush = dir ? FUSED_FLUSH_COST_GATHER : FUSED_FLUSH_COST_SPREAD;
+   int nb = A->nbatch, i, c, assigned = 0, big = 0, rc = -1;
+   double *cost = (double *)b200_xcalloc((size_t)nb, sizeof(double)), total = 0.0;
+   int *wbeg = (int *)b200_xcalloc((size_t)nb + 1, sizeof(int)), *wcnt = (int *)b200_xcalloc((size_t)nb, sizeof(int));
    b200_mma_win *hw = (b200_mma_win *)b200_xcalloc((size_t)nb, sizeof(b200_mma_win));
    for (i = 0; i < nb; i++)
    {
+      const int *hc = A->win[i]->h_chunks;
+      int prev = -1;
+      for (c = 0; c < A->win[i]->h_nchunk; c++)
+      {
+         cost[i] += chunk_cost(hc, c, prev, flush);
+         prev = hc[4 * c + 2];
+      }
+      total += cost[i];
+   }
+   for (i = 0; i < nb; i++)
+   {
+      wcnt[i] = (int)(total_warps * cost[i] / total);
+      if (wcnt[i] < 1)
+         wcnt[i] = 1;
+      assigned += wcnt[i];
+      if (cost[i] > cost[big])
+         big = i;
+   }
+   wcnt[big] += total_warps - assigned;
+   if (wcnt[big] < 1)
+      goto done;
+   for (i = 0; i < nb; i++)
+      wbeg[i + 1] = wbeg[i] + wcnt[i];
+   A->d_fused_cfirst[dir] = (int **)b200_xcalloc((size_t)nb, sizeof(int *));
+   for (i = 0; i < nb; i++)
+   {
+      const int *hc = A->win[i]->h_chunks;
       b200_win_dev *v = &A->win[i]->dev;
+      int nch = A->win[i]->h_nchunk, r = 0, prev = -1, *hr = (int *)b200_xcalloc((size_t)wcnt[i] + 1, sizeof(int)), bad;
+      double acc = 0.0, target = cost[i] / (double)wcnt[i];
+      for (c = 0; c < nch; c++)
+      {
+         while (r + 1 < wcnt[i] && acc >= target * (double)(r + 1))
+            hr[++r] = c;
+         acc += chunk_cost(hc, c, prev, flush);
+         prev = hc[4 * c + 2];
+      }
+      while (r + 1 < wcnt[i])
+         hr[++r] = nch;
+      hr[wcnt[i]] = nch;
+      A->d_fused_cfirst[dir][i] = (int *)b200_malloc(sizeof(int) * ((size_t)wcnt[i] + 1));
+      bad = !A->d_fused_cfirst[dir][i] || b200_h2d(A->d_fused_cfirst[dir][i], hr, sizeof(int) * ((size_t)wcnt[i] + 1)) || b200_sync();
+      free(hr);
+      if (bad)
+         goto done;
       hw[i].psi = v->psi;
       hw[i].a = v->a;
       hw[i].chunks = v->chunks;
-      hw[i].cfirst = A->d_fused_cfirst[i];
+      hw[i].cfirst = A->d_fused_cfirst[dir][i];
       hw[i].grid = v->grid;
-      hw[i].f = channel ? v->f2 : v->f;
+      hw[i].f = v->f;
       hw[i].warp_begin = wbeg[i];
       hw[i].nwarps = wcnt[i];
    }
-   if (!A->d_fused[channel])
-      A->d_fused[channel] = b200_malloc(sizeof(b200_mma_win) * (size_t)nb);
-   rc = !A->d_fused[channel] || b200_h2d(A->d_fused[channel], hw, sizeof(b200_mma_win) * (size_t)nb) || b200_sync();
+   A->d_fused[dir] = b200_malloc(sizeof(b200_mma_win) * (size_t)nb);
+   rc = (!A->d_fused[dir] || b200_h2d(A->d_fused[dir], hw, sizeof(b200_mma_win) * (size_t)nb) || b200_sync()) ? -1 : 0;
+done:
+   free(cost);
+   free(wbeg);
+   free(wcnt);
    free(hw);
-   return rc ? -1 : 0;
+   return rc;
 }
 
 /* returns 1 when the fused path is available */
 static int additive_fused_prepare(b200_additive *A)
 {
    int nb = A->nbatch, i, c, total_warps = b200k_warp_ranges();
-   int *wbeg, *wcnt, *hn;
+   int *hn;
    const int **hperm;
-   double **ha, *cost, total = 0.0;
+   double **ha;
    if (g_variant_spread3 >= 0 || g_variant_gather3 >= 0)
       return 0; /* an explicit kernel variant was requested (A/B runs): per-window launches */
    if (A->fused_ready)
@@ -1045,73 +1106,6 @@ static int additive_fused_prepare(b200_additive *A)
       if (!A->win[i]->h_chunks || v->nchunk <= 0 || v->nseg <= 0 || v->n / v->nseg < B200_MMA_MIN_POINTS_PER_CELL)
          return 0; /* a sparse or empty window: per-window launches (DFMA kernels with register-tile shifting) */
    }
-   cost = (double *)b200_xcalloc((size_t)nb, sizeof(double));
-   wbeg = (int *)b200_xcalloc((size_t)nb + 1, sizeof(int));
-   wcnt = (int *)b200_xcalloc((size_t)nb, sizeof(int));
-   for (i = 0; i < nb; i++)
-   {
-      const int *hc = A->win[i]->h_chunks;
-      int prev = -1;
-      for (c = 0; c < A->win[i]->h_nchunk; c++)
-      {
-         cost[i] += chunk_cost(hc, c, prev);
-         prev = hc[4 * c + 2];
-      }
-      total += cost[i];
-   }
-   /* warps per window in proportion to cost (at least one), summing to the size of the wave */
-   {
-      int assigned = 0, big = 0;
-      for (i = 0; i < nb; i++)
-      {
-         wcnt[i] = (int)(total_warps * cost[i] / total);
-         if (wcnt[i] < 1)
-            wcnt[i] = 1;
-         assigned += wcnt[i];
-         if (cost[i] > cost[big])
-            big = i;
-      }
-      wcnt[big] += total_warps - assigned;
-      if (wcnt[big] < 1)
-      {
-         free(cost);
-         free(wbeg);
-         free(wcnt);
-         return 0;
-      }
-      for (i = 0; i < nb; i++)
-         wbeg[i + 1] = wbeg[i] + wcnt[i];
-   }
-   A->d_fused_cfirst = (int **)b200_xcalloc((size_t)nb, sizeof(int *));
-   for (i = 0; i < nb; i++)
-   {
-      const int *hc = A->win[i]->h_chunks;
-      int nch = A->win[i]->h_nchunk, r = 0, prev = -1, *hw = (int *)b200_xcalloc((size_t)wcnt[i] + 1, sizeof(int));
-      double acc = 0.0, target = cost[i] / (double)wcnt[i];
-      for (c = 0; c < nch; c++)
-      {
-         while (r + 1 < wcnt[i] && acc >= target * (double)(r + 1))
-            hw[++r] = c;
-         acc += chunk_cost(hc, c, prev);
-         prev = hc[4 * c + 2];
-      }
-      while (r + 1 < wcnt[i])
-         hw[++r] = nch;
-      hw[wcnt[i]] = nch;
-      A->d_fused_cfirst[i] = (int *)b200_malloc(sizeof(int) * ((size_t)wcnt[i] + 1));
-      if (!A->d_fused_cfirst[i] || b200_h2d(A->d_fused_cfirst[i], hw, sizeof(int) * ((size_t)wcnt[i] + 1)) || b200_sync())
-      {
-         free(hw);
-         free(cost);
-         free(wbeg);
-         free(wcnt);
-         additive_fused_release(A);
-         A->fused_ready = -1;
-         return 0;
-      }
-      free(hw);
-   }
-   A->fused_warps = total_warps;
    /* per-window pointers of the batched prep kernel */
    hperm = (const int **)b200_xcalloc((size_t)nb, sizeof(int *));
    ha = (double **)b200_xcalloc((size_t)nb, sizeof(double *));
@@ -1128,43 +1122,40 @@ static int additive_fused_prepare(b200_additive *A)
    A->d_prep_perm = (const int **)b200_malloc(sizeof(int *) * (size_t)nb);
    A->d_prep_a = (double **)b200_malloc(sizeof(double *) * (size_t)nb);
    A->d_prep_n = (int *)b200_malloc(sizeof(int) * (size_t)nb);
-   c = b200_h2d((void *)A->d_prep_perm, hperm, sizeof(int *) * (size_t)nb) || b200_h2d(A->d_prep_a, ha, sizeof(double *) * (size_t)nb) ||
-       b200_h2d(A->d_prep_n, hn, sizeof(int) * (size_t)nb) || additive_fused_upload(A, 0, wbeg, wcnt);
+   c = !A->d_prep_perm || !A->d_prep_a || !A->d_prep_n || b200_h2d((void *)A->d_prep_perm, hperm, sizeof(int *) * (size_t)nb) ||
+       b200_h2d(A->d_prep_a, ha, sizeof(double *) * (size_t)nb) || b200_h2d(A->d_prep_n, hn, sizeof(int) * (size_t)nb) ||
+       additive_fused_partition(A, 0, total_warps) || additive_fused_partition(A, 1, total_warps);
    free(hperm);
    free(ha);
    free(hn);
-   free(cost);
    if (c)
    {
-      free(wbeg);
-      free(wcnt);
       additive_fused_release(A);
       A->fused_ready = -1;
       return 0;
    }
-   free(wbeg);
-   free(wcnt);
+   A->fused_warps = total_warps;
    A->fused_ready = 1;
    return 1;
 }
 
-/* derivative channel: same descriptors with f2 as the output */
+/* derivative channel of the gather: the gather descriptors with f2 as the output */
 static int additive_fused_channel1(b200_additive *A)
 {
    int nb = A->nbatch, i, rc;
    b200_mma_win *hw;
-   if (A->d_fused[1])
+   if (A->d_fused[2])
       return 0;
    hw = (b200_mma_win *)b200_xcalloc((size_t)nb, sizeof(b200_mma_win));
-   if (b200_d2h(hw, A->d_fused[0], sizeof(b200_mma_win) * (size_t)nb))
+   if (b200_d2h(hw, A->d_fused[1], sizeof(b200_mma_win) * (size_t)nb))
    {
       free(hw);
       return -1;
    }
    for (i = 0; i < nb; i++)
       hw[i].f = A->win[i]->dev.f2;
-   A->d_fused[1] = b200_malloc(sizeof(b200_mma_win) * (size_t)nb);
-   rc = !A->d_fused[1] || b200_h2d(A->d_fused[1], hw, sizeof(b200_mma_win) * (size_t)nb) || b200_sync();
+   A->d_fused[2] = b200_malloc(sizeof(b200_mma_win) * (size_t)nb);
+   rc = !A->d_fused[2] || b200_h2d(A->d_fused[2], hw, sizeof(b200_mma_win) * (size_t)nb) || b200_sync();
    free(hw);
    return rc ? -1 : 0;
 }
@@ -1199,7 +1190,7 @@ static int additive_apply_windows(b200_additive *A, const double *d_x, double s,
          return -1;
       if (fused)
       {
-         if (b200k_gather_batch_begin() || b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[0], A->nbatch, A->fused_warps) ||
+         if (b200k_gather_batch_begin() || b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[1], A->nbatch, A->fused_warps) ||
              b200k_gather_batch_end())
             return -1;
       }
@@ -1217,7 +1208,7 @@ static int additive_apply_windows(b200_additive *A, const double *d_x, double s,
          if (fused)
          {
             if (additive_fused_channel1(A) || b200k_gather_batch_begin() ||
-                b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[1], A->nbatch, A->fused_warps) || b200k_gather_batch_end())
+                b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[2], A->nbatch, A->fused_warps) || b200k_gather_batch_end())
                return -1;
          }
          else

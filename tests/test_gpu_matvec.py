@@ -21,7 +21,7 @@ def _pair(gpu, case, cloud=uniform_cloud):
 
 
 @pytest.mark.parametrize("case", MATVEC_CASES, ids=[c[0] for c in MATVEC_CASES])
-@pytest.mark.parametrize("variant", [1, 0], ids=["tiled", "generic"])
+@pytest.mark.parametrize("variant", [-1, 5, 1, 0], ids=["auto", "dmma", "dfma", "generic"])
 def test_matvec_matches_oracle(gpu, case, variant):
     L = gpu.lib()
     L.Nfft4GPB200SetVariant(b"spread3d", variant)
@@ -37,8 +37,40 @@ def test_matvec_matches_oracle(gpu, case, variant):
         A.free()
         B.free()
     finally:
-        L.Nfft4GPB200SetVariant(b"spread3d", 1)
-        L.Nfft4GPB200SetVariant(b"gather3d", 1)
+        L.Nfft4GPB200SetVariant(b"spread3d", -1)
+        L.Nfft4GPB200SetVariant(b"gather3d", -1)
+
+
+@pytest.mark.parametrize("cloud", [uniform_cloud, gaussian_cloud], ids=["uniform", "gaussian"])
+def test_dense_windows_fused_tensor_core_path(gpu, cloud):
+    """n large enough (>= 24 points per occupied cell) for the automatic choice to take the fused fp64 tensor-core launches
+    (all three windows in one persistent wave): matvec and gradient matvec (shared adjoint, second gather channel)."""
+    case = ("dense", 250000, 9, list(range(9)), 3, 3, "gaussian", 1.0, 0.25 * 250000 ** (1.0 / 9), 0.01)
+    A, B, n = _pair(gpu, case, cloud=cloud)
+    for w in range(3):
+        dim, scale, nseg = A.window_info(w)
+        assert n / nseg >= 24, "case is not dense enough to exercise the fused path"
+    x = rand_vec(n)
+    y0 = rand_vec(n, seed=5)
+    for alpha, beta in [(1.0, 0.0), (0.7, 0.3)]:
+        assert rel_l2(A.matvec(x, alpha, beta, y0), B.matvec(x, alpha, beta, y0)) <= TOL
+    yg, yo = A.grad_matvec(x), B.grad_matvec(x)
+    for blk in range(3):
+        sl = slice(blk * n, (blk + 1) * n)
+        assert rel_l2(yg[sl], yo[sl]) <= TOL, blk
+    # same handle, explicit per-window variants must agree with the fused result
+    L = gpu.lib()
+    y_auto = A.matvec(x)
+    try:
+        for v in (5, 1):
+            L.Nfft4GPB200SetVariant(b"spread3d", v)
+            L.Nfft4GPB200SetVariant(b"gather3d", v)
+            assert rel_l2(A.matvec(x), y_auto) <= 1e-13
+    finally:
+        L.Nfft4GPB200SetVariant(b"spread3d", -1)
+        L.Nfft4GPB200SetVariant(b"gather3d", -1)
+    A.free()
+    B.free()
 
 
 @pytest.mark.parametrize("case", MATVEC_CASES[:7], ids=[c[0] for c in MATVEC_CASES[:7]])
