@@ -97,12 +97,21 @@ __device__ __forceinline__ void m_stage_issue(double *st, const double *__restri
 }
 
 // ---------------------------------------------------------------------------------------------------- spread
+// Writing a cell's footprint straight to the L2-resident grid costs 1040 fp64 REDs per cell change and warp -- 21 M per
+// launch at n = 10^6, independent of n, and the L2 atomic units made that 190 of the 338 us of the fused spread.
+// Consecutive cells of a range are neighbours along l3, so every warp keeps a private 10-plane ring of the footprint in
+// shared memory (plane u = c3 + z lives in slot u mod 10): on a cell change the register tile is added to the ring and only
+// the d planes that LEAVE the footprint go to global memory (100 REDs per plane, as in the DFMA kernels' register shift).
+#define CB_PLANE 100
+#define CB_DOUBLES (TAPS * CB_PLANE)
+
 // main accumulators: tile i < 10: rows y = g, x = i; tile 10 + i': rows (x = 4 i' + g / 2, y = 8 + (g & 1)); columns z = 2 t + {0, 1}
 // edge accumulators: tile (i, j): rows x = 8 i + g; columns 8 j + 2 t + {0, 1} <-> y = 4 j + t, z = 8 + {0, 1}
-__device__ __forceinline__ void m_spread_flush(double *__restrict__ grid, int key, int g, int t, double acc[MT][2], double ace[2][3][2])
+__device__ __forceinline__ void m_acc_to_ring(double *__restrict__ cb, int key, int g, int t, double acc[MT][2], double ace[2][3][2])
 {
-   const int c1 = (key >> 12) & 63, c2 = (key >> 6) & 63, c3 = key & 63;
-   const int z0 = m_tap_idx(c3, 2 * t), z1 = m_tap_idx(c3, 2 * t + 1);
+   const int c3 = key & 63;
+   const int s0 = ((c3 + 2 * t) % TAPS) * CB_PLANE, s1 = ((c3 + 2 * t + 1) % TAPS) * CB_PLANE;
+   const int s8 = ((c3 + 8) % TAPS) * CB_PLANE, s9 = ((c3 + 9) % TAPS) * CB_PLANE;
 #pragma unroll
    for (int i = 0; i < MT; i++)
    {
@@ -110,9 +119,8 @@ __device__ __forceinline__ void m_spread_flush(double *__restrict__ grid, int ke
       const int y = i < 10 ? g : 8 + (g & 1);
       if (x < TAPS)
       {
-         double *rowp = grid + (size_t)(m_tap_idx(c1, x) * NOS + m_tap_idx(c2, y)) * NOS;
-         m_red_add(rowp + z0, acc[i][0]);
-         m_red_add(rowp + z1, acc[i][1]);
+         cb[s0 + x * TAPS + y] += acc[i][0];
+         cb[s1 + x * TAPS + y] += acc[i][1];
       }
       acc[i][0] = acc[i][1] = 0.0;
    }
@@ -124,21 +132,40 @@ __device__ __forceinline__ void m_spread_flush(double *__restrict__ grid, int ke
          const int x = 8 * i + g, y = 4 * j + t;
          if (x < TAPS && y < TAPS)
          {
-            double *rowp = grid + (size_t)(m_tap_idx(c1, x) * NOS + m_tap_idx(c2, y)) * NOS;
-            m_red_add(rowp + m_tap_idx(c3, 8), ace[i][j][0]);
-            m_red_add(rowp + m_tap_idx(c3, 9), ace[i][j][1]);
+            cb[s8 + x * TAPS + y] += ace[i][j][0];
+            cb[s9 + x * TAPS + y] += ace[i][j][1];
          }
          ace[i][j][0] = ace[i][j][1] = 0.0;
       }
 }
 
+// planes z in [0, nz) of the footprint of cell `key` leave the ring: add them to the grid and clear their slots
+__device__ __forceinline__ void m_ring_flush(double *__restrict__ cb, double *__restrict__ grid, int key, int nz, int lane)
+{
+   const int c1 = (key >> 12) & 63, c2 = (key >> 6) & 63, c3 = key & 63;
+   for (int z = 0; z < nz; z++)
+   {
+      double *plane = cb + ((c3 + z) % TAPS) * CB_PLANE;
+      const int gz = m_tap_idx(c3, z);
+      for (int e = lane; e < CB_PLANE; e += 32)
+      {
+         const int x = e / TAPS, y = e - TAPS * x;
+         m_red_add(grid + (size_t)(m_tap_idx(c1, x) * NOS + m_tap_idx(c2, y)) * NOS + gz, plane[e]);
+         plane[e] = 0.0;
+      }
+   }
+}
+
 // one warp streams the chunks [c0, c1) of one window
 __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, const double *__restrict__ a, const int4 *__restrict__ chunks,
-                                               int c0, int c1, double *__restrict__ grid, double (*st)[STAGE_D], int lane)
+                                               int c0, int c1, double *__restrict__ grid, double (*st)[STAGE_D], double *__restrict__ cb,
+                                               int lane)
 {
    const int g = lane >> 2, t = lane & 3;
    if (c0 >= c1)
       return;
+   for (int e = lane; e < CB_DOUBLES; e += 32)
+      cb[e] = 0.0;
 
    double acc[MT][2], ace[2][3][2];
 #pragma unroll
@@ -170,10 +197,15 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
          m_stage_issue(st[(c - c0 + MWNS - 1) % MWNS], psi, a, dissue, lane);
       m_commit();
 
-      if (dcur.z != key) // warp-uniform: the stream enters another cell -> write the footprint out
+      if (dcur.z != key) // warp-uniform: the stream enters another cell
       {
-         m_spread_flush(grid, key, g, t, acc, ace);
-         key = dcur.z;
+         const int knew = dcur.z, d = knew - key;
+         m_acc_to_ring(cb, key, g, t, acc, ace);
+         __syncwarp();
+         // same (c1, c2) column, c3 advanced by d: only the d planes that leave the footprint are written out
+         m_ring_flush(cb, grid, key, ((knew >> 6) == (key >> 6) && d > 0 && d < TAPS) ? d : TAPS, lane);
+         __syncwarp();
+         key = knew;
       }
 
       const double *stage = st[(c - c0) % MWNS];
@@ -228,17 +260,23 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
       dcur = dnext;
       dissue = dissue_next;
    }
-   m_spread_flush(grid, key, g, t, acc, ace);
+   m_acc_to_ring(cb, key, g, t, acc, ace);
+   __syncwarp();
+   m_ring_flush(cb, grid, key, TAPS, lane);
 }
+
+// dynamic shared memory of the spread kernels: the cp.async stages of the CTA's warps, then their footprint rings
+#define SPREAD_SMEM_BYTES (sizeof(double) * (size_t)MWARPS_PER_CTA * (MWNS * STAGE_D + CB_DOUBLES))
 
 __global__ void __launch_bounds__(MWARPS_PER_CTA * 32, MCTAS_PER_SM)
 k_spread3_mma(const double *__restrict__ psi, const double *__restrict__ a, const int4 *__restrict__ chunks,
               const int *__restrict__ cfirst, double *__restrict__ grid)
 {
-   __shared__ __align__(16) double smem[MWARPS_PER_CTA][MWNS][STAGE_D];
+   extern __shared__ __align__(16) double dsm[];
+   double(*smem)[MWNS][STAGE_D] = reinterpret_cast<double(*)[MWNS][STAGE_D]>(dsm);
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
    const int gw = blockIdx.x * MWARPS_PER_CTA + wid;
-   m_spread_range(psi, a, chunks, cfirst[gw], cfirst[gw + 1], grid, smem[wid], lane);
+   m_spread_range(psi, a, chunks, cfirst[gw], cfirst[gw + 1], grid, smem[wid], dsm + MWARPS_PER_CTA * MWNS * STAGE_D + wid * CB_DOUBLES, lane);
 }
 
 // all windows of an additive kernel in ONE persistent wave: warp gw belongs to the window w with
@@ -246,7 +284,8 @@ k_spread3_mma(const double *__restrict__ psi, const double *__restrict__ a, cons
 __global__ void __launch_bounds__(MWARPS_PER_CTA * 32, MCTAS_PER_SM)
 k_spread3_mma_batch(const b200_mma_win *__restrict__ W, int P)
 {
-   __shared__ __align__(16) double smem[MWARPS_PER_CTA][MWNS][STAGE_D];
+   extern __shared__ __align__(16) double dsm[];
+   double(*smem)[MWNS][STAGE_D] = reinterpret_cast<double(*)[MWNS][STAGE_D]>(dsm);
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
    const int gw = blockIdx.x * MWARPS_PER_CTA + wid;
    int w = 0;
@@ -255,7 +294,8 @@ k_spread3_mma_batch(const b200_mma_win *__restrict__ W, int P)
    const int r = gw - W[w].warp_begin;
    if (r >= W[w].nwarps)
       return;
-   m_spread_range(W[w].psi, W[w].a, (const int4 *)W[w].chunks, W[w].cfirst[r], W[w].cfirst[r + 1], W[w].grid, smem[wid], lane);
+   m_spread_range(W[w].psi, W[w].a, (const int4 *)W[w].chunks, W[w].cfirst[r], W[w].cfirst[r + 1], W[w].grid, smem[wid],
+                  dsm + MWARPS_PER_CTA * MWNS * STAGE_D + wid * CB_DOUBLES, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------- gather
@@ -425,7 +465,9 @@ int b200k_spread3_mma(const b200_win_dev *w)
 {
    if (w->nchunk <= 0)
       return 0;
-   k_spread3_mma<<<w->nwr / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, 0, b200_stream()>>>(w->psi, w->a, (const int4 *)w->chunks, w->cfirst, w->grid);
+   B200_CHECK(cudaFuncSetAttribute(k_spread3_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPREAD_SMEM_BYTES));
+   k_spread3_mma<<<w->nwr / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, SPREAD_SMEM_BYTES, b200_stream()>>>(w->psi, w->a, (const int4 *)w->chunks,
+                                                                                                   w->cfirst, w->grid);
    B200_LAUNCHED();
    return 0;
 }
@@ -442,7 +484,8 @@ int b200k_gather3_mma(const b200_win_dev *w, double *d_f)
 // fused launches over the P windows described by d_batch (device array); total_warps = sum of nwarps, a multiple of the CTA size
 int b200k_spread3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps)
 {
-   k_spread3_mma_batch<<<total_warps / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, 0, b200_stream()>>>(d_batch, P);
+   B200_CHECK(cudaFuncSetAttribute(k_spread3_mma_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPREAD_SMEM_BYTES));
+   k_spread3_mma_batch<<<total_warps / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, SPREAD_SMEM_BYTES, b200_stream()>>>(d_batch, P);
    B200_LAUNCHED();
    return 0;
 }

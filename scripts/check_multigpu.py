@@ -29,7 +29,7 @@ dist.broadcast(uid, 0)
 assert L.Nfft4GPB200CommInit(rank, world, bytes(uid.cpu().numpy().tobytes())) == 0
 
 rng = np.random.default_rng(5)
-n, d = 20000, 9
+n, d = (int(float(sys.argv[1])) if len(sys.argv) > 1 else 20000), 9  # dense (fused tensor-core path) from ~ 2e5 points per rank
 X = rng.random((d, n)) * n ** (1.0 / d)
 x = rng.random(n) - 0.5
 y0 = rng.random(n) - 0.5
