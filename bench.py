@@ -156,7 +156,7 @@ def run_reference(args):
     return 0
 
 
-def run_pcg_section(pkg, L, A, X, rhs, windows, hp, args, hbm_peak):
+def run_pcg_section(pkg, L, A, X, rhs, windows, hp, args, hbm_peak, ranks=None):
     """Second half of BASELINE.json's metric: AFN-preconditioned CG on the NFFT additive matvec to 1e-6 relative residual
     (config C3, n = 10^6, d = 9, Gaussian).  Two landmark ranks: the one BASELINE.json names (500; too small for n = 10^6 at
     mu = 0.01 -- reported with an iteration cap) and one that converges.  Setup (GPU: KNN pattern, FSAI rows, landmark GEMMs
@@ -164,20 +164,36 @@ def run_pcg_section(pkg, L, A, X, rhs, windows, hp, args, hbm_peak):
     pass of 50 iterations gives the per-class kernel times of one iteration and the HBM fraction of the AFN apply."""
     n = X.shape[1]
     mu = args.pcg_mu
+    rank, world, dist, torch = ranks if ranks else (0, 1, None, None)
+
+    def sync_all():
+        L.Nfft4GPB200DeviceSynchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     A.build(hp["f"], hp["l"], mu)
     D = pkg.DenseAdditiveKernel(X, windows, 3, 3, "gaussian").set_hyper(hp["f"], hp["l"], mu)
     out = {"config": f"C3: AFN-PCG to 1e-6 rel. residual, n={n}, d=9, Gaussian, f={hp['f']}, l={hp['l']:.4f}, mu={mu}, lfil=100, rhs=U(0,1)-0.5",
            "unit": "s", "runs": []}
-    for rank, maxits in ((500, 300), (args.pcg_rank, 3000)):
+    for lrank, maxits in ((500, 300), (args.pcg_rank, 3000)):
+        sync_all()
         t0 = time.perf_counter()
-        P = pkg.AfnPrecond().setup(D, rank, 100, numests=0, noran=1)
-        L.Nfft4GPB200DeviceSynchronize()
-        setup_s = time.perf_counter() - t0
+        P = pkg.AfnPrecond().setup(D, lrank, 100, numests=0, noran=1)   # N > 1: replicated on every rank; the apply is sharded
+        sync_all()
+        setup_s = max_over_ranks(time.perf_counter() - t0)
         L.Nfft4GPB200LaunchCountReset()
+        sync_all()
         t0 = time.perf_counter()
         xs, rel, hist, its = pkg.solver_pcg(A.K, n, A.matvec_fn(), P.h, P.solve_fn(), np.zeros(n), rhs, maxits, 0, 1e-6)
-        L.Nfft4GPB200DeviceSynchronize()
-        solve_s = time.perf_counter() - t0
+        sync_all()
+        solve_s = max_over_ranks(time.perf_counter() - t0)
         launches = int(L.Nfft4GPB200LaunchCount())
         done = its if its > 0 else maxits
         # profiled pass: 50 iterations with per-launch events
@@ -187,10 +203,11 @@ def run_pcg_section(pkg, L, A, X, rhs, windows, hp, args, hbm_peak):
         counts = (C.c_longlong * len(PROF_CLASSES))()
         L.Nfft4GPB200ProfileStop(sums, counts, len(PROF_CLASSES))
         per_it = {PROF_CLASSES[i]: round(sums[i] / 51.0, 5) for i in range(len(PROF_CLASSES)) if counts[i] > 0}
-        n2 = n - rank
-        gemv_bytes = 2.0 * 8.0 * rank * n2          # two passes over K12 per apply
-        csr_bytes = 2.0 * 12.0 * 100.0 * n2         # G and G' (value + column index) per apply
-        run = {"precond": f"AFN rank {rank} + FSAI(lfil 100) of the Schur complement", "setup_s": setup_s, "solve_s": solve_s,
+        n2 = (n - lrank) / world
+        gemv_bytes = 2.0 * 8.0 * lrank * n2          # two passes over this rank's columns of K12 per apply
+        csr_bytes = 2.0 * 12.0 * 100.0 * n2          # this rank's rows of G and G' (value + column index) per apply
+        run = {"precond": f"AFN rank {lrank} + FSAI(lfil 100) of the Schur complement" + (f", apply sharded over {world} GPUs (2 allreduces of k, 2 of n-k doubles)" if world > 1 else ""),
+               "setup_s": setup_s, "solve_s": solve_s,
                "iters": its, "converged": bool(its > 0), "rel_res": rel, "ms_per_iter": 1000.0 * solve_s / max(done, 1),
                "gpu_launches": launches, "per_class_ms_per_iter": per_it,
                "afn_apply_hbm": {"gemv_GBs": gemv_bytes / (per_it.get("gemv", float("nan")) * 1e-3) / 1e9,
@@ -334,6 +351,10 @@ def main():
     e2e_val = args.steps / e2e_s
     y_host = np.ctypeslib.as_array(hyp, shape=(n,)).copy()
 
+    pcg_multi = None
+    if world > 1 and mode == 2 and not args.no_pcg:
+        pcg_multi = run_pcg_section(pkg, L, A, X, x, windows, hp, args, float(peaks()[0]["hbm_gbs"]), ranks=(rank, world, dist, torch))
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -398,7 +419,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "pcg": pcg,
+        "pcg": pcg if pcg is not None else pcg_multi,
     }
     print(json.dumps(line))
     if dist is not None:

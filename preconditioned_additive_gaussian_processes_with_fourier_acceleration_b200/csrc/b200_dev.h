@@ -119,6 +119,11 @@ int b200k_copy(int n, const double *src, double *dst);
 int b200k_fill(int n, double v, double *dst);
 int b200k_scale(int n, double a, double *x);
 int b200k_axpy(int n, double a, const double *x, double *y);
+/* sharded applies: gather / scatter through an index array with holes (idx < 0), Nystrom coefficient, local factor rows */
+int b200k_gather_idx(int m, const int *idx, const double *src, double *dst);
+int b200k_scatter_idx(int m, const int *idx, const double *src, double *dst);
+int b200k_nys_coef(int k, const double *s, double inv_eta, const double *z, double *c);
+int b200k_gather_rows_T(int nl, int k, const int *pos, const double *U, int ldu, double *UT);
 
 /* ---- preconditioner kernels (precond_kernels.cu) ---- */
 /* Nystrom: y = rhs(perm); z = U'y; out(perm) = y/eta + U((s - 1/eta) .* z) -- two passes over U (n x k col-major) */

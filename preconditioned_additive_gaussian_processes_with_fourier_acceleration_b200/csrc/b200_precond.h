@@ -22,6 +22,9 @@ typedef struct
    double *d_x, *d_rhs; /* staging for the host-pointer solve */
    int cap;
    double tset;
+   /* point-block-sharded apply (one process per GPU): this rank's rows of U, transposed (k x nl), built on first use */
+   int sh_lo, sh_hi;
+   double *d_UT_loc, *d_sh_work; /* work: 2k */
 } b200_nys;
 
 /* FSAI: G lower-triangular CSR (diagonal last in each row, INC/_preconds.h:271) and its explicit transpose. */
@@ -58,6 +61,11 @@ typedef struct
    double *d_x, *d_rhs;
    int cap;
    double tset;
+   /* point-block-sharded apply, built on first use: owned landmarks / Schur points of the block [sh_lo, sh_hi) */
+   int sh_ready, sh_lo, sh_hi, sh_plo, sh_phi; /* [sh_plo, sh_phi): this rank's range of Schur indices (0-based in n - k) */
+   int *d_lm_idx;     /* [k]   local index of landmark p, -1 when another rank owns it */
+   int *d_sc_idx;     /* [n2l] local index of Schur point sh_plo + j */
+   double *d_sh_work; /* 4k + 2 (n - k) + 2 n2l */
 } b200_afn;
 
 int b200_nys_set_device_factors(b200_nys *s, int n, int k, const int *h_perm, double *d_U_owned, const double *h_s, double eta);

@@ -33,9 +33,14 @@ static int scal_init(void)
    return 0;
 }
 
+/* point-block sharding (one process per GPU): vectors hold the rank's block, every dot product is completed by an
+ * allreduce of the device scalar (SURVEY.md 8(e) iii) */
+static int g_pcg_sharded = 0, g_pcg_nglobal = 0;
+
 static int dev_dot(int n, const double *x, const double *y, double *out)
 {
-   if (b200k_dot(n, x, y, g_scal_dev) || b200_d2h(g_scal_host, g_scal_dev, sizeof(double)))
+   if (b200k_dot(n, x, y, g_scal_dev) || (g_pcg_sharded && b200_comm_allreduce_sum(g_scal_dev, 1)) ||
+       b200_d2h(g_scal_host, g_scal_dev, sizeof(double)))
       return -1;
    *out = g_scal_host[0];
    return 0;
@@ -63,8 +68,8 @@ int b200_pcg_device(void *mat, int n, b200_dev_matvec mv, void *prec, b200_dev_s
       return b200_sync();
    }
    tolb = atol ? tol : tol * normb;
-   if (maxits > n)
-      maxits = n;
+   if (maxits > (g_pcg_sharded ? g_pcg_nglobal : n))
+      maxits = g_pcg_sharded ? g_pcg_nglobal : n;
    r = (double *)b200_malloc(bytes);
    z = (double *)b200_malloc(bytes);
    p = (double *)b200_malloc(bytes);
@@ -141,7 +146,8 @@ int b200_pcg_device(void *mat, int n, b200_dev_matvec mv, void *prec, b200_dev_s
          break;
       }
       alpha = rho / pq;
-      if (b200k_pcg_update(n, alpha, p, q, d_x, r, g_scal_dev) || b200_d2h(g_scal_host, g_scal_dev, sizeof(double)))
+      if (b200k_pcg_update(n, alpha, p, q, d_x, r, g_scal_dev) || (g_pcg_sharded && b200_comm_allreduce_sum(g_scal_dev, 1)) ||
+          b200_d2h(g_scal_host, g_scal_dev, sizeof(double)))
          goto done;
       rr = g_scal_host[0];
       normr = sqrt(rr);
@@ -248,12 +254,32 @@ int Nfft4GPSolverPcg(void *mat_data, int n, func_symmatvec matvec, void *prec_da
       ps = foreign_solve_dev;
       dev_prec = &fps;
    }
-   d_x = (double *)b200_malloc(bytes);
-   d_rhs = (double *)b200_malloc(bytes);
-   if (!b200_h2d(d_x, x, bytes) && !b200_h2d(d_rhs, rhs, bytes))
-      rc = b200_pcg_device(dev_mat, n, mv, dev_prec, ps, d_x, d_rhs, maxits, atol, tol, prel_res, prel_res_v, piter, print_level);
-   if (!rc)
-      rc = b200_d2h(x, d_x, bytes);
+   {
+      /* point-block sharding: x and rhs are FULL host vectors on every rank (reference semantics); each rank moves and
+       * solves for its own block [lo, hi) and fills those entries of x */
+      int lo = 0, hi = n;
+      b200_additive *A = (matvec == Nfft4GPAdditiveNFFTMatSymv) ? b200_additive_from_handle(mat_data) : NULL;
+      if (A && A->shard_mode == 2 && b200_comm_size() > 1)
+      {
+         if (fmv.mv || fps.ps)
+         {
+            printf("Error: point-block-sharded PCG needs this library's own matvec and preconditioner.\n");
+            return -1;
+         }
+         lo = A->blk_lo;
+         hi = A->blk_hi;
+         g_pcg_sharded = 1;
+         g_pcg_nglobal = n;
+      }
+      bytes = sizeof(double) * (size_t)(hi - lo);
+      d_x = (double *)b200_malloc(bytes);
+      d_rhs = (double *)b200_malloc(bytes);
+      if (!b200_h2d(d_x, x + lo, bytes) && !b200_h2d(d_rhs, rhs + lo, bytes))
+         rc = b200_pcg_device(dev_mat, hi - lo, mv, dev_prec, ps, d_x, d_rhs, maxits, atol, tol, prel_res, prel_res_v, piter, print_level);
+      if (!rc)
+         rc = b200_d2h(x + lo, d_x, bytes);
+      g_pcg_sharded = 0;
+   }
    b200_free(d_x);
    b200_free(d_rhs);
    b200_host_free(fmv.hx);
@@ -275,5 +301,17 @@ int Nfft4GPB200SolverPcgDevice(void *mat_data, int n, func_symmatvec matvec, voi
       printf("Error: Nfft4GPB200SolverPcgDevice needs this library's own matvec / preconditioner entry points.\n");
       return -1;
    }
-   return b200_pcg_device(dev_mat, n, mv, prec_data, ps, d_x, d_rhs, maxits, atol, tol, prel_res, prel_res_v, piter, print_level);
+   {
+      /* device vectors hold the rank's block under point-block sharding (n = block length) */
+      b200_additive *A = (matvec == Nfft4GPAdditiveNFFTMatSymv) ? b200_additive_from_handle(mat_data) : NULL;
+      int rc;
+      if (A && A->shard_mode == 2 && b200_comm_size() > 1)
+      {
+         g_pcg_sharded = 1;
+         g_pcg_nglobal = A->n;
+      }
+      rc = b200_pcg_device(dev_mat, n, mv, prec_data, ps, d_x, d_rhs, maxits, atol, tol, prel_res, prel_res_v, piter, print_level);
+      g_pcg_sharded = 0;
+      return rc;
+   }
 }

@@ -44,10 +44,13 @@ static void nys_release_factors(b200_nys *s)
    b200_free(s->d_U);
    b200_free(s->d_s);
    b200_free(s->d_work);
+   b200_free(s->d_UT_loc);
+   b200_free(s->d_sh_work);
    s->d_perm = NULL;
-   s->d_U = s->d_s = s->d_work = NULL;
+   s->d_U = s->d_s = s->d_work = s->d_UT_loc = s->d_sh_work = NULL;
    s->work_doubles = 0;
    s->n = s->k = 0;
+   s->sh_lo = s->sh_hi = 0;
 }
 
 void Nfft4GPPrecondNysReset(void *str) /* nys.c:78-98: keep permutation */
@@ -132,9 +135,63 @@ int Nfft4GPB200PrecondNysGetFactors(void *nys, int *n, int *k, int *perm, double
    return 0;
 }
 
+/* Point-block-sharded Nystrom apply: vectors hold this rank's block [lo, hi) of the points in the original
+ * order; rows of U that belong to the block are kept transposed (k x nl).  z = U'r needs ONE allreduce of k doubles. */
+static int nys_solve_sharded(b200_nys *s, int nl, double *d_x, const double *d_rhs)
+{
+   int rank = b200_comm_rank(), size = b200_comm_size(), k = s->k;
+   int lo = (int)((long long)s->n * rank / size), hi = (int)((long long)s->n * (rank + 1) / size);
+   double *z, *c;
+   if (nl != hi - lo)
+   {
+      printf("Error: sharded Nystrom apply: block of %d points expected, got %d.\n", hi - lo, nl);
+      return -1;
+   }
+   if (!s->d_UT_loc || s->sh_lo != lo || s->sh_hi != hi)
+   {
+      /* positions (in the permuted order of U) of the local points, by local index */
+      int *perm = (int *)b200_xmalloc(sizeof(int) * (size_t)s->n), *pos = (int *)b200_xmalloc(sizeof(int) * (size_t)(nl ? nl : 1)), i, *d_pos;
+      if (s->d_perm)
+      {
+         if (b200_d2h(perm, s->d_perm, sizeof(int) * (size_t)s->n))
+            return -1;
+      }
+      else
+         for (i = 0; i < s->n; i++)
+            perm[i] = i;
+      for (i = 0; i < s->n; i++)
+         if (perm[i] >= lo && perm[i] < hi)
+            pos[perm[i] - lo] = i;
+      b200_free(s->d_UT_loc);
+      b200_free(s->d_sh_work);
+      s->d_UT_loc = (double *)b200_malloc(sizeof(double) * (size_t)k * (size_t)(nl ? nl : 1));
+      s->d_sh_work = (double *)b200_malloc(sizeof(double) * 2 * (size_t)k);
+      d_pos = (int *)b200_malloc(sizeof(int) * (size_t)(nl ? nl : 1));
+      i = !s->d_UT_loc || !s->d_sh_work || !d_pos || b200_h2d(d_pos, pos, sizeof(int) * (size_t)nl) ||
+          b200k_gather_rows_T(nl, k, d_pos, s->d_U, s->n, s->d_UT_loc) || b200_sync();
+      b200_free(d_pos);
+      free(perm);
+      free(pos);
+      if (i)
+         return -1;
+      s->sh_lo = lo;
+      s->sh_hi = hi;
+   }
+   z = s->d_sh_work;
+   c = z + k;
+   /* z = U_loc' r (k x nl times nl), allreduce, x = r / eta + U_loc ((s - 1/eta) .* z) */
+   if (b200k_gemv('N', k, nl, 1.0, s->d_UT_loc, d_rhs, 0.0, z) || b200_comm_allreduce_sum(z, (size_t)k) ||
+       b200k_nys_coef(k, s->d_s, 1.0 / s->eta, z, c) || b200k_copy(nl, d_rhs, d_x) || b200k_scale(nl, 1.0 / s->eta, d_x) ||
+       b200k_gemv('T', k, nl, 1.0, s->d_UT_loc, c, 1.0, d_x))
+      return -1;
+   return 0;
+}
+
 int b200_nys_solve_dev(void *vnys, int n, double *d_x, const double *d_rhs)
 {
    b200_nys *s = (b200_nys *)vnys;
+   if (s && s->magic == B200_MAGIC_NYS && s->d_U && n != s->n && b200_comm_size() > 1)
+      return nys_solve_sharded(s, n, d_x, d_rhs);
    if (!s || s->magic != B200_MAGIC_NYS || !s->d_U || n != s->n)
    {
       printf("Error: Nystrom preconditioner is not set up for n = %d.\n", n);
@@ -303,8 +360,13 @@ void b200_afn_release(b200_afn *s)
    b200_free(s->d_Linv);
    b200_free(s->d_K12);
    b200_free(s->d_work);
+   b200_free(s->d_lm_idx);
+   b200_free(s->d_sc_idx);
+   b200_free(s->d_sh_work);
    s->d_perm = NULL;
-   s->d_Linv = s->d_K12 = s->d_work = NULL;
+   s->d_lm_idx = s->d_sc_idx = NULL;
+   s->d_Linv = s->d_K12 = s->d_work = s->d_sh_work = NULL;
+   s->sh_ready = 0;
    b200_fsai_release(&s->schur);
    if (s->nys)
    {
@@ -399,6 +461,115 @@ int Nfft4GPB200PrecondAFNSetFactors(void *afn, int n, int k, const int *perm, co
    return b200_afn_set_device_factors(s, n, k, perm, L, d_K12, ia, ja, a);
 }
 
+/* Point-block-sharded AFN apply.  Vectors hold this rank's block [lo, hi) of the points in the original
+ * order.  The k landmark unknowns are replicated (two allreduces of k doubles); the Schur unknowns are sharded -- the
+ * non-landmark points are in ascending original order, so a block owns a CONTIGUOUS range [plo, phi) of Schur indices, i.e.
+ * a column range of K12 and a row range of G and G' -- and the two FSAI products read the full Schur vector, assembled by
+ * an allreduce of n - k doubles each.  Same arithmetic as afn_solve.m:39-69. */
+static int afn_shard_prepare(b200_afn *s, int lo, int hi)
+{
+   int n = s->n, k = s->k, n2 = n - k, p, nl = hi - lo, n2l, rc;
+   int *perm, *lm, *sc;
+   if (s->sh_ready && s->sh_lo == lo && s->sh_hi == hi)
+      return 0;
+   perm = (int *)b200_xmalloc(sizeof(int) * (size_t)n);
+   if (b200_d2h(perm, s->d_perm, sizeof(int) * (size_t)n))
+   {
+      free(perm);
+      return -1;
+   }
+   lm = (int *)b200_xmalloc(sizeof(int) * (size_t)k);
+   for (p = 0; p < k; p++)
+      lm[p] = (perm[p] >= lo && perm[p] < hi) ? perm[p] - lo : -1;
+   s->sh_plo = n2;
+   s->sh_phi = n2;
+   for (p = k; p < n; p++)
+      if (perm[p] >= lo)
+      {
+         s->sh_plo = p - k;
+         break;
+      }
+   for (p = k + s->sh_plo; p < n; p++)
+      if (perm[p] >= hi)
+      {
+         s->sh_phi = p - k;
+         break;
+      }
+   n2l = s->sh_phi - s->sh_plo;
+   sc = (int *)b200_xmalloc(sizeof(int) * (size_t)(n2l ? n2l : 1));
+   for (p = 0; p < n2l; p++)
+      sc[p] = perm[k + s->sh_plo + p] - lo;
+   b200_free(s->d_lm_idx);
+   b200_free(s->d_sc_idx);
+   b200_free(s->d_sh_work);
+   s->d_lm_idx = (int *)b200_malloc(sizeof(int) * (size_t)k);
+   s->d_sc_idx = (int *)b200_malloc(sizeof(int) * (size_t)(n2l ? n2l : 1));
+   s->d_sh_work = (double *)b200_malloc(sizeof(double) * (4 * (size_t)k + 2 * (size_t)n2 + 2 * (size_t)n2l + 8));
+   rc = !s->d_lm_idx || !s->d_sc_idx || !s->d_sh_work || b200_h2d(s->d_lm_idx, lm, sizeof(int) * (size_t)k) ||
+        b200_h2d(s->d_sc_idx, sc, sizeof(int) * (size_t)n2l) || b200_sync();
+   free(perm);
+   free(lm);
+   free(sc);
+   (void)nl;
+   if (rc)
+      return -1;
+   s->sh_lo = lo;
+   s->sh_hi = hi;
+   s->sh_ready = 1;
+   return 0;
+}
+
+static int afn_solve_sharded(b200_afn *s, int nl, double *d_x, const double *d_rhs)
+{
+   int rank = b200_comm_rank(), size = b200_comm_size(), k = s->k, n2 = s->n - s->k, n2l, plo;
+   int lo = (int)((long long)s->n * rank / size), hi = (int)((long long)s->n * (rank + 1) / size);
+   double *rp1, *y1, *t, *u, *full, *wfull, *rp2l, *y2l;
+   b200_fsai *G = &s->schur;
+   if (nl != hi - lo)
+   {
+      printf("Error: sharded AFN apply: block of %d points expected, got %d.\n", hi - lo, nl);
+      return -1;
+   }
+   if (afn_shard_prepare(s, lo, hi))
+      return -1;
+   plo = s->sh_plo;
+   n2l = s->sh_phi - s->sh_plo;
+   rp1 = s->d_sh_work;
+   y1 = rp1 + k;
+   t = y1 + k;
+   u = t + k;
+   full = u + k;
+   wfull = full + n2;
+   rp2l = wfull + n2;
+   y2l = rp2l + n2l;
+   /* rp1 = r(perm[0:k]) (owned entries, allreduce), y1 = A11^{-1} rp1 */
+   if (b200k_gather_idx(k, s->d_lm_idx, d_rhs, rp1) || b200_comm_allreduce_sum(rp1, (size_t)k) ||
+       b200k_gemv('N', k, k, 1.0, s->d_Linv, rp1, 0.0, t) || b200k_gemv('T', k, k, 1.0, s->d_Linv, t, 0.0, y1))
+      return -1;
+   if (n2 > 0)
+   {
+      /* rp2 = r(perm2) - K12' y1 on the local Schur range; assemble the full vector */
+      if (b200k_gather_idx(n2l, s->d_sc_idx, d_rhs, rp2l) ||
+          (n2l > 0 && b200k_gemv('T', k, n2l, -1.0, s->d_K12 + (size_t)k * plo, y1, 1.0, rp2l)) || b200k_fill(n2, 0.0, full) ||
+          (n2l > 0 && b200_d2d(full + plo, rp2l, sizeof(double) * (size_t)n2l)) || b200_comm_allreduce_sum(full, (size_t)n2))
+         return -1;
+      /* y2 = G' (G rp2): local rows of G, assemble, local rows of G' */
+      if (b200k_fill(n2, 0.0, wfull) || (n2l > 0 && b200k_csr_mv(n2l, G->d_ia + plo, G->d_ja, G->d_a, full, wfull + plo)) ||
+          b200_comm_allreduce_sum(wfull, (size_t)n2) ||
+          (n2l > 0 && b200k_csr_mv(n2l, G->d_iat + plo, G->d_jat, G->d_at, wfull, y2l)))
+         return -1;
+      /* rp1 -= K12 y2 (local columns, allreduce), y1 = A11^{-1} rp1 */
+      if (b200k_fill(k, 0.0, u) || (n2l > 0 && b200k_gemv('N', k, n2l, 1.0, s->d_K12 + (size_t)k * plo, y2l, 0.0, u)) ||
+          b200_comm_allreduce_sum(u, (size_t)k) || b200k_axpy(k, -1.0, u, rp1) || b200k_gemv('N', k, k, 1.0, s->d_Linv, rp1, 0.0, t) ||
+          b200k_gemv('T', k, k, 1.0, s->d_Linv, t, 0.0, y1))
+         return -1;
+   }
+   /* x(perm) = [y1; y2] restricted to the block */
+   if (b200k_scatter_idx(k, s->d_lm_idx, y1, d_x) || (n2 > 0 && b200k_scatter_idx(n2l, s->d_sc_idx, y2l, d_x)))
+      return -1;
+   return 0;
+}
+
 int b200_afn_solve_dev(void *va, int n, double *d_x, const double *d_rhs)
 {
    b200_afn *s = (b200_afn *)va;
@@ -408,6 +579,8 @@ int b200_afn_solve_dev(void *va, int n, double *d_x, const double *d_rhs)
       return -1;
    if (s->nys) /* rank < max rank: Nystrom on the FPS ordering (afn_setup.m:80-100, afn_solve.m:41-44) */
       return b200_nys_solve_dev(s->nys, n, d_x, d_rhs);
+   if (s->d_Linv && n != s->n && b200_comm_size() > 1)
+      return afn_solve_sharded(s, n, d_x, d_rhs);
    if (!s->d_Linv || n != s->n)
    {
       printf("Error: AFN preconditioner is not set up for n = %d.\n", n);

@@ -144,6 +144,47 @@ static int red_blocks(int n)
    return b;
 }
 
+
+// ---- index gather / scatter with holes (idx < 0 = not owned by this rank), used by the point-block-sharded applies
+__global__ void k_gather_idx(int m, const int *__restrict__ idx, const double *__restrict__ src, double *__restrict__ dst)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < m)
+   {
+      int j = idx[i];
+      dst[i] = j >= 0 ? src[j] : 0.0;
+   }
+}
+
+__global__ void k_scatter_idx(int m, const int *__restrict__ idx, const double *__restrict__ src, double *__restrict__ dst)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < m)
+   {
+      int j = idx[i];
+      if (j >= 0)
+         dst[j] = src[i];
+   }
+}
+
+// c[i] = (s[i] - 1 / eta) * z[i]   (Nystrom apply, nys.c:141-160 folded into one coefficient vector)
+__global__ void k_nys_coef(int k, const double *__restrict__ s, double inv_eta, const double *__restrict__ z, double *__restrict__ c)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < k)
+      c[i] = (s[i] - inv_eta) * z[i];
+}
+
+// UT(c, j) = U(pos[j], c): local rows of the Nystrom factor, transposed (k x nl, column = point)
+__global__ void k_gather_rows_T(int nl, int k, const int *__restrict__ pos, const double *__restrict__ U, int ldu, double *__restrict__ UT)
+{
+   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= (size_t)nl * k)
+      return;
+   int c = (int)(e % k), j = (int)(e / k);
+   UT[e] = U[(size_t)c * ldu + pos[j]];
+}
+
 extern "C" {
 
 int b200k_dot(int n, const double *x, const double *y, double *d_out)
@@ -226,6 +267,44 @@ int b200k_axpy(int n, double a, const double *x, double *y)
 {
    B200ProfScope prof_scope_(PC_VEC);
    k_axpy<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, a, x, y);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_gather_idx(int m, const int *idx, const double *src, double *dst)
+{
+   B200ProfScope prof_scope_(PC_VEC);
+   if (m <= 0)
+      return 0;
+   k_gather_idx<<<b200_cdiv(m, 256), 256, 0, b200_stream()>>>(m, idx, src, dst);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_scatter_idx(int m, const int *idx, const double *src, double *dst)
+{
+   B200ProfScope prof_scope_(PC_VEC);
+   if (m <= 0)
+      return 0;
+   k_scatter_idx<<<b200_cdiv(m, 256), 256, 0, b200_stream()>>>(m, idx, src, dst);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_nys_coef(int k, const double *s, double inv_eta, const double *z, double *c)
+{
+   B200ProfScope prof_scope_(PC_NYS);
+   k_nys_coef<<<b200_cdiv(k, 256), 256, 0, b200_stream()>>>(k, s, inv_eta, z, c);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_gather_rows_T(int nl, int k, const int *pos, const double *U, int ldu, double *UT)
+{
+   B200ProfScope prof_scope_(PC_OTHER);
+   if (nl <= 0)
+      return 0;
+   k_gather_rows_T<<<b200_cdiv((long long)nl * k, 256), 256, 0, b200_stream()>>>(nl, k, pos, U, ldu, UT);
    B200_LAUNCHED();
    return 0;
 }

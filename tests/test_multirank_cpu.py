@@ -87,3 +87,83 @@ def test_two_rank_window_and_block_sharding():
     for r in range(world):
         assert ret[r][0] <= 1e-13, ret[r]
     assert ret[0][1] <= 1e-13
+
+
+def _sharded_precond_worker(rank, world, port, q):
+    """NumPy restatement of the point-block-sharded AFN and Nystrom applies (precond_host.c: afn_solve_sharded,
+    nys_solve_sharded) with gloo collectives, against the unsharded oracle applies (oracle/np_setup.py)."""
+    sys.path.insert(0, ROOT)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    from oracle import np_setup as S
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+    def allreduce(v):
+        t = torch.from_numpy(np.ascontiguousarray(v))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    n, d, k, lfil = 400, 6, 30, 12
+    rng = np.random.default_rng(3)
+    X = rng.random((d, n)) * n ** (1.0 / d)
+    wins = [[0, 1, 2], [3, 4, 5]]
+    f, l, mu = 1.1, 0.9, 0.05
+    r = rng.random(n) - 0.5
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    r_loc = r[lo:hi]
+    # ---- AFN
+    F = S.afn_setup(X, k, lfil, f, l, mu, "gaussian", wins)
+    perm, Lc, K12, G = F["perm"], F["L"], F["K12"], F["G"]
+    n2 = n - k
+    a11 = lambda v: np.linalg.solve(Lc.T, np.linalg.solve(Lc, v))
+    lm = np.array([p - lo if lo <= p < hi else -1 for p in perm[:k]])
+    sch = perm[k:]
+    plo = int(np.searchsorted(sch, lo))
+    phi = int(np.searchsorted(sch, hi))
+    sc = sch[plo:phi] - lo
+    rp1 = allreduce(np.where(lm >= 0, r_loc[np.maximum(lm, 0)], 0.0))
+    y1 = a11(rp1)
+    rp2l = r_loc[sc] - K12[:, plo:phi].T @ y1
+    full = np.zeros(n2)
+    full[plo:phi] = rp2l
+    full = allreduce(full)
+    w = np.zeros(n2)
+    w[plo:phi] = G[plo:phi, :] @ full
+    w = allreduce(w)
+    y2l = G.T[plo:phi, :] @ w
+    u = allreduce(K12[:, plo:phi] @ y2l)
+    y1 = a11(rp1 - u)
+    out = np.zeros(hi - lo)
+    out[lm[lm >= 0]] = y1[lm >= 0]
+    out[sc] = y2l
+    ref = S.afn_apply(F, r)[lo:hi]
+    e_afn = float(np.linalg.norm(out - ref) / np.linalg.norm(ref))
+    # ---- Nystrom
+    permn = np.random.default_rng(4).permutation(n).astype(np.int32)
+    U, s, eta = S.nys_setup(X, permn, k, f, l, mu, "gaussian", wins)
+    pos = np.zeros(hi - lo, dtype=int)
+    for i, p in enumerate(permn):
+        if lo <= p < hi:
+            pos[p - lo] = i
+    UT = U[pos, :].T
+    z = allreduce(UT @ r_loc)
+    outn = r_loc / eta + UT.T @ ((s - 1.0 / eta) * z)
+    refn = S.nys_apply(permn, U, s, eta, r)[lo:hi]
+    e_nys = float(np.linalg.norm(outn - refn) / np.linalg.norm(refn))
+    q.put((rank, e_afn, e_nys))
+    dist.destroy_process_group()
+
+
+def test_sharded_preconditioner_algebra_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_precond_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, e_afn, e_nys in res:
+        assert e_afn <= 1e-10, (rank, e_afn)
+        assert e_nys <= 1e-10, (rank, e_nys)
