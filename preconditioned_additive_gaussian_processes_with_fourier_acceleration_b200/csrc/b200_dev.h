@@ -78,6 +78,9 @@ int b200k_backward_fft_batch(const b200_win_dev *w, int nb, int which);
 int b200k_warp_ranges(void);
 int b200k_spread3_warp(const b200_win_dev *w);
 int b200k_gather3_warp(const b200_win_dev *w, double *d_f);
+/* nfft12_stream.cu: 1-D / 2-D windows, warp-per-range with the footprint in registers */
+int b200k_spread_stream(const b200_win_dev *w);
+int b200k_gather_stream(const b200_win_dev *w, double *d_f);
 /* nfft3d_mma.cu: the same streaming decomposition on the fp64 tensor cores (DMMA) */
 int b200k_spread3_mma(const b200_win_dev *w);
 int b200k_gather3_mma(const b200_win_dev *w, double *d_f);
