@@ -82,6 +82,7 @@ int b200k_gather3_warp(const b200_win_dev *w, double *d_f);
 int b200k_spread_stream(const b200_win_dev *w);
 int b200k_gather_stream(const b200_win_dev *w, double *d_f);
 /* nfft3d_mma.cu: the same streaming decomposition on the fp64 tensor cores (DMMA) */
+int b200k_mma_warp_ranges(void);
 int b200k_spread3_mma(const b200_win_dev *w);
 int b200k_gather3_mma(const b200_win_dev *w, double *d_f);
 /* all (equally shaped, dense) 3-D windows of an additive kernel in one launch: per-window pointers and the window's own

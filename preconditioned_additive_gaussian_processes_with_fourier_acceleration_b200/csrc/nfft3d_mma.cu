@@ -221,21 +221,21 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
          const double b0 = aj * row[2 * TAPS + g];
          const double p2 = row[TAPS + g];
          const double p2e = row[TAPS + 8 + (g & 1)];
-         // all operand products of the k-step first, then the tensor instructions back to back: DMUL and DMMA share one
-         // unit, and a DMMA that waits for its own DMUL leaves that unit idle (ncu: 38 % of the stall samples sat there)
-         double af[MT], be[3];
+         // operand products right in front of their tensor instruction (keeps the register count at 4 CTAs per SM; hoisting
+         // all products of a k-step in front of the DMMAs was measured to make no difference)
 #pragma unroll
          for (int i = 0; i < 10; i += 2)
          {
             const double2 p1 = *reinterpret_cast<const double2 *>(row + i);
-            af[i] = p1.x * p2;
-            af[i + 1] = p1.y * p2;
+            m_dmma(acc[i][0], acc[i][1], p1.x * p2, b0);
+            m_dmma(acc[i + 1][0], acc[i + 1][1], p1.y * p2, b0);
          }
 #pragma unroll
          for (int i = 0; i < 3; i++)
          {
             const int x = 4 * i + (g >> 1);
-            af[10 + i] = (i < 2 || g < 4) ? row[x < TAPS ? x : TAPS - 1] * p2e : 0.0;
+            const double af = (i < 2 || g < 4) ? row[x < TAPS ? x : TAPS - 1] * p2e : 0.0;
+            m_dmma(acc[10 + i][0], acc[10 + i][1], af, b0);
          }
          // edge part: A(x, k) = a psi1[x], B(k, n = g of tile j) = psi2[4 j + g / 2] psi3[8 + (g & 1)]
          const double p3 = row[2 * TAPS + 8 + (g & 1)];
@@ -245,16 +245,9 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
          for (int j = 0; j < 3; j++)
          {
             const int y = 4 * j + (g >> 1);
-            be[j] = (j < 2 || g < 4) ? row[TAPS + (y < TAPS ? y : TAPS - 1)] * p3 : 0.0;
-         }
-#pragma unroll
-         for (int i = 0; i < MT; i++)
-            m_dmma(acc[i][0], acc[i][1], af[i], b0);
-#pragma unroll
-         for (int j = 0; j < 3; j++)
-         {
-            m_dmma(ace[0][j][0], ace[0][j][1], ae0, be[j]);
-            m_dmma(ace[1][j][0], ace[1][j][1], ae1, be[j]);
+            const double be = (j < 2 || g < 4) ? row[TAPS + (y < TAPS ? y : TAPS - 1)] * p3 : 0.0;
+            m_dmma(ace[0][j][0], ace[0][j][1], ae0, be);
+            m_dmma(ace[1][j][0], ace[1][j][1], ae1, be);
          }
       }
       dcur = dnext;
@@ -367,32 +360,28 @@ __device__ __forceinline__ void m_gather_range(const double *__restrict__ psi, c
       double ca[2] = {0.0, 0.0}, cb[2] = {0.0, 0.0}, cc[2] = {0.0, 0.0}, cd[2] = {0.0, 0.0};
       {
          const double q0 = row[TAPS + t], q1 = row[TAPS + 4 + t], q2 = row[TAPS + 8 + (t & 1)];
-         double af[KS]; // all operand products first, then the tensor instructions back to back (see the spread)
 #pragma unroll
          for (int x = 0; x < 10; x += 2)
          {
             const double2 p1 = *reinterpret_cast<const double2 *>(row + x);
-            af[2 * x] = p1.x * q0;
-            af[2 * x + 1] = p1.x * q1;
-            af[2 * x + 2] = p1.y * q0;
-            af[2 * x + 3] = p1.y * q1;
+            m_dmma(ca[0], ca[1], p1.x * q0, hb[2 * x]);
+            m_dmma(cb[0], cb[1], p1.x * q1, hb[2 * x + 1]);
+            m_dmma(cc[0], cc[1], p1.y * q0, hb[2 * x + 2]);
+            m_dmma(cd[0], cd[1], p1.y * q1, hb[2 * x + 3]);
          }
 #pragma unroll
          for (int s = 0; s < 5; s++)
-            af[20 + s] = row[2 * s + (t >> 1)] * q2;
-#pragma unroll
-         for (int s = 0; s < 20; s += 4)
          {
-            m_dmma(ca[0], ca[1], af[s], hb[s]);
-            m_dmma(cb[0], cb[1], af[s + 1], hb[s + 1]);
-            m_dmma(cc[0], cc[1], af[s + 2], hb[s + 2]);
-            m_dmma(cd[0], cd[1], af[s + 3], hb[s + 3]);
+            const double af = row[2 * s + (t >> 1)] * q2;
+            if ((s & 3) == 0)
+               m_dmma(ca[0], ca[1], af, hb[20 + s]);
+            else if ((s & 3) == 1)
+               m_dmma(cb[0], cb[1], af, hb[20 + s]);
+            else if ((s & 3) == 2)
+               m_dmma(cc[0], cc[1], af, hb[20 + s]);
+            else
+               m_dmma(cd[0], cd[1], af, hb[20 + s]);
          }
-         m_dmma(ca[0], ca[1], af[20], hb[20]);
-         m_dmma(cb[0], cb[1], af[21], hb[21]);
-         m_dmma(cc[0], cc[1], af[22], hb[22]);
-         m_dmma(cd[0], cd[1], af[23], hb[23]);
-         m_dmma(ca[0], ca[1], af[24], hb[24]);
          ca[0] += cb[0] + (cc[0] + cd[0]);
          ca[1] += cb[1] + (cc[1] + cd[1]);
       }
@@ -458,8 +447,14 @@ k_gather3_mma_batch(const b200_mma_win *__restrict__ W, int P)
 // ---------------------------------------------------------------------------------------------------- launch layer
 extern "C" {
 
-int b200k_mma_warps_per_cta(void) { return MWARPS_PER_CTA; }
-int b200k_mma_ctas_per_sm(void) { return MCTAS_PER_SM; }
+// warps of one resident wave of the tensor-core kernels (the fused launches size their partitions with it)
+int b200k_mma_warp_ranges(void)
+{
+   int sm = 148, dev = 0;
+   if (cudaGetDevice(&dev) == cudaSuccess)
+      cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+   return sm * MCTAS_PER_SM * MWARPS_PER_CTA;
+}
 
 int b200k_spread3_mma(const b200_win_dev *w)
 {

@@ -1089,7 +1089,7 @@ done:
 /* returns 1 when the fused path is available */
 static int additive_fused_prepare(b200_additive *A)
 {
-   int nb = A->nbatch, i, c, total_warps = b200k_warp_ranges();
+   int nb = A->nbatch, i, c, total_warps = b200k_mma_warp_ranges();
    int *hn;
    const int **hperm;
    double **ha;
