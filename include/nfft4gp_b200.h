@@ -117,6 +117,15 @@ int Nfft4GPSolverPcg(void *mat_data, int n, func_symmatvec matvec, void *prec_da
                      NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs, int maxits, int atol, NFFT4GP_DOUBLE tol,
                      NFFT4GP_DOUBLE *prel_res, NFFT4GP_DOUBLE **prel_res_v, int *piter, int print_level);
 
+/* Flexible GMRES with restarts (INC/_solvers.h:137, SRC/solvers/fgmres.c:3-252) -- the solver the reference's GP loss,
+ * prediction and TESTS drivers call.  Same control flow and quirks (restart scaled by the estimated residual norm, Givens
+ * breakdown leaves without updating x, the end-of-cycle message is printed at print_level == 0, *prel_res_v has
+ * maxits + 1 entries).  Krylov bases, Arnoldi step (modified Gram-Schmidt, no re-orthogonalisation) and all vector
+ * operations run on the GPU; foreign function pointers are honoured as in Nfft4GPSolverPcg. */
+int Nfft4GPSolverFgmres(void *mat_data, int n, func_symmatvec matvec, void *prec_data, func_solve precondfunc,
+                        NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs, int kdim, int maxits, int atol, NFFT4GP_DOUBLE tol,
+                        NFFT4GP_DOUBLE *prel_res, NFFT4GP_DOUBLE **prel_res_v, int *piter, int print_level);
+
 /* ------------------------------------------------------------------------------------------
  * Part 1c: preconditioners (INC/_preconds.h; SRC/preconds/nys.c, fsai.c, afn.c/afn.h)
  * Handles are opaque here (the reference's callers only use the functions).
@@ -204,6 +213,10 @@ int Nfft4GPB200PrecondSolveDevice(void *prec, func_solve which, int n, double *d
 int Nfft4GPB200SolverPcgDevice(void *mat_data, int n, func_symmatvec matvec, void *prec_data, func_solve precondfunc,
                                double *d_x, const double *d_rhs, int maxits, int atol, double tol,
                                double *prel_res, double **prel_res_v, int *piter, int print_level);
+
+int Nfft4GPB200SolverFgmresDevice(void *mat_data, int n, func_symmatvec matvec, void *prec_data, func_solve precondfunc,
+                                  double *d_x, const double *d_rhs, int kdim, int maxits, int atol, double tol,
+                                  double *prel_res, double **prel_res_v, int *piter, int print_level);
 
 /* Upload precomputed factors (e.g. produced by the reference's CPU setup) instead of running the setup here. */
 int Nfft4GPB200PrecondNysSetFactors(void *nys, int n, int k, const int *perm, const double *U /* n x k col-major */,

@@ -15,7 +15,8 @@ from .capi import (  # noqa: F401
     NysPrecond,
     build_library,
     lib,
+    solver_fgmres,
     solver_pcg,
 )
 
-__all__ = ["LIB_PATH", "AdditiveNFFTKernel", "DenseAdditiveKernel", "DensePlainKernel", "NysPrecond", "FsaiPrecond", "AfnPrecond", "build_library", "lib", "solver_pcg"]
+__all__ = ["LIB_PATH", "AdditiveNFFTKernel", "DenseAdditiveKernel", "DensePlainKernel", "NysPrecond", "FsaiPrecond", "AfnPrecond", "build_library", "lib", "solver_pcg", "solver_fgmres"]

@@ -64,6 +64,8 @@ def lib():
         "Nfft4GPNFFTMatSymv": (i, margs),
         "Nfft4GPNFFTGradMatSymv": (i, margs),
         "Nfft4GPSolverPcg": (i, [vp, i, vp, vp, vp, c_double_p, c_double_p, i, i, d, c_double_p, C.POINTER(c_double_p), c_int_p, i]),
+        "Nfft4GPSolverFgmres": (i, [vp, i, vp, vp, vp, c_double_p, c_double_p, i, i, i, d, c_double_p, C.POINTER(c_double_p), c_int_p, i]),
+        "Nfft4GPB200SolverFgmresDevice": (i, [vp, i, vp, vp, vp, vp, vp, i, i, i, d, c_double_p, C.POINTER(c_double_p), c_int_p, i]),
         "Nfft4GPPrecondNysCreate": (vp, []), "Nfft4GPPrecondNysFree": (None, [vp]), "Nfft4GPPrecondNysReset": (None, [vp]),
         "Nfft4GPPrecondNysSetRank": (None, [vp, i]), "Nfft4GPPrecondNysSetPerm": (None, [vp, c_int_p, i]),
         "Nfft4GPPrecondNysSolve": (i, [vp, i, c_double_p, c_double_p]),
@@ -484,6 +486,26 @@ def solver_pcg(mat, n, matvec_fn, prec, solve_fn, x0, rhs, maxits, atol, tol, pr
     m = min(maxits, n) + 1
     if it.value == 0 and not atol and rel.value <= tol:
         m = 1  # early exits of pcg.c:32-41 / 70-84 allocate a single entry
+    hist = np.ctypeslib.as_array(relv, shape=(m,)).copy() if relv else np.zeros(0)
+    if relv:
+        L.free(relv)
+    return x, rel.value, hist, it.value
+
+
+def solver_fgmres(mat, n, matvec_fn, prec, solve_fn, x0, rhs, kdim, maxits, atol, tol, print_level=1):
+    """Nfft4GPSolverFgmres with host vectors.  Returns (x, rel_res, rel_res_v, iters).  print_level defaults to 1 because the
+    reference prints its end-of-cycle message at level 0 (fgmres.c:198-201); use -1 for silence."""
+    L = lib()
+    x = np.array(x0, dtype=np.float64)
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    rel = C.c_double(0.0)
+    relv = c_double_p()
+    it = C.c_int(0)
+    rc = L.Nfft4GPSolverFgmres(mat, n, matvec_fn, prec, solve_fn, dptr(x), dptr(rhs), kdim, maxits, atol, tol,
+                               C.byref(rel), C.byref(relv), C.byref(it), print_level)
+    if rc != 0:
+        raise RuntimeError("Nfft4GPSolverFgmres failed")
+    m = maxits + 1 if it.value > 0 else 1
     hist = np.ctypeslib.as_array(relv, shape=(m,)).copy() if relv else np.zeros(0)
     if relv:
         L.free(relv)

@@ -124,6 +124,10 @@ int b200k_fill(int n, double v, double *dst);
 int b200k_scale(int n, double a, double *x);
 int b200k_axpy(int n, double a, const double *x, double *y);
 /* sharded applies: gather / scatter through an index array with holes (idx < 0), Nystrom coefficient, local factor rows */
+/* device-resident modified Gram-Schmidt step, scaling by a device-side norm, x += Z coef (FGMRES) */
+int b200k_mgs_step(int n, double *w, const double *v_prev, const double *d_t_prev, const double *v_next, double *d_out);
+int b200k_scale_by_inv_norm(int n, double *w, const double *d_nrm2, double *d_t_out);
+int b200k_multi_axpy(int n, int m, const double *Z, size_t ldz, const double *d_coef, double *x);
 int b200k_gather_idx(int m, const int *idx, const double *src, double *dst);
 int b200k_scatter_idx(int m, const int *idx, const double *src, double *dst);
 int b200k_nys_coef(int k, const double *s, double inv_eta, const double *z, double *c);

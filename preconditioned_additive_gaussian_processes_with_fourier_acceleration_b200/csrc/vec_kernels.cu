@@ -145,6 +145,54 @@ static int red_blocks(int n)
 }
 
 
+// ---- modified Gram-Schmidt without host round trips (FGMRES, SRC/linearalg/matops.c:274-346): one fused pass per basis
+// vector:  w -= (*t_prev) * v_prev  (the update of the PREVIOUS step, coefficient read from device memory), then the partial
+// sums of  w . v_next  (v_next == nullptr: w . w).  The coefficients never leave the device inside an Arnoldi step.
+__global__ void __launch_bounds__(RED_THREADS)
+k_mgs_stage1(int n, double *__restrict__ w, const double *__restrict__ v_prev, const double *__restrict__ t_prev,
+             const double *__restrict__ v_next)
+{
+   __shared__ double sh[32];
+   const double tp = v_prev ? *t_prev : 0.0;
+   double s = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+   {
+      double wi = w[i];
+      if (v_prev)
+      {
+         wi = fma(-tp, v_prev[i], wi);
+         w[i] = wi;
+      }
+      s = fma(wi, v_next ? v_next[i] : wi, s);
+   }
+   double r = block_sum(s, sh);
+   if (threadIdx.x == 0)
+      g_partial[blockIdx.x] = r;
+}
+
+// t = sqrt(*nrm2) -> *t_out ; w *= 1 / t   (matops.c:336-341)
+__global__ void k_scale_by_inv_norm(int n, double *__restrict__ w, const double *__restrict__ nrm2, double *__restrict__ t_out)
+{
+   const double t = sqrt(*nrm2);
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i == 0)
+      *t_out = t;
+   if (i < n)
+      w[i] *= 1.0 / t;
+}
+
+// x += Z(:, 0:m) * coef   (Z column-major with leading dimension ldz, coefficients in device memory; fgmres.c:215-219)
+__global__ void k_multi_axpy(int n, int m, const double *__restrict__ Z, size_t ldz, const double *__restrict__ coef, double *__restrict__ x)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n)
+      return;
+   double xi = x[i];
+   for (int j = 0; j < m; j++)
+      xi = fma(coef[j], Z[(size_t)j * ldz + i], xi); // same order as the reference's sequence of axpys
+   x[i] = xi;
+}
+
 // ---- index gather / scatter with holes (idx < 0 = not owned by this rank), used by the point-block-sharded applies
 __global__ void k_gather_idx(int m, const int *__restrict__ idx, const double *__restrict__ src, double *__restrict__ dst)
 {
@@ -305,6 +353,35 @@ int b200k_gather_rows_T(int nl, int k, const int *pos, const double *U, int ldu,
    if (nl <= 0)
       return 0;
    k_gather_rows_T<<<b200_cdiv((long long)nl * k, 256), 256, 0, b200_stream()>>>(nl, k, pos, U, ldu, UT);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_mgs_step(int n, double *w, const double *v_prev, const double *d_t_prev, const double *v_next, double *d_out)
+{
+   B200ProfScope prof_scope_(PC_VEC);
+   int nb = red_blocks(n);
+   k_mgs_stage1<<<nb, RED_THREADS, 0, b200_stream()>>>(n, w, v_prev, d_t_prev, v_next);
+   B200_LAUNCHED();
+   k_reduce_stage2<<<1, RED_THREADS, 0, b200_stream()>>>(nb, 1, d_out);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_scale_by_inv_norm(int n, double *w, const double *d_nrm2, double *d_t_out)
+{
+   B200ProfScope prof_scope_(PC_VEC);
+   k_scale_by_inv_norm<<<b200_cdiv(n > 0 ? n : 1, 256), 256, 0, b200_stream()>>>(n, w, d_nrm2, d_t_out);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_multi_axpy(int n, int m, const double *Z, size_t ldz, const double *d_coef, double *x)
+{
+   B200ProfScope prof_scope_(PC_VEC);
+   if (n <= 0 || m <= 0)
+      return 0;
+   k_multi_axpy<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, m, Z, ldz, d_coef, x);
    B200_LAUNCHED();
    return 0;
 }

@@ -167,7 +167,50 @@ def nys_plain_case():
     print("wrote nys plain case: nys-pcg it", itn, "plain pcg it", it0)
 
 
+def fgmres_case():
+    """Reference Nfft4GPSolverFgmres (SRC/solvers/fgmres.c) on the reference's dense Gaussian kernel, with restarts (kdim 15),
+    without and with the reference's Nystrom preconditioner, plus a run that stops at the iteration limit."""
+    z = np.load(os.path.join(OUT, "nys_gauss300.npz"))
+    X, f, l, mu, rhs, perm, k = z["X"], float(z["f"]), float(z["l"]), float(z["mu"]), z["rhs"], z["perm"], int(z["k"])
+    n, d = X.shape[1], X.shape[0]
+    L.Nfft4GPKernelParamCreate.restype = C.c_void_p
+    L.Nfft4GPKernelParamCreate.argtypes = [C.c_int, C.c_int]
+    kh = L.Nfft4GPKernelParamCreate(n, 1)
+    R.set_hyper(kh, f, l, mu)
+    K = C.c_void_p()
+    assert L.Nfft4GPKernelGaussianKernel(kh, R.dptr(X), n, n, d, None, 0, None, 0, C.byref(K), None) == 0
+    nys = L.Nfft4GPPrecondNysCreate()
+    L.Nfft4GPPrecondNysSetRank(nys, k)
+    L.Nfft4GPPrecondNysSetPerm(nys, R.iptr(perm), 0)
+    assert L.Nfft4GPPrecondNysSetupWithKernel(R.dptr(X), n, n, d, C.cast(L.Nfft4GPKernelGaussianKernel, C.c_void_p), kh, 0, nys) == 0
+    L.Nfft4GPSolverFgmres.restype = C.c_int
+    L.Nfft4GPSolverFgmres.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, R.c_double_p, R.c_double_p, C.c_int,
+                                      C.c_int, C.c_int, C.c_double, R.c_double_p, C.POINTER(R.c_double_p), R.c_int_p, C.c_int]
+
+    def run(prec, pf, kdim, maxits, tol):
+        x = np.zeros(n)
+        rel = C.c_double(0.0)
+        relv = R.c_double_p()
+        it = C.c_int(0)
+        L.Nfft4GPSolverFgmres(K, n, C.cast(L.Nfft4GPDenseMatSymv, C.c_void_p), prec, C.cast(pf, C.c_void_p) if pf else None, R.dptr(x),
+                              R.dptr(rhs), kdim, maxits, 0, tol, C.byref(rel), C.byref(relv), C.byref(it), 1)
+        hist = np.ctypeslib.as_array(relv, shape=(maxits + 1,)).copy()
+        return x, rel.value, hist, it.value
+
+    out = {}
+    for tag, (prec, pf, kdim, maxits, tol) in {"plain": (None, None, 15, 300, 1e-8), "nys": (nys, L.Nfft4GPPrecondNysSolve, 15, 300, 1e-8),
+                                                "cap": (None, None, 10, 25, 1e-12)}.items():
+        x, rel, hist, it = run(prec, pf, kdim, maxits, tol)
+        out.update({f"{tag}_x": x, f"{tag}_rel": rel, f"{tag}_hist": hist, f"{tag}_it": it, f"{tag}_kdim": kdim, f"{tag}_maxits": maxits,
+                    f"{tag}_tol": tol})
+        print("fgmres", tag, "iterations", it, "rel", rel)
+    np.savez_compressed(os.path.join(OUT, "fgmres_dense300.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "fgmres":
+        fgmres_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "nys":
         nys_plain_case()
         sys.exit(0)
@@ -179,3 +222,4 @@ if __name__ == "__main__":
     solver_case()
     fsai_case()
     nys_plain_case()
+    fgmres_case()
