@@ -79,3 +79,19 @@ def test_fgmres_on_nfft_matvec_with_afn(gpu):
     B.free()
     Af.free()
     D.free()
+
+
+def test_fgmres_early_exits(gpu):
+    """fgmres.c:43-54 (zero right-hand side: x = 0, one history entry) and :75-92 (the initial guess already solves it)."""
+    n, d = 1200, 3
+    X = uniform_cloud(n, d)
+    win = np.arange(3, dtype=np.int32)
+    A = gpu.AdditiveNFFTKernel(X, win, 1, 3, "gaussian").build(1.0, 1.0, 0.5)
+    x, rel, hist, it = gpu.solver_fgmres(A.K, n, A.matvec_fn(), None, None, np.ones(n), np.zeros(n), 10, 50, 0, 1e-8)
+    assert it == 0 and rel == 0.0 and hist.size == 1 and np.all(x == 0.0)
+    rhs = rand_vec(n, 3)
+    xs, rels, hs, its = gpu.solver_fgmres(A.K, n, A.matvec_fn(), None, None, np.zeros(n), rhs, 30, 200, 0, 1e-10)
+    assert its > 0 and rels <= 1e-10
+    x2, rel2, h2, it2 = gpu.solver_fgmres(A.K, n, A.matvec_fn(), None, None, xs, rhs, 30, 200, 0, 1e-6)
+    assert it2 <= 1 and rel2 <= 1e-6
+    A.free()

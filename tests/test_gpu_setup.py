@@ -259,3 +259,85 @@ def test_afn_pcg_on_nfft_matvec(gpu):
     B.free()
     Af.free()
     D.free()
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_setup_edge_cases(gpu):
+    L = gpu.lib()
+    X = uniform_cloud(90, 3, seed=5)
+    P = gpu.DensePlainKernel(X, "gaussian").set_hyper(1.0, 0.9, 0.05)
+    K = S.dense_matrix(X, 1.0, 0.9, 0.05)
+    r = rand_vec(90, 1)
+    # FSAI with lfil >= n: dense lower pattern (kernels.c:135-146) -> G'G = K^{-1} exactly
+    F = gpu.FsaiPrecond().setup(P, 128)
+    assert rel_l2(F.solve(r), np.linalg.solve(K, r)) <= 1e-9
+    ia, ja, a = F.get_factors()
+    assert ia[-1] == 90 * 91 // 2
+    F.free()
+    # lfil = 1: diagonal scaling 1 / sqrt(K_ii)
+    F = gpu.FsaiPrecond().setup(P, 1)
+    assert rel_l2(F.solve(r), r / np.diag(K)) <= 1e-13
+    F.free()
+    # lfil beyond the shared-memory row block is refused loudly, never silently truncated
+    F = gpu.FsaiPrecond()
+    L.Nfft4GPPrecondFsaiSetLfil(F.h, 200)
+    X2 = uniform_cloud(400, 3, seed=6)
+    P2 = gpu.DensePlainKernel(X2, "gaussian").set_hyper(1.0, 0.9, 0.05)
+    rc = L.Nfft4GPPrecondFsaiSetupWithKernel(gpu.capi.dptr(P2.X), 400, 400, 3, P2.fn(), P2.h, 0, F.h)
+    assert rc == -1
+    # require_grad is not built: -1, not a silent K-only setup
+    assert L.Nfft4GPPrecondFsaiSetupWithKernel(gpu.capi.dptr(P2.X), 400, 400, 3, P2.fn(), P2.h, 1, F.h) == -1
+    F.free()
+    P2.free()
+    # Nystrom with k = n: exact inverse of K (up to the stabilising shift); AFN with k = n: pure Cholesky block
+    N = gpu.NysPrecond().setup(P, np.arange(90, dtype=np.int32), 90)
+    assert rel_l2(N.solve(r), np.linalg.solve(K, r)) <= 1e-6
+    N.free()
+    Af = gpu.AfnPrecond().setup(P, 90, 10, numests=0, noran=1)
+    assert rel_l2(Af.solve(r), np.linalg.solve(K, r)) <= 1e-8
+    Af.free()
+    P.free()
+
+
+def test_nystrom_setup_with_foreign_kernel(gpu):
+    """A caller's own CPU func_kernel (here: NumPy through a ctypes callback) is honoured by the Nystrom setup exactly as the
+    reference calls it (nys.c:597: K(perm, perm[0:k]) without noise); the factorisation still runs on the GPU."""
+    n, d, k = 500, 4, 40
+    X = uniform_cloud(n, d, seed=8)
+    f, l, mu = 1.2, 0.8, 0.03
+    calls = []
+    keep = []
+
+    def fkernel(_str, data, nn, ldim, dd, permr, kr, permc, kc, Kp, dKp):
+        pr = np.ctypeslib.as_array(permr, shape=(kr,)).copy()
+        pc = np.ctypeslib.as_array(permc, shape=(kc,)).copy()
+        calls.append((kr, kc))
+        blk = np.asfortranarray(S.dense_kernel(X, pr, pc, f, l))
+        import ctypes as C
+        libc = C.CDLL(None)                                     # *Kp == NULL: the callee allocates with malloc, the library frees it
+        libc.malloc.restype = C.c_void_p
+        libc.malloc.argtypes = [C.c_size_t]
+        mem = libc.malloc(8 * kr * kc)
+        C.memmove(mem, blk.ctypes.data, 8 * kr * kc)
+        Kp[0] = C.cast(mem, gpu.capi.c_double_p)
+        return 0
+
+    import ctypes as C
+    FK = C.CFUNCTYPE(C.c_int, C.c_void_p, gpu.capi.c_double_p, C.c_int, C.c_int, C.c_int, gpu.capi.c_int_p, C.c_int, gpu.capi.c_int_p, C.c_int,
+                     C.POINTER(gpu.capi.c_double_p), C.POINTER(gpu.capi.c_double_p))
+    cb = FK(fkernel)
+    keep.append(cb)
+    L = gpu.lib()
+    kh = L.Nfft4GPKernelParamCreate(n, 1)
+    gpu.capi._set_hyper(kh, f, l, mu)
+    perm = np.random.default_rng(9).permutation(n).astype(np.int32)
+    N = gpu.NysPrecond()
+    L.Nfft4GPPrecondNysSetPerm(N.h, gpu.capi.iptr(perm), 0)
+    L.Nfft4GPPrecondNysSetRank(N.h, k)
+    assert L.Nfft4GPPrecondNysSetupWithKernel(gpu.capi.dptr(X), n, n, d, C.cast(cb, C.c_void_p), kh, 0, N.h) == 0
+    assert calls == [(n, k)]
+    Uo, so, eta = S.nys_setup(X, perm, k, f, l, mu)
+    r = rand_vec(n, 2)
+    assert rel_l2(N.solve(r), S.nys_apply(perm, Uo, so, eta, r)) <= 1e-6
+    N.free()
+    L.Nfft4GPKernelParamFree(kh)
