@@ -15,9 +15,13 @@ extern "C" {
 #define B200_NOS 64   /* oversampled FFT length (sigma = 2)   */
 #define B200_MCUT 4   /* window cut-off m                     */
 #define B200_TAPS 10  /* 2m + 2                               */
-/* 3-D windows: average points per occupied cell from which the tensor-core spread / gather (full footprint flush per
- * cell change) beats the DFMA kernels (register-tile shift along l3): measured cross-over, see profiles/README.md */
-#define B200_MMA_MIN_POINTS_PER_CELL 24
+/* 3-D windows: average points per occupied cell from which the tensor-core spread / gather are used instead of the DFMA
+ * kernels.  With the shared-memory footprint ring and the fused launches the tensor-core path wins down to ~ 2 points per
+ * cell (n = 10^4 .. 10^5 measured, profiles/README.md); below that almost every chunk holds one point and 3 of the 4
+ * k-slots of a DMMA are empty. */
+#ifndef B200_MMA_MIN_POINTS_PER_CELL
+#define B200_MMA_MIN_POINTS_PER_CELL 2
+#endif
 
 /* device-side state of one feature window */
 typedef struct

@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")/.."
 CS=preconditioned_additive_gaussian_processes_with_fourier_acceleration_b200/csrc
-touch $CS/nfft3d_warp.cu $CS/nfft3d_mma.cu
-make -C $CS -j8 NVEXTRA="$1" > /dev/null 2>&1
+touch $CS/*.cu $CS/*.c
+make -C $CS -j8 NVEXTRA="$1" CFLAGS_EXTRA="$1" > /dev/null 2>&1
 shift
 python scripts/quick_time.py "$@" 2>&1 | grep "variant"
