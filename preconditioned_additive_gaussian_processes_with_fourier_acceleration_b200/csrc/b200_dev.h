@@ -64,7 +64,13 @@ int b200_event_record(void *ev);
 float b200_event_elapsed_ms(void *a, void *b);
 long long b200_launch_count(void);
 void b200_launch_count_reset(void);
+void b200_launch_count_add(long long k);
 void *b200_stream_handle(void); /* cudaStream_t, for NCCL */
+int b200_prof_active(void);
+int b200_graph_begin(void);
+void *b200_graph_end(void);
+int b200_graph_launch(void *exec);
+void b200_graph_destroy(void *exec);
 void b200_prof_start(void);
 int b200_prof_stop(double *sums_ms, long long *counts, int ncls);
 

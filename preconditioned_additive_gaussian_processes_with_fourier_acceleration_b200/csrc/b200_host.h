@@ -67,6 +67,16 @@ typedef struct b200_additive
    double **d_prep_a;
    int *d_prep_n;
    int prep_nmax;
+   /* CUDA graphs of the device-resident matvec, keyed by its arguments (the launch sequence is fixed per handle) */
+   struct
+   {
+      const double *x;
+      double *y;
+      double alpha, beta;
+      void *exec;
+      long long launches; /* kernels inside the graph (the launch counter is advanced by this on replay) */
+   } graph[4];
+   int graph_next, graph_off; /* graph_off: capture failed once or NFFT4GP_B200_NO_GRAPH is set */
    int nlocal;     /* windows owned by this rank under mode 1 */
    const double **d_fptr_local;
    const int **d_invptr_local;

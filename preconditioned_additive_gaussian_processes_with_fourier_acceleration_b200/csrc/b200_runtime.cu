@@ -78,6 +78,52 @@ int b200_prof_stop(double *sums, long long *counts, int ncls)
    return n;
 }
 
+int b200_prof_active(void) { return g_prof_on ? 1 : 0; }
+
+// ---- CUDA graphs: the launch sequence of one matvec (11 kernels + 1 memset for three 3-D windows) is captured once per
+// (x, y, alpha, beta) signature and replayed; at small per-GPU sizes (multi-GPU strong scaling) the matvec is otherwise
+// bound by the host's launch rate, not by the GPU.
+int b200_graph_begin(void)
+{
+   if (cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+   {
+      cudaGetLastError();
+      return -1;
+   }
+   return 0;
+}
+
+// ends the capture; returns an executable graph or NULL (capture invalidated: the caller falls back to plain launches)
+void *b200_graph_end(void)
+{
+   cudaGraph_t g = nullptr;
+   cudaGraphExec_t ex = nullptr;
+   if (cudaStreamEndCapture(g_stream, &g) != cudaSuccess || !g)
+   {
+      cudaGetLastError();
+      return nullptr;
+   }
+   if (cudaGraphInstantiate(&ex, g, 0) != cudaSuccess)
+   {
+      cudaGetLastError();
+      ex = nullptr;
+   }
+   cudaGraphDestroy(g);
+   return (void *)ex;
+}
+
+int b200_graph_launch(void *exec)
+{
+   B200_CHECK(cudaGraphLaunch((cudaGraphExec_t)exec, g_stream));
+   return 0;
+}
+
+void b200_graph_destroy(void *exec)
+{
+   if (exec)
+      cudaGraphExecDestroy((cudaGraphExec_t)exec);
+}
+
 int b200_device_count(void)
 {
    int c = 0;
@@ -246,6 +292,7 @@ float b200_event_elapsed_ms(void *a, void *b)
 
 long long b200_launch_count(void) { return g_launches.load(); }
 void b200_launch_count_reset(void) { g_launches.store(0); }
+void b200_launch_count_add(long long k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
 void *b200_stream_handle(void) { return (void *)g_stream; }
 
 } // extern "C"

@@ -139,20 +139,41 @@ __device__ __forceinline__ void m_acc_to_ring(double *__restrict__ cb, int key, 
       }
 }
 
-// planes z in [0, nz) of the footprint of cell `key` leave the ring: add them to the grid and clear their slots
-__device__ __forceinline__ void m_ring_flush(double *__restrict__ cb, double *__restrict__ grid, int key, int nz, int lane)
+// Per (c1, c2) column of cells: the grid offsets of the (up to) four (x, y) footprint entries e = lane + 32 k that this lane
+// writes out when a plane leaves the ring.  Computed once per column change, so that flushing a plane is 4 x (LDS, RED, STS).
+struct m_col_offsets
 {
-   const int c1 = (key >> 12) & 63, c2 = (key >> 6) & 63, c3 = key & 63;
+   int o[4];
+};
+__device__ __forceinline__ m_col_offsets m_column_offsets(int key, int lane)
+{
+   const int c1 = (key >> 12) & 63, c2 = (key >> 6) & 63;
+   m_col_offsets r;
+#pragma unroll
+   for (int k = 0; k < 4; k++)
+   {
+      const int e = lane + 32 * k;
+      const int x = e / TAPS, y = e - TAPS * x;
+      r.o[k] = e < CB_PLANE ? (m_tap_idx(c1, x) * NOS + m_tap_idx(c2, y)) * NOS : -1;
+   }
+   return r;
+}
+
+// planes z in [0, nz) of the footprint of cell `key` leave the ring: add them to the grid and clear their slots
+__device__ __forceinline__ void m_ring_flush(double *__restrict__ cb, double *__restrict__ grid, int key, int nz, int lane, const m_col_offsets &co)
+{
+   const int c3 = key & 63;
    for (int z = 0; z < nz; z++)
    {
-      double *plane = cb + ((c3 + z) % TAPS) * CB_PLANE;
-      const int gz = m_tap_idx(c3, z);
-      for (int e = lane; e < CB_PLANE; e += 32)
-      {
-         const int x = e / TAPS, y = e - TAPS * x;
-         m_red_add(grid + (size_t)(m_tap_idx(c1, x) * NOS + m_tap_idx(c2, y)) * NOS + gz, plane[e]);
-         plane[e] = 0.0;
-      }
+      double *plane = cb + ((c3 + z) % TAPS) * CB_PLANE + lane;
+      double *gp = grid + m_tap_idx(c3, z);
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+         if (co.o[k] >= 0)
+         {
+            m_red_add(gp + co.o[k], plane[32 * k]);
+            plane[32 * k] = 0.0;
+         }
    }
 }
 
@@ -166,6 +187,7 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
       return;
    for (int e = lane; e < CB_DOUBLES; e += 32)
       cb[e] = 0.0;
+   m_col_offsets co;
 
    double acc[MT][2], ace[2][3][2];
 #pragma unroll
@@ -179,6 +201,7 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
 
    int4 dcur = chunks[c0];
    int key = dcur.z;
+   co = m_column_offsets(key, lane);
 #pragma unroll
    for (int s = 0; s < MWNS - 1; s++)
    {
@@ -200,11 +223,14 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
       if (dcur.z != key) // warp-uniform: the stream enters another cell
       {
          const int knew = dcur.z, d = knew - key;
+         const bool same_column = (knew >> 6) == (key >> 6);
          m_acc_to_ring(cb, key, g, t, acc, ace);
          __syncwarp();
          // same (c1, c2) column, c3 advanced by d: only the d planes that leave the footprint are written out
-         m_ring_flush(cb, grid, key, ((knew >> 6) == (key >> 6) && d > 0 && d < TAPS) ? d : TAPS, lane);
+         m_ring_flush(cb, grid, key, (same_column && d > 0 && d < TAPS) ? d : TAPS, lane, co);
          __syncwarp();
+         if (!same_column)
+            co = m_column_offsets(knew, lane);
          key = knew;
       }
 
@@ -255,7 +281,7 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
    }
    m_acc_to_ring(cb, key, g, t, acc, ace);
    __syncwarp();
-   m_ring_flush(cb, grid, key, TAPS, lane);
+   m_ring_flush(cb, grid, key, TAPS, lane, co);
 }
 
 // dynamic shared memory of the spread kernels: the cp.async stages of the CTA's warps, then their footprint rings
@@ -479,7 +505,12 @@ int b200k_gather3_mma(const b200_win_dev *w, double *d_f)
 // fused launches over the P windows described by d_batch (device array); total_warps = sum of nwarps, a multiple of the CTA size
 int b200k_spread3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps)
 {
-   B200_CHECK(cudaFuncSetAttribute(k_spread3_mma_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPREAD_SMEM_BYTES));
+   static bool attr_set = false; // once: this call may sit inside a stream capture (CUDA graph of the matvec)
+   if (!attr_set)
+   {
+      B200_CHECK(cudaFuncSetAttribute(k_spread3_mma_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPREAD_SMEM_BYTES));
+      attr_set = true;
+   }
    k_spread3_mma_batch<<<total_warps / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, SPREAD_SMEM_BYTES, b200_stream()>>>(d_batch, P);
    B200_LAUNCHED();
    return 0;

@@ -855,6 +855,8 @@ static int additive_ensure_device(b200_additive *A)
    return 0;
 }
 
+static void additive_graphs_release(b200_additive *A);
+
 static int additive_kernel_build(void *str, int kernel, double *data, int n, int ldim, int d, double **Kp, double **dKp)
 {
    nfft4gp_kernel *k = (nfft4gp_kernel *)str;
@@ -932,6 +934,7 @@ static int additive_kernel_build(void *str, int kernel, double *data, int n, int
    }
    A->kernel = kernel;
    A->built = 1;
+   additive_graphs_release(A); /* hyper-parameters are baked into the captured kernel arguments */
    if (additive_ensure_device(A) || b200_comm_build_local_windows(A))
       return -1;
    *Kp = (double *)str; /* :730-731 */
@@ -1229,18 +1232,78 @@ static int additive_apply_windows(b200_additive *A, const double *d_x, double s,
 
 /* device-resident body of Nfft4GPAdditiveNFFTMatSymv (nfft_interface.c:796-817).
  * n = length of d_x / d_y = the rank's block under point-block sharding, the full n otherwise. */
-int b200_additive_matvec_dev(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y)
+static void additive_graphs_release(b200_additive *A)
+{
+   int i;
+   for (i = 0; i < 4; i++)
+   {
+      b200_graph_destroy(A->graph[i].exec);
+      A->graph[i].exec = NULL;
+   }
+   A->graph_next = 0;
+}
+
+static int additive_matvec_body(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y)
 {
    double s = 1.0 / (double)A->P * alpha; /* :806 */
    double f = A->win[0]->kernel_scale;
+   if (additive_apply_windows(A, d_x, s, 0))
+      return -1;
+   return b200_additive_epilogue(A, n, d_x, s, f * f, A->win[0]->mu, beta, d_y);
+}
+
+int b200_additive_matvec_dev(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y)
+{
+   int i;
    if (!A->built || n != additive_local_n(A))
    {
       printf("Error: additive NFFT matvec on a kernel that was not built for n = %d.\n", n);
       return -1;
    }
-   if (additive_apply_windows(A, d_x, s, 0))
-      return -1;
-   return b200_additive_epilogue(A, n, d_x, s, f * f, A->win[0]->mu, beta, d_y);
+   /* CUDA graph of the whole launch sequence (fused tensor-core path only), one per argument signature */
+   if (!A->graph_off && !b200_prof_active() && additive_fused_prepare(A))
+   {
+      long long before;
+      void *exec;
+      for (i = 0; i < 4; i++)
+         if (A->graph[i].exec && A->graph[i].x == d_x && A->graph[i].y == d_y && A->graph[i].alpha == alpha && A->graph[i].beta == beta)
+         {
+            b200_launch_count_add(A->graph[i].launches);
+            return b200_graph_launch(A->graph[i].exec);
+         }
+      if (getenv("NFFT4GP_B200_NO_GRAPH"))
+         A->graph_off = 1;
+      else if (b200_graph_begin() == 0)
+      {
+         before = b200_launch_count();
+         i = additive_matvec_body(A, n, alpha, d_x, beta, d_y);
+         exec = b200_graph_end();
+         if (i || !exec)
+         {
+            /* capture refused (e.g. a collective that cannot be captured): plain launches from now on */
+            b200_graph_destroy(exec);
+            A->graph_off = 1;
+            if (i)
+               return -1;
+         }
+         else
+         {
+            int slot = A->graph_next;
+            A->graph_next = (A->graph_next + 1) % 4;
+            b200_graph_destroy(A->graph[slot].exec);
+            A->graph[slot].x = d_x;
+            A->graph[slot].y = d_y;
+            A->graph[slot].alpha = alpha;
+            A->graph[slot].beta = beta;
+            A->graph[slot].exec = exec;
+            A->graph[slot].launches = b200_launch_count() - before;
+            return b200_graph_launch(exec);
+         }
+      }
+      else
+         A->graph_off = 1;
+   }
+   return additive_matvec_body(A, n, alpha, d_x, beta, d_y);
 }
 
 /* device-resident body of Nfft4GPAdditiveNFFTGradMatSymv (nfft_interface.c:819-840) */
@@ -1373,6 +1436,7 @@ void Nfft4GPAdditiveNFFTKernelFree(void *str)
       b200_free((void *)A->d_fptr_local);
       b200_free((void *)A->d_invptr_local);
       additive_fused_release(A);
+      additive_graphs_release(A);
       free(A);
    }
    if (k->_own_buffer)
