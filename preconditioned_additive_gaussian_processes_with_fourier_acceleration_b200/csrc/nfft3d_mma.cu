@@ -241,37 +241,49 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
          if (kk == 1 && dcur.y <= 4) // warp-uniform: the second k-step holds only zero-weight points
             break;
          const double *row = stage + (4 * kk + t) * RS;   // operand column / row k = t: the point of this thread
+         // ---- all shared-memory operands of the k-step first (18 loads in flight together: their latency is paid once, not
+         // in front of every product -- ncu showed the products stalled on the short scoreboard)
          const double aj = stage[WS * RS + 4 * kk + t];    // zero past the end of the chunk
-         // main part: B(k, n = g) = a psi3[g];  A(m, k) = psi1[x] psi2[y] with (x, y) = (i, g) for the tiles i < 10 and
-         // (4 i' + g / 2, 8 + (g & 1)) for the tiles 10 + i'
-         const double b0 = aj * row[2 * TAPS + g];
+         const double r3g = row[2 * TAPS + g];
          const double p2 = row[TAPS + g];
          const double p2e = row[TAPS + 8 + (g & 1)];
-         // operand products right in front of their tensor instruction (keeps the register count at 4 CTAs per SM; hoisting
-         // all products of a k-step in front of the DMMAs was measured to make no difference)
+         const double p3 = row[2 * TAPS + 8 + (g & 1)];
+         const double r1g = row[g];
+         const double r1e = row[8 + (g & 1)];
+         double2 p1[5];
 #pragma unroll
-         for (int i = 0; i < 10; i += 2)
+         for (int i = 0; i < 5; i++)
+            p1[i] = *reinterpret_cast<const double2 *>(row + 2 * i);
+         double x1[3], y2[3];
+#pragma unroll
+         for (int i = 0; i < 3; i++)
          {
-            const double2 p1 = *reinterpret_cast<const double2 *>(row + i);
-            m_dmma(acc[i][0], acc[i][1], p1.x * p2, b0);
-            m_dmma(acc[i + 1][0], acc[i + 1][1], p1.y * p2, b0);
+            const int x = 4 * i + (g >> 1), y = 4 * i + (g >> 1);
+            x1[i] = row[x < TAPS ? x : TAPS - 1];
+            y2[i] = row[TAPS + (y < TAPS ? y : TAPS - 1)];
+         }
+         // ---- main part: B(k, n = g) = a psi3[g];  A(m, k) = psi1[x] psi2[y] with (x, y) = (i, g) for the tiles i < 10 and
+         // (4 i' + g / 2, 8 + (g & 1)) for the tiles 10 + i'
+         const double b0 = aj * r3g;
+#pragma unroll
+         for (int i = 0; i < 5; i++)
+         {
+            m_dmma(acc[2 * i][0], acc[2 * i][1], p1[i].x * p2, b0);
+            m_dmma(acc[2 * i + 1][0], acc[2 * i + 1][1], p1[i].y * p2, b0);
          }
 #pragma unroll
          for (int i = 0; i < 3; i++)
          {
-            const int x = 4 * i + (g >> 1);
-            const double af = (i < 2 || g < 4) ? row[x < TAPS ? x : TAPS - 1] * p2e : 0.0;
+            const double af = (i < 2 || g < 4) ? x1[i] * p2e : 0.0;
             m_dmma(acc[10 + i][0], acc[10 + i][1], af, b0);
          }
-         // edge part: A(x, k) = a psi1[x], B(k, n = g of tile j) = psi2[4 j + g / 2] psi3[8 + (g & 1)]
-         const double p3 = row[2 * TAPS + 8 + (g & 1)];
-         const double ae0 = aj * row[g];
-         const double ae1 = (g < 2) ? aj * row[8 + g] : 0.0;
+         // ---- edge part: A(x, k) = a psi1[x], B(k, n = g of tile j) = psi2[4 j + g / 2] psi3[8 + (g & 1)]
+         const double ae0 = aj * r1g;
+         const double ae1 = (g < 2) ? aj * r1e : 0.0;
 #pragma unroll
          for (int j = 0; j < 3; j++)
          {
-            const int y = 4 * j + (g >> 1);
-            const double be = (j < 2 || g < 4) ? row[TAPS + (y < TAPS ? y : TAPS - 1)] * p3 : 0.0;
+            const double be = (j < 2 || g < 4) ? y2[j] * p3 : 0.0;
             m_dmma(ace[0][j][0], ace[0][j][1], ae0, be);
             m_dmma(ace[1][j][0], ace[1][j][1], ae1, be);
          }
