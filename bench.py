@@ -30,8 +30,8 @@ sys.path.insert(0, ROOT)
 METRIC = "nfft_additive_matvecs_per_s"
 UNIT = "matvecs/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused three-window kernels at n = 10^6, from the one
-# `ncu --set full` capture of this command (profiles/r1_e_ncu_set_full_fused_spread_gather.csv); per-window launches: a third
-NCU_TRAFFIC_BYTES = {"spread": 751.607e6 + 5.597e6, "gather": 727.822e6 + 25.113e6}
+# `ncu --set full` capture of this command (profiles/r1_g_ncu_set_full_fused_spread_gather.csv); per-window launches: a third
+NCU_TRAFFIC_BYTES = {"spread": 751.906e6 + 4.873e6, "gather": 727.848e6 + 24.889e6}
 PROF_CLASSES = ["prep", "spread", "fft_fwd", "fft_inv", "gather", "combine", "vec", "nys", "csr", "gemv", "other"]
 
 
