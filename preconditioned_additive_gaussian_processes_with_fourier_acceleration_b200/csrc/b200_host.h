@@ -73,7 +73,7 @@ typedef struct b200_additive
       const double *x;
       double *y;
       double alpha, beta;
-      void *exec;
+      void *exec, *exec2; /* exec2: second half (after the collective) under point-block sharding */
       long long launches; /* kernels inside the graph (the launch counter is advanced by this on replay) */
    } graph[4];
    int graph_next, graph_off; /* graph_off: capture failed once or NFFT4GP_B200_NO_GRAPH is set */

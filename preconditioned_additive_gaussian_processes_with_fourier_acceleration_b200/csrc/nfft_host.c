@@ -1164,9 +1164,15 @@ static int additive_fused_channel1(b200_additive *A)
 }
 
 /* spread of all windows, then (mode 2) the ONE collective of the matvec, then FFT / scale / inverse FFT / gather */
-static int additive_apply_windows(b200_additive *A, const double *d_x, double s, int with_derivative)
+#define PHASE_SPREAD 1
+#define PHASE_COLLECTIVE 2
+#define PHASE_FINISH 4
+#define PHASE_ALL 7
+static int additive_apply_windows(b200_additive *A, const double *d_x, double s, int with_derivative, int phases)
 {
    int i, fused = additive_fused_prepare(A);
+   if (!(phases & PHASE_SPREAD))
+      goto collective;
    if (fused)
    {
       /* batched prep, one memset of the contiguous grids, one persistent wave for the spread of all batch windows */
@@ -1183,8 +1189,11 @@ static int additive_apply_windows(b200_additive *A, const double *d_x, double s,
       for (i = 0; i < A->P; i++)
          if (b200_comm_owns_window(A, i) && window_spread(A->win[i], d_x, s))
             return -1;
-   if (A->shard_mode == 2 && b200_comm_size() > 1 && b200_comm_allreduce_sum(A->d_grids, A->grids_doubles))
+collective:
+   if ((phases & PHASE_COLLECTIVE) && A->shard_mode == 2 && b200_comm_size() > 1 && b200_comm_allreduce_sum(A->d_grids, A->grids_doubles))
       return -1;
+   if (!(phases & PHASE_FINISH))
+      return 0;
    if (!(A->shard_mode == 1 && b200_comm_size() > 1) && A->nbatch > 1)
    {
       /* equally shaped leading windows: every FFT pass is ONE launch over the batch */
@@ -1238,17 +1247,20 @@ static void additive_graphs_release(b200_additive *A)
    for (i = 0; i < 4; i++)
    {
       b200_graph_destroy(A->graph[i].exec);
-      A->graph[i].exec = NULL;
+      b200_graph_destroy(A->graph[i].exec2);
+      A->graph[i].exec = A->graph[i].exec2 = NULL;
    }
    A->graph_next = 0;
 }
 
-static int additive_matvec_body(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y)
+static int additive_matvec_body(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y, int phases)
 {
    double s = 1.0 / (double)A->P * alpha; /* :806 */
    double f = A->win[0]->kernel_scale;
-   if (additive_apply_windows(A, d_x, s, 0))
+   if (additive_apply_windows(A, d_x, s, 0, phases))
       return -1;
+   if (!(phases & PHASE_FINISH))
+      return 0;
    return b200_additive_epilogue(A, n, d_x, s, f * f, A->win[0]->mu, beta, d_y);
 }
 
@@ -1260,30 +1272,51 @@ int b200_additive_matvec_dev(b200_additive *A, int n, double alpha, const double
       printf("Error: additive NFFT matvec on a kernel that was not built for n = %d.\n", n);
       return -1;
    }
-   /* CUDA graph of the whole launch sequence (fused tensor-core path only), one per argument signature */
-   if (!A->graph_off && !b200_prof_active() && additive_fused_prepare(A))
+   /* CUDA graph of the launch sequence (fused tensor-core path only), one per argument signature.  Under point-block
+    * sharding the collective is NOT captured: two graphs around a plainly enqueued allreduce (a captured NCCL kernel next
+    * to the caller's own communicator deadlocked in a 2-GPU bench run). */
+   if (!A->graph_off && !b200_prof_active() && !(A->shard_mode == 1 && b200_comm_size() > 1) && additive_fused_prepare(A))
    {
+      const int split = (A->shard_mode == 2 && b200_comm_size() > 1);
       long long before;
-      void *exec;
+      void *exec, *exec2 = NULL;
       for (i = 0; i < 4; i++)
          if (A->graph[i].exec && A->graph[i].x == d_x && A->graph[i].y == d_y && A->graph[i].alpha == alpha && A->graph[i].beta == beta)
          {
             b200_launch_count_add(A->graph[i].launches);
-            return b200_graph_launch(A->graph[i].exec);
+            if (!split)
+               return b200_graph_launch(A->graph[i].exec);
+            return (b200_graph_launch(A->graph[i].exec) || additive_matvec_body(A, n, alpha, d_x, beta, d_y, PHASE_COLLECTIVE) ||
+                    b200_graph_launch(A->graph[i].exec2)) ? -1 : 0;
          }
       if (getenv("NFFT4GP_B200_NO_GRAPH"))
          A->graph_off = 1;
       else if (b200_graph_begin() == 0)
       {
+         int rc2 = 0;
          before = b200_launch_count();
-         i = additive_matvec_body(A, n, alpha, d_x, beta, d_y);
+         i = additive_matvec_body(A, n, alpha, d_x, beta, d_y, split ? PHASE_SPREAD : PHASE_ALL);
          exec = b200_graph_end();
-         if (i || !exec)
+         if (!i && exec && split)
          {
-            /* capture refused (e.g. a collective that cannot be captured): plain launches from now on */
+            if (b200_graph_begin() == 0)
+            {
+               rc2 = additive_matvec_body(A, n, alpha, d_x, beta, d_y, PHASE_FINISH);
+               exec2 = b200_graph_end();
+            }
+            if (rc2 || !exec2)
+            {
+               b200_graph_destroy(exec);
+               exec = NULL;
+            }
+         }
+         if (i || rc2 || !exec)
+         {
+            /* capture refused: plain launches from now on */
             b200_graph_destroy(exec);
+            b200_graph_destroy(exec2);
             A->graph_off = 1;
-            if (i)
+            if (i || rc2)
                return -1;
          }
          else
@@ -1291,19 +1324,24 @@ int b200_additive_matvec_dev(b200_additive *A, int n, double alpha, const double
             int slot = A->graph_next;
             A->graph_next = (A->graph_next + 1) % 4;
             b200_graph_destroy(A->graph[slot].exec);
+            b200_graph_destroy(A->graph[slot].exec2);
             A->graph[slot].x = d_x;
             A->graph[slot].y = d_y;
             A->graph[slot].alpha = alpha;
             A->graph[slot].beta = beta;
             A->graph[slot].exec = exec;
+            A->graph[slot].exec2 = exec2;
             A->graph[slot].launches = b200_launch_count() - before;
-            return b200_graph_launch(exec);
+            if (!split)
+               return b200_graph_launch(exec);
+            return (b200_graph_launch(exec) || additive_matvec_body(A, n, alpha, d_x, beta, d_y, PHASE_COLLECTIVE) ||
+                    b200_graph_launch(exec2)) ? -1 : 0;
          }
       }
       else
          A->graph_off = 1;
    }
-   return additive_matvec_body(A, n, alpha, d_x, beta, d_y);
+   return additive_matvec_body(A, n, alpha, d_x, beta, d_y, PHASE_ALL);
 }
 
 /* device-resident body of Nfft4GPAdditiveNFFTGradMatSymv (nfft_interface.c:819-840) */
@@ -1324,7 +1362,7 @@ int b200_additive_grad_matvec_dev(b200_additive *A, int n, double alpha, const d
       printf("Error: the gradient matvec is not available under window sharding; use point-block sharding (mode 2).\n");
       return -1;
    }
-   if (additive_apply_windows(A, d_x, s, 1))
+   if (additive_apply_windows(A, d_x, s, 1, PHASE_ALL))
       return -1;
    c1 = (double *)b200_xmalloc(sizeof(double) * (size_t)A->P);
    fp = (const double **)b200_xmalloc(sizeof(double *) * (size_t)A->P);
