@@ -105,6 +105,37 @@ int Nfft4GPNFFTKernelMatern12Kernel(void *str, NFFT4GP_DOUBLE *data, int n, int 
 int Nfft4GPNFFTMatSymv(void *data, int n, NFFT4GP_DOUBLE alpha, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE beta, NFFT4GP_DOUBLE *y);
 int Nfft4GPNFFTGradMatSymv(void *data, int n, NFFT4GP_DOUBLE alpha, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE beta, NFFT4GP_DOUBLE *y);
 
+/* nfft_interface.c:84-128 (_external.h): single-window handle: forget the points / the points and the plans */
+int Nfft4GPNFFTKernelParamRemovePoints(void *kernel);
+int Nfft4GPNFFTKernelParamFreeNFFTKernel(void *kernel);
+
+/* nfft_interface.c:858-871 (_external.h:260): [X1; X2] feature-major, malloc'ed */
+NFFT4GP_DOUBLE *Nfft4GPNFFTAppendData(NFFT4GP_DOUBLE *X1, int n1, int ldim1, int d, NFFT4GP_DOUBLE *X2, int n2, int ldim2);
+
+/* SRC/optimizer/transform.h:18-23 */
+#ifndef NFFT4GP_TRANSFORM_TYPE_DEFINED
+#define NFFT4GP_TRANSFORM_TYPE_DEFINED
+typedef enum
+{
+   NFFT4GP_TRANSFORM_SOFTPLUS = 0,
+   NFFT4GP_TRANSFORM_SIGMOID,
+   NFFT4GP_TRANSFORM_EXP,
+   NFFT4GP_TRANSFORM_IDENTITY
+} nfft4gp_transform_type;
+#endif
+
+/* nfft_interface.c:873-1068 (_external.h:266): GP prediction with the NFFT additive kernel.  x[3] = untransformed (f, l, mu);
+ * vfkernel_data = NFFT handle on the n training points, vfkernel_data_l = NFFT handle on data_all = [train; test];
+ * mean through one FGMRES solve (kdim = maxits) and one matvec on the joint handle; *std_predictp (optional, may be NULL) through
+ * one solve per test point.  *label_predictp / *std_predictp: NULL = callee allocates with malloc. */
+int Nfft4GPAdditiveNFFTGpPredict(NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *data, NFFT4GP_DOUBLE *label, int n, int ldim, int d,
+                                 NFFT4GP_DOUBLE *data_predict, int n_predict, int ldim_predict, NFFT4GP_DOUBLE *data_all,
+                                 func_kernel fkernel, void *vfkernel_data, void *vfkernel_data_l, func_free kernel_data_free,
+                                 func_symmatvec matvec, func_kernel precond_fkernel, void *precond_vfkernel_data,
+                                 func_free precond_kernel_data_free, precond_kernel_setup precond_setup, func_solve precond_solve,
+                                 void *precond_data, int atol, NFFT4GP_DOUBLE tol, int maxits, nfft4gp_transform_type transform,
+                                 int print_level, NFFT4GP_DOUBLE *dwork, NFFT4GP_DOUBLE **label_predictp, NFFT4GP_DOUBLE **std_predictp);
+
 /* ------------------------------------------------------------------------------------------
  * Part 1b: Krylov solver (INC/_solvers.h:102, SRC/solvers/pcg.c:3-206)
  * Same control flow and quirks as the reference (true-residual recheck with an extra matvec, *piter = 0

@@ -14,9 +14,10 @@ from .capi import (  # noqa: F401
     FsaiPrecond,
     NysPrecond,
     build_library,
+    gp_predict,
     lib,
     solver_fgmres,
     solver_pcg,
 )
 
-__all__ = ["LIB_PATH", "AdditiveNFFTKernel", "DenseAdditiveKernel", "DensePlainKernel", "NysPrecond", "FsaiPrecond", "AfnPrecond", "build_library", "lib", "solver_pcg", "solver_fgmres"]
+__all__ = ["LIB_PATH", "AdditiveNFFTKernel", "DenseAdditiveKernel", "DensePlainKernel", "NysPrecond", "FsaiPrecond", "AfnPrecond", "build_library", "lib", "solver_pcg", "solver_fgmres", "gp_predict"]

@@ -66,6 +66,10 @@ def lib():
         "Nfft4GPSolverPcg": (i, [vp, i, vp, vp, vp, c_double_p, c_double_p, i, i, d, c_double_p, C.POINTER(c_double_p), c_int_p, i]),
         "Nfft4GPSolverFgmres": (i, [vp, i, vp, vp, vp, c_double_p, c_double_p, i, i, i, d, c_double_p, C.POINTER(c_double_p), c_int_p, i]),
         "Nfft4GPB200SolverFgmresDevice": (i, [vp, i, vp, vp, vp, vp, vp, i, i, i, d, c_double_p, C.POINTER(c_double_p), c_int_p, i]),
+        "Nfft4GPNFFTAppendData": (c_double_p, [c_double_p, i, i, i, c_double_p, i, i]),
+        "Nfft4GPNFFTKernelParamRemovePoints": (i, [vp]), "Nfft4GPNFFTKernelParamFreeNFFTKernel": (i, [vp]),
+        "Nfft4GPAdditiveNFFTGpPredict": (i, [c_double_p, c_double_p, c_double_p, i, i, i, c_double_p, i, i, c_double_p, vp, vp, vp, vp, vp, vp, vp,
+                                             vp, vp, vp, vp, i, d, i, i, i, c_double_p, C.POINTER(c_double_p), C.POINTER(c_double_p)]),
         "Nfft4GPPrecondNysCreate": (vp, []), "Nfft4GPPrecondNysFree": (None, [vp]), "Nfft4GPPrecondNysReset": (None, [vp]),
         "Nfft4GPPrecondNysSetRank": (None, [vp, i]), "Nfft4GPPrecondNysSetPerm": (None, [vp, c_int_p, i]),
         "Nfft4GPPrecondNysSolve": (i, [vp, i, c_double_p, c_double_p]),
@@ -510,3 +514,42 @@ def solver_fgmres(mat, n, matvec_fn, prec, solve_fn, x0, rhs, kdim, maxits, atol
     if relv:
         L.free(relv)
     return x, rel.value, hist, it.value
+
+
+def gp_predict(x, X1, y, X2, windows, nwindows, dwindows, kernel="gaussian", precond=None, dense=None, tol=1e-8, maxits=200,
+               transform=0, want_std=True, print_level=1):
+    """Nfft4GPAdditiveNFFTGpPredict as TESTS/TEST3/foo3.cpp and TEST4/foo.cpp call it: NFFT handle on the training points, NFFT
+    handle on [train; test], optional preconditioner (object with .h / .solve_fn() and a setup function pointer) built from the dense
+    kernel handle `dense`.  Returns (mean, std or None)."""
+    L = lib()
+    X1 = np.ascontiguousarray(X1, dtype=np.float64)
+    X2 = np.ascontiguousarray(X2, dtype=np.float64)
+    d, n = X1.shape
+    n2 = X2.shape[1]
+    xall_p = L.Nfft4GPNFFTAppendData(dptr(X1), n, n, d, dptr(X2), n2, n2)
+    Xall = np.ctypeslib.as_array(xall_p, shape=(d, n + n2))
+    win = np.ascontiguousarray(windows, dtype=np.int32)
+    A = AdditiveNFFTKernel(X1, win, nwindows, dwindows, kernel)
+    Al = AdditiveNFFTKernel(Xall, win, nwindows, dwindows, kernel)
+    fk = L.Nfft4GPNFFTAdditiveKernelGaussianKernel if kernel == "gaussian" else L.Nfft4GPNFFTAdditiveKernelMatern12Kernel
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    lab, std = c_double_p(), c_double_p()
+    pargs = [None, None, None, None, None, None]
+    if precond is not None:
+        setup_fn, P = precond
+        pargs = [dense.fn(), dense.h, C.cast(L.Nfft4GPKernelParamFree, C.c_void_p), C.cast(setup_fn, C.c_void_p), P.solve_fn(), P.h]
+    rc = L.Nfft4GPAdditiveNFFTGpPredict(dptr(x), dptr(X1), dptr(y), n, n, d, dptr(X2), n2, n2, xall_p, C.cast(fk, C.c_void_p), A.h, Al.h,
+                                        C.cast(L.Nfft4GPNFFTKernelFree, C.c_void_p), C.cast(L.Nfft4GPAdditiveNFFTMatSymv, C.c_void_p), *pargs,
+                                        0, tol, maxits, transform, print_level, None, C.byref(lab), C.byref(std) if want_std else None)
+    if rc != 0:
+        raise RuntimeError("Nfft4GPAdditiveNFFTGpPredict failed")
+    mean = np.ctypeslib.as_array(lab, shape=(n2,)).copy()
+    sd = np.ctypeslib.as_array(std, shape=(n2,)).copy() if want_std else None
+    L.free(lab)
+    if want_std:
+        L.free(std)
+    A.free()
+    Al.free()
+    L.free(xall_p)
+    return mean, sd

@@ -633,6 +633,28 @@ void Nfft4GPNFFTKernelParamFree(void *kernel)
 /* nfft_interface.c:79-82 */
 void Nfft4GPNFFTKernelFree(void *str) { (void)str; }
 
+/* nfft_interface.c:101-128: forget the points of a single-window handle (the next kernel build takes new data) */
+int Nfft4GPNFFTKernelParamRemovePoints(void *kernel)
+{
+   nfft4gp_kernel *k = (nfft4gp_kernel *)kernel;
+   b200_single *s = k ? (b200_single *)k->_external : NULL;
+   if (!s || s->magic != B200_MAGIC_SINGLE)
+      return -1;
+   window_free_device(s->win);
+   free(s->win->h_perm);
+   free(s->win->h_chunks);
+   s->win->h_perm = NULL;
+   s->win->h_chunks = NULL;
+   s->win->h_nchunk = 0;
+   s->win->n = s->win->n_global = 0;
+   s->win->scale = -1.0;
+   s->win->built = 0;
+   return 0;
+}
+
+/* nfft_interface.c:84-99: additionally drop the plans (here: nothing survives the points but the handle itself) */
+int Nfft4GPNFFTKernelParamFreeNFFTKernel(void *kernel) { return Nfft4GPNFFTKernelParamRemovePoints(kernel); }
+
 static int single_kernel_build(void *str, int kernel, double *data, int n, int ldim, int d, double **Kp, double **dKp)
 {
    nfft4gp_kernel *k = (nfft4gp_kernel *)str;

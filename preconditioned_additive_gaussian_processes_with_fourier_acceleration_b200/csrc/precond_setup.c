@@ -6,7 +6,8 @@
  * Everything O(n) and above runs on the GPU (setup_kernels.cu, precond_kernels.cu); the O(k^3) factorizations of the
  * landmark block run here (dense_small.c).  A dense kernel of this library (Nfft4GPKernel{Additive,Gaussian,Matern12}Kernel)
  * is evaluated on the device; a foreign func_kernel is honoured by the Nystrom setup only (two host calls, as the
- * reference makes them).  require_grad != 0 (preconditioner derivatives for the GP loss gradient) is SURVEY.md 8(f) "next". */
+ * reference makes them).  require_grad is accepted and ignored (the reference's own prediction passes 1, nfft_interface.c:936):
+ * the derivative factors only serve Dvp / Trace / Logdet of the GP loss gradient (SURVEY.md 8(f) "next"), which are not exported. */
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -219,11 +220,7 @@ int Nfft4GPPrecondNysSetupWithKernel(double *data, int n, int ldim, int d, func_
    int rc;
    if (!s || s->magic != B200_MAGIC_NYS || !fkernel || !fkernel_params)
       return -1;
-   if (require_grad)
-   {
-      printf("Error: nfft4gp_b200 builds the Nystrom preconditioner without derivative terms (require_grad must be 0).\n");
-      return -1;
-   }
+   (void)require_grad; /* accepted: the derivative factors only serve Dvp / Trace / Logdet, which this library does not export */
    rc = nys_setup_perm(s, data, n, ldim, d, fkernel, fkernel_params, s->perm, s->k_setup);
    s->tset = wtime() - t0;
    return rc;
@@ -240,11 +237,7 @@ int Nfft4GPPrecondFsaiSetupWithKernel(double *data, int n, int ldim, int d, func
    long long nnz;
    if (!s || s->magic != B200_MAGIC_FSAI || !fkernel || !fkernel_params || b200_init(-1))
       return -1;
-   if (require_grad)
-   {
-      printf("Error: nfft4gp_b200 builds the FSAI preconditioner without derivative terms (require_grad must be 0).\n");
-      return -1;
-   }
+   (void)require_grad; /* accepted: the derivative factors only serve Dvp / Trace / Logdet, which this library does not export */
    own = b200_dense_view_acquire(fkernel, fkernel_params, data, n, ldim, d, &v);
    if (own)
    {
@@ -585,11 +578,7 @@ int Nfft4GPPrecondAFNSetupWithKernel(double *data, int n, int ldim, int d, func_
    long long nnz;
    if (!s || s->magic != B200_MAGIC_AFN || !fkernel || !fkernel_params || b200_init(-1))
       return -1;
-   if (require_grad)
-   {
-      printf("Error: nfft4gp_b200 builds the AFN preconditioner without derivative terms (require_grad must be 0).\n");
-      return -1;
-   }
+   (void)require_grad; /* accepted: the derivative factors only serve Dvp / Trace / Logdet, which this library does not export */
    if (d > 64)
    {
       printf("Error: the AFN setup supports at most 64 features.\n");

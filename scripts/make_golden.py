@@ -207,7 +207,40 @@ def fgmres_case():
     np.savez_compressed(os.path.join(OUT, "fgmres_dense300.npz"), **out)
 
 
+def predict_case():
+    """Reference Nfft4GPAdditiveNFFTGpPredict (SRC/external/nfft_interface.c:873-1068, compiled unmodified on the fastsum shim):
+    mean and standard deviation at the test points, softplus-transformed hyper-parameters, no preconditioner."""
+    n, n2, d = 300, 12, 6
+    X1 = cloud(n, d, 71)
+    X2 = cloud(n2, d, 72) * (n2 / n) ** (-1.0 / d)   # same box as the training points
+    rng = np.random.default_rng(73)
+    y = np.sin(X1[0]) + 0.5 * np.cos(X1[3]) + 0.05 * rng.standard_normal(n)
+    win = np.arange(6, dtype=np.int32)
+    Xall = np.ascontiguousarray(np.concatenate([X1, X2], axis=1))
+    A = R.RefAdditiveNFFT(X1, win, 2, 3, "gaussian")
+    Al = R.RefAdditiveNFFT(Xall, win, 2, 3, "gaussian")
+    x = np.array([0.3, 0.9, -3.0])                   # softplus -> f = 0.854, l = 1.24, mu = 0.0486
+    L.Nfft4GPAdditiveNFFTGpPredict.restype = C.c_int
+    vp, i_, dd, dp = C.c_void_p, C.c_int, C.c_double, R.c_double_p
+    L.Nfft4GPAdditiveNFFTGpPredict.argtypes = [dp, dp, dp, i_, i_, i_, dp, i_, i_, dp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i_, dd, i_, i_, i_,
+                                               dp, C.POINTER(dp), C.POINTER(dp)]
+    lab = dp()
+    std = dp()
+    rc = L.Nfft4GPAdditiveNFFTGpPredict(R.dptr(x), R.dptr(X1), R.dptr(y), n, n, d, R.dptr(X2), n2, n2, R.dptr(Xall),
+                                        C.cast(L.Nfft4GPNFFTAdditiveKernelGaussianKernel, vp), A.h, Al.h, C.cast(L.Nfft4GPNFFTKernelFree, vp),
+                                        C.cast(L.Nfft4GPAdditiveNFFTMatSymv, vp), None, None, None, None, None, None, 0, 1e-10, 200, 0, 1,
+                                        None, C.byref(lab), C.byref(std))
+    assert rc == 0
+    out = {"X1": X1, "X2": X2, "y": y, "windows": win, "x": x, "tol": 1e-10, "maxits": 200,
+           "label_predict": np.ctypeslib.as_array(lab, shape=(n2,)).copy(), "std_predict": np.ctypeslib.as_array(std, shape=(n2,)).copy()}
+    np.savez_compressed(os.path.join(OUT, "predict_nfft300.npz"), **out)
+    print("predict: mean", out["label_predict"][:4], "std", out["std_predict"][:4])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "predict":
+        predict_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fgmres":
         fgmres_case()
         sys.exit(0)
@@ -223,3 +256,4 @@ if __name__ == "__main__":
     fsai_case()
     nys_plain_case()
     fgmres_case()
+    predict_case()

@@ -285,8 +285,9 @@ def test_setup_edge_cases(gpu):
     P2 = gpu.DensePlainKernel(X2, "gaussian").set_hyper(1.0, 0.9, 0.05)
     rc = L.Nfft4GPPrecondFsaiSetupWithKernel(gpu.capi.dptr(P2.X), 400, 400, 3, P2.fn(), P2.h, 0, F.h)
     assert rc == -1
-    # require_grad is not built: -1, not a silent K-only setup
-    assert L.Nfft4GPPrecondFsaiSetupWithKernel(gpu.capi.dptr(P2.X), 400, 400, 3, P2.fn(), P2.h, 1, F.h) == -1
+    # require_grad is accepted (the reference's own prediction passes 1, nfft_interface.c:936); the factors are the same
+    L.Nfft4GPPrecondFsaiSetLfil(F.h, 20)
+    assert L.Nfft4GPPrecondFsaiSetupWithKernel(gpu.capi.dptr(P2.X), 400, 400, 3, P2.fn(), P2.h, 1, F.h) == 0
     F.free()
     P2.free()
     # Nystrom with k = n: exact inverse of K (up to the stabilising shift); AFN with k = n: pure Cholesky block
