@@ -35,6 +35,9 @@ typedef int (*func_solve)(void *precond, int n, double *x, double *rhs);        
 typedef int (*func_symmatvec)(void *matrix, int n, double alpha, double *x, double beta, double *y);      /* _solvers.h:51  */
 typedef int (*func_kernel)(void *str, NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *permr, int kr,
                            int *permc, int kc, NFFT4GP_DOUBLE **Kp, NFFT4GP_DOUBLE **dKp);                /* _linearalg.h:404 */
+typedef int (*func_trace)(void *str, NFFT4GP_DOUBLE **tracesp);                                          /* _solvers.h:59  */
+typedef NFFT4GP_DOUBLE (*func_logdet)(void *str);                                                        /* _solvers.h:67  */
+typedef int (*func_dvp)(void *str, int n, int *mask, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE **yp);             /* _solvers.h:80  */
 typedef void *(*func_create)(void);                                                                      /* _utils.h:430   */
 typedef void (*func_free)(void *str);                                                                    /* _utils.h:438   */
 typedef int (*precond_kernel_setup)(NFFT4GP_DOUBLE *data, int n, int ldim, int d, func_kernel fkernel,
@@ -104,6 +107,23 @@ int Nfft4GPNFFTKernelMatern12Kernel(void *str, NFFT4GP_DOUBLE *data, int n, int 
                                     int *permc, int kc, NFFT4GP_DOUBLE **Kp, NFFT4GP_DOUBLE **dKp);
 int Nfft4GPNFFTMatSymv(void *data, int n, NFFT4GP_DOUBLE alpha, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE beta, NFFT4GP_DOUBLE *y);
 int Nfft4GPNFFTGradMatSymv(void *data, int n, NFFT4GP_DOUBLE alpha, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE beta, NFFT4GP_DOUBLE *y);
+
+/* Preconditioned Lanczos solver (INC/_solvers.h:176, SRC/solvers/lanczos.c:3-419): solves A x = rhs and returns the Lanczos
+ * tridiagonal matrix T (*TDp diagonal, *TEp sub-diagonal, *tsize rows; NULL on entry = callee allocates with malloc), which
+ * keeps being extended up to wsize rows after convergence.  Bases, orthogonalisation (Nfft4GPModifiedGS2, matops.c:348-434) and
+ * all vector operations on the GPU; single GPU. */
+int Nfft4GPSolverLanczos(void *mat_data, int n, func_symmatvec matvec, void *prec_data, func_solve precondfunc,
+                         NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs, int wsize, int maxits, int atol, NFFT4GP_DOUBLE tol,
+                         NFFT4GP_DOUBLE *prel_res, NFFT4GP_DOUBLE **prel_res_v, int *piter, int *tsize, NFFT4GP_DOUBLE **TDp,
+                         NFFT4GP_DOUBLE **TEp, int print_level);
+/* Stochastic Lanczos quadrature (INC/_solvers.h:216, lanczos.c:421-610): *logdet = log det(A) / n and (*dlogdetp)[3] = its
+ * derivatives w.r.t. (f, l, mu) / n from nvecs Rademacher probes (radamacher: n x nvecs given probes, or NULL = rand() as
+ * vecops.c:27-45).  dmatvec = the gradient matvec (y of length 3n).  tracefunc / logdetfunc / dvpfunc are only called when
+ * prec_data != NULL (they belong to the preconditioner; this library exports none). */
+int Nfft4GPLanczosQuadratureLogdet(void *mat_data, void *dmat_data, int n, func_symmatvec matvec, func_symmatvec dmatvec,
+                                   void *prec_data, func_solve precondfunc, func_trace tracefunc, func_logdet logdetfunc,
+                                   func_dvp dvpfunc, int maxits, int nvecs, NFFT4GP_DOUBLE *radamacher, int print_level,
+                                   NFFT4GP_DOUBLE *logdet, NFFT4GP_DOUBLE **dlogdetp);
 
 /* nfft_interface.c:84-128 (_external.h): single-window handle: forget the points / the points and the plans */
 int Nfft4GPNFFTKernelParamRemovePoints(void *kernel);

@@ -16,8 +16,10 @@ from .capi import (  # noqa: F401
     build_library,
     gp_predict,
     lib,
+    lanczos_quadrature_logdet,
     solver_fgmres,
+    solver_lanczos,
     solver_pcg,
 )
 
-__all__ = ["LIB_PATH", "AdditiveNFFTKernel", "DenseAdditiveKernel", "DensePlainKernel", "NysPrecond", "FsaiPrecond", "AfnPrecond", "build_library", "lib", "solver_pcg", "solver_fgmres", "gp_predict"]
+__all__ = ["LIB_PATH", "AdditiveNFFTKernel", "DenseAdditiveKernel", "DensePlainKernel", "NysPrecond", "FsaiPrecond", "AfnPrecond", "build_library", "lib", "solver_pcg", "solver_fgmres", "gp_predict", "solver_lanczos", "lanczos_quadrature_logdet"]

@@ -66,6 +66,9 @@ def lib():
         "Nfft4GPSolverPcg": (i, [vp, i, vp, vp, vp, c_double_p, c_double_p, i, i, d, c_double_p, C.POINTER(c_double_p), c_int_p, i]),
         "Nfft4GPSolverFgmres": (i, [vp, i, vp, vp, vp, c_double_p, c_double_p, i, i, i, d, c_double_p, C.POINTER(c_double_p), c_int_p, i]),
         "Nfft4GPB200SolverFgmresDevice": (i, [vp, i, vp, vp, vp, vp, vp, i, i, i, d, c_double_p, C.POINTER(c_double_p), c_int_p, i]),
+        "Nfft4GPSolverLanczos": (i, [vp, i, vp, vp, vp, c_double_p, c_double_p, i, i, i, d, c_double_p, C.POINTER(c_double_p), c_int_p, c_int_p,
+                                     C.POINTER(c_double_p), C.POINTER(c_double_p), i]),
+        "Nfft4GPLanczosQuadratureLogdet": (i, [vp, vp, i, vp, vp, vp, vp, vp, vp, vp, i, i, c_double_p, i, c_double_p, C.POINTER(c_double_p)]),
         "Nfft4GPNFFTAppendData": (c_double_p, [c_double_p, i, i, i, c_double_p, i, i]),
         "Nfft4GPNFFTKernelParamRemovePoints": (i, [vp]), "Nfft4GPNFFTKernelParamFreeNFFTKernel": (i, [vp]),
         "Nfft4GPAdditiveNFFTGpPredict": (i, [c_double_p, c_double_p, c_double_p, i, i, i, c_double_p, i, i, c_double_p, vp, vp, vp, vp, vp, vp, vp,
@@ -553,3 +556,41 @@ def gp_predict(x, X1, y, X2, windows, nwindows, dwindows, kernel="gaussian", pre
     Al.free()
     L.free(xall_p)
     return mean, sd
+
+
+def solver_lanczos(mat, n, matvec_fn, prec, solve_fn, x0, rhs, wsize, maxits, atol, tol, print_level=1):
+    """Nfft4GPSolverLanczos with host vectors.  Returns (x, rel_res, rel_res_v, iters, TD, TE) with T of tsize rows."""
+    L = lib()
+    x = np.array(x0, dtype=np.float64)
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    rel = C.c_double(0.0)
+    relv, TD, TE = c_double_p(), c_double_p(), c_double_p()
+    it, ts = C.c_int(0), C.c_int(0)
+    rc = L.Nfft4GPSolverLanczos(mat, n, matvec_fn, prec, solve_fn, dptr(x), dptr(rhs), wsize, maxits, atol, tol, C.byref(rel), C.byref(relv),
+                                C.byref(it), C.byref(ts), C.byref(TD), C.byref(TE), print_level)
+    if rc != 0:
+        raise RuntimeError("Nfft4GPSolverLanczos failed")
+    hist = np.ctypeslib.as_array(relv, shape=(maxits + 1,)).copy() if it.value > 0 else np.zeros(1)
+    td = np.ctypeslib.as_array(TD, shape=(ts.value,)).copy() if TD else np.zeros(0)
+    te = np.ctypeslib.as_array(TE, shape=(max(ts.value - 1, 0),)).copy() if TE else np.zeros(0)
+    for ptr in (relv, TD, TE):
+        if ptr:
+            L.free(ptr)
+    return x, rel.value, hist, it.value, td, te
+
+
+def lanczos_quadrature_logdet(mat, dmat, n, matvec_fn, dmatvec_fn, maxits, probes, print_level=1):
+    """Nfft4GPLanczosQuadratureLogdet without a preconditioner, with given Rademacher probes (nvecs, n).  Returns (logdet / n,
+    dlogdet[3] / n)."""
+    L = lib()
+    probes = np.ascontiguousarray(probes, dtype=np.float64)
+    nvecs = probes.shape[0]
+    val = C.c_double(0.0)
+    dval = c_double_p()
+    rc = L.Nfft4GPLanczosQuadratureLogdet(mat, dmat, n, matvec_fn, dmatvec_fn, None, None, None, None, None, maxits, nvecs, dptr(probes),
+                                          print_level, C.byref(val), C.byref(dval))
+    if rc != 0:
+        raise RuntimeError("Nfft4GPLanczosQuadratureLogdet failed")
+    out = np.ctypeslib.as_array(dval, shape=(3,)).copy()
+    L.free(dval)
+    return val.value, out

@@ -87,6 +87,7 @@ double b200_chol_shift(int n, double fro);
 int b200_potrf_lower(int n, double *A, int lda);
 int b200_syev(int n, double *A, double *w);
 int b200_syev_values(int n, double *A, double *w);
+int b200_stev(int n, double *d, double *e, double *Zm);
 double b200_spd_norm2(int m, const double *S, int lds, double *work);
 
 /* dense_host.c: device view of a dense kernel handle that this library can evaluate on the GPU */

@@ -366,3 +366,25 @@ double b200_spd_norm2(int m, const double *S, int lds, double *work /* 2m */)
    }
    return lam;
 }
+
+/* symmetric tridiagonal eigen-decomposition (dstev 'V'): d[n] diagonal -> ascending eigenvalues, e[n-1] sub-diagonal
+ * (destroyed), Zm n x n column-major eigenvectors.  Used by the stochastic Lanczos quadrature (lanczos.c:539). */
+int b200_stev(int n, double *d, double *e, double *Zm)
+{
+   double *e2;
+   int i, rc;
+   if (n <= 0)
+      return 0;
+   memset(Zm, 0, sizeof(double) * (size_t)n * n);
+   for (i = 0; i < n; i++)
+      Zm[(size_t)i * n + i] = 1.0;
+   if (n == 1)
+      return 0;
+   e2 = (double *)b200_xmalloc(sizeof(double) * (size_t)n);
+   e2[0] = 0.0;
+   for (i = 1; i < n; i++)
+      e2[i] = e[i - 1]; /* ql_implicit expects the sub-diagonal in e[1..n-1] */
+   rc = ql_implicit(n, Zm, d, e2, 1);
+   free(e2);
+   return rc;
+}

@@ -237,7 +237,65 @@ def predict_case():
     print("predict: mean", out["label_predict"][:4], "std", out["std_predict"][:4])
 
 
+def lanczos_case():
+    """Reference Nfft4GPSolverLanczos (SRC/solvers/lanczos.c:3-419) on the reference's dense Gaussian kernel, without and with the
+    reference's Nystrom preconditioner, and Nfft4GPLanczosQuadratureLogdet (:421-610) on the NFFT additive kernel with given
+    Rademacher probes (no preconditioner)."""
+    z = np.load(os.path.join(OUT, "nys_gauss300.npz"))
+    X, f, l, mu, rhs, perm, k = z["X"], float(z["f"]), float(z["l"]), float(z["mu"]), z["rhs"], z["perm"], int(z["k"])
+    n, d = X.shape[1], X.shape[0]
+    L.Nfft4GPKernelParamCreate.restype = C.c_void_p
+    L.Nfft4GPKernelParamCreate.argtypes = [C.c_int, C.c_int]
+    kh = L.Nfft4GPKernelParamCreate(n, 1)
+    R.set_hyper(kh, f, l, mu)
+    K = C.c_void_p()
+    assert L.Nfft4GPKernelGaussianKernel(kh, R.dptr(X), n, n, d, None, 0, None, 0, C.byref(K), None) == 0
+    nys = L.Nfft4GPPrecondNysCreate()
+    L.Nfft4GPPrecondNysSetRank(nys, k)
+    L.Nfft4GPPrecondNysSetPerm(nys, R.iptr(perm), 0)
+    assert L.Nfft4GPPrecondNysSetupWithKernel(R.dptr(X), n, n, d, C.cast(L.Nfft4GPKernelGaussianKernel, C.c_void_p), kh, 0, nys) == 0
+    dp = R.c_double_p
+    L.Nfft4GPSolverLanczos.restype = C.c_int
+    L.Nfft4GPSolverLanczos.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, dp, dp, C.c_int, C.c_int, C.c_int, C.c_double, dp,
+                                       C.POINTER(dp), R.c_int_p, R.c_int_p, C.POINTER(dp), C.POINTER(dp), C.c_int]
+    out = {}
+    for tag, (prec, pf, maxits, tol) in {"plain": (None, None, 120, 1e-8), "nys": (nys, L.Nfft4GPPrecondNysSolve, 80, 1e-8)}.items():
+        x = np.zeros(n)
+        rel = C.c_double(0.0)
+        relv, TD, TE = dp(), dp(), dp()
+        it, ts = C.c_int(0), C.c_int(0)
+        L.Nfft4GPSolverLanczos(K, n, C.cast(L.Nfft4GPDenseMatSymv, C.c_void_p), prec, C.cast(pf, C.c_void_p) if pf else None, R.dptr(x), R.dptr(rhs),
+                               maxits, maxits, 0, tol, C.byref(rel), C.byref(relv), C.byref(it), C.byref(ts), C.byref(TD), C.byref(TE), 1)
+        out.update({f"{tag}_x": x, f"{tag}_rel": rel.value, f"{tag}_it": it.value, f"{tag}_tsize": ts.value, f"{tag}_maxits": maxits, f"{tag}_tol": tol,
+                    f"{tag}_hist": np.ctypeslib.as_array(relv, shape=(maxits + 1,)).copy(),
+                    f"{tag}_TD": np.ctypeslib.as_array(TD, shape=(ts.value,)).copy(),
+                    f"{tag}_TE": np.ctypeslib.as_array(TE, shape=(ts.value - 1,)).copy()})
+        print("lanczos", tag, "iterations", it.value, "tsize", ts.value, "rel", rel.value)
+    # stochastic Lanczos quadrature on the NFFT additive kernel
+    n2, d2 = 300, 6
+    X2 = cloud(n2, d2, 81)
+    win = np.arange(6, dtype=np.int32)
+    f2, l2, mu2 = 1.1, 0.9, 0.05
+    A = R.RefAdditiveNFFT(X2, win, 2, 3, "gaussian").build(f2, l2, mu2)
+    probes = np.where(np.random.default_rng(82).random((4, n2)) < 0.5, -1.0, 1.0)
+    L.Nfft4GPLanczosQuadratureLogdet.restype = C.c_int
+    L.Nfft4GPLanczosQuadratureLogdet.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_int, C.c_int, dp, C.c_int, dp, C.POINTER(dp)]
+    val = C.c_double(0.0)
+    dval = dp()
+    rc = L.Nfft4GPLanczosQuadratureLogdet(A.K, A.dK, n2, C.cast(L.Nfft4GPAdditiveNFFTMatSymv, C.c_void_p), C.cast(L.Nfft4GPAdditiveNFFTGradMatSymv, C.c_void_p),
+                                          None, None, None, None, None, 60, 4, R.dptr(np.ascontiguousarray(probes)), 1, C.byref(val), C.byref(dval))
+    assert rc == 0
+    out.update(slq_X=X2, slq_windows=win, slq_f=f2, slq_l=l2, slq_mu=mu2, slq_probes=probes, slq_maxits=60, slq_logdet=val.value,
+               slq_dlogdet=np.ctypeslib.as_array(dval, shape=(3,)).copy())
+    print("slq logdet/n", val.value, "dlogdet/n", out["slq_dlogdet"])
+    np.savez_compressed(os.path.join(OUT, "lanczos_dense300.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "lanczos":
+        lanczos_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "predict":
         predict_case()
         sys.exit(0)
@@ -257,3 +315,4 @@ if __name__ == "__main__":
     nys_plain_case()
     fgmres_case()
     predict_case()
+    lanczos_case()
