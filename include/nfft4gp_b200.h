@@ -198,6 +198,20 @@ int Nfft4GPPrecondFsaiSolve(void *vfsai_mat, int n, NFFT4GP_DOUBLE *x, NFFT4GP_D
 int Nfft4GPPrecondFsaiSetupWithKernel(NFFT4GP_DOUBLE *data, int n, int ldim, int d, func_kernel fkernel,
                                       void *fkernel_params, int require_grad, void *vfsai_mat); /* fsai.c:302-673 (:264) */
 
+/* Dense Cholesky (the exact solver of the small-n experiments), SRC/preconds/chol.c; with require_grad the setup keeps
+ * K and dK/dl in HBM and Trace / Dvp / Logdet are available (the reference's Dvp dereferences a NULL mask copy when the
+ * caller passes a mask, chol.c:145-150; here a given mask is honoured). */
+void *Nfft4GPPrecondCholCreate(void);                                    /* chol.c:8-27    (_preconds.h:79) */
+void Nfft4GPPrecondCholFree(void *str);                                  /* chol.c:29-64   (:86) */
+void Nfft4GPPrecondCholReset(void *str);                                 /* chol.c:66-99   (:93) */
+void Nfft4GPPrecondCholSetStable(void *str, int stable);                 /* chol.c:101-109 (:100) */
+int Nfft4GPPrecondCholSolve(void *vchol_mat, int n, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs); /* chol.c:111-136 (:111) */
+int Nfft4GPPrecondCholDvp(void *vchol_mat, int n, int *mask, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE **yp); /* chol.c:138-229 (:124) */
+int Nfft4GPPrecondCholTrace(void *vchol_mat, NFFT4GP_DOUBLE **tracesp);  /* chol.c:231-291 (:132) */
+NFFT4GP_DOUBLE Nfft4GPPrecondCholLogdet(void *vchol_mat);                /* chol.c:293-311 (:140) */
+int Nfft4GPPrecondCholSetupWithKernel(NFFT4GP_DOUBLE *data, int n, int ldim, int d, func_kernel fkernel,
+                                      void *fkernel_params, int require_grad, void *vchol_mat); /* chol.c:428-640 (:156) */
+
 /* AFN: SRC/preconds/afn.c is not compiled by the reference (SURVEY.md finding 2); names follow afn.h:65-132,
  * the algorithm follows MATLAB afn_setup.m:30-109 / afn_solve.m:39-69. */
 void *Nfft4GPPrecondAFNCreate(void);
@@ -210,7 +224,7 @@ int Nfft4GPPrecondAFNSetupWithKernel(NFFT4GP_DOUBLE *data, int n, int ldim, int 
 
 /* Dense additive kernel used by the preconditioner setups (SRC/linearalg/kernels.c:3046-3494; _linearalg.h:717,740).
  * Same func_kernel contract: full lower (permr NULL), K(permr,permr) lower, K(permr,permc) full, column-major;
- * Kp only (dKp must be NULL in this library: the gradient blocks belong to the optimizer, out of scope). */
+ * dKp (optional) receives the three gradient blocks stacked [d/df; d/dl; d/dmu] in the same shape. */
 void *Nfft4GPKernelAdditiveKernelParamCreate(NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *windows, int nwindows,
                                              int dwindows, func_kernel fkernel);
 int Nfft4GPKernelAdditiveKernel(void *str, NFFT4GP_DOUBLE *data, int n, int ldim, int d, int *permr, int kr,

@@ -9,6 +9,7 @@ from .capi import (  # noqa: F401
     LIB_PATH,
     AdditiveNFFTKernel,
     AfnPrecond,
+    CholPrecond,
     DenseAdditiveKernel,
     DensePlainKernel,
     FsaiPrecond,
@@ -22,4 +23,4 @@ from .capi import (  # noqa: F401
     solver_pcg,
 )
 
-__all__ = ["LIB_PATH", "AdditiveNFFTKernel", "DenseAdditiveKernel", "DensePlainKernel", "NysPrecond", "FsaiPrecond", "AfnPrecond", "build_library", "lib", "solver_pcg", "solver_fgmres", "gp_predict", "solver_lanczos", "lanczos_quadrature_logdet"]
+__all__ = ["LIB_PATH", "AdditiveNFFTKernel", "DenseAdditiveKernel", "DensePlainKernel", "NysPrecond", "FsaiPrecond", "AfnPrecond", "CholPrecond", "build_library", "lib", "solver_pcg", "solver_fgmres", "gp_predict", "solver_lanczos", "lanczos_quadrature_logdet"]

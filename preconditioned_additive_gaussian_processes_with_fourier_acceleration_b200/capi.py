@@ -81,6 +81,13 @@ def lib():
         "Nfft4GPPrecondFsaiSetLfil": (None, [vp, i]),
         "Nfft4GPPrecondFsaiSolve": (i, [vp, i, c_double_p, c_double_p]),
         "Nfft4GPPrecondFsaiSetupWithKernel": (i, [c_double_p, i, i, i, vp, vp, i, vp]),
+        "Nfft4GPPrecondCholCreate": (vp, []), "Nfft4GPPrecondCholFree": (None, [vp]), "Nfft4GPPrecondCholReset": (None, [vp]),
+        "Nfft4GPPrecondCholSetStable": (None, [vp, i]),
+        "Nfft4GPPrecondCholSolve": (i, [vp, i, c_double_p, c_double_p]),
+        "Nfft4GPPrecondCholDvp": (i, [vp, i, c_int_p, c_double_p, C.POINTER(c_double_p)]),
+        "Nfft4GPPrecondCholTrace": (i, [vp, C.POINTER(c_double_p)]),
+        "Nfft4GPPrecondCholLogdet": (d, [vp]),
+        "Nfft4GPPrecondCholSetupWithKernel": (i, [c_double_p, i, i, i, vp, vp, i, vp]),
         "Nfft4GPPrecondAFNCreate": (vp, []), "Nfft4GPPrecondAFNFree": (None, [vp]),
         "Nfft4GPPrecondAFNSetRank": (None, [vp, i]), "Nfft4GPPrecondAFNSetLfil": (None, [vp, i]),
         "Nfft4GPPrecondAFNSolve": (i, [vp, i, c_double_p, c_double_p]),
@@ -257,8 +264,8 @@ class DenseAdditiveKernel:
     def fn(self):
         return C.cast(lib().Nfft4GPKernelAdditiveKernel, C.c_void_p)
 
-    def block(self, permr=None, permc=None):
-        return _kernel_block(lib().Nfft4GPKernelAdditiveKernel, self.h, self.X, permr, permc)
+    def block(self, permr=None, permc=None, grad=False):
+        return _kernel_block(lib().Nfft4GPKernelAdditiveKernel, self.h, self.X, permr, permc, grad)
 
     def free(self):
         if self.h:
@@ -283,8 +290,8 @@ class DensePlainKernel:
     def fn(self):
         return C.cast(self._fn, C.c_void_p)
 
-    def block(self, permr=None, permc=None):
-        return _kernel_block(self._fn, self.h, self.X, permr, permc)
+    def block(self, permr=None, permc=None, grad=False):
+        return _kernel_block(self._fn, self.h, self.X, permr, permc, grad)
 
     def free(self):
         if self.h:
@@ -292,21 +299,76 @@ class DensePlainKernel:
             self.h = None
 
 
-def _kernel_block(fn, h, X, permr, permc):
-    """func_kernel call shapes of kernels.c:701-991; returns the column-major block as an (nr, nc) array."""
+def _kernel_block(fn, h, X, permr, permc, grad=False):
+    """func_kernel call shapes of kernels.c:701-991; returns the column-major block as an (nr, nc) array, with grad=True
+    also the stacked gradient blocks [d/df, d/dl, d/dmu] as a (3, nr, nc) array."""
     d, n = X.shape
     K = C.c_void_p()
+    dK = C.c_void_p()
     pr = None if permr is None else np.ascontiguousarray(permr, dtype=np.int32)
     pc = None if permc is None else np.ascontiguousarray(permc, dtype=np.int32)
     rc = fn(h, dptr(X), n, n, d, iptr(pr) if pr is not None else None, 0 if pr is None else pr.size,
-            iptr(pc) if pc is not None else None, 0 if pc is None else pc.size, C.byref(K), None)
+            iptr(pc) if pc is not None else None, 0 if pc is None else pc.size, C.byref(K), C.byref(dK) if grad else None)
     if rc != 0:
         raise RuntimeError("dense kernel evaluation failed")
     nr = n if pr is None else pr.size
     nc = nr if pc is None else pc.size
     out = np.ctypeslib.as_array(C.cast(K, c_double_p), shape=(nc, nr)).T.copy()
     lib().Nfft4GPKernelFree(K)
+    if grad:
+        dout = np.ctypeslib.as_array(C.cast(dK, c_double_p), shape=(3, nc, nr)).transpose(0, 2, 1).copy()
+        lib().Nfft4GPKernelFree(dK)
+        return out, dout
     return out
+
+
+class CholPrecond:
+    """Dense Cholesky preconditioner (SRC/preconds/chol.c)."""
+
+    def __init__(self, stable=0):
+        self.h = lib().Nfft4GPPrecondCholCreate()
+        lib().Nfft4GPPrecondCholSetStable(self.h, stable)
+
+    def setup(self, kernel, require_grad=0):
+        rc = lib().Nfft4GPPrecondCholSetupWithKernel(dptr(kernel.X), kernel.n, kernel.n, kernel.d, kernel.fn(), kernel.h, require_grad, self.h)
+        if rc != 0:
+            raise RuntimeError("Nfft4GPPrecondCholSetupWithKernel failed")
+        self.n = kernel.n
+        return self
+
+    def solve(self, rhs):
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        x = np.zeros_like(rhs)
+        if lib().Nfft4GPPrecondCholSolve(self.h, rhs.size, dptr(x), dptr(rhs)) != 0:
+            raise RuntimeError("Nfft4GPPrecondCholSolve failed")
+        return x
+
+    def logdet(self):
+        return lib().Nfft4GPPrecondCholLogdet(self.h)
+
+    def trace(self):
+        tr = np.zeros(3)
+        p = dptr(tr)
+        if lib().Nfft4GPPrecondCholTrace(self.h, C.byref(p)) != 0:
+            raise RuntimeError("Nfft4GPPrecondCholTrace failed")
+        return tr
+
+    def dvp(self, x, mask=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros(3 * x.size)
+        p = dptr(y)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.int32)
+        if lib().Nfft4GPPrecondCholDvp(self.h, x.size, iptr(m) if m is not None else None, dptr(x), C.byref(p)) != 0:
+            raise RuntimeError("Nfft4GPPrecondCholDvp failed")
+        return y.reshape(3, x.size)
+
+    def solve_fn(self):
+        return C.cast(lib().Nfft4GPPrecondCholSolve, C.c_void_p)
+
+    def free(self):
+        if self.h:
+            lib().Nfft4GPPrecondCholFree(self.h)
+            self.h = None
 
 
 class NysPrecond:

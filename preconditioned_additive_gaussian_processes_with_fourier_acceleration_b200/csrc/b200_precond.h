@@ -80,6 +80,7 @@ void b200_tril_inverse(int k, const double *L, double *Linv);
 int b200_nys_solve_dev(void *vnys, int n, double *d_x, const double *d_rhs);
 int b200_fsai_solve_dev(void *vf, int n, double *d_x, const double *d_rhs);
 int b200_afn_solve_dev(void *va, int n, double *d_x, const double *d_rhs);
+int b200_chol_solve_dev(void *vc, int n, double *d_x, const double *d_rhs);
 
 /* dense_small.c: O(k^3) host factorizations of the k x k landmark block */
 double b200_sym_fro_lower(int n, const double *A, int lda);
@@ -107,5 +108,7 @@ void b200_dense_view_release(b200_dense_view *v);
 /* K(rows, cols) on the device: rows/cols device index arrays (NULL = 0..), column-major with leading dimension ldk */
 int b200_dense_view_block(const b200_dense_view *v, double noise_diag, const int *d_rows, int nr, const int *d_cols, int nc,
                           int lower_only, double *d_K, int ldk);
+int b200_dense_view_block_dl(const b200_dense_view *v, const int *d_rows, int nr, const int *d_cols, int nc, int lower_only, double *d_K,
+                             int ldk);
 
 #endif

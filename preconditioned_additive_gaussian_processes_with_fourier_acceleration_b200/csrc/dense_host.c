@@ -241,19 +241,25 @@ int b200_dense_view_block(const b200_dense_view *v, double noise_diag, const int
                                lower_only, d_K, ldk);
 }
 
+/* dK/dl of the same block (no noise term; zero on the diagonal) */
+int b200_dense_view_block_dl(const b200_dense_view *v, const int *d_rows, int nr, const int *d_cols, int nc, int lower_only, double *d_K,
+                             int ldk)
+{
+   if (lower_only && b200_memset(d_K, 0, sizeof(double) * (size_t)ldk * (size_t)nc))
+      return -1;
+   return b200k_dense_additive(v->d_Xw, v->n, v->P, v->dw, v->d_dims, v->kernel + 2, v->f * v->f, v->l, 0.0, d_rows, nr, d_cols, nc,
+                               lower_only, d_K, ldk);
+}
+
 /* ------------------------------------------------------------------ func_kernel entry points (host in, host out) */
 static int dense_call(func_kernel self, void *str, double *data, int n, int ldim, int d, int *permr, int kr, int *permc, int kc,
                       double **Kp, double **dKp)
 {
    b200_dense_view v;
    int rc, nr, nc, lower, *d_rows = NULL, *d_cols = NULL;
-   double *d_K, *K, noise;
-   if (dKp)
-   {
-      printf("Error: nfft4gp_b200 dense kernels build K only (gradient blocks are outside the hot path).\n");
-      return -1;
-   }
-   if (!Kp)
+   double *d_K, *K, *dK = NULL, noise;
+   size_t cnt, i;
+   if (!Kp && !dKp)
       return 0;
    rc = b200_dense_view_acquire(self, str, data, n, ldim, d, &v);
    if (rc)
@@ -292,19 +298,43 @@ static int dense_call(func_kernel self, void *str, double *data, int n, int ldim
       b200_h2d(d_cols, permc, sizeof(int) * (size_t)nc);
    }
    rc = b200_dense_view_block(&v, noise, d_rows, nr, permc ? d_cols : d_rows, nc, lower, d_K, nr);
-   K = *Kp ? *Kp : (double *)b200_xmalloc(sizeof(double) * (size_t)nr * nc);
-   rc = rc || b200_d2h(K, d_K, sizeof(double) * (size_t)nr * nc);
+   cnt = (size_t)nr * nc;
+   K = (Kp && *Kp) ? *Kp : (double *)b200_xmalloc(sizeof(double) * cnt);
+   rc = rc || b200_d2h(K, d_K, sizeof(double) * cnt);
+   if (!rc && dKp)
+   {
+      /* gradient blocks stacked [d/df; d/dl; d/dmu] (kernels.c:495-549, 2218-2222): d/df = (2/f) K including the noise
+       * diagonal of the symmetric call shapes, d/dmu = f^2 on that diagonal and zero in the K(permr, permc) shape */
+      dK = *dKp ? *dKp : (double *)b200_xmalloc(sizeof(double) * 3 * cnt);
+      rc = b200_dense_view_block_dl(&v, d_rows, nr, permc ? d_cols : d_rows, nc, lower, d_K, nr) ||
+           b200_d2h(dK + cnt, d_K, sizeof(double) * cnt);
+      for (i = 0; i < cnt; i++)
+      {
+         dK[i] = 2.0 / v.f * K[i];
+         dK[2 * cnt + i] = 0.0;
+      }
+      if (lower)
+         for (i = 0; i < (size_t)nr; i++)
+            dK[2 * cnt + i * nr + i] = v.f * v.f;
+   }
    b200_free(d_K);
    b200_free(d_rows);
    b200_free(d_cols);
    b200_dense_view_release(&v);
    if (rc)
    {
-      if (!*Kp)
+      if (!(Kp && *Kp))
          free(K);
+      if (dKp && !*dKp)
+         free(dK);
       return -1;
    }
-   *Kp = K;
+   if (Kp)
+      *Kp = K;
+   else
+      free(K);
+   if (dKp)
+      *dKp = dK;
    return 0;
 }
 

@@ -662,6 +662,8 @@ b200_dev_solve b200_lookup_dev_solve(void *host_fn)
       return b200_fsai_solve_dev;
    if (host_fn == (void *)Nfft4GPPrecondAFNSolve)
       return b200_afn_solve_dev;
+   if (host_fn == (void *)Nfft4GPPrecondCholSolve)
+      return b200_chol_solve_dev;
    return NULL;
 }
 

@@ -240,7 +240,12 @@ k_dense_additive(const double *__restrict__ Xw, int n, int P, int dw, const int 
          double df = __ldg(col + ia) - __ldg(col + ib);
          r2 = fma(df, df, r2);
       }
-      acc += (kernel == 0) ? exp(-r2 / (2.0 * l * l)) : exp(-sqrt(r2) / l);
+      // kernel 0 / 1: Gauss / Matern-1/2 value; 2 / 3: their derivative in the length scale (kernels.c:495-523, 2218-2222)
+      double r = sqrt(r2);
+      double e = (kernel & 1) ? exp(-r / l) : exp(-r2 / (2.0 * l * l));
+      if (kernel >= 2)
+         e *= (kernel & 1) ? r / (l * l) : r2 / (l * l * l);
+      acc += e;
    }
    acc = ff * (acc / (double)P);
    if (ia == ib)

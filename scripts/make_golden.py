@@ -167,6 +167,53 @@ def nys_plain_case():
     print("wrote nys plain case: nys-pcg it", itn, "plain pcg it", it0)
 
 
+def chol_case():
+    """Reference dense Cholesky preconditioner (SRC/preconds/chol.c) with gradients on the reference's plain Gaussian kernel:
+    kernel value + gradient blocks, solve, log det, traces tr(K^-1 dK_i) and derivative-vector products K^-1 dK_i x."""
+    z = np.load(os.path.join(OUT, "nys_gauss300.npz"))
+    X, f, l, mu, rhs = z["X"], float(z["f"]), float(z["l"]), float(z["mu"]), z["rhs"]
+    n, d = X.shape[1], X.shape[0]
+    L.Nfft4GPKernelParamCreate.restype = C.c_void_p
+    L.Nfft4GPKernelParamCreate.argtypes = [C.c_int, C.c_int]
+    kh = L.Nfft4GPKernelParamCreate(n, 1)
+    R.set_hyper(kh, f, l, mu)
+    fk = C.cast(L.Nfft4GPKernelGaussianKernel, C.c_void_p)
+    out = {}
+    # gradient blocks of the three call shapes
+    rows = np.random.default_rng(71).permutation(n)[:25].astype(np.int32)
+    cols = np.random.default_rng(72).permutation(n)[:17].astype(np.int32)
+    K, dK = C.c_void_p(), C.c_void_p()
+    assert L.Nfft4GPKernelGaussianKernel(kh, R.dptr(X), n, n, d, R.iptr(rows), 25, R.iptr(cols), 17, C.byref(K), C.byref(dK)) == 0
+    out["cross_K"] = np.ctypeslib.as_array(C.cast(K, R.c_double_p), shape=(17, 25)).T.copy()
+    out["cross_dK"] = np.ctypeslib.as_array(C.cast(dK, R.c_double_p), shape=(3, 17, 25)).transpose(0, 2, 1).copy()
+    K, dK = C.c_void_p(), C.c_void_p()
+    assert L.Nfft4GPKernelGaussianKernel(kh, R.dptr(X), n, n, d, R.iptr(rows), 25, None, 0, C.byref(K), C.byref(dK)) == 0
+    out["sym_K"] = np.ctypeslib.as_array(C.cast(K, R.c_double_p), shape=(25, 25)).T.copy()
+    out["sym_dK"] = np.ctypeslib.as_array(C.cast(dK, R.c_double_p), shape=(3, 25, 25)).transpose(0, 2, 1).copy()
+    out["rows"], out["cols"] = rows, cols
+    for stable in (0, 1):
+        ch = L.Nfft4GPPrecondCholCreate()
+        L.Nfft4GPPrecondCholSetStable(ch, stable)
+        assert L.Nfft4GPPrecondCholSetupWithKernel(R.dptr(X), n, n, d, fk, kh, 1, ch) == 0
+        x = np.zeros(n)
+        L.Nfft4GPPrecondCholSolve(ch, n, R.dptr(x), R.dptr(rhs))
+        L.Nfft4GPPrecondCholLogdet.restype = C.c_double
+        L.Nfft4GPPrecondCholLogdet.argtypes = [C.c_void_p]
+        ld = L.Nfft4GPPrecondCholLogdet(ch)
+        tr = np.zeros(3)
+        trp = R.dptr(tr)
+        L.Nfft4GPPrecondCholTrace.argtypes = [C.c_void_p, C.POINTER(R.c_double_p)]
+        assert L.Nfft4GPPrecondCholTrace(ch, C.byref(trp)) == 0
+        y = np.zeros(3 * n)
+        yp = R.dptr(y)
+        L.Nfft4GPPrecondCholDvp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, R.c_double_p, C.POINTER(R.c_double_p)]
+        assert L.Nfft4GPPrecondCholDvp(ch, n, None, R.dptr(rhs), C.byref(yp)) == 0
+        out[f"solve{stable}"], out[f"logdet{stable}"], out[f"trace{stable}"], out[f"dvp{stable}"] = x, ld, tr, y
+        print("chol stable", stable, "logdet", ld, "traces", tr)
+    out.update({"X": X, "f": f, "l": l, "mu": mu, "rhs": rhs})
+    np.savez_compressed(os.path.join(OUT, "chol_gauss300.npz"), **out)
+
+
 def fgmres_case():
     """Reference Nfft4GPSolverFgmres (SRC/solvers/fgmres.c) on the reference's dense Gaussian kernel, with restarts (kdim 15),
     without and with the reference's Nystrom preconditioner, plus a run that stops at the iteration limit."""
@@ -293,6 +340,9 @@ def lanczos_case():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "chol":
+        chol_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "lanczos":
         lanczos_case()
         sys.exit(0)
