@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnfft4gp_b200.so")
+LIB_PATH = os.environ.get("NFFT4GP_B200_LIB") or os.path.join(HERE, "libnfft4gp_b200.so")  # override: A/B builds of the kernels
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)

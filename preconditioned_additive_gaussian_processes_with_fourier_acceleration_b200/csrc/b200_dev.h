@@ -108,8 +108,12 @@ typedef struct
    int warp_begin;
    int nwarps;
 } b200_mma_win;
-int b200k_spread3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps);
-int b200k_gather3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps);
+/* `rounds` > 1: window w owns rounds * nwarps consecutive ranges (cfirst has rounds * nwarps + 1 entries); range
+ * (round k, slot q of the wave) is cfirst[k * nwarps + q - warp_begin].  Every warp starts with the round-0 range of its
+ * slot and then takes the remaining ranges in order from a device counter (dynamic: the warp schedulers do not serve the
+ * resident warps evenly, so equal static shares do not end together). */
+int b200k_spread3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps, int rounds);
+int b200k_gather3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps, int rounds);
 int b200k_spread_batch_begin(double *d_grids, size_t doubles);
 int b200k_spread_batch_end(void);
 int b200k_gather_batch_begin(void);

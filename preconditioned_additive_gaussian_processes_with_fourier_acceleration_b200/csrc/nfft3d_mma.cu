@@ -42,6 +42,9 @@
 #define STAGE_D (WS * RS + WS)
 #define CP16_PER_ROW (ROW * 8 / 16)
 #define CP16_PER_STAGE (WS * CP16_PER_ROW)
+#ifndef MX_CLK
+#define MX_CLK 0 /* development aid: in-kernel clocks of the spread, printed by a few warps */
+#endif
 #define MT 13 /* m-tiles: 13 * 8 = 104 >= 100 (x,y) pairs */
 #define KS 25 /* gather k-steps: 25 * 4 = 100 (x,y) pairs */
 
@@ -107,7 +110,11 @@ __device__ __forceinline__ void m_stage_issue(double *st, const double *__restri
 
 // main accumulators: tile i < 10: rows y = g, x = i; tile 10 + i': rows (x = 4 i' + g / 2, y = 8 + (g & 1)); columns z = 2 t + {0, 1}
 // edge accumulators: tile (i, j): rows x = 8 i + g; columns 8 j + 2 t + {0, 1} <-> y = 4 j + t, z = 8 + {0, 1}
-__device__ __forceinline__ void m_acc_to_ring(double *__restrict__ cb, int key, int g, int t, double acc[MT][2], double ace[2][3][2])
+// The register tile IS the running total of the cell's footprint: on a cell change it is stored to the ring (LOAD = false),
+// the planes that leave are written out, and the tile of the next cell is loaded back (LOAD = true) -- no fp64 additions,
+// which would queue behind the tensor instructions of the other warps on the one fp64 unit.
+template <bool LOAD>
+__device__ __forceinline__ void m_acc_ring(double *__restrict__ cb, int key, int g, int t, double acc[MT][2], double ace[2][3][2])
 {
    const int c3 = key & 63;
    const int s0 = ((c3 + 2 * t) % TAPS) * CB_PLANE, s1 = ((c3 + 2 * t + 1) % TAPS) * CB_PLANE;
@@ -119,10 +126,19 @@ __device__ __forceinline__ void m_acc_to_ring(double *__restrict__ cb, int key, 
       const int y = i < 10 ? g : 8 + (g & 1);
       if (x < TAPS)
       {
-         cb[s0 + x * TAPS + y] += acc[i][0];
-         cb[s1 + x * TAPS + y] += acc[i][1];
+         if (LOAD)
+         {
+            acc[i][0] = cb[s0 + x * TAPS + y];
+            acc[i][1] = cb[s1 + x * TAPS + y];
+         }
+         else
+         {
+            cb[s0 + x * TAPS + y] = acc[i][0];
+            cb[s1 + x * TAPS + y] = acc[i][1];
+         }
       }
-      acc[i][0] = acc[i][1] = 0.0;
+      else if (LOAD)
+         acc[i][0] = acc[i][1] = 0.0;
    }
 #pragma unroll
    for (int i = 0; i < 2; i++)
@@ -132,10 +148,19 @@ __device__ __forceinline__ void m_acc_to_ring(double *__restrict__ cb, int key, 
          const int x = 8 * i + g, y = 4 * j + t;
          if (x < TAPS && y < TAPS)
          {
-            cb[s8 + x * TAPS + y] += ace[i][j][0];
-            cb[s9 + x * TAPS + y] += ace[i][j][1];
+            if (LOAD)
+            {
+               ace[i][j][0] = cb[s8 + x * TAPS + y];
+               ace[i][j][1] = cb[s9 + x * TAPS + y];
+            }
+            else
+            {
+               cb[s8 + x * TAPS + y] = ace[i][j][0];
+               cb[s9 + x * TAPS + y] = ace[i][j][1];
+            }
          }
-         ace[i][j][0] = ace[i][j][1] = 0.0;
+         else if (LOAD)
+            ace[i][j][0] = ace[i][j][1] = 0.0;
       }
 }
 
@@ -210,8 +235,17 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
       m_commit();
    }
    int4 dissue = chunks[c0 + MWNS - 1];
+#if MX_CLK
+   long long tk_stage = 0, tk_flush = 0, tk_comp = 0, tk_n = 0, tk_cells = 0, tk_f[3] = {0, 0, 0};
+   const long long tk_begin = clock64();
+   unsigned long long tk_ns0;
+   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tk_ns0));
+#endif
    for (int c = c0; c < c1; c++)
    {
+#if MX_CLK
+      const long long tk0 = clock64();
+#endif
       const int4 dnext = chunks[c + 1];
       const int4 dissue_next = chunks[c + MWNS];
       m_wait<MWNS - 2>();
@@ -219,21 +253,43 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
       if (c + MWNS - 1 < c1)
          m_stage_issue(st[(c - c0 + MWNS - 1) % MWNS], psi, a, dissue, lane);
       m_commit();
+#if MX_CLK
+      const long long tk1 = clock64();
+      tk_cells += dcur.z != key;
+#endif
 
       if (dcur.z != key) // warp-uniform: the stream enters another cell
       {
          const int knew = dcur.z, d = knew - key;
          const bool same_column = (knew >> 6) == (key >> 6);
-         m_acc_to_ring(cb, key, g, t, acc, ace);
+#if MX_CLK
+         const long long tf0 = clock64();
+#endif
+         m_acc_ring<false>(cb, key, g, t, acc, ace);
          __syncwarp();
+#if MX_CLK
+         const long long tf1 = clock64();
+#endif
          // same (c1, c2) column, c3 advanced by d: only the d planes that leave the footprint are written out
          m_ring_flush(cb, grid, key, (same_column && d > 0 && d < TAPS) ? d : TAPS, lane, co);
          __syncwarp();
          if (!same_column)
             co = m_column_offsets(knew, lane);
          key = knew;
+#if MX_CLK
+         const long long tf2 = clock64();
+#endif
+         m_acc_ring<true>(cb, key, g, t, acc, ace); // planes that stay keep their totals, the new ones were cleared
+#if MX_CLK
+         tk_f[0] += tf1 - tf0;
+         tk_f[1] += tf2 - tf1;
+         tk_f[2] += clock64() - tf2;
+#endif
       }
 
+#if MX_CLK
+      const long long tk2 = clock64();
+#endif
       const double *stage = st[(c - c0) % MWNS];
 #pragma unroll
       for (int kk = 0; kk < 2; kk++)
@@ -288,12 +344,36 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
             m_dmma(ace[1][j][0], ace[1][j][1], ae1, be);
          }
       }
+#if MX_CLK
+      {
+         const long long tk3 = clock64();
+         tk_stage += tk1 - tk0;
+         tk_flush += tk2 - tk1;
+         tk_comp += tk3 - tk2;
+         tk_n++;
+      }
+#endif
       dcur = dnext;
       dissue = dissue_next;
    }
-   m_acc_to_ring(cb, key, g, t, acc, ace);
+#if MX_CLK
+   if (lane == 0 && ((blockIdx.x * MWARPS_PER_CTA + (threadIdx.x >> 5)) % 97) == 0)
+   {
+      unsigned long long tk_ns1;
+      unsigned smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tk_ns1));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const long long tot = clock64() - tk_begin;
+      printf("warp %4d sm %3u: [%7llu .. %7llu ns] chunks %3lld cells %2lld total %lld clk %.3f GHz | per chunk: stage %lld flush %lld compute %lld | per cell: store %lld planes %lld load %lld\n",
+             blockIdx.x * MWARPS_PER_CTA + (threadIdx.x >> 5), smid, tk_ns0 % 10000000ull, tk_ns1 % 10000000ull, tk_n, tk_cells, tot,
+             (double)tot / (double)(tk_ns1 - tk_ns0), tk_stage / tk_n, tk_flush / tk_n, tk_comp / tk_n, tk_f[0] / (tk_cells + 1), tk_f[1] / (tk_cells + 1),
+             tk_f[2] / (tk_cells + 1));
+   }
+#endif
+   m_acc_ring<false>(cb, key, g, t, acc, ace);
    __syncwarp();
    m_ring_flush(cb, grid, key, TAPS, lane, co);
+   __syncwarp();
 }
 
 // dynamic shared memory of the spread kernels: the cp.async stages of the CTA's warps, then their footprint rings
@@ -312,21 +392,48 @@ k_spread3_mma(const double *__restrict__ psi, const double *__restrict__ a, cons
 
 // all windows of an additive kernel in ONE persistent wave: warp gw belongs to the window w with
 // wbeg[w] <= gw < wbeg[w + 1] and streams range gw - wbeg[w] of that window's own partition
+// range (round k, slot q) of the fused launches -> window, chunk interval; returns false when the slot is empty
+__device__ __forceinline__ bool m_range_lookup(const b200_mma_win *__restrict__ W, int P, int total, int r, int &w, int &c0, int &c1)
+{
+   const int k = r / total, q = r - k * total;
+   w = 0;
+   while (w + 1 < P && q >= W[w + 1].warp_begin)
+      w++;
+   const int j = q - W[w].warp_begin;
+   if (j >= W[w].nwarps)
+      return false;
+   const int *cf = W[w].cfirst + k * W[w].nwarps + j;
+   c0 = cf[0];
+   c1 = cf[1];
+   return true;
+}
+__device__ int g_mma_range_counter[2]; // next dynamic range of the running fused spread [0] / gather [1]
+__device__ __forceinline__ int m_range_next(int *counter, int total, int lane)
+{
+   int nx = 0;
+   if (lane == 0)
+      nx = atomicAdd(counter, 1);
+   return total + __shfl_sync(0xffffffffu, nx, 0);
+}
+
 __global__ void __launch_bounds__(MWARPS_PER_CTA * 32, MCTAS_PER_SM)
-k_spread3_mma_batch(const b200_mma_win *__restrict__ W, int P)
+k_spread3_mma_batch(const b200_mma_win *__restrict__ W, int P, int rounds)
 {
    extern __shared__ __align__(16) double dsm[];
    double(*smem)[MWNS][STAGE_D] = reinterpret_cast<double(*)[MWNS][STAGE_D]>(dsm);
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-   const int gw = blockIdx.x * MWARPS_PER_CTA + wid;
-   int w = 0;
-   while (w + 1 < P && gw >= W[w + 1].warp_begin)
-      w++;
-   const int r = gw - W[w].warp_begin;
-   if (r >= W[w].nwarps)
-      return;
-   m_spread_range(W[w].psi, W[w].a, (const int4 *)W[w].chunks, W[w].cfirst[r], W[w].cfirst[r + 1], W[w].grid, smem[wid],
-                  dsm + MWARPS_PER_CTA * MWNS * STAGE_D + wid * CB_DOUBLES, lane);
+   const int total = gridDim.x * MWARPS_PER_CTA;
+   int r = blockIdx.x * MWARPS_PER_CTA + wid;
+   while (r < total * rounds)
+   {
+      int w, c0, c1;
+      if (m_range_lookup(W, P, total, r, w, c0, c1))
+         m_spread_range(W[w].psi, W[w].a, (const int4 *)W[w].chunks, c0, c1, W[w].grid, smem[wid],
+                        dsm + MWARPS_PER_CTA * MWNS * STAGE_D + wid * CB_DOUBLES, lane);
+      if (rounds == 1)
+         break;
+      r = m_range_next(&g_mma_range_counter[0], total, lane);
+   }
 }
 
 // ---------------------------------------------------------------------------------------------------- gather
@@ -468,18 +575,22 @@ k_gather3_mma(const double *__restrict__ psi, const int4 *__restrict__ chunks, c
 }
 
 __global__ void __launch_bounds__(MWARPS_PER_CTA * 32, MCTAS_PER_SM)
-k_gather3_mma_batch(const b200_mma_win *__restrict__ W, int P)
+k_gather3_mma_batch(const b200_mma_win *__restrict__ W, int P, int rounds)
 {
    __shared__ __align__(16) double smem[MWARPS_PER_CTA][MWNS][STAGE_D];
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-   const int gw = blockIdx.x * MWARPS_PER_CTA + wid;
-   int w = 0;
-   while (w + 1 < P && gw >= W[w + 1].warp_begin)
-      w++;
-   const int r = gw - W[w].warp_begin;
-   if (r >= W[w].nwarps)
-      return;
-   m_gather_range(W[w].psi, (const int4 *)W[w].chunks, W[w].cfirst[r], W[w].cfirst[r + 1], W[w].grid, W[w].f, smem[wid], lane);
+   const int total = gridDim.x * MWARPS_PER_CTA;
+   int r = blockIdx.x * MWARPS_PER_CTA + wid;
+   while (r < total * rounds)
+   {
+      int w, c0, c1;
+      if (m_range_lookup(W, P, total, r, w, c0, c1))
+         m_gather_range(W[w].psi, (const int4 *)W[w].chunks, c0, c1, W[w].grid, W[w].f, smem[wid], lane);
+      if (rounds == 1)
+         break;
+      __syncwarp(); // the stages are reused by the next range
+      r = m_range_next(&g_mma_range_counter[1], total, lane);
+   }
 }
 
 // ---------------------------------------------------------------------------------------------------- launch layer
@@ -515,7 +626,16 @@ int b200k_gather3_mma(const b200_win_dev *w, double *d_f)
 }
 
 // fused launches over the P windows described by d_batch (device array); total_warps = sum of nwarps, a multiple of the CTA size
-int b200k_spread3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps)
+static int mma_counter_reset(int which)
+{
+   static int *addr = nullptr;
+   if (!addr)
+      B200_CHECK(cudaGetSymbolAddress((void **)&addr, g_mma_range_counter));
+   B200_CHECK(cudaMemsetAsync(addr + which, 0, sizeof(int), b200_stream())); // a memset node when the matvec is being captured
+   return 0;
+}
+
+int b200k_spread3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps, int rounds)
 {
    static bool attr_set = false; // once: this call may sit inside a stream capture (CUDA graph of the matvec)
    if (!attr_set)
@@ -523,14 +643,18 @@ int b200k_spread3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps)
       B200_CHECK(cudaFuncSetAttribute(k_spread3_mma_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPREAD_SMEM_BYTES));
       attr_set = true;
    }
-   k_spread3_mma_batch<<<total_warps / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, SPREAD_SMEM_BYTES, b200_stream()>>>(d_batch, P);
+   if (rounds > 1 && mma_counter_reset(0))
+      return -1;
+   k_spread3_mma_batch<<<total_warps / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, SPREAD_SMEM_BYTES, b200_stream()>>>(d_batch, P, rounds);
    B200_LAUNCHED();
    return 0;
 }
 
-int b200k_gather3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps)
+int b200k_gather3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps, int rounds)
 {
-   k_gather3_mma_batch<<<total_warps / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, 0, b200_stream()>>>(d_batch, P);
+   if (rounds > 1 && mma_counter_reset(1))
+      return -1;
+   k_gather3_mma_batch<<<total_warps / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, 0, b200_stream()>>>(d_batch, P, rounds);
    B200_LAUNCHED();
    return 0;
 }

@@ -1006,6 +1006,36 @@ static int additive_local_n(const b200_additive *A) { return A->blk_hi - A->blk_
  * the sparse periphery makes the difference (profiles/README.md); uniform clouds are insensitive */
 #define FUSED_FLUSH_COST_SPREAD 60.0
 #define FUSED_FLUSH_COST_GATHER 24.0
+/* Work distribution of the fused launches: every warp of the persistent wave gets one large range up front and then
+ * takes progressively smaller ones from a device counter (guided self-scheduling).  Equal static shares finish far
+ * apart -- in-kernel clocks showed 326 k .. 641 k cycles per warp -- because the warp schedulers serve the resident warps
+ * of a sub-partition unevenly and the cost model is only approximate.  NFFT4GP_B200_ROUNDS="w0,w1,..." overrides. */
+#define FUSED_MAX_ROUNDS 8
+static int g_fused_rounds = 0;
+static double g_fused_weight[FUSED_MAX_ROUNDS] = {8.0, 4.0, 2.0, 1.0, 1.0};
+static void fused_rounds_init(void)
+{
+   const char *e = getenv("NFFT4GP_B200_ROUNDS");
+   if (g_fused_rounds)
+      return;
+   g_fused_rounds = 5;
+   if (e && *e)
+   {
+      int k = 0;
+      while (*e && k < FUSED_MAX_ROUNDS)
+      {
+         char *end;
+         double v = strtod(e, &end);
+         if (end == e || !(v > 0.0))
+            break;
+         g_fused_weight[k++] = v;
+         e = (*end == ',') ? end + 1 : end;
+      }
+      if (k > 0)
+         g_fused_rounds = k;
+   }
+}
+
 static double chunk_cost(const int *hc, int c, int prev_key, double flush)
 {
    return (double)hc[4 * c + 1] + 1.0 + (hc[4 * c + 2] != prev_key ? flush : 0.0);
@@ -1041,8 +1071,9 @@ static void additive_fused_release(b200_additive *A)
 static int additive_fused_partition(b200_additive *A, int dir, int total_warps)
 {
    const double flush = dir ? FUSED_FLUSH_COST_GATHER : FUSED_FLUSH_COST_SPREAD;
-   int nb = A->nbatch, i, c, assigned = 0, big = 0, rc = -1;
-   double *cost = (double *)b200_xcalloc((size_t)nb, sizeof(double)), total = 0.0;
+   int nb = A->nbatch, i, c, k, assigned = 0, big = 0, rc = -1;
+   double *cost = (double *)b200_xcalloc((size_t)nb, sizeof(double)), total = 0.0, wsum = 0.0;
+   fused_rounds_init();
    int *wbeg = (int *)b200_xcalloc((size_t)nb + 1, sizeof(int)), *wcnt = (int *)b200_xcalloc((size_t)nb, sizeof(int));
    b200_mma_win *hw = (b200_mma_win *)b200_xcalloc((size_t)nb, sizeof(b200_mma_win));
    for (i = 0; i < nb; i++)
@@ -1071,24 +1102,35 @@ static int additive_fused_partition(b200_additive *A, int dir, int total_warps)
    for (i = 0; i < nb; i++)
       wbeg[i + 1] = wbeg[i] + wcnt[i];
    A->d_fused_cfirst[dir] = (int **)b200_xcalloc((size_t)nb, sizeof(int *));
+   for (k = 0; k < g_fused_rounds; k++)
+      wsum += g_fused_weight[k];
    for (i = 0; i < nb; i++)
    {
+      /* rounds * wcnt consecutive ranges: round k holds wcnt ranges of the cost share weight[k] / wsum / wcnt each */
       const int *hc = A->win[i]->h_chunks;
       b200_win_dev *v = &A->win[i]->dev;
-      int nch = A->win[i]->h_nchunk, r = 0, prev = -1, *hr = (int *)b200_xcalloc((size_t)wcnt[i] + 1, sizeof(int)), bad;
-      double acc = 0.0, target = cost[i] / (double)wcnt[i];
+      int nr = g_fused_rounds * wcnt[i];
+      int nch = A->win[i]->h_nchunk, r = 0, prev = -1, *hr = (int *)b200_xcalloc((size_t)nr + 1, sizeof(int)), bad;
+      double acc = 0.0, *start = (double *)b200_xcalloc((size_t)nr + 1, sizeof(double)), wacc = 0.0;
+      for (k = 0; k < g_fused_rounds; k++)
+      {
+         for (c = 0; c < wcnt[i]; c++)
+            start[k * wcnt[i] + c] = cost[i] * (wacc + g_fused_weight[k] * (double)c / (double)wcnt[i]) / wsum;
+         wacc += g_fused_weight[k];
+      }
       for (c = 0; c < nch; c++)
       {
-         while (r + 1 < wcnt[i] && acc >= target * (double)(r + 1))
+         while (r + 1 < nr && acc >= start[r + 1])
             hr[++r] = c;
          acc += chunk_cost(hc, c, prev, flush);
          prev = hc[4 * c + 2];
       }
-      while (r + 1 < wcnt[i])
+      while (r + 1 < nr)
          hr[++r] = nch;
-      hr[wcnt[i]] = nch;
-      A->d_fused_cfirst[dir][i] = (int *)b200_malloc(sizeof(int) * ((size_t)wcnt[i] + 1));
-      bad = !A->d_fused_cfirst[dir][i] || b200_h2d(A->d_fused_cfirst[dir][i], hr, sizeof(int) * ((size_t)wcnt[i] + 1)) || b200_sync();
+      hr[nr] = nch;
+      free(start);
+      A->d_fused_cfirst[dir][i] = (int *)b200_malloc(sizeof(int) * ((size_t)nr + 1));
+      bad = !A->d_fused_cfirst[dir][i] || b200_h2d(A->d_fused_cfirst[dir][i], hr, sizeof(int) * ((size_t)nr + 1)) || b200_sync();
       free(hr);
       if (bad)
          goto done;
@@ -1200,7 +1242,7 @@ static int additive_apply_windows(b200_additive *A, const double *d_x, double s,
       /* batched prep, one memset of the contiguous grids, one persistent wave for the spread of all batch windows */
       size_t gsz = ipow(B200_NOS, 3) * (size_t)A->nbatch;
       if (b200k_prep_batch(A->nbatch, A->d_prep_perm, A->d_prep_a, A->d_prep_n, A->prep_nmax, d_x, s) ||
-          b200k_spread_batch_begin(A->d_grids, gsz) || b200k_spread3_mma_batch((const b200_mma_win *)A->d_fused[0], A->nbatch, A->fused_warps) ||
+          b200k_spread_batch_begin(A->d_grids, gsz) || b200k_spread3_mma_batch((const b200_mma_win *)A->d_fused[0], A->nbatch, A->fused_warps, g_fused_rounds) ||
           b200k_spread_batch_end())
          return -1;
       for (i = A->nbatch; i < A->P; i++)
@@ -1224,7 +1266,7 @@ collective:
          return -1;
       if (fused)
       {
-         if (b200k_gather_batch_begin() || b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[1], A->nbatch, A->fused_warps) ||
+         if (b200k_gather_batch_begin() || b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[1], A->nbatch, A->fused_warps, g_fused_rounds) ||
              b200k_gather_batch_end())
             return -1;
       }
@@ -1242,7 +1284,7 @@ collective:
          if (fused)
          {
             if (additive_fused_channel1(A) || b200k_gather_batch_begin() ||
-                b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[2], A->nbatch, A->fused_warps) || b200k_gather_batch_end())
+                b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[2], A->nbatch, A->fused_warps, g_fused_rounds) || b200k_gather_batch_end())
                return -1;
          }
          else
