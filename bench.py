@@ -14,6 +14,7 @@ cpu_baseline / --impl reference: the reference's own CPU implementation of the p
 """
 import argparse
 import ctypes as C
+import io
 import json
 import os
 import statistics
@@ -429,5 +430,29 @@ def main():
     return 0
 
 
+def _main_with_clean_stdout():
+    """The C libraries print progress lines with printf (the reference does: 'Initializing NFFT kernel ...').  Route
+    everything written to fd 1 during the run to stderr so that stdout carries exactly ONE line: the JSON result."""
+    import ctypes
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = io.StringIO()
+    py_stdout, sys.stdout = sys.stdout, out
+    try:
+        rc = main()
+    finally:
+        sys.stdout = py_stdout
+        try:
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    sys.stdout.write(out.getvalue())
+    sys.stdout.flush()
+    return rc
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(_main_with_clean_stdout())
