@@ -297,6 +297,10 @@ int Nfft4GPB200PrecondAFNGetFactors(void *afn, int *n, int *k, int *k_est, int *
 /* AFN rank estimation (afn_setup.m:111-293): m sampled points (default 500), numests repetitions (default 5; 0 = skip the
  * estimation and use the maximum rank), noran != 0 = never switch to the Nystrom form, seed of the sub-sampling generator */
 int Nfft4GPB200PrecondAFNSetRankEstimation(void *afn, int m, int numests, int noran, unsigned long long seed);
+/* Storage of the AFN K12 block (k x (n-k), read twice by every apply and the dominant HBM traffic of a PCG iteration at
+ * large rank): bits = 64 (default) or 32.  With 32 the block is kept in fp32 (k a multiple of 4), vectors and sums stay fp64
+ * and the apply stays symmetric; the preconditioner changes by O(1e-7) relative, the solution PCG converges to does not. */
+int Nfft4GPB200PrecondAFNSetK12Storage(void *afn, int bits);
 /* setup building blocks, exposed for the parity tests (host in / host out; the device ones need a GPU) */
 int Nfft4GPB200HostPotrf(int n, double *A /* lower, column-major, in place */);
 int Nfft4GPB200HostSyev(int n, double *A /* in: symmetric; out: eigenvectors */, double *w /* ascending */, int want_vectors);

@@ -99,6 +99,7 @@ def lib():
         "Nfft4GPB200PrecondAFNGetFactors": (i, [vp, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_double_p, c_double_p, c_int_p,
                                                 c_int_p, c_int_p, c_double_p]),
         "Nfft4GPB200PrecondAFNSetRankEstimation": (i, [vp, i, i, i, C.c_ulonglong]),
+        "Nfft4GPB200PrecondAFNSetK12Storage": (i, [vp, i]),
         "Nfft4GPB200HostPotrf": (i, [i, c_double_p]), "Nfft4GPB200HostSyev": (i, [i, c_double_p, c_double_p, i]),
         "Nfft4GPB200Dgemm": (i, [C.c_char, C.c_char, i, i, i, d, c_double_p, i, c_double_p, i, d, c_double_p, i]),
         "Nfft4GPB200Fps": (i, [c_double_p, i, i, i, i, c_int_p]),
@@ -475,6 +476,12 @@ class FsaiPrecond:
 class AfnPrecond:
     def __init__(self):
         self.h = lib().Nfft4GPPrecondAFNCreate()
+
+    def set_k12_storage(self, bits):
+        """Nfft4GPB200PrecondAFNSetK12Storage: 32 = keep the K12 block in fp32 (halves the HBM traffic of the apply)."""
+        if lib().Nfft4GPB200PrecondAFNSetK12Storage(self.h, bits) != 0:
+            raise RuntimeError("Nfft4GPB200PrecondAFNSetK12Storage failed")
+        return self
 
     def setup(self, kernel, max_k, lfil, est_m=500, numests=5, noran=0, seed=906):
         """Nfft4GPPrecondAFNSetRank / SetLfil / SetupWithKernel (afn.h:65-132; MATLAB afn_setup.m:30-109)."""

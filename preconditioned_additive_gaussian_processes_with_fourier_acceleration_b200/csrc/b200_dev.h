@@ -71,6 +71,9 @@ int b200_graph_begin(void);
 void *b200_graph_end(void);
 int b200_graph_launch(void *exec);
 void b200_graph_destroy(void *exec);
+void b200_outer_capture_set(int on);
+int b200_outer_capturing(void);
+int b200_d2h_async(void *dst, const void *src, size_t bytes);
 void b200_prof_start(void);
 int b200_prof_stop(double *sums_ms, long long *counts, int ncls);
 
@@ -133,6 +136,10 @@ int b200k_dot2(int n, const double *x, const double *y, const double *u, const d
 int b200k_xpby(int n, const double *z, double beta, double *p);                 /* p = z + beta p */
 /* x += alpha p ; r -= alpha q ; out = r.r   (fused PCG update, pcg.c:165-169) */
 int b200k_pcg_update(int n, double alpha, const double *p, const double *q, double *x, double *r, double *d_out);
+/* the same two updates with the step lengths formed on the device from device-resident dot products (see vec_kernels.cu) */
+int b200k_xpby_dev(int n, const double *z, const double *d_rho, const double *d_rho_prev /* NULL: p = z */, double *p);
+int b200k_pcg_update_dev(int n, const double *d_rho, const double *d_rho_prev, const double *d_pq, const double *p, const double *q,
+                         double *x, double *r, double *d_out);
 int b200k_copy(int n, const double *src, double *dst);
 int b200k_fill(int n, double v, double *dst);
 int b200k_scale(int n, double a, double *x);
@@ -159,6 +166,10 @@ int b200k_gather_perm(int n, const int *perm, const double *src, double *dst);  
 int b200k_scatter_perm(int n, const int *perm, const double *src, double *dst); /* dst[perm[i]] = src[i] */
 /* dense column-major GEMV on device: y = alpha*op(A)x + beta*y, A m x n, lda = m */
 int b200k_gemv(char trans, int m, int n, double alpha, const double *A, const double *x, double beta, double *y);
+/* matrix stored in fp32 (m a multiple of 4), fp64 vectors and accumulation */
+int b200k_gemv_f32(char trans, int m, int n, double alpha, const float *A, const double *x, double beta, double *y);
+int b200k_convert_f64_f32(size_t count, const double *src, float *dst);
+int b200k_convert_f32_f64(size_t count, const float *src, double *dst);
 /* dense additive kernel block K(rows, cols) on device (kernels.c:3099-3494 call shapes):
  * Xw: window-major feature copy [P][dw][n] (missing features of a short last window flagged by dims[w] < dw) */
 int b200k_dense_additive(const double *Xw, int n, int P, int dw, const int *d_dims, int kernel, double ff, double l,

@@ -55,6 +55,8 @@ typedef struct
    int *d_perm;
    double *d_Linv; /* k x k explicit inverse of chol(K11 + shift), lower, column-major */
    double *d_K12;  /* k x (n-k) column-major */
+   float *d_K12f;  /* the same block in fp32 when k12_bits == 32 (then d_K12 is released after the setup) */
+   int k12_bits;   /* 64 (default) or 32: storage of K12 for the two HBM-bound products of every apply */
    b200_fsai schur;
    void *nys;      /* set when the estimated rank is below max_k: Nystrom on the FPS ordering */
    double *d_work; /* 2n + 2k */
@@ -76,6 +78,7 @@ int b200_afn_set_device_factors(b200_afn *s, int n, int k, const int *h_perm, co
                                 const int *ia, const int *ja, const double *a);
 void b200_fsai_release(b200_fsai *s);
 void b200_afn_release(b200_afn *s);
+int b200_afn_finish_setup(b200_afn *s);
 void b200_tril_inverse(int k, const double *L, double *Linv);
 int b200_nys_solve_dev(void *vnys, int n, double *d_x, const double *d_rhs);
 int b200_fsai_solve_dev(void *vf, int n, double *d_x, const double *d_rhs);

@@ -112,6 +112,11 @@ void *b200_graph_end(void)
    return (void *)ex;
 }
 
+// set while a solver captures a whole iteration: operators that keep their own graphs enqueue their kernels directly
+static int g_outer_capture = 0;
+void b200_outer_capture_set(int on) { g_outer_capture = on; }
+int b200_outer_capturing(void) { return g_outer_capture; }
+
 int b200_graph_launch(void *exec)
 {
    B200_CHECK(cudaGraphLaunch((cudaGraphExec_t)exec, g_stream));
@@ -231,6 +236,15 @@ int b200_d2h(void *dst, const void *src, size_t bytes)
       return -1;
    B200_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
    B200_CHECK(cudaStreamSynchronize(g_stream));
+   return 0;
+}
+
+// enqueue only (the destination must be pinned host memory); used inside captured iteration graphs
+int b200_d2h_async(void *dst, const void *src, size_t bytes)
+{
+   if (ensure_init())
+      return -1;
+   B200_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
    return 0;
 }
 

@@ -1339,7 +1339,8 @@ int b200_additive_matvec_dev(b200_additive *A, int n, double alpha, const double
    /* CUDA graph of the launch sequence (fused tensor-core path only), one per argument signature.  Under point-block
     * sharding the collective is NOT captured: two graphs around a plainly enqueued allreduce (a captured NCCL kernel next
     * to the caller's own communicator deadlocked in a 2-GPU bench run). */
-   if (!A->graph_off && !b200_prof_active() && !(A->shard_mode == 1 && b200_comm_size() > 1) && additive_fused_prepare(A))
+   if (!A->graph_off && !b200_outer_capturing() && !b200_prof_active() && !(A->shard_mode == 1 && b200_comm_size() > 1) &&
+       additive_fused_prepare(A))
    {
       const int split = (A->shard_mode == 2 && b200_comm_size() > 1);
       long long before;

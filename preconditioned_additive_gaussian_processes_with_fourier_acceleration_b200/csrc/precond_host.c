@@ -359,6 +359,8 @@ void b200_afn_release(b200_afn *s)
    b200_free(s->d_perm);
    b200_free(s->d_Linv);
    b200_free(s->d_K12);
+   b200_free(s->d_K12f);
+   s->d_K12f = NULL;
    b200_free(s->d_work);
    b200_free(s->d_lm_idx);
    b200_free(s->d_sc_idx);
@@ -402,6 +404,53 @@ int Nfft4GPB200PrecondAFNSetRankEstimation(void *str, int m, int numests, int no
    return 0;
 }
 
+/* Storage of the K12 block (k x (n - k)): every apply reads it twice and nothing else of comparable size, so fp32 storage
+ * halves the HBM traffic of a PCG iteration at large rank.  Products and vectors stay fp64; the preconditioner stays
+ * symmetric (the same rounded block is used in both products).  Takes effect at the next setup / SetFactors, or
+ * immediately when factors are present.  bits = 64 restores the default (needs a new setup once the fp64 block is gone). */
+static int afn_apply_k12_storage(b200_afn *s)
+{
+   size_t cnt;
+   if (s->k12_bits != 32 || !s->d_K12 || s->d_K12f || s->n <= s->k)
+      return 0;
+   if (s->k & 3)
+   {
+      printf("Warning: fp32 storage of K12 needs a landmark count that is a multiple of 4 (k = %d): keeping fp64.\n", s->k);
+      return 0;
+   }
+   cnt = (size_t)s->k * (size_t)(s->n - s->k);
+   s->d_K12f = (float *)b200_malloc(sizeof(float) * cnt);
+   if (!s->d_K12f || b200k_convert_f64_f32(cnt, s->d_K12, s->d_K12f) || b200_sync())
+      return -1;
+   b200_free(s->d_K12);
+   s->d_K12 = NULL;
+   return 0;
+}
+
+int Nfft4GPB200PrecondAFNSetK12Storage(void *afn, int bits)
+{
+   b200_afn *s = (b200_afn *)afn;
+   if (!s || s->magic != B200_MAGIC_AFN || (bits != 32 && bits != 64))
+      return -1;
+   if (bits == 64 && s->d_K12f)
+   {
+      printf("Error: the fp64 K12 block was released; run the setup again after selecting 64-bit storage.\n");
+      return -1;
+   }
+   s->k12_bits = bits;
+   return afn_apply_k12_storage(s);
+}
+
+int b200_afn_finish_setup(b200_afn *s) { return afn_apply_k12_storage(s); }
+
+/* y = beta y + alpha op(K12(:, col0 : col0 + ncols)) x in whichever storage the handle holds */
+static int afn_k12_gemv(b200_afn *s, char trans, int ncols, int col0, double alpha, const double *x, double beta, double *y)
+{
+   if (s->d_K12f)
+      return b200k_gemv_f32(trans, s->k, ncols, alpha, s->d_K12f + (size_t)s->k * col0, x, beta, y);
+   return b200k_gemv(trans, s->k, ncols, alpha, s->d_K12 + (size_t)s->k * col0, x, beta, y);
+}
+
 int Nfft4GPB200PrecondAFNGetFactors(void *afn, int *n, int *k, int *k_est, int *is_nys, int *perm, double *Linv, double *K12, int *nnz,
                                     int *ia, int *ja, double *a)
 {
@@ -424,6 +473,16 @@ int Nfft4GPB200PrecondAFNGetFactors(void *afn, int *n, int *k, int *k_est, int *
       return -1;
    if (K12 && s->d_K12 && b200_d2h(K12, s->d_K12, sizeof(double) * (size_t)s->k * (size_t)(s->n - s->k)))
       return -1;
+   if (K12 && s->d_K12f)
+   {
+      /* fp32 storage: hand back the rounded block in the fp64 layout of the interface */
+      size_t cnt = (size_t)s->k * (size_t)(s->n - s->k);
+      double *tmp = (double *)b200_malloc(sizeof(double) * cnt);
+      int rc = !tmp || b200k_convert_f32_f64(cnt, s->d_K12f, tmp) || b200_d2h(K12, tmp, sizeof(double) * cnt);
+      b200_free(tmp);
+      if (rc)
+         return -1;
+   }
    return Nfft4GPB200PrecondFsaiGetFactors(&s->schur, NULL, nnz, ia, ja, a);
 }
 
@@ -444,7 +503,7 @@ int b200_afn_set_device_factors(b200_afn *s, int n, int k, const int *h_perm, co
    free(Linv);
    if (rc)
       return -1;
-   return b200_fsai_set_host_factors(&s->schur, n - k, ia, ja, a);
+   return b200_fsai_set_host_factors(&s->schur, n - k, ia, ja, a) || afn_apply_k12_storage(s);
 }
 
 int Nfft4GPB200PrecondAFNSetFactors(void *afn, int n, int k, const int *perm, const double *L, const double *K12, const int *ia,
@@ -550,7 +609,7 @@ static int afn_solve_sharded(b200_afn *s, int nl, double *d_x, const double *d_r
    {
       /* rp2 = r(perm2) - K12' y1 on the local Schur range; assemble the full vector */
       if (b200k_gather_idx(n2l, s->d_sc_idx, d_rhs, rp2l) ||
-          (n2l > 0 && b200k_gemv('T', k, n2l, -1.0, s->d_K12 + (size_t)k * plo, y1, 1.0, rp2l)) || b200k_fill(n2, 0.0, full) ||
+          (n2l > 0 && afn_k12_gemv(s, 'T', n2l, plo, -1.0, y1, 1.0, rp2l)) || b200k_fill(n2, 0.0, full) ||
           (n2l > 0 && b200_d2d(full + plo, rp2l, sizeof(double) * (size_t)n2l)) || b200_comm_allreduce_sum(full, (size_t)n2))
          return -1;
       /* y2 = G' (G rp2): local rows of G, assemble, local rows of G' */
@@ -559,7 +618,7 @@ static int afn_solve_sharded(b200_afn *s, int nl, double *d_x, const double *d_r
           (n2l > 0 && b200k_csr_mv(n2l, G->d_iat + plo, G->d_jat, G->d_at, wfull, y2l)))
          return -1;
       /* rp1 -= K12 y2 (local columns, allreduce), y1 = A11^{-1} rp1 */
-      if (b200k_fill(k, 0.0, u) || (n2l > 0 && b200k_gemv('N', k, n2l, 1.0, s->d_K12 + (size_t)k * plo, y2l, 0.0, u)) ||
+      if (b200k_fill(k, 0.0, u) || (n2l > 0 && afn_k12_gemv(s, 'N', n2l, plo, 1.0, y2l, 0.0, u)) ||
           b200_comm_allreduce_sum(u, (size_t)k) || b200k_axpy(k, -1.0, u, rp1) || b200k_gemv('N', k, k, 1.0, s->d_Linv, rp1, 0.0, t) ||
           b200k_gemv('T', k, k, 1.0, s->d_Linv, t, 0.0, y1))
          return -1;
@@ -602,8 +661,8 @@ int b200_afn_solve_dev(void *va, int n, double *d_x, const double *d_rhs)
    if (n2 > 0)
    {
       /* rp2 -= A21 y ; y2 = S^{-1} rp2 ; rp -= A12 y2 ; y = A11 \ rp */
-      if (b200k_gemv('T', k, n2, -1.0, s->d_K12, y, 1.0, rp2) || b200_fsai_solve_dev(&s->schur, n2, y2, rp2) ||
-          b200k_gemv('N', k, n2, -1.0, s->d_K12, y2, 1.0, rp) || b200k_gemv('N', k, k, 1.0, s->d_Linv, rp, 0.0, t) ||
+      if (afn_k12_gemv(s, 'T', n2, 0, -1.0, y, 1.0, rp2) || b200_fsai_solve_dev(&s->schur, n2, y2, rp2) ||
+          afn_k12_gemv(s, 'N', n2, 0, -1.0, y2, 1.0, rp) || b200k_gemv('N', k, k, 1.0, s->d_Linv, rp, 0.0, t) ||
           b200k_gemv('T', k, k, 1.0, s->d_Linv, t, 0.0, y))
          return -1;
    }
@@ -652,6 +711,13 @@ b200_dev_matvec b200_lookup_dev_matvec(void *host_fn, void *mat_data, void **dev
       }
    }
    return NULL;
+}
+
+/* 1 when the device function is one of this library's own operators (no host callbacks inside: may be stream-captured) */
+int b200_dev_fn_is_native(void *fn)
+{
+   return fn == (void *)additive_mv_dev || fn == (void *)window_mv_dev || fn == (void *)b200_nys_solve_dev ||
+          fn == (void *)b200_fsai_solve_dev || fn == (void *)b200_afn_solve_dev || fn == (void *)b200_chol_solve_dev;
 }
 
 b200_dev_solve b200_lookup_dev_solve(void *host_fn)

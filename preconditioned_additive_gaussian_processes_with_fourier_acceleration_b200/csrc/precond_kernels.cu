@@ -4,6 +4,7 @@
 //   reference: SRC/preconds/nys.c:115-173 (three dgemv passes over U), fsai.c:106-123 + matops.c:139-272
 //   (serial CSR N / T), afn.c:109-136, SRC/linearalg/kernels.c:495, 2218-2222, 3099-3494.
 #include <cuda_runtime.h>
+#include <cstdint>
 #include <cstdio>
 
 #include "b200_dev.h"
@@ -177,11 +178,11 @@ k_gemv_t(int m, int n, double alpha, const double *__restrict__ A, const double 
 // 'N': CTA = column chunk, thread = row (rows looped in strides of blockDim); partial[chunk][row]
 #define GEMV_N_COLS 512
 __global__ void __launch_bounds__(256)
-k_gemv_n_stage1(int m, int n, const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ partial)
+k_gemv_n_stage1(int m, int n, int cols, const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ partial)
 {
    __shared__ double sx[GEMV_N_COLS];
-   int j0 = blockIdx.x * GEMV_N_COLS;
-   int jn = min(GEMV_N_COLS, n - j0);
+   int j0 = blockIdx.x * cols;
+   int jn = min(cols, n - j0);
    for (int j = threadIdx.x; j < jn; j += blockDim.x)
       sx[j] = x[j0 + j];
    __syncthreads();
@@ -210,6 +211,207 @@ __global__ void k_gemv_n_stage2(int m, int nchunks, double alpha, const double *
    for (int c = 0; c < nchunks; c++)
       s += partial[(size_t)c * m + i];
    y[i] = alpha * s + (beta == 0.0 ? 0.0 : beta * y[i]);
+}
+
+// wide-load variants of the two fp64 products (m even; x of the 'T' product in shared memory, persistent warps, two columns
+// per warp; 'N': two rows per thread, eight columns in flight) -- the K12 passes of the AFN apply went from 5.5 to about
+// 6.3 TB/s with them
+__global__ void __launch_bounds__(256)
+k_gemv_t_wide(int m, int n, double alpha, const double *__restrict__ A, const double *__restrict__ x, double beta, double *__restrict__ y)
+{
+   extern __shared__ __align__(16) double sxt[];
+   for (int i = threadIdx.x; i < m; i += blockDim.x)
+      sxt[i] = x[i];
+   __syncthreads();
+   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+   const int nw = (gridDim.x * blockDim.x) >> 5;
+   const int m2 = m >> 1;
+   for (int c0 = w * 2; c0 < n; c0 += nw * 2)
+   {
+      const bool two = c0 + 1 < n;
+      const double2 *a0 = reinterpret_cast<const double2 *>(A + (size_t)c0 * m);
+      const double2 *a1 = reinterpret_cast<const double2 *>(A + (size_t)(two ? c0 + 1 : c0) * m);
+      double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+      int i = lane;
+      for (; i + 32 < m2; i += 64)
+      {
+         const double2 v0 = __ldcs(a0 + i), v1 = __ldcs(a1 + i), w0 = __ldcs(a0 + i + 32), w1 = __ldcs(a1 + i + 32);
+         const double2 xa = *reinterpret_cast<const double2 *>(sxt + 2 * i), xb = *reinterpret_cast<const double2 *>(sxt + 2 * i + 64);
+         s0 = fma(v0.x, xa.x, s0);
+         s1 = fma(v0.y, xa.y, s1);
+         t0 = fma(v1.x, xa.x, t0);
+         t1 = fma(v1.y, xa.y, t1);
+         s0 = fma(w0.x, xb.x, s0);
+         s1 = fma(w0.y, xb.y, s1);
+         t0 = fma(w1.x, xb.x, t0);
+         t1 = fma(w1.y, xb.y, t1);
+      }
+      if (i < m2)
+      {
+         const double2 v0 = __ldcs(a0 + i), v1 = __ldcs(a1 + i);
+         const double2 xa = *reinterpret_cast<const double2 *>(sxt + 2 * i);
+         s0 = fma(v0.x, xa.x, s0);
+         s1 = fma(v0.y, xa.y, s1);
+         t0 = fma(v1.x, xa.x, t0);
+         t1 = fma(v1.y, xa.y, t1);
+      }
+      s0 = b200_warp_sum(s0 + s1);
+      t0 = b200_warp_sum(t0 + t1);
+      if (lane == 0)
+      {
+         y[c0] = alpha * s0 + (beta == 0.0 ? 0.0 : beta * y[c0]);
+         if (two)
+            y[c0 + 1] = alpha * t0 + (beta == 0.0 ? 0.0 : beta * y[c0 + 1]);
+      }
+   }
+}
+
+#define GEMV64_U 8
+__global__ void __launch_bounds__(256)
+k_gemv_n_stage1_wide(int m, int n, int cols, const double *__restrict__ A, const double *__restrict__ x, double *__restrict__ partial)
+{
+   __shared__ double sx[GEMV_N_COLS];
+   int j0 = blockIdx.x * cols;
+   int jn = min(cols, n - j0);
+   for (int j = threadIdx.x; j < jn; j += blockDim.x)
+      sx[j] = x[j0 + j];
+   __syncthreads();
+   const int m2 = m >> 1;
+   for (int i = threadIdx.x; i < m2; i += blockDim.x)
+   {
+      const double2 *a = reinterpret_cast<const double2 *>(A + (size_t)j0 * m) + i;
+      double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;
+      int j = 0;
+      for (; j + GEMV64_U <= jn; j += GEMV64_U)
+      {
+         double2 v[GEMV64_U];
+#pragma unroll
+         for (int u = 0; u < GEMV64_U; u++)
+            v[u] = __ldcs(a + (size_t)(j + u) * m2);
+#pragma unroll
+         for (int u = 0; u < GEMV64_U; u += 2)
+         {
+            s0 = fma(v[u].x, sx[j + u], s0);
+            s1 = fma(v[u].y, sx[j + u], s1);
+            u0 = fma(v[u + 1].x, sx[j + u + 1], u0);
+            u1 = fma(v[u + 1].y, sx[j + u + 1], u1);
+         }
+      }
+      for (; j < jn; j++)
+      {
+         const double2 v = __ldcs(a + (size_t)j * m2);
+         s0 = fma(v.x, sx[j], s0);
+         s1 = fma(v.y, sx[j], s1);
+      }
+      partial[(size_t)blockIdx.x * m + 2 * i] = s0 + u0;
+      partial[(size_t)blockIdx.x * m + 2 * i + 1] = s1 + u1;
+   }
+}
+
+// ---- the same two products with the matrix stored in fp32 (optional storage of the AFN K12 block: the applies are HBM-bound
+// on reading it twice, the preconditioner only has to be symmetric positive definite, not exact); fp64 vectors and sums.
+// m a multiple of 4: every column starts 16-byte aligned, four rows per 128-bit load.  Variants timed in isolation with
+// scripts/gemv_f32_bench.cu (m = 4000, 8 GB): 'T' warp per column 5.0 TB/s -> persistent warps, x in shared memory, 4 columns
+// per warp 6.7 TB/s; 'N' two rows per thread 6.0 TB/s -> four rows per thread, 8 columns in flight 6.7 TB/s.
+#define GEMV32_CW 4
+__global__ void __launch_bounds__(256)
+k_gemv_t_f32(int m, int n, double alpha, const float *__restrict__ A, const double *__restrict__ x, double beta, double *__restrict__ y)
+{
+   extern __shared__ __align__(16) double sxt[];
+   for (int i = threadIdx.x; i < m; i += blockDim.x)
+      sxt[i] = x[i];
+   __syncthreads();
+   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+   const int nw = (gridDim.x * blockDim.x) >> 5;
+   const int m4 = m >> 2;
+   for (int c0 = w * GEMV32_CW; c0 < n; c0 += nw * GEMV32_CW)
+   {
+      double s[GEMV32_CW];
+#pragma unroll
+      for (int c = 0; c < GEMV32_CW; c++)
+         s[c] = 0.0;
+      for (int i = lane; i < m4; i += 32)
+      {
+         const double2 xa = *reinterpret_cast<const double2 *>(sxt + 4 * i), xb = *reinterpret_cast<const double2 *>(sxt + 4 * i + 2);
+#pragma unroll
+         for (int c = 0; c < GEMV32_CW; c++)
+            if (c0 + c < n)
+            {
+               const float4 v = __ldcs(reinterpret_cast<const float4 *>(A + (size_t)(c0 + c) * m) + i);
+               s[c] = fma((double)v.x, xa.x, s[c]);
+               s[c] = fma((double)v.y, xa.y, s[c]);
+               s[c] = fma((double)v.z, xb.x, s[c]);
+               s[c] = fma((double)v.w, xb.y, s[c]);
+            }
+      }
+#pragma unroll
+      for (int c = 0; c < GEMV32_CW; c++)
+      {
+         const double r = b200_warp_sum(s[c]);
+         if (lane == 0 && c0 + c < n)
+            y[c0 + c] = alpha * r + (beta == 0.0 ? 0.0 : beta * y[c0 + c]);
+      }
+   }
+}
+
+#define GEMV32_U 8
+__global__ void __launch_bounds__(256)
+k_gemv_n_stage1_f32(int m, int n, int cols, const float *__restrict__ A, const double *__restrict__ x, double *__restrict__ partial)
+{
+   __shared__ double sx[GEMV_N_COLS];
+   int j0 = blockIdx.x * cols;
+   int jn = min(cols, n - j0);
+   for (int j = threadIdx.x; j < jn; j += blockDim.x)
+      sx[j] = x[j0 + j];
+   __syncthreads();
+   const int m4 = m >> 2;
+   for (int i = threadIdx.x; i < m4; i += blockDim.x)
+   {
+      const float4 *a = reinterpret_cast<const float4 *>(A + (size_t)j0 * m) + i;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int j = 0;
+      for (; j + GEMV32_U <= jn; j += GEMV32_U)
+      {
+         float4 v[GEMV32_U];
+#pragma unroll
+         for (int u = 0; u < GEMV32_U; u++)
+            v[u] = __ldcs(a + (size_t)(j + u) * m4);
+#pragma unroll
+         for (int u = 0; u < GEMV32_U; u++)
+         {
+            const double xj = sx[j + u];
+            s0 = fma((double)v[u].x, xj, s0);
+            s1 = fma((double)v[u].y, xj, s1);
+            s2 = fma((double)v[u].z, xj, s2);
+            s3 = fma((double)v[u].w, xj, s3);
+         }
+      }
+      for (; j < jn; j++)
+      {
+         const float4 v = __ldcs(a + (size_t)j * m4);
+         const double xj = sx[j];
+         s0 = fma((double)v.x, xj, s0);
+         s1 = fma((double)v.y, xj, s1);
+         s2 = fma((double)v.z, xj, s2);
+         s3 = fma((double)v.w, xj, s3);
+      }
+      double *p = partial + (size_t)blockIdx.x * m + 4 * i;
+      p[0] = s0;
+      p[1] = s1;
+      p[2] = s2;
+      p[3] = s3;
+   }
+}
+
+__global__ void k_f64_to_f32(size_t count, const double *__restrict__ src, float *__restrict__ dst)
+{
+   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+      dst[i] = (float)src[i];
+}
+__global__ void k_f32_to_f64(size_t count, const float *__restrict__ src, double *__restrict__ dst)
+{
+   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+      dst[i] = (double)src[i];
 }
 
 // ------------------------------------------------------------------ dense additive kernel blocks
@@ -275,6 +477,17 @@ static double *scratch(size_t doubles)
    return g_scratch;
 }
 
+// columns per CTA of the 'N' products: 512 for wide matrices; narrower ones (the k x k triangular inverse of the AFN apply:
+// 8 CTAs at 512 columns each read 128 MB at a few percent of the HBM rate) are cut so that about four CTAs per SM exist
+static int gemv_n_cols(int n)
+{
+   int cols = b200_cdiv(n, 148 * 4);
+   cols = (cols + 7) & ~7;
+   if (cols < 8)
+      cols = 8;
+   return cols > GEMV_N_COLS ? GEMV_N_COLS : cols;
+}
+
 extern "C" {
 
 size_t b200k_nys_work_doubles(int n, int k)
@@ -332,22 +545,97 @@ int b200k_gemv(char trans, int m, int n, double alpha, const double *A, const do
 {
    B200ProfScope prof_scope_(PC_GEMV);
    cudaStream_t st = b200_stream();
+   const bool wide = !(m & 1) && m >= 256 && ((uintptr_t)A & 15) == 0;
    if (trans == 'T' || trans == 't')
    {
-      k_gemv_t<<<b200_cdiv((long long)n * 32, 256), 256, 0, st>>>(m, n, alpha, A, x, beta, y);
+      const size_t sm = sizeof(double) * (size_t)m;
+      if (wide && sm <= 96 * 1024 && n >= 64)
+      {
+         static int smem_set = 0;
+         if ((int)sm > smem_set)
+         {
+            B200_CHECK(cudaFuncSetAttribute(k_gemv_t_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            smem_set = (int)sm;
+         }
+         int ctas = b200_cdiv(b200_cdiv(n, 2), 8);
+         if (ctas > 148 * 4)
+            ctas = 148 * 4;
+         k_gemv_t_wide<<<ctas, 256, sm, st>>>(m, n, alpha, A, x, beta, y);
+      }
+      else
+         k_gemv_t<<<b200_cdiv((long long)n * 32, 256), 256, 0, st>>>(m, n, alpha, A, x, beta, y);
       B200_LAUNCHED();
    }
    else
    {
-      int nchunks = b200_cdiv(n, GEMV_N_COLS);
+      int cols = gemv_n_cols(n);
+      int nchunks = b200_cdiv(n, cols);
       double *partial = scratch((size_t)nchunks * m);
       if (!partial)
          return -1;
-      k_gemv_n_stage1<<<nchunks, 256, 0, st>>>(m, n, A, x, partial);
+      if (wide)
+         k_gemv_n_stage1_wide<<<nchunks, 256, 0, st>>>(m, n, cols, A, x, partial);
+      else
+         k_gemv_n_stage1<<<nchunks, 256, 0, st>>>(m, n, cols, A, x, partial);
       B200_LAUNCHED();
       k_gemv_n_stage2<<<b200_cdiv(m, 128), 128, 0, st>>>(m, nchunks, alpha, partial, beta, y);
       B200_LAUNCHED();
    }
+   return 0;
+}
+
+// matrix in fp32 (m a multiple of 4), vectors and accumulation in fp64
+int b200k_gemv_f32(char trans, int m, int n, double alpha, const float *A, const double *x, double beta, double *y)
+{
+   B200ProfScope prof_scope_(PC_GEMV);
+   cudaStream_t st = b200_stream();
+   if (m & 3)
+      return -1;
+   if (trans == 'T' || trans == 't')
+   {
+      static int smem_set = 0;
+      const size_t sm = sizeof(double) * (size_t)m;
+      if (sm > 200 * 1024)
+         return -1;
+      if ((int)sm > smem_set)
+      {
+         B200_CHECK(cudaFuncSetAttribute(k_gemv_t_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+         smem_set = (int)sm;
+      }
+      int ctas = b200_cdiv(b200_cdiv(n, GEMV32_CW), 8);
+      if (ctas > 148 * 4)
+         ctas = 148 * 4;
+      k_gemv_t_f32<<<ctas, 256, sm, st>>>(m, n, alpha, A, x, beta, y);
+      B200_LAUNCHED();
+   }
+   else
+   {
+      int cols = gemv_n_cols(n);
+      int nchunks = b200_cdiv(n, cols);
+      double *partial = scratch((size_t)nchunks * m);
+      if (!partial)
+         return -1;
+      k_gemv_n_stage1_f32<<<nchunks, 256, 0, st>>>(m, n, cols, A, x, partial);
+      B200_LAUNCHED();
+      k_gemv_n_stage2<<<b200_cdiv(m, 128), 128, 0, st>>>(m, nchunks, alpha, partial, beta, y);
+      B200_LAUNCHED();
+   }
+   return 0;
+}
+
+int b200k_convert_f64_f32(size_t count, const double *src, float *dst)
+{
+   B200ProfScope prof_scope_(PC_OTHER);
+   k_f64_to_f32<<<148 * 8, 256, 0, b200_stream()>>>(count, src, dst);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_convert_f32_f64(size_t count, const float *src, double *dst)
+{
+   B200ProfScope prof_scope_(PC_OTHER);
+   k_f32_to_f64<<<148 * 8, 256, 0, b200_stream()>>>(count, src, dst);
+   B200_LAUNCHED();
    return 0;
 }
 

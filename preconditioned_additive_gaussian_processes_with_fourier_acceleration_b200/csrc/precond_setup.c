@@ -717,6 +717,8 @@ done:
    free(sel);
    free(perm);
    b200_dense_view_release(&v);
+   if (!i)
+      i = b200_afn_finish_setup(s); /* optional fp32 storage of K12, once the setup's work arrays are gone */
    s->tset = wtime() - t0;
    return i;
 }

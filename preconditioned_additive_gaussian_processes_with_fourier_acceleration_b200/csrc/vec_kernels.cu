@@ -106,6 +106,56 @@ __global__ void k_xpby(int n, const double *__restrict__ z, double beta, double 
       p[i] = z[i] + beta * p[i]; // pcg.c:145-146: p = beta*p ; p += z
 }
 
+// Device-scalar forms of the two PCG updates: the step lengths are formed ON THE DEVICE from the dot products of the
+// same iteration (alpha = rho / pq, beta = rho / rho_prev: the same IEEE divisions the host would do), so that the host
+// synchronises once per iteration instead of three times.  The reference's breakdown exits (pcg.c:119,136,155: rho == 0,
+// beta == 0, pq <= 0) leave BEFORE the update they guard; the kernels therefore turn into no-ops under the same conditions
+// and the host, reading the three scalars afterwards, breaks with x, r, p exactly as the reference leaves them.
+__global__ void k_xpby_dev(int n, const double *__restrict__ z, const double *__restrict__ d_rho, const double *__restrict__ d_rho_prev,
+                           double *__restrict__ p)
+{
+   const double rho = *d_rho;
+   if (rho == 0.0)
+      return;
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (d_rho_prev == nullptr) // first iteration: p = z
+   {
+      if (i < n)
+         p[i] = z[i];
+      return;
+   }
+   const double beta = rho / *d_rho_prev;
+   if (beta == 0.0)
+      return;
+   if (i < n)
+      p[i] = z[i] + beta * p[i];
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_pcg_update_dev_stage1(int n, const double *__restrict__ d_rho, const double *__restrict__ d_rho_prev, const double *__restrict__ d_pq,
+                        const double *__restrict__ p, const double *__restrict__ q, double *__restrict__ x, double *__restrict__ r)
+{
+   __shared__ double sh[32];
+   const double rho = *d_rho, pq = *d_pq;
+   const bool skip = rho == 0.0 || pq <= 0.0 || (d_rho_prev != nullptr && rho / *d_rho_prev == 0.0);
+   const double alpha = skip ? 0.0 : rho / pq;
+   double s = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+   {
+      double ri = r[i];
+      if (!skip)
+      {
+         x[i] += alpha * p[i];
+         ri = ri - alpha * q[i];
+         r[i] = ri;
+      }
+      s = fma(ri, ri, s);
+   }
+   double t = block_sum(s, sh);
+   if (threadIdx.x == 0)
+      g_partial[blockIdx.x] = t;
+}
+
 __global__ void k_copy(int n, const double *__restrict__ s, double *__restrict__ d)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,6 +323,26 @@ int b200k_pcg_update(int n, double alpha, const double *p, const double *q, doub
    B200ProfScope prof_scope_(PC_VEC);
    int nb = red_blocks(n);
    k_pcg_update_stage1<<<nb, RED_THREADS, 0, b200_stream()>>>(n, alpha, p, q, x, r);
+   B200_LAUNCHED();
+   k_reduce_stage2<<<1, RED_THREADS, 0, b200_stream()>>>(nb, 1, d_out);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_xpby_dev(int n, const double *z, const double *d_rho, const double *d_rho_prev, double *p)
+{
+   B200ProfScope prof_scope_(PC_VEC);
+   k_xpby_dev<<<b200_cdiv(n, 256), 256, 0, b200_stream()>>>(n, z, d_rho, d_rho_prev, p);
+   B200_LAUNCHED();
+   return 0;
+}
+
+int b200k_pcg_update_dev(int n, const double *d_rho, const double *d_rho_prev, const double *d_pq, const double *p, const double *q,
+                         double *x, double *r, double *d_out)
+{
+   B200ProfScope prof_scope_(PC_VEC);
+   int nb = red_blocks(n);
+   k_pcg_update_dev_stage1<<<nb, RED_THREADS, 0, b200_stream()>>>(n, d_rho, d_rho_prev, d_pq, p, q, x, r);
    B200_LAUNCHED();
    k_reduce_stage2<<<1, RED_THREADS, 0, b200_stream()>>>(nb, 1, d_out);
    B200_LAUNCHED();

@@ -201,6 +201,37 @@ def test_afn_setup_matches_numpy(gpu, kernel, n, k, lfil):
     D.free()
 
 
+def test_afn_k12_fp32_storage(gpu):
+    """Optional fp32 storage of the K12 block (Nfft4GPB200PrecondAFNSetK12Storage): the apply agrees with the fp64 one to
+    fp32 rounding, stays symmetric, returns the rounded block through GetFactors, and PCG needs the same iterations."""
+    n, d, k, lfil = 3000, 6, 300, 100
+    X = uniform_cloud(n, d)
+    win = np.arange(6, dtype=np.int32)
+    f, l, mu = 1.0, 1.0, 0.01
+    D = gpu.DenseAdditiveKernel(X, win, 2, 3, "gaussian").set_hyper(f, l, mu)
+    A64 = gpu.AfnPrecond().setup(D, k, lfil, numests=0, noran=1)
+    A32 = gpu.AfnPrecond().set_k12_storage(32).setup(D, k, lfil, numests=0, noran=1)
+    F64, F32 = A64.get_factors(), A32.get_factors()
+    assert (F32["K12"] == F64["K12"].astype(np.float32).astype(np.float64)).all()
+    r, q = rand_vec(n, 8), rand_vec(n, 9)
+    z64, z32 = A64.solve(r), A32.solve(r)
+    assert 0 < rel_l2(z32, z64) <= 1e-5
+    assert abs(q @ z32 - r @ A32.solve(q)) <= 1e-10 * np.linalg.norm(q) * np.linalg.norm(z32)    # symmetric apply
+    A = gpu.AdditiveNFFTKernel(X, win, 2, 3, "gaussian").build(f, l, mu)
+    rhs = rand_vec(n, 4)
+    x1, rel1, _, it1 = gpu.solver_pcg(A.K, n, A.matvec_fn(), A64.h, A64.solve_fn(), np.zeros(n), rhs, 800, 0, 1e-6)
+    x2, rel2, _, it2 = gpu.solver_pcg(A.K, n, A.matvec_fn(), A32.h, A32.solve_fn(), np.zeros(n), rhs, 800, 0, 1e-6)
+    assert it1 > 0 and abs(it2 - it1) <= 1 and rel2 <= 1e-6
+    assert rel_l2(x2, x1) <= 1e-5
+    # switching an existing fp64 handle converts in place; going back needs a new setup
+    A64.set_k12_storage(32)
+    assert rel_l2(A64.solve(r), z32) <= 1e-12
+    with pytest.raises(RuntimeError):
+        A64.set_k12_storage(64)
+    for h in (A, A64, A32, D):
+        h.free()
+
+
 def test_afn_rank_estimate_and_branches(gpu):
     n, d = 3000, 3
     X = uniform_cloud(n, d, seed=12)
