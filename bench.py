@@ -32,7 +32,7 @@ METRIC = "nfft_additive_matvecs_per_s"
 UNIT = "matvecs/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused three-window kernels at n = 10^6, from the one
 # `ncu --set full` capture of this command (profiles/r1_g_ncu_set_full_fused_spread_gather.csv); per-window launches: a third
-NCU_TRAFFIC_BYTES = {"spread": 751.906e6 + 4.873e6, "gather": 727.848e6 + 24.889e6}
+NCU_TRAFFIC_BYTES = {"spread": 752.503e6 + 4.831e6, "gather": 728.311e6 + 25.661e6}  # profiles/r1_k_ncu_set_full_fused_spread_gather.csv
 PROF_CLASSES = ["prep", "spread", "fft_fwd", "fft_inv", "gather", "combine", "vec", "nys", "csr", "gemv", "other"]
 
 
