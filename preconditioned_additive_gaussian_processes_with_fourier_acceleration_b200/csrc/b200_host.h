@@ -61,6 +61,8 @@ typedef struct b200_additive
    /* fused spread / gather of the leading nbatch dense 3-D windows in one launch (nfft3d_mma.cu) */
    int fused_ready;      /* 0 = not examined, 1 = descriptors built, -1 = not applicable */
    int fused_warps;
+   int fused_rounds;        /* rounds of the guided dynamic range scheduling (1 = static shares) and their cost weights */
+   double fused_weight[8];
    void *d_fused[3];        /* b200_mma_win[nbatch]: spread, gather (f), gather of the derivative channel (f2) */
    int **d_fused_cfirst[2]; /* host arrays of nbatch device pointers (owned): range partitions for spread and gather */
    const int **d_prep_perm;

@@ -1011,29 +1011,41 @@ static int additive_local_n(const b200_additive *A) { return A->blk_hi - A->blk_
  * apart -- in-kernel clocks showed 326 k .. 641 k cycles per warp -- because the warp schedulers serve the resident warps
  * of a sub-partition unevenly and the cost model is only approximate.  NFFT4GP_B200_ROUNDS="w0,w1,..." overrides. */
 #define FUSED_MAX_ROUNDS 8
-static int g_fused_rounds = 0;
-static double g_fused_weight[FUSED_MAX_ROUNDS] = {8.0, 4.0, 2.0, 1.0, 1.0};
-static void fused_rounds_init(void)
+#define FUSED_MIN_RANGE_CHUNKS 12 /* a range start costs about 1.5 chunks (ring reset, pipeline refill, final 10-plane flush) */
+static int g_fused_rounds_env = -1; /* -1 not read, 0 no override */
+static double g_fused_weight_env[FUSED_MAX_ROUNDS];
+/* weights of the rounds for a wave whose warps get `chunks_per_warp` chunks each on average: 8:4:2:1:1 when the smallest
+ * range still has FUSED_MIN_RANGE_CHUNKS chunks, static shares otherwise */
+static int fused_rounds_choose(double chunks_per_warp, double *w)
 {
-   const char *e = getenv("NFFT4GP_B200_ROUNDS");
-   if (g_fused_rounds)
-      return;
-   g_fused_rounds = 5;
-   if (e && *e)
+   static const double full[5] = {8.0, 4.0, 2.0, 1.0, 1.0};
+   int k, rounds;
+   if (g_fused_rounds_env < 0)
    {
-      int k = 0;
-      while (*e && k < FUSED_MAX_ROUNDS)
+      const char *e = getenv("NFFT4GP_B200_ROUNDS");
+      g_fused_rounds_env = 0;
+      while (e && *e && g_fused_rounds_env < FUSED_MAX_ROUNDS)
       {
          char *end;
          double v = strtod(e, &end);
          if (end == e || !(v > 0.0))
             break;
-         g_fused_weight[k++] = v;
+         g_fused_weight_env[g_fused_rounds_env++] = v;
          e = (*end == ',') ? end + 1 : end;
       }
-      if (k > 0)
-         g_fused_rounds = k;
    }
+   if (g_fused_rounds_env > 0)
+   {
+      memcpy(w, g_fused_weight_env, sizeof(double) * (size_t)g_fused_rounds_env);
+      return g_fused_rounds_env;
+   }
+   /* measured (uniform cloud, one GPU): 217 chunks per warp (n = 10^6) dynamic = static, Gaussian cloud 18 % faster;
+    * 108 chunks (n = 5 10^5) 3.5 % slower, 54 chunks 10 % slower with the shorter round lists: dynamic only for long lists */
+   (void)k;
+   rounds = (chunks_per_warp / 16.0 >= FUSED_MIN_RANGE_CHUNKS) ? 5 : 1;
+   for (k = 0; k < rounds; k++)
+      w[k] = full[5 - rounds + k];
+   return rounds;
 }
 
 static double chunk_cost(const int *hc, int c, int prev_key, double flush)
@@ -1073,7 +1085,6 @@ static int additive_fused_partition(b200_additive *A, int dir, int total_warps)
    const double flush = dir ? FUSED_FLUSH_COST_GATHER : FUSED_FLUSH_COST_SPREAD;
    int nb = A->nbatch, i, c, k, assigned = 0, big = 0, rc = -1;
    double *cost = (double *)b200_xcalloc((size_t)nb, sizeof(double)), total = 0.0, wsum = 0.0;
-   fused_rounds_init();
    int *wbeg = (int *)b200_xcalloc((size_t)nb + 1, sizeof(int)), *wcnt = (int *)b200_xcalloc((size_t)nb, sizeof(int));
    b200_mma_win *hw = (b200_mma_win *)b200_xcalloc((size_t)nb, sizeof(b200_mma_win));
    for (i = 0; i < nb; i++)
@@ -1102,21 +1113,21 @@ static int additive_fused_partition(b200_additive *A, int dir, int total_warps)
    for (i = 0; i < nb; i++)
       wbeg[i + 1] = wbeg[i] + wcnt[i];
    A->d_fused_cfirst[dir] = (int **)b200_xcalloc((size_t)nb, sizeof(int *));
-   for (k = 0; k < g_fused_rounds; k++)
-      wsum += g_fused_weight[k];
+   for (k = 0; k < A->fused_rounds; k++)
+      wsum += A->fused_weight[k];
    for (i = 0; i < nb; i++)
    {
       /* rounds * wcnt consecutive ranges: round k holds wcnt ranges of the cost share weight[k] / wsum / wcnt each */
       const int *hc = A->win[i]->h_chunks;
       b200_win_dev *v = &A->win[i]->dev;
-      int nr = g_fused_rounds * wcnt[i];
+      int nr = A->fused_rounds * wcnt[i];
       int nch = A->win[i]->h_nchunk, r = 0, prev = -1, *hr = (int *)b200_xcalloc((size_t)nr + 1, sizeof(int)), bad;
       double acc = 0.0, *start = (double *)b200_xcalloc((size_t)nr + 1, sizeof(double)), wacc = 0.0;
-      for (k = 0; k < g_fused_rounds; k++)
+      for (k = 0; k < A->fused_rounds; k++)
       {
          for (c = 0; c < wcnt[i]; c++)
-            start[k * wcnt[i] + c] = cost[i] * (wacc + g_fused_weight[k] * (double)c / (double)wcnt[i]) / wsum;
-         wacc += g_fused_weight[k];
+            start[k * wcnt[i] + c] = cost[i] * (wacc + A->fused_weight[k] * (double)c / (double)wcnt[i]) / wsum;
+         wacc += A->fused_weight[k];
       }
       for (c = 0; c < nch; c++)
       {
@@ -1157,6 +1168,7 @@ done:
 static int additive_fused_prepare(b200_additive *A)
 {
    int nb = A->nbatch, i, c, total_warps = b200k_mma_warp_ranges();
+   long long total_chunks = 0;
    int *hn;
    const int **hperm;
    double **ha;
@@ -1172,6 +1184,7 @@ static int additive_fused_prepare(b200_additive *A)
       b200_win_dev *v = &A->win[i]->dev;
       if (!A->win[i]->h_chunks || v->nchunk <= 0 || v->nseg <= 0 || v->n / v->nseg < B200_MMA_MIN_POINTS_PER_CELL)
          return 0; /* a sparse or empty window: per-window launches (DFMA kernels with register-tile shifting) */
+      total_chunks += v->nchunk;
    }
    /* per-window pointers of the batched prep kernel */
    hperm = (const int **)b200_xcalloc((size_t)nb, sizeof(int *));
@@ -1191,6 +1204,7 @@ static int additive_fused_prepare(b200_additive *A)
    A->d_prep_n = (int *)b200_malloc(sizeof(int) * (size_t)nb);
    c = !A->d_prep_perm || !A->d_prep_a || !A->d_prep_n || b200_h2d((void *)A->d_prep_perm, hperm, sizeof(int *) * (size_t)nb) ||
        b200_h2d(A->d_prep_a, ha, sizeof(double *) * (size_t)nb) || b200_h2d(A->d_prep_n, hn, sizeof(int) * (size_t)nb) ||
+       (A->fused_rounds = fused_rounds_choose((double)total_chunks / (double)total_warps, A->fused_weight)) < 1 ||
        additive_fused_partition(A, 0, total_warps) || additive_fused_partition(A, 1, total_warps);
    free(hperm);
    free(ha);
@@ -1242,7 +1256,7 @@ static int additive_apply_windows(b200_additive *A, const double *d_x, double s,
       /* batched prep, one memset of the contiguous grids, one persistent wave for the spread of all batch windows */
       size_t gsz = ipow(B200_NOS, 3) * (size_t)A->nbatch;
       if (b200k_prep_batch(A->nbatch, A->d_prep_perm, A->d_prep_a, A->d_prep_n, A->prep_nmax, d_x, s) ||
-          b200k_spread_batch_begin(A->d_grids, gsz) || b200k_spread3_mma_batch((const b200_mma_win *)A->d_fused[0], A->nbatch, A->fused_warps, g_fused_rounds) ||
+          b200k_spread_batch_begin(A->d_grids, gsz) || b200k_spread3_mma_batch((const b200_mma_win *)A->d_fused[0], A->nbatch, A->fused_warps, A->fused_rounds) ||
           b200k_spread_batch_end())
          return -1;
       for (i = A->nbatch; i < A->P; i++)
@@ -1266,7 +1280,7 @@ collective:
          return -1;
       if (fused)
       {
-         if (b200k_gather_batch_begin() || b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[1], A->nbatch, A->fused_warps, g_fused_rounds) ||
+         if (b200k_gather_batch_begin() || b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[1], A->nbatch, A->fused_warps, A->fused_rounds) ||
              b200k_gather_batch_end())
             return -1;
       }
@@ -1284,7 +1298,7 @@ collective:
          if (fused)
          {
             if (additive_fused_channel1(A) || b200k_gather_batch_begin() ||
-                b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[2], A->nbatch, A->fused_warps, g_fused_rounds) || b200k_gather_batch_end())
+                b200k_gather3_mma_batch((const b200_mma_win *)A->d_fused[2], A->nbatch, A->fused_warps, A->fused_rounds) || b200k_gather_batch_end())
                return -1;
          }
          else

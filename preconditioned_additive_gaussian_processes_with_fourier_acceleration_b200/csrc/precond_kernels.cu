@@ -216,6 +216,7 @@ __global__ void k_gemv_n_stage2(int m, int nchunks, double alpha, const double *
 // wide-load variants of the two fp64 products (m even; x of the 'T' product in shared memory, persistent warps, two columns
 // per warp; 'N': two rows per thread, eight columns in flight) -- the K12 passes of the AFN apply went from 5.5 to about
 // 6.3 TB/s with them
+#define GEMV64_CW 4
 __global__ void __launch_bounds__(256)
 k_gemv_t_wide(int m, int n, double alpha, const double *__restrict__ A, const double *__restrict__ x, double beta, double *__restrict__ y)
 {
@@ -226,42 +227,36 @@ k_gemv_t_wide(int m, int n, double alpha, const double *__restrict__ A, const do
    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
    const int nw = (gridDim.x * blockDim.x) >> 5;
    const int m2 = m >> 1;
-   for (int c0 = w * 2; c0 < n; c0 += nw * 2)
+   for (int c0 = w * GEMV64_CW; c0 < n; c0 += nw * GEMV64_CW)
    {
-      const bool two = c0 + 1 < n;
-      const double2 *a0 = reinterpret_cast<const double2 *>(A + (size_t)c0 * m);
-      const double2 *a1 = reinterpret_cast<const double2 *>(A + (size_t)(two ? c0 + 1 : c0) * m);
-      double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
-      int i = lane;
-      for (; i + 32 < m2; i += 64)
+      double s[GEMV64_CW], t[GEMV64_CW];
+      const double2 *a[GEMV64_CW];
+#pragma unroll
+      for (int c = 0; c < GEMV64_CW; c++)
       {
-         const double2 v0 = __ldcs(a0 + i), v1 = __ldcs(a1 + i), w0 = __ldcs(a0 + i + 32), w1 = __ldcs(a1 + i + 32);
-         const double2 xa = *reinterpret_cast<const double2 *>(sxt + 2 * i), xb = *reinterpret_cast<const double2 *>(sxt + 2 * i + 64);
-         s0 = fma(v0.x, xa.x, s0);
-         s1 = fma(v0.y, xa.y, s1);
-         t0 = fma(v1.x, xa.x, t0);
-         t1 = fma(v1.y, xa.y, t1);
-         s0 = fma(w0.x, xb.x, s0);
-         s1 = fma(w0.y, xb.y, s1);
-         t0 = fma(w1.x, xb.x, t0);
-         t1 = fma(w1.y, xb.y, t1);
+         s[c] = t[c] = 0.0;
+         a[c] = reinterpret_cast<const double2 *>(A + (size_t)(c0 + c < n ? c0 + c : c0) * m);
       }
-      if (i < m2)
+      for (int i = lane; i < m2; i += 32)
       {
-         const double2 v0 = __ldcs(a0 + i), v1 = __ldcs(a1 + i);
+         double2 v[GEMV64_CW];
+#pragma unroll
+         for (int c = 0; c < GEMV64_CW; c++)
+            v[c] = __ldcs(a[c] + i);
          const double2 xa = *reinterpret_cast<const double2 *>(sxt + 2 * i);
-         s0 = fma(v0.x, xa.x, s0);
-         s1 = fma(v0.y, xa.y, s1);
-         t0 = fma(v1.x, xa.x, t0);
-         t1 = fma(v1.y, xa.y, t1);
+#pragma unroll
+         for (int c = 0; c < GEMV64_CW; c++)
+         {
+            s[c] = fma(v[c].x, xa.x, s[c]);
+            t[c] = fma(v[c].y, xa.y, t[c]);
+         }
       }
-      s0 = b200_warp_sum(s0 + s1);
-      t0 = b200_warp_sum(t0 + t1);
-      if (lane == 0)
+#pragma unroll
+      for (int c = 0; c < GEMV64_CW; c++)
       {
-         y[c0] = alpha * s0 + (beta == 0.0 ? 0.0 : beta * y[c0]);
-         if (two)
-            y[c0 + 1] = alpha * t0 + (beta == 0.0 ? 0.0 : beta * y[c0 + 1]);
+         const double r = b200_warp_sum(s[c] + t[c]);
+         if (lane == 0 && c0 + c < n)
+            y[c0 + c] = alpha * r + (beta == 0.0 ? 0.0 : beta * y[c0 + c]);
       }
    }
 }
@@ -557,7 +552,7 @@ int b200k_gemv(char trans, int m, int n, double alpha, const double *A, const do
             B200_CHECK(cudaFuncSetAttribute(k_gemv_t_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             smem_set = (int)sm;
          }
-         int ctas = b200_cdiv(b200_cdiv(n, 2), 8);
+         int ctas = b200_cdiv(b200_cdiv(n, GEMV64_CW), 8);
          if (ctas > 148 * 4)
             ctas = 148 * 4;
          k_gemv_t_wide<<<ctas, 256, sm, st>>>(m, n, alpha, A, x, beta, y);
