@@ -189,6 +189,11 @@ void Nfft4GPPrecondNysSetPerm(void *str, int *perm, int own_perm);       /* nys.
 int Nfft4GPPrecondNysSolve(void *vnys_mat, int n, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs);   /* nys.c:115-173 (:400) */
 int Nfft4GPPrecondNysSetupWithKernel(NFFT4GP_DOUBLE *data, int n, int ldim, int d, func_kernel fkernel,
                                      void *fkernel_params, int require_grad, void *vnys_mat); /* nys.c:518-660 (:444) */
+/* gradient side (what TESTS/TEST3/foo3.cpp hands to the GP problem); Dvp / Trace need a setup with require_grad != 0 and one
+ * of this library's dense kernels.  The trace is formed from two k x k Gram matrices instead of k products of length n. */
+int Nfft4GPPrecondNysDvp(void *vnys_mat, int n, int *mask, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE **yp); /* nys.c:175-330 (:413) */
+int Nfft4GPPrecondNysTrace(void *vnys_mat, NFFT4GP_DOUBLE **tracesp);                          /* nys.c:332-484 (:421) */
+NFFT4GP_DOUBLE Nfft4GPPrecondNysLogdet(void *vnys_mat);                                        /* nys.c:486-516 (:429) */
 
 void *Nfft4GPPrecondFsaiCreate(void);                                    /* fsai.c:7-30    (_preconds.h:187) */
 void Nfft4GPPrecondFsaiFree(void *str);                                  /* fsai.c:32-66   (:194) */

@@ -77,6 +77,9 @@ def lib():
         "Nfft4GPPrecondNysSetRank": (None, [vp, i]), "Nfft4GPPrecondNysSetPerm": (None, [vp, c_int_p, i]),
         "Nfft4GPPrecondNysSolve": (i, [vp, i, c_double_p, c_double_p]),
         "Nfft4GPPrecondNysSetupWithKernel": (i, [c_double_p, i, i, i, vp, vp, i, vp]),
+        "Nfft4GPPrecondNysDvp": (i, [vp, i, c_int_p, c_double_p, C.POINTER(c_double_p)]),
+        "Nfft4GPPrecondNysTrace": (i, [vp, C.POINTER(c_double_p)]),
+        "Nfft4GPPrecondNysLogdet": (d, [vp]),
         "Nfft4GPPrecondFsaiCreate": (vp, []), "Nfft4GPPrecondFsaiFree": (None, [vp]), "Nfft4GPPrecondFsaiReset": (None, [vp]),
         "Nfft4GPPrecondFsaiSetLfil": (None, [vp, i]),
         "Nfft4GPPrecondFsaiSolve": (i, [vp, i, c_double_p, c_double_p]),
@@ -377,14 +380,33 @@ class NysPrecond:
         self.h = lib().Nfft4GPPrecondNysCreate()
         self._keep = []
 
-    def setup(self, kernel, perm, k):
+    def logdet(self):
+        return lib().Nfft4GPPrecondNysLogdet(self.h)
+
+    def trace(self):
+        tr = np.zeros(3)
+        p = dptr(tr)
+        if lib().Nfft4GPPrecondNysTrace(self.h, C.byref(p)) != 0:
+            raise RuntimeError("Nfft4GPPrecondNysTrace failed")
+        return tr
+
+    def dvp(self, x, mask=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros(3 * x.size)
+        p = dptr(y)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.int32)
+        if lib().Nfft4GPPrecondNysDvp(self.h, x.size, iptr(m) if m is not None else None, dptr(x), C.byref(p)) != 0:
+            raise RuntimeError("Nfft4GPPrecondNysDvp failed")
+        return y.reshape(3, x.size)
+
+    def setup(self, kernel, perm, k, require_grad=0):
         """Nfft4GPPrecondNysSetPerm / SetRank / SetupWithKernel (TESTS/TEST3/foo3.cpp:262-265, nys.c:518-660)."""
         L = lib()
         self._perm = None if perm is None else np.ascontiguousarray(perm, dtype=np.int32)
         if self._perm is not None:
             L.Nfft4GPPrecondNysSetPerm(self.h, iptr(self._perm), 0)
         L.Nfft4GPPrecondNysSetRank(self.h, k)
-        rc = L.Nfft4GPPrecondNysSetupWithKernel(dptr(kernel.X), kernel.n, kernel.n, kernel.d, kernel.fn(), kernel.h, 0, self.h)
+        rc = L.Nfft4GPPrecondNysSetupWithKernel(dptr(kernel.X), kernel.n, kernel.n, kernel.d, kernel.fn(), kernel.h, require_grad, self.h)
         if rc != 0:
             raise RuntimeError("Nfft4GPPrecondNysSetupWithKernel failed")
         self.n = kernel.n

@@ -25,6 +25,16 @@ typedef struct
    /* point-block-sharded apply (one process per GPU): this rank's rows of U, transposed (k x nl), built on first use */
    int sh_lo, sh_hi;
    double *d_UT_loc, *d_sh_work; /* work: 2k */
+   /* setup with require_grad (nys.c:555-610): what Dvp / Trace need, all in the permuted order of the setup */
+   int has_grad;
+   double f;          /* kernel scale of the setup: dK1/df = (2/f) K1 */
+   double *d_gK1;     /* K1 = K(perm, perm[0:k]), n x k, no noise */
+   double *d_gdK1l;   /* dK1/dl, n x k */
+   double *d_gLinv;   /* inverse Cholesky factor of K11 + shift, k x k */
+   double *d_gG[2];   /* L^{-1} (dK11/df) L^{-T}, L^{-1} (dK11/dl) L^{-T}  (the reference's _GdKG_data) */
+   double *d_gvec;    /* 4 n + 8 k work */
+   double traces[3];
+   int traces_ready;
 } b200_nys;
 
 /* FSAI: G lower-triangular CSR (diagonal last in each row, INC/_preconds.h:271) and its explicit transpose. */

@@ -46,6 +46,14 @@ static void nys_release_factors(b200_nys *s)
    b200_free(s->d_work);
    b200_free(s->d_UT_loc);
    b200_free(s->d_sh_work);
+   b200_free(s->d_gK1);
+   b200_free(s->d_gdK1l);
+   b200_free(s->d_gLinv);
+   b200_free(s->d_gG[0]);
+   b200_free(s->d_gG[1]);
+   b200_free(s->d_gvec);
+   s->d_gK1 = s->d_gdK1l = s->d_gLinv = s->d_gG[0] = s->d_gG[1] = s->d_gvec = NULL;
+   s->has_grad = s->traces_ready = 0;
    s->d_perm = NULL;
    s->d_U = s->d_s = s->d_work = s->d_UT_loc = s->d_sh_work = NULL;
    s->work_doubles = 0;

@@ -91,7 +91,7 @@ static int landmark_cholesky(int k, double *d_K11, double *d_Linv)
 
 /* ================================================================== Nystrom (nys.c:518-660) */
 static int nys_setup_perm(b200_nys *s, double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params,
-                          const int *perm_in, int k)
+                          const int *perm_in, int k, int require_grad)
 {
    nfft4gp_kernel *pk = (nfft4gp_kernel *)fkernel_params;
    b200_dense_view v;
@@ -99,6 +99,7 @@ static int nys_setup_perm(b200_nys *s, double *data, int n, int ldim, int d, fun
    double *K11 = NULL, *AA = NULL, *w = NULL, *sv = NULL, *Vs = NULL;
    double *d_K1 = NULL, *d_U = NULL, *d_small = NULL, *d_small2 = NULL;
    double noise_level, f2, eta;
+   double *grad_keep[5] = {NULL, NULL, NULL, NULL, NULL};
    size_t kk;
    if (b200_init(-1))
       return -1;
@@ -161,6 +162,49 @@ static int nys_setup_perm(b200_nys *s, double *data, int n, int ldim, int d, fun
    /* K11 + shift = L L' (chol.c:439-466), G = L^{-1} (nys.c:576), U = K1 G' (dtrmm R,L,T: nys.c:602) */
    if (landmark_cholesky(k, d_small2, d_small) || b200k_dgemm('N', 'T', n, k, k, 1.0, d_K1, n, d_small, k, 0.0, d_U, n))
       goto done;
+   if (require_grad)
+   {
+      /* nys.c:555-610 with require_grad: keep K1, dK1/dl, L^{-1} and G_g = L^{-1} dK11_g L^{-T} (g = f, l) for Dvp / Trace */
+      double *g_K1, *g_dK1l, *g_Linv, *g_G0, *g_G1, *t1, *t2;
+      if (own != 0)
+      {
+         printf("Error: the Nystrom setup with require_grad needs one of this library's dense kernels.\n");
+         goto done;
+      }
+      g_K1 = (double *)b200_malloc(sizeof(double) * (size_t)n * k);
+      g_dK1l = (double *)b200_malloc(sizeof(double) * (size_t)n * k);
+      g_Linv = (double *)b200_malloc(sizeof(double) * kk);
+      g_G0 = (double *)b200_malloc(sizeof(double) * kk);
+      g_G1 = (double *)b200_malloc(sizeof(double) * kk);
+      t1 = (double *)b200_malloc(sizeof(double) * kk);
+      t2 = (double *)b200_malloc(sizeof(double) * kk);
+      i = !g_K1 || !g_dK1l || !g_Linv || !g_G0 || !g_G1 || !t1 || !t2 ||
+          b200_d2d(g_K1, d_K1, sizeof(double) * (size_t)n * k) || b200_d2d(g_Linv, d_small, sizeof(double) * kk) ||
+          b200_dense_view_block_dl(&v, d_perm, n, d_perm, k, 0, g_dK1l, n) ||
+          /* dK11/df = (2/f) K11 (noise 0, no shift): G_0 = (2/f) L^{-1} K11 L^{-T} */
+          b200_dense_view_block(&v, 0.0, d_perm, k, d_perm, k, 0, t1, k) ||
+          b200k_dgemm('N', 'N', k, k, k, 2.0 / pk->_params[0], d_small, k, t1, k, 0.0, t2, k) ||
+          b200k_dgemm('N', 'T', k, k, k, 1.0, t2, k, d_small, k, 0.0, g_G0, k) ||
+          b200_dense_view_block_dl(&v, d_perm, k, d_perm, k, 0, t1, k) ||
+          b200k_dgemm('N', 'N', k, k, k, 1.0, d_small, k, t1, k, 0.0, t2, k) ||
+          b200k_dgemm('N', 'T', k, k, k, 1.0, t2, k, d_small, k, 0.0, g_G1, k) || b200_sync();
+      b200_free(t1);
+      b200_free(t2);
+      if (i)
+      {
+         b200_free(g_K1);
+         b200_free(g_dK1l);
+         b200_free(g_Linv);
+         b200_free(g_G0);
+         b200_free(g_G1);
+         goto done;
+      }
+      grad_keep[0] = g_K1;
+      grad_keep[1] = g_dK1l;
+      grad_keep[2] = g_Linv;
+      grad_keep[3] = g_G0;
+      grad_keep[4] = g_G1;
+   }
    /* SVD of U through the eigen-decomposition of U'U (matops.c:65-137): U = W S V'  =>  W = U V S^{-1} */
    AA = (double *)b200_xmalloc(sizeof(double) * kk);
    w = (double *)b200_xmalloc(sizeof(double) * (size_t)k);
@@ -195,7 +239,22 @@ static int nys_setup_perm(b200_nys *s, double *data, int n, int ldim, int d, fun
    /* the handle takes ownership of d_K1 (= W) */
    rc = b200_nys_set_device_factors(s, n, k, perm, d_K1, sv, eta);
    d_K1 = NULL;
+   if (!rc && require_grad)
+   {
+      s->d_gK1 = grad_keep[0];
+      s->d_gdK1l = grad_keep[1];
+      s->d_gLinv = grad_keep[2];
+      s->d_gG[0] = grad_keep[3];
+      s->d_gG[1] = grad_keep[4];
+      s->d_gvec = (double *)b200_malloc(sizeof(double) * (4 * (size_t)n + 8 * (size_t)k));
+      s->f = pk->_params[0];
+      s->has_grad = 1;
+      memset(grad_keep, 0, sizeof(grad_keep));
+      rc = s->d_gvec ? 0 : -1;
+   }
 done:
+   for (i = 0; i < 5; i++)
+      b200_free(grad_keep[i]);
    b200_free(d_K1);
    b200_free(d_U);
    b200_free(d_small);
@@ -220,8 +279,7 @@ int Nfft4GPPrecondNysSetupWithKernel(double *data, int n, int ldim, int d, func_
    int rc;
    if (!s || s->magic != B200_MAGIC_NYS || !fkernel || !fkernel_params)
       return -1;
-   (void)require_grad; /* accepted: the derivative factors only serve Dvp / Trace / Logdet, which this library does not export */
-   rc = nys_setup_perm(s, data, n, ldim, d, fkernel, fkernel_params, s->perm, s->k_setup);
+   rc = nys_setup_perm(s, data, n, ldim, d, fkernel, fkernel_params, s->perm, s->k_setup, require_grad);
    s->tset = wtime() - t0;
    return rc;
 }
@@ -554,7 +612,7 @@ static int *expand_perm(const int *sel, int k, int n)
 static int afn_use_nystrom(b200_afn *s, double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params, int *perm, int k)
 {
    void *nys = Nfft4GPPrecondNysCreate();
-   int rc = nys_setup_perm((b200_nys *)nys, data, n, ldim, d, fkernel, fkernel_params, perm, k);
+   int rc = nys_setup_perm((b200_nys *)nys, data, n, ldim, d, fkernel, fkernel_params, perm, k, 0);
    if (rc)
    {
       Nfft4GPPrecondNysFree(nys);

@@ -214,6 +214,37 @@ def chol_case():
     np.savez_compressed(os.path.join(OUT, "chol_gauss300.npz"), **out)
 
 
+def nys_grad_case():
+    """Reference Nystrom preconditioner set up with require_grad (nys.c:518-660) on the reference's plain Gaussian kernel:
+    log det, traces tr(M^-1 dM_i) and derivative-vector products M^-1 dM_i x (nys.c:175-516)."""
+    z = np.load(os.path.join(OUT, "nys_gauss300.npz"))
+    X, f, l, mu, rhs, perm, k = z["X"], float(z["f"]), float(z["l"]), float(z["mu"]), z["rhs"], z["perm"], int(z["k"])
+    n, d = X.shape[1], X.shape[0]
+    L.Nfft4GPKernelParamCreate.restype = C.c_void_p
+    L.Nfft4GPKernelParamCreate.argtypes = [C.c_int, C.c_int]
+    kh = L.Nfft4GPKernelParamCreate(n, 1)
+    R.set_hyper(kh, f, l, mu)
+    nys = L.Nfft4GPPrecondNysCreate()
+    L.Nfft4GPPrecondNysSetRank(nys, k)
+    L.Nfft4GPPrecondNysSetPerm(nys, R.iptr(perm), 0)
+    assert L.Nfft4GPPrecondNysSetupWithKernel(R.dptr(X), n, n, d, C.cast(L.Nfft4GPKernelGaussianKernel, C.c_void_p), kh, 1, nys) == 0
+    L.Nfft4GPPrecondNysLogdet.restype = C.c_double
+    L.Nfft4GPPrecondNysLogdet.argtypes = [C.c_void_p]
+    ld = L.Nfft4GPPrecondNysLogdet(nys)
+    tr = np.zeros(3)
+    trp = R.dptr(tr)
+    L.Nfft4GPPrecondNysTrace.argtypes = [C.c_void_p, C.POINTER(R.c_double_p)]
+    assert L.Nfft4GPPrecondNysTrace(nys, C.byref(trp)) == 0
+    y = np.zeros(3 * n)
+    yp = R.dptr(y)
+    L.Nfft4GPPrecondNysDvp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, R.c_double_p, C.POINTER(R.c_double_p)]
+    assert L.Nfft4GPPrecondNysDvp(nys, n, None, R.dptr(rhs), C.byref(yp)) == 0
+    zs = np.zeros(n)
+    L.Nfft4GPPrecondNysSolve(nys, n, R.dptr(zs), R.dptr(rhs))
+    print("nys grad: logdet", ld, "traces", tr)
+    np.savez_compressed(os.path.join(OUT, "nys_grad_gauss300.npz"), logdet=ld, trace=tr, dvp=y, solve=zs)
+
+
 def fgmres_case():
     """Reference Nfft4GPSolverFgmres (SRC/solvers/fgmres.c) on the reference's dense Gaussian kernel, with restarts (kdim 15),
     without and with the reference's Nystrom preconditioner, plus a run that stops at the iteration limit."""
@@ -340,6 +371,9 @@ def lanczos_case():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "nysgrad":
+        nys_grad_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "chol":
         chol_case()
         sys.exit(0)
