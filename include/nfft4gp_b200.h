@@ -202,6 +202,7 @@ void Nfft4GPPrecondFsaiSetLfil(void *str, int lfil);                     /* fsai
 int Nfft4GPPrecondFsaiSolve(void *vfsai_mat, int n, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs); /* fsai.c:106-123 (:220) */
 int Nfft4GPPrecondFsaiSetupWithKernel(NFFT4GP_DOUBLE *data, int n, int ldim, int d, func_kernel fkernel,
                                       void *fkernel_params, int require_grad, void *vfsai_mat); /* fsai.c:302-673 (:264) */
+NFFT4GP_DOUBLE Nfft4GPPrecondFsaiLogdet(void *vfsai_mat);                /* fsai.c:278-300 (:246); Dvp / Trace: not built */
 
 /* Dense Cholesky (the exact solver of the small-n experiments), SRC/preconds/chol.c; with require_grad the setup keeps
  * K and dK/dl in HBM and Trace / Dvp / Logdet are available (the reference's Dvp dereferences a NULL mask copy when the

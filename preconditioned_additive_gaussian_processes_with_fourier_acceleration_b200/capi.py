@@ -83,6 +83,7 @@ def lib():
         "Nfft4GPPrecondFsaiCreate": (vp, []), "Nfft4GPPrecondFsaiFree": (None, [vp]), "Nfft4GPPrecondFsaiReset": (None, [vp]),
         "Nfft4GPPrecondFsaiSetLfil": (None, [vp, i]),
         "Nfft4GPPrecondFsaiSolve": (i, [vp, i, c_double_p, c_double_p]),
+        "Nfft4GPPrecondFsaiLogdet": (d, [vp]),
         "Nfft4GPPrecondFsaiSetupWithKernel": (i, [c_double_p, i, i, i, vp, vp, i, vp]),
         "Nfft4GPPrecondCholCreate": (vp, []), "Nfft4GPPrecondCholFree": (None, [vp]), "Nfft4GPPrecondCholReset": (None, [vp]),
         "Nfft4GPPrecondCholSetStable": (None, [vp, i]),

@@ -347,6 +347,36 @@ int Nfft4GPPrecondFsaiSolve(void *vfsai_mat, int n, double *x, double *rhs) /* f
    return b200_d2h(x, s->d_x, sizeof(double) * (size_t)n);
 }
 
+/* log det of the FSAI preconditioner M = (G'G)^{-1}: -2 sum log G_ii, the diagonal being the last entry of every row
+ * (fsai.c:278-300).  Needs no gradient data. */
+double Nfft4GPPrecondFsaiLogdet(void *vfsai_mat)
+{
+   b200_fsai *s = (b200_fsai *)vfsai_mat;
+   int *ia, i;
+   double *diag, *d_diag, val = 0.0;
+   int *d_idx;
+   if (!s || s->magic != B200_MAGIC_FSAI || !s->d_a || s->n <= 0)
+      return 0.0;
+   ia = (int *)b200_xmalloc(sizeof(int) * ((size_t)s->n + 1));
+   diag = (double *)b200_xmalloc(sizeof(double) * (size_t)s->n);
+   d_idx = (int *)b200_malloc(sizeof(int) * (size_t)s->n);
+   d_diag = (double *)b200_malloc(sizeof(double) * (size_t)s->n);
+   if (d_idx && d_diag && !b200_d2h(ia, s->d_ia, sizeof(int) * ((size_t)s->n + 1)))
+   {
+      for (i = 0; i < s->n; i++)
+         ia[i] = ia[i + 1] - 1;
+      if (!b200_h2d(d_idx, ia, sizeof(int) * (size_t)s->n) && !b200k_gather_idx(s->n, d_idx, s->d_a, d_diag) &&
+          !b200_d2h(diag, d_diag, sizeof(double) * (size_t)s->n))
+         for (i = 0; i < s->n; i++)
+            val += log(1.0 / diag[i]);
+   }
+   b200_free(d_idx);
+   b200_free(d_diag);
+   free(ia);
+   free(diag);
+   return 2.0 * val;
+}
+
 /* ================================================================== AFN */
 void *Nfft4GPPrecondAFNCreate(void)
 {

@@ -105,6 +105,10 @@ def test_fsai_setup_matches_reference_golden(gpu):
         assert ja[ia[i + 1] - 1] == i
     x = F.solve(z["rhs"])
     assert rel_l2(x, z["fsai_z"]) <= 1e-10
+    # log det of (G'G)^{-1} (fsai.c:278-300) from the reference's factor values
+    ld_ref = -2.0 * np.log(z["fsai_a"][z["fsai_ia"][1:] - 1]).sum()
+    ld = gpu.lib().Nfft4GPPrecondFsaiLogdet(F.h)
+    assert abs(ld - ld_ref) <= 1e-10 * abs(ld_ref)
     F.free()
     P.free()
 
