@@ -11,6 +11,8 @@ EXE = os.path.join(ROOT, "examples", "test3_solve")
 
 
 def _build():
+    import preconditioned_additive_gaussian_processes_with_fourier_acceleration_b200 as pkg
+    pkg.build_library()   # the driver links against the in-tree library: make sure it exists (no-op when it does)
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")], stdout=subprocess.DEVNULL)
     assert os.path.exists(EXE)
 
