@@ -1,0 +1,100 @@
+"""BASELINE config C2 at its FULL size (n = 10^6, d = 9, three 3-D windows) -- where the CPU oracle takes minutes --
+through size-independent properties of the operator: linearity, symmetry (the spread is the adjoint of the gather),
+positivity, agreement of the two independent kernel families (fp64 tensor-core path vs DFMA path), the alpha / beta
+contract, rows of the result against the dense kernel sum, and the gradient matvec's three blocks."""
+import numpy as np
+import pytest
+
+from common import rand_vec, rel_l2, uniform_cloud
+
+pytestmark = pytest.mark.gpu
+N, D = 1000000, 9
+F, MU = 1.0, 0.01
+L_SCALE = 0.25 * N ** (1.0 / D)
+
+
+@pytest.fixture(scope="module")
+def full(gpu):
+    X = uniform_cloud(N, D)
+    A = gpu.AdditiveNFFTKernel(X, np.arange(9, dtype=np.int32), 3, 3, "gaussian").build(F, L_SCALE, MU)
+    yield gpu, X, A
+    A.free()
+
+
+def test_linearity_symmetry_positivity(full):
+    gpu, X, A = full
+    x, y = rand_vec(N, 1), rand_vec(N, 2)
+    Kx, Ky = A.matvec(x), A.matvec(y)
+    assert rel_l2(A.matvec(0.3 * x - 1.7 * y), 0.3 * Kx - 1.7 * Ky) <= 1e-12
+    assert abs(Kx @ y - x @ Ky) <= 1e-11 * np.linalg.norm(Kx) * np.linalg.norm(y)
+    assert x @ Kx > 0.0 and y @ Ky > 0.0
+    # alpha / beta contract of nfft_interface.c:796-817
+    y0 = rand_vec(N, 3)
+    assert rel_l2(A.matvec(x, alpha=-0.5, beta=2.0, y=y0.copy()), 2.0 * y0 - 0.5 * Kx) <= 1e-12
+
+
+def test_kernel_families_agree_at_full_size(full):
+    gpu, X, A = full
+    x = rand_vec(N, 4)
+    L = gpu.lib()
+    out = {}
+    for variant in (-1, 5, 1):          # fused tensor-core launches, per-window tensor-core kernels, DFMA kernels
+        L.Nfft4GPB200SetVariant(b"spread3d", variant)
+        L.Nfft4GPB200SetVariant(b"gather3d", variant)
+        out[variant] = A.matvec(x)
+    L.Nfft4GPB200SetVariant(b"spread3d", -1)
+    L.Nfft4GPB200SetVariant(b"gather3d", -1)
+    assert rel_l2(out[5], out[1]) <= 1e-12 and rel_l2(out[-1], out[1]) <= 1e-12
+
+
+def test_rows_against_dense_kernel_sum(full):
+    """(K x)_i for 64 random rows against the O(n) dense sums f^2 ( mean_w exp(-r_w^2 / 2 l^2) + mu delta ): the NFFT is
+    an approximation of the kernel (3e-8 at this length scale), so the bar is the approximation's, not 1e-10."""
+    gpu, X, A = full
+    x = rand_vec(N, 5)
+    Kx = A.matvec(x)
+    rows = np.random.default_rng(6).choice(N, 64, replace=False)
+    ref = np.zeros(64)
+    for w in range(3):
+        Xw = X[3 * w:3 * w + 3]
+        for k, i in enumerate(rows):
+            r2 = ((Xw - Xw[:, i:i + 1]) ** 2).sum(0)
+            ref[k] += F * F * (np.exp(-r2 / (2 * L_SCALE ** 2)) @ x) / 3.0
+    ref += F * F * MU * x[rows]
+    assert np.abs(Kx[rows] - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
+def test_gradient_blocks_at_full_size(full):
+    gpu, X, A = full
+    x = rand_vec(N, 7)
+    Kx = A.matvec(x)
+    g = A.grad_matvec(x)
+    assert rel_l2(g[:N], 2.0 / F * Kx) <= 1e-12                     # dK/df x = (2/f) K x   (nfft_interface.c:547)
+    assert rel_l2(g[2 * N:], F * F * x) <= 1e-14                    # dK/dmu x = f^2 x       (:549)
+    # dK/dl x against a central difference of the matvec in l (kernel rebuild = hyper-parameter change)
+    h = 1e-4 * L_SCALE
+    Kp = A.build(F, L_SCALE + h, MU).matvec(x)
+    Km = A.build(F, L_SCALE - h, MU).matvec(x)
+    A.build(F, L_SCALE, MU)
+    assert rel_l2(g[N:2 * N], (Kp - Km) / (2 * h)) <= 1e-5
+
+
+@pytest.mark.parametrize("dw", [2, 1])
+def test_c4_style_windows_at_full_size(gpu, dw):
+    """BASELINE config C4 in kind (many 1-D / 2-D windows, Matern-1/2) at n = 10^6: linearity, symmetry and agreement of the
+    streaming kernels with the thread-per-point cross-check kernels."""
+    n, d = 1000000, 8
+    X = uniform_cloud(n, d, seed=11)
+    A = gpu.AdditiveNFFTKernel(X, np.arange(d, dtype=np.int32), d // dw, dw, "matern12").build(1.1, 0.5 * n ** (1.0 / d), 0.02)
+    x, y = rand_vec(n, 1), rand_vec(n, 2)
+    Kx, Ky = A.matvec(x), A.matvec(y)
+    assert rel_l2(A.matvec(2.0 * x + 0.25 * y), 2.0 * Kx + 0.25 * Ky) <= 1e-12
+    assert abs(Kx @ y - x @ Ky) <= 1e-11 * np.linalg.norm(Kx) * np.linalg.norm(y)
+    L = gpu.lib()
+    for name in (b"spread3d", b"gather3d"):      # the switch selects the kernel family for every window dimension
+        assert L.Nfft4GPB200SetVariant(name, 0) == 0
+    K0 = A.matvec(x)
+    for name in (b"spread3d", b"gather3d"):
+        assert L.Nfft4GPB200SetVariant(name, -1) == 0
+    assert rel_l2(Kx, K0) <= 1e-12
+    A.free()
