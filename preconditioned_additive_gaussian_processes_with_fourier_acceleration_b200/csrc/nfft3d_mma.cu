@@ -58,6 +58,13 @@ __device__ __forceinline__ void m_red_add(double *p, double v)
 {
    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
 }
+// fp64 product as a volatile PTX instruction: keeps its place in front of the tensor instructions in the PTX stream
+__device__ __forceinline__ double m_vmul(double a, double b)
+{
+   double r;
+   asm volatile("mul.f64 %0, %1, %2;" : "=d"(r) : "d"(a), "d"(b));
+   return r;
+}
 __device__ __forceinline__ int m_tap_idx(int keyfield, int lj) { return (keyfield + 28 + lj) & 63; }
 __device__ __forceinline__ void m_cpa16(void *smem, const void *gmem)
 {
@@ -99,6 +106,35 @@ __device__ __forceinline__ void m_stage_issue(double *st, const double *__restri
    }
 }
 
+// range (round k, slot q) of the fused launches -> window, chunk interval; returns false when the slot is empty
+__device__ __forceinline__ bool m_range_lookup(const b200_mma_win *__restrict__ W, int P, int total, int r, int &w, int &c0, int &c1)
+{
+   const int k = r / total, q = r - k * total;
+   w = 0;
+   while (w + 1 < P && q >= W[w + 1].warp_begin)
+      w++;
+   const int j = q - W[w].warp_begin;
+   if (j >= W[w].nwarps)
+      return false;
+   const int *cf = W[w].cfirst + k * W[w].nwarps + j;
+   c0 = cf[0];
+   c1 = cf[1];
+   return true;
+}
+static __device__ int g_mma_range_counter; // next dynamic range of the running fused launch of this translation unit
+__device__ __forceinline__ int m_range_next(int *counter, int total, int lane)
+{
+   int nx = 0;
+   if (lane == 0)
+      nx = atomicAdd(counter, 1);
+   return total + __shfl_sync(0xffffffffu, nx, 0);
+}
+
+#ifndef MMA_PART
+#define MMA_PART 0 /* 1: spread only, 2: gather only (the Makefile builds the two halves with different ptxas levels) */
+#endif
+
+#if MMA_PART != 2
 // ---------------------------------------------------------------------------------------------------- spread
 // Writing a cell's footprint straight to the L2-resident grid costs 1040 fp64 REDs per cell change and warp -- 21 M per
 // launch at n = 10^6, independent of n, and the L2 atomic units made that 190 of the 338 us of the fused spread.
@@ -318,30 +354,46 @@ __device__ __forceinline__ void m_spread_range(const double *__restrict__ psi, c
             x1[i] = row[x < TAPS ? x : TAPS - 1];
             y2[i] = row[TAPS + (y < TAPS ? y : TAPS - 1)];
          }
-         // ---- main part: B(k, n = g) = a psi3[g];  A(m, k) = psi1[x] psi2[y] with (x, y) = (i, g) for the tiles i < 10 and
+         // ---- all operand products of the k-step first, then its 19 tensor instructions.  The spread half of this file is
+         // built with `-Xptxas -O1` (Makefile), which keeps this order; at the default level ptxas sinks every load and product
+         // next to its DMMA, and the warp then pays the shared-memory and product latencies once per tensor instruction
+         // instead of once per k-step (measured: 327 -> 321 us per fused launch at n = 10^6, 119 -> 114 us at 2.5 10^5; the gather
+         // loses 6 us with -O1 and keeps the default level).
+         // main part: B(k, n = g) = a psi3[g];  A(m, k) = psi1[x] psi2[y] with (x, y) = (i, g) for the tiles i < 10 and
          // (4 i' + g / 2, 8 + (g & 1)) for the tiles 10 + i'
-         const double b0 = aj * r3g;
+         // edge part: A(x, k) = a psi1[x], B(k, n = g of tile j) = psi2[4 j + g / 2] psi3[8 + (g & 1)]
+         const double b0 = m_vmul(aj, r3g);
+         double af[MT];
 #pragma unroll
          for (int i = 0; i < 5; i++)
          {
-            m_dmma(acc[2 * i][0], acc[2 * i][1], p1[i].x * p2, b0);
-            m_dmma(acc[2 * i + 1][0], acc[2 * i + 1][1], p1[i].y * p2, b0);
+            af[2 * i] = m_vmul(p1[i].x, p2);
+            af[2 * i + 1] = m_vmul(p1[i].y, p2);
          }
 #pragma unroll
          for (int i = 0; i < 3; i++)
          {
-            const double af = (i < 2 || g < 4) ? x1[i] * p2e : 0.0;
-            m_dmma(acc[10 + i][0], acc[10 + i][1], af, b0);
+            const double v = m_vmul(x1[i], p2e);
+            af[10 + i] = (i < 2 || g < 4) ? v : 0.0;
          }
-         // ---- edge part: A(x, k) = a psi1[x], B(k, n = g of tile j) = psi2[4 j + g / 2] psi3[8 + (g & 1)]
-         const double ae0 = aj * r1g;
-         const double ae1 = (g < 2) ? aj * r1e : 0.0;
+         const double ae0 = m_vmul(aj, r1g);
+         const double ae1v = m_vmul(aj, r1e);
+         const double ae1 = (g < 2) ? ae1v : 0.0;
+         double be[3];
 #pragma unroll
          for (int j = 0; j < 3; j++)
          {
-            const double be = (j < 2 || g < 4) ? y2[j] * p3 : 0.0;
-            m_dmma(ace[0][j][0], ace[0][j][1], ae0, be);
-            m_dmma(ace[1][j][0], ace[1][j][1], ae1, be);
+            const double v = m_vmul(y2[j], p3);
+            be[j] = (j < 2 || g < 4) ? v : 0.0;
+         }
+#pragma unroll
+         for (int i = 0; i < MT; i++)
+            m_dmma(acc[i][0], acc[i][1], af[i], b0);
+#pragma unroll
+         for (int j = 0; j < 3; j++)
+         {
+            m_dmma(ace[0][j][0], ace[0][j][1], ae0, be[j]);
+            m_dmma(ace[1][j][0], ace[1][j][1], ae1, be[j]);
          }
       }
 #if MX_CLK
@@ -392,30 +444,6 @@ k_spread3_mma(const double *__restrict__ psi, const double *__restrict__ a, cons
 
 // all windows of an additive kernel in ONE persistent wave: warp gw belongs to the window w with
 // wbeg[w] <= gw < wbeg[w + 1] and streams range gw - wbeg[w] of that window's own partition
-// range (round k, slot q) of the fused launches -> window, chunk interval; returns false when the slot is empty
-__device__ __forceinline__ bool m_range_lookup(const b200_mma_win *__restrict__ W, int P, int total, int r, int &w, int &c0, int &c1)
-{
-   const int k = r / total, q = r - k * total;
-   w = 0;
-   while (w + 1 < P && q >= W[w + 1].warp_begin)
-      w++;
-   const int j = q - W[w].warp_begin;
-   if (j >= W[w].nwarps)
-      return false;
-   const int *cf = W[w].cfirst + k * W[w].nwarps + j;
-   c0 = cf[0];
-   c1 = cf[1];
-   return true;
-}
-__device__ int g_mma_range_counter[2]; // next dynamic range of the running fused spread [0] / gather [1]
-__device__ __forceinline__ int m_range_next(int *counter, int total, int lane)
-{
-   int nx = 0;
-   if (lane == 0)
-      nx = atomicAdd(counter, 1);
-   return total + __shfl_sync(0xffffffffu, nx, 0);
-}
-
 __global__ void __launch_bounds__(MWARPS_PER_CTA * 32, MCTAS_PER_SM)
 k_spread3_mma_batch(const b200_mma_win *__restrict__ W, int P, int rounds)
 {
@@ -432,10 +460,13 @@ k_spread3_mma_batch(const b200_mma_win *__restrict__ W, int P, int rounds)
                         dsm + MWARPS_PER_CTA * MWNS * STAGE_D + wid * CB_DOUBLES, lane);
       if (rounds == 1)
          break;
-      r = m_range_next(&g_mma_range_counter[0], total, lane);
+      r = m_range_next(&g_mma_range_counter, total, lane);
    }
 }
 
+#endif // MMA_PART != 2
+
+#if MMA_PART != 1
 // ---------------------------------------------------------------------------------------------------- gather
 // B operands (constant per cell).  main k-steps: s < 20: row k = t <-> (x = s / 2, y = 4 (s & 1) + t); s = 20 + s':
 // (x = 2 s' + t / 2, y = 8 + (t & 1)); column n = g <-> z = g.
@@ -589,13 +620,25 @@ k_gather3_mma_batch(const b200_mma_win *__restrict__ W, int P, int rounds)
       if (rounds == 1)
          break;
       __syncwarp(); // the stages are reused by the next range
-      r = m_range_next(&g_mma_range_counter[1], total, lane);
+      r = m_range_next(&g_mma_range_counter, total, lane);
    }
 }
+
+#endif // MMA_PART != 1
 
 // ---------------------------------------------------------------------------------------------------- launch layer
 extern "C" {
 
+static int mma_counter_reset(void)
+{
+   static int *addr = nullptr;
+   if (!addr)
+      B200_CHECK(cudaGetSymbolAddress((void **)&addr, g_mma_range_counter));
+   B200_CHECK(cudaMemsetAsync(addr, 0, sizeof(int), b200_stream())); // a memset node when the matvec is being captured
+   return 0;
+}
+
+#if MMA_PART != 2
 // warps of one resident wave of the tensor-core kernels (the fused launches size their partitions with it)
 int b200k_mma_warp_ranges(void)
 {
@@ -616,6 +659,8 @@ int b200k_spread3_mma(const b200_win_dev *w)
    return 0;
 }
 
+#endif // MMA_PART != 2
+#if MMA_PART != 1
 int b200k_gather3_mma(const b200_win_dev *w, double *d_f)
 {
    if (w->nchunk <= 0)
@@ -626,15 +671,8 @@ int b200k_gather3_mma(const b200_win_dev *w, double *d_f)
 }
 
 // fused launches over the P windows described by d_batch (device array); total_warps = sum of nwarps, a multiple of the CTA size
-static int mma_counter_reset(int which)
-{
-   static int *addr = nullptr;
-   if (!addr)
-      B200_CHECK(cudaGetSymbolAddress((void **)&addr, g_mma_range_counter));
-   B200_CHECK(cudaMemsetAsync(addr + which, 0, sizeof(int), b200_stream())); // a memset node when the matvec is being captured
-   return 0;
-}
-
+#endif // MMA_PART != 1
+#if MMA_PART != 2
 int b200k_spread3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps, int rounds)
 {
    static bool attr_set = false; // once: this call may sit inside a stream capture (CUDA graph of the matvec)
@@ -643,20 +681,24 @@ int b200k_spread3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps,
       B200_CHECK(cudaFuncSetAttribute(k_spread3_mma_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPREAD_SMEM_BYTES));
       attr_set = true;
    }
-   if (rounds > 1 && mma_counter_reset(0))
+   if (rounds > 1 && mma_counter_reset())
       return -1;
    k_spread3_mma_batch<<<total_warps / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, SPREAD_SMEM_BYTES, b200_stream()>>>(d_batch, P, rounds);
    B200_LAUNCHED();
    return 0;
 }
 
+#endif // MMA_PART != 2
+#if MMA_PART != 1
 int b200k_gather3_mma_batch(const b200_mma_win *d_batch, int P, int total_warps, int rounds)
 {
-   if (rounds > 1 && mma_counter_reset(1))
+   if (rounds > 1 && mma_counter_reset())
       return -1;
    k_gather3_mma_batch<<<total_warps / MWARPS_PER_CTA, MWARPS_PER_CTA * 32, 0, b200_stream()>>>(d_batch, P, rounds);
    B200_LAUNCHED();
    return 0;
 }
+
+#endif // MMA_PART != 1
 
 } // extern "C"
