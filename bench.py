@@ -415,7 +415,11 @@ def main():
 
     pcg = None
     if world == 1 and not args.no_pcg:
-        pcg = run_pcg_section(pkg, L, A, X, x, windows, hp, args, peak)
+        try:
+            pcg = run_pcg_section(pkg, L, A, X, x, windows, hp, args, peak)
+        except Exception as exc:  # the headline metric of this line is the matvec: report the failure, keep the line
+            print(f"bench.py: the C3 (AFN-PCG) section failed: {exc!r}", file=sys.stderr)
+            pcg = {"error": repr(exc)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
