@@ -308,6 +308,8 @@ int Nfft4GPB200PrecondAFNSetRankEstimation(void *afn, int m, int numests, int no
  * and the apply stays symmetric; the preconditioner changes by O(1e-7) relative, the solution PCG converges to does not. */
 int Nfft4GPB200PrecondAFNSetK12Storage(void *afn, int bits);
 /* setup building blocks, exposed for the parity tests (host in / host out; the device ones need a GPU) */
+int Nfft4GPB200DebugPartitionChunks(const int *chunks /* int4 per chunk */, int nchunk, int wcnt, int rounds, const double *weight,
+                                    double flush, int *first /* rounds * wcnt + 1 */);
 int Nfft4GPB200HostPotrf(int n, double *A /* lower, column-major, in place */);
 int Nfft4GPB200HostSyev(int n, double *A /* in: symmetric; out: eigenvectors */, double *w /* ascending */, int want_vectors);
 int Nfft4GPB200Dgemm(char transa, char transb, int M, int N, int K, double alpha, const double *A, int lda, const double *B, int ldb,

@@ -107,3 +107,12 @@ int Nfft4GPB200KnnPattern(const double *data, int n, int ldim, int d, int lfil, 
    b200_free(d_ja);
    return rc ? -1 : 0;
 }
+
+/* host-only: the range partition of the fused spread / gather launches (nfft_host.c:b200_partition_chunks) */
+int Nfft4GPB200DebugPartitionChunks(const int *chunks, int nchunk, int wcnt, int rounds, const double *weight, double flush, int *first)
+{
+   if (!chunks || nchunk < 0 || wcnt < 1 || rounds < 1 || !weight || !first)
+      return -1;
+   b200_partition_chunks(chunks, nchunk, wcnt, rounds, weight, flush, first);
+   return 0;
+}

@@ -89,6 +89,7 @@ void *b200_xmalloc(size_t bytes);
 void *b200_xcalloc(size_t n, size_t sz);
 
 b200_additive *b200_additive_from_handle(void *data);
+void b200_partition_chunks(const int *hc, int nch, int wcnt, int rounds, const double *weight, double flush, int *first);
 int b200_additive_matvec_dev(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y);
 int b200_additive_grad_matvec_dev(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y);
 int b200_window_matvec_dev(b200_window *w, int n, double alpha, const double *d_x, double beta, double *d_y);

@@ -1078,13 +1078,49 @@ static void additive_fused_release(b200_additive *A)
    A->fused_ready = 0;
 }
 
+/* Cut one window's chunk list (int4 descriptors {first point, count, cell key, 0}) into rounds * wcnt consecutive ranges:
+ * round k holds wcnt ranges of the cost share weight[k] / sum(weight) / wcnt each, cost = points + 1 per chunk + `flush` per
+ * cell change.  first[0] = 0, first[rounds * wcnt] = nch.  Pure host code (exported for the CPU tests as
+ * Nfft4GPB200DebugPartitionChunks). */
+void b200_partition_chunks(const int *hc, int nch, int wcnt, int rounds, const double *weight, double flush, int *first)
+{
+   int nr = rounds * wcnt, r = 0, prev = -1, c, k;
+   double acc = 0.0, total = 0.0, wsum = 0.0, wacc = 0.0, *start = (double *)b200_xcalloc((size_t)nr + 1, sizeof(double));
+   for (c = 0; c < nch; c++)
+   {
+      total += chunk_cost(hc, c, prev, flush);
+      prev = hc[4 * c + 2];
+   }
+   for (k = 0; k < rounds; k++)
+      wsum += weight[k];
+   for (k = 0; k < rounds; k++)
+   {
+      for (c = 0; c < wcnt; c++)
+         start[k * wcnt + c] = total * (wacc + weight[k] * (double)c / (double)wcnt) / wsum;
+      wacc += weight[k];
+   }
+   first[0] = 0;
+   prev = -1;
+   for (c = 0; c < nch; c++)
+   {
+      while (r + 1 < nr && acc >= start[r + 1])
+         first[++r] = c;
+      acc += chunk_cost(hc, c, prev, flush);
+      prev = hc[4 * c + 2];
+   }
+   while (r + 1 < nr)
+      first[++r] = nch;
+   first[nr] = nch;
+   free(start);
+}
+
 /* cut every batch window's chunk list into ranges of equal cost; the warps of the wave are divided among the windows in
  * proportion to their cost.  dir 0 = spread, 1 = gather.  Fills d_fused[dir] (gather: output f) and d_fused_cfirst[dir]. */
 static int additive_fused_partition(b200_additive *A, int dir, int total_warps)
 {
    const double flush = dir ? FUSED_FLUSH_COST_GATHER : FUSED_FLUSH_COST_SPREAD;
-   int nb = A->nbatch, i, c, k, assigned = 0, big = 0, rc = -1;
-   double *cost = (double *)b200_xcalloc((size_t)nb, sizeof(double)), total = 0.0, wsum = 0.0;
+   int nb = A->nbatch, i, c, assigned = 0, big = 0, rc = -1;
+   double *cost = (double *)b200_xcalloc((size_t)nb, sizeof(double)), total = 0.0;
    int *wbeg = (int *)b200_xcalloc((size_t)nb + 1, sizeof(int)), *wcnt = (int *)b200_xcalloc((size_t)nb, sizeof(int));
    b200_mma_win *hw = (b200_mma_win *)b200_xcalloc((size_t)nb, sizeof(b200_mma_win));
    for (i = 0; i < nb; i++)
@@ -1113,33 +1149,14 @@ static int additive_fused_partition(b200_additive *A, int dir, int total_warps)
    for (i = 0; i < nb; i++)
       wbeg[i + 1] = wbeg[i] + wcnt[i];
    A->d_fused_cfirst[dir] = (int **)b200_xcalloc((size_t)nb, sizeof(int *));
-   for (k = 0; k < A->fused_rounds; k++)
-      wsum += A->fused_weight[k];
    for (i = 0; i < nb; i++)
    {
       /* rounds * wcnt consecutive ranges: round k holds wcnt ranges of the cost share weight[k] / wsum / wcnt each */
       const int *hc = A->win[i]->h_chunks;
       b200_win_dev *v = &A->win[i]->dev;
       int nr = A->fused_rounds * wcnt[i];
-      int nch = A->win[i]->h_nchunk, r = 0, prev = -1, *hr = (int *)b200_xcalloc((size_t)nr + 1, sizeof(int)), bad;
-      double acc = 0.0, *start = (double *)b200_xcalloc((size_t)nr + 1, sizeof(double)), wacc = 0.0;
-      for (k = 0; k < A->fused_rounds; k++)
-      {
-         for (c = 0; c < wcnt[i]; c++)
-            start[k * wcnt[i] + c] = cost[i] * (wacc + A->fused_weight[k] * (double)c / (double)wcnt[i]) / wsum;
-         wacc += A->fused_weight[k];
-      }
-      for (c = 0; c < nch; c++)
-      {
-         while (r + 1 < nr && acc >= start[r + 1])
-            hr[++r] = c;
-         acc += chunk_cost(hc, c, prev, flush);
-         prev = hc[4 * c + 2];
-      }
-      while (r + 1 < nr)
-         hr[++r] = nch;
-      hr[nr] = nch;
-      free(start);
+      int nch = A->win[i]->h_nchunk, *hr = (int *)b200_xcalloc((size_t)nr + 1, sizeof(int)), bad;
+      b200_partition_chunks(hc, nch, wcnt[i], A->fused_rounds, A->fused_weight, flush, hr);
       A->d_fused_cfirst[dir][i] = (int *)b200_malloc(sizeof(int) * ((size_t)nr + 1));
       bad = !A->d_fused_cfirst[dir][i] || b200_h2d(A->d_fused_cfirst[dir][i], hr, sizeof(int) * ((size_t)nr + 1)) || b200_sync();
       free(hr);
