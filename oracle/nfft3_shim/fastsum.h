@@ -8,9 +8,10 @@
  * NFFT3 is a third-party dependency absent from /root/reference and from this
  * image, un-pinned by the reference (API evidence: >= 3.5.2).  This file restates
  * its published algorithm (Potts/Steidl fastsum on top of the Keiner/Kunis/Potts
- * NFFT with the default Kaiser-Bessel window).  PARITY UNPINNED: no golden
- * vectors for this boundary exist in the reference; the arbiter is the
- * reference's dense additive kernel (see oracle/README.md).
+ * NFFT with the default Kaiser-Bessel window).  The reference holds no golden vector AT this boundary; parity is pinned
+ * one level up, on the 400 numbers it ships from its authors' real NFFT3 build (TESTS/TEST2/foo_0_nfft.txt, reproduced
+ * to the printed precision: tests/test_real_nfft3_pin.py), and arbitrated by the reference's dense additive kernel
+ * (see oracle/README.md).
  */
 #ifndef ORACLE_NFFT3_SHIM_FASTSUM_H
 #define ORACLE_NFFT3_SHIM_FASTSUM_H

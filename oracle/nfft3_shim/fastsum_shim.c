@@ -5,7 +5,10 @@
  * SRC/external/nfft_interface.c (plan build :223-254 / :359-390, execute :426 and
  * :533-534, teardown :56-59, :93-98, :110-113).  NFFT3 is an external, un-pinned
  * dependency that is absent from /root/reference and cannot be installed here
- * (no network): PARITY UNPINNED at this boundary.  What is restated is the
+ * (no network).  PARITY AT THIS BOUNDARY IS PINNED INDIRECTLY: the reference ships the output of its authors' real
+ * NFFT3 build for the 1-D toy problem (TESTS/TEST2/foo_0_nfft.txt, 200 predicted means + 200 standard deviations, 10
+ * decimals); with three fitted hyper-parameters the reference's own prediction routine, compiled on THIS file, reproduces
+ * all 400 values to 5.5e-10 / 5.1e-11 (scripts/pin_test2.py, tests/test_real_nfft3_pin.py).  What is restated is the
  * published algorithm, with the parameters the reference fixes
  * (nfft_interface.c:18-27): expansion degree N=32, oversampled FFT length 64,
  * window cut-off m=4, eps_I=eps_B=0 (no near field, no boundary regularisation),

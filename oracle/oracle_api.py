@@ -3,7 +3,8 @@
 ctypes binding of ``oracle/liboracle_nfft4gp.so`` (oracle_path.c + nfft3_shim): the
 self-contained CPU restatement of the reference's hot path.  Only tests/,
 ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` / ``--impl reference`` legs
-may import this module.  PARITY UNPINNED at the NFFT3 fastsum boundary.
+may import this module.  The NFFT3 fastsum boundary is a restatement, pinned on the reference's shipped real-NFFT3 output
+(TESTS/TEST2/foo_0_nfft.txt; tests/test_real_nfft3_pin.py).
 """
 import ctypes as C
 import os

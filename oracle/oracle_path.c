@@ -1,5 +1,6 @@
 /* ORACLE (test infrastructure, not product code) -- see oracle_path.h.
- * PARITY UNPINNED at the NFFT3 fastsum boundary (nfft3_shim/); everything in this
+ * The NFFT3 fastsum boundary (nfft3_shim/) is pinned on the reference's shipped real-NFFT3 output (TESTS/TEST2, see
+ * nfft3_shim/fastsum.h); everything in this
  * file is validated against the reference's own sources (oracle/_ref) by
  * tests/test_oracle_vs_ref.py where /root/reference is available and against the
  * golden fixtures of tests/golden elsewhere. */

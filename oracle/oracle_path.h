@@ -1,8 +1,9 @@
 /* ORACLE (test infrastructure, not product code).
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
- * legs may load this library.  PARITY UNPINNED at the NFFT3 fastsum boundary
- * (see nfft3_shim/fastsum.h); everything above that boundary is validated against
- * the reference's own sources compiled into oracle/_ref (see oracle/README.md).
+ * legs may load this library.  The NFFT3 fastsum boundary is a restatement (NFFT3 is absent), PINNED on the 400 numbers
+ * the reference ships from its authors' real NFFT3 build (TESTS/TEST2/foo_0_nfft.txt; see nfft3_shim/fastsum.h and
+ * tests/test_real_nfft3_pin.py); everything above that boundary is validated against the reference's own sources
+ * compiled into oracle/_ref (see oracle/README.md).
  *
  * Self-contained CPU restatement of the hot path of the reference:
  *   - window setup and NFFT additive matvec / gradient matvec
