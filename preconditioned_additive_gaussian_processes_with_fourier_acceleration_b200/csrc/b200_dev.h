@@ -30,6 +30,8 @@ typedef struct
    int n;        /* number of points                                             */
    int nseg;     /* number of (cell, warp-range) segments (information only)     */
    double *psi;  /* [n + pad][d*10] Kaiser-Bessel taps, cell-sorted point order  */
+   double *xs;   /* [n][d] sorted scaled coordinates, kept only for 1-D / 2-D windows when the window is evaluated in the kernels
+                    (NFFT4GP_B200_WINDOW_EVAL=1); NULL otherwise                  */
    int *key;     /* [n] packed cell index ((c1+32)<<12 | (c2+32)<<6 | (c3+32))    */
    int *perm;    /* [n] sorted position -> original point                        */
    int *inv;     /* [n] original point -> sorted position                        */

@@ -14,6 +14,7 @@
 
 #include "b200_dev.h"
 #include "b200_cuda_util.cuh"
+#include "kb_window_coeffs.h"
 
 #define TAPS B200_TAPS
 #define NOS B200_NOS
@@ -53,8 +54,42 @@ __device__ __forceinline__ void s_stage(StreamSmem<D> &sm, int wid, int lane, co
    sm.key[wid][lane] = j < jend ? key[j] : -1;
 }
 
-// ---------------------------------------------------------------------------------------------------- spread
+// Opt-in alternative to reading the tabulated taps (NFFT4GP_B200_WINDOW_EVAL=1): evaluate the Kaiser-Bessel window here.
+// Per tap j the argument t = u + 4 - j stays inside ONE unit interval while the point's fractional grid offset u runs over
+// [0, 1), so psi is ten smooth pieces; each is a degree-14 polynomial in v = 2u - 1 (kb_window_coeffs.h, 4.6e-16 phi(0)).
+// Lane = point of the batch: 8 bytes per dimension from HBM instead of 80, ~150 FMAs per dimension, coefficients in constant
+// memory (all lanes read the same entry).  The staged rows are the same as the tabulated ones to rounding.
+__constant__ double c_kb_poly[TAPS][KB_POLY_DEG + 1] = KB_POLY_TABLE;
+
 template <int D>
+__device__ __forceinline__ void s_stage_eval(StreamSmem<D> &sm, int wid, int lane, const double *__restrict__ xs, const double *__restrict__ a,
+                                             const int *__restrict__ key, int j0, int jend)
+{
+   const int j = j0 + lane;
+   const bool ok = j < jend;
+#pragma unroll
+   for (int t = 0; t < D; t++)
+   {
+      const double xj = ok ? xs[(size_t)j * D + t] : 0.0;
+      const double xn = xj * (double)NOS;
+      const double v = 2.0 * (xn - floor(xn)) - 1.0;
+#pragma unroll
+      for (int lj = 0; lj < TAPS; lj++)
+      {
+         double acc = c_kb_poly[lj][KB_POLY_DEG];
+#pragma unroll
+         for (int k = KB_POLY_DEG - 1; k >= 0; k--)
+            acc = fma(acc, v, c_kb_poly[lj][k]);
+         sm.rows[wid][lane][t * TAPS + lj] = ok ? acc : 0.0;
+      }
+   }
+   if (a != nullptr)
+      sm.a[wid][lane] = ok ? a[j] : 0.0;
+   sm.key[wid][lane] = ok ? key[j] : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------- spread
+template <int D, bool EVAL>
 __global__ void __launch_bounds__(SWARPS * 32, SCTAS_PER_SM)
 k_spread_stream(const double *__restrict__ psi, const int *__restrict__ key, const double *__restrict__ a, double *__restrict__ grid, int n,
                 int per_warp)
@@ -93,7 +128,10 @@ k_spread_stream(const double *__restrict__ psi, const int *__restrict__ key, con
    for (int j0 = jb; j0 < je; j0 += SBATCH)
    {
       __syncwarp();
-      s_stage<D>(sm, wid, lane, psi, a, key, j0, je);
+      if (EVAL)
+         s_stage_eval<D>(sm, wid, lane, psi /* = sorted scaled coordinates */, a, key, j0, je);
+      else
+         s_stage<D>(sm, wid, lane, psi, a, key, j0, je);
       __syncwarp();
       const int cnt = min(SBATCH, je - j0);
       // fast path (the common case: thousands of sorted points per cell): the whole batch lies in the current cell
@@ -149,7 +187,7 @@ k_spread_stream(const double *__restrict__ psi, const int *__restrict__ key, con
 }
 
 // ---------------------------------------------------------------------------------------------------- gather
-template <int D>
+template <int D, bool EVAL>
 __global__ void __launch_bounds__(SWARPS * 32, SCTAS_PER_SM)
 k_gather_stream(const double *__restrict__ psi, const int *__restrict__ key, const double *__restrict__ h, double *__restrict__ f, int n,
                 int per_warp)
@@ -188,7 +226,10 @@ k_gather_stream(const double *__restrict__ psi, const int *__restrict__ key, con
    for (int j0 = jb; j0 < je; j0 += SBATCH)
    {
       __syncwarp();
-      s_stage<D>(sm, wid, lane, psi, nullptr, key, j0, je);
+      if (EVAL)
+         s_stage_eval<D>(sm, wid, lane, psi /* = sorted scaled coordinates */, nullptr, key, j0, je);
+      else
+         s_stage<D>(sm, wid, lane, psi, nullptr, key, j0, je);
       __syncwarp();
       const int cnt = min(SBATCH, je - j0);
       for (int p0 = 0; p0 < cnt; p0 += 8)
@@ -269,10 +310,14 @@ int b200k_spread_stream(const b200_win_dev *w)
    if (w->n <= 0)
       return 0;
    int per, blocks = stream_grid(w->n, &per);
-   if (w->d == 1)
-      k_spread_stream<1><<<blocks, SWARPS * 32, 0, b200_stream()>>>(w->psi, w->key, w->a, w->grid, w->n, per);
+   if (w->xs && w->d == 1)
+      k_spread_stream<1, true><<<blocks, SWARPS * 32, 0, b200_stream()>>>(w->xs, w->key, w->a, w->grid, w->n, per);
+   else if (w->xs)
+      k_spread_stream<2, true><<<blocks, SWARPS * 32, 0, b200_stream()>>>(w->xs, w->key, w->a, w->grid, w->n, per);
+   else if (w->d == 1)
+      k_spread_stream<1, false><<<blocks, SWARPS * 32, 0, b200_stream()>>>(w->psi, w->key, w->a, w->grid, w->n, per);
    else
-      k_spread_stream<2><<<blocks, SWARPS * 32, 0, b200_stream()>>>(w->psi, w->key, w->a, w->grid, w->n, per);
+      k_spread_stream<2, false><<<blocks, SWARPS * 32, 0, b200_stream()>>>(w->psi, w->key, w->a, w->grid, w->n, per);
    B200_LAUNCHED();
    return 0;
 }
@@ -282,10 +327,14 @@ int b200k_gather_stream(const b200_win_dev *w, double *d_f)
    if (w->n <= 0)
       return 0;
    int per, blocks = stream_grid(w->n, &per);
-   if (w->d == 1)
-      k_gather_stream<1><<<blocks, SWARPS * 32, 0, b200_stream()>>>(w->psi, w->key, w->grid, d_f, w->n, per);
+   if (w->xs && w->d == 1)
+      k_gather_stream<1, true><<<blocks, SWARPS * 32, 0, b200_stream()>>>(w->xs, w->key, w->grid, d_f, w->n, per);
+   else if (w->xs)
+      k_gather_stream<2, true><<<blocks, SWARPS * 32, 0, b200_stream()>>>(w->xs, w->key, w->grid, d_f, w->n, per);
+   else if (w->d == 1)
+      k_gather_stream<1, false><<<blocks, SWARPS * 32, 0, b200_stream()>>>(w->psi, w->key, w->grid, d_f, w->n, per);
    else
-      k_gather_stream<2><<<blocks, SWARPS * 32, 0, b200_stream()>>>(w->psi, w->key, w->grid, d_f, w->n, per);
+      k_gather_stream<2, false><<<blocks, SWARPS * 32, 0, b200_stream()>>>(w->psi, w->key, w->grid, d_f, w->n, per);
    B200_LAUNCHED();
    return 0;
 }

@@ -261,6 +261,7 @@ static void window_free_device(b200_window *w)
 {
    b200_win_dev *v = &w->dev;
    b200_free(v->psi);
+   b200_free(v->xs);
    b200_free(v->key);
    b200_free(v->perm);
    b200_free(v->inv);
@@ -497,7 +498,11 @@ static int window_setup_points(b200_window *w, const double *cols, int n_all, in
       }
       if (b200k_psi(v, d_xs) || b200_sync())
          return -1;
-      b200_free(d_xs);
+      /* opt-in: 1-D / 2-D windows evaluate the window in the kernels from the coordinates (nfft12_stream.cu) */
+      if (d < 3 && getenv("NFFT4GP_B200_WINDOW_EVAL") && atoi(getenv("NFFT4GP_B200_WINDOW_EVAL")) > 0)
+         v->xs = d_xs;
+      else
+         b200_free(d_xs);
    }
    free(w->h_perm);
    w->h_perm = perm;
