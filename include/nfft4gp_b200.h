@@ -312,6 +312,7 @@ int Nfft4GPB200DebugPartitionChunks(const int *chunks /* int4 per chunk */, int 
                                     double flush, int *first /* rounds * wcnt + 1 */);
 int Nfft4GPB200HostPotrf(int n, double *A /* lower, column-major, in place */);
 int Nfft4GPB200HostSyev(int n, double *A /* in: symmetric; out: eigenvectors */, double *w /* ascending */, int want_vectors);
+int Nfft4GPB200HostStev(int n, double *d /* diagonal -> eigenvalues */, double *e /* sub-diagonal, destroyed */, double *Z /* n x n */);
 int Nfft4GPB200Dgemm(char transa, char transb, int M, int N, int K, double alpha, const double *A, int lda, const double *B, int ldb,
                      double beta, double *C, int ldc);
 int Nfft4GPB200Fps(const double *data, int n, int ldim, int d, int k, int *perm_out /* k */);

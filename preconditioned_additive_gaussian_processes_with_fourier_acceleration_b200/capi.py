@@ -106,6 +106,7 @@ def lib():
         "Nfft4GPB200PrecondAFNSetK12Storage": (i, [vp, i]),
         "Nfft4GPB200DebugPartitionChunks": (i, [c_int_p, i, i, i, c_double_p, d, c_int_p]),
         "Nfft4GPB200HostPotrf": (i, [i, c_double_p]), "Nfft4GPB200HostSyev": (i, [i, c_double_p, c_double_p, i]),
+        "Nfft4GPB200HostStev": (i, [i, c_double_p, c_double_p, c_double_p]),
         "Nfft4GPB200Dgemm": (i, [C.c_char, C.c_char, i, i, i, d, c_double_p, i, c_double_p, i, d, c_double_p, i]),
         "Nfft4GPB200Fps": (i, [c_double_p, i, i, i, i, c_int_p]),
         "Nfft4GPB200KnnPattern": (i, [c_double_p, i, i, i, i, c_int_p, c_int_p]),

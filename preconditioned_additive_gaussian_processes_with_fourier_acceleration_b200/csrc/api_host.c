@@ -34,6 +34,9 @@ int Nfft4GPB200ProfileStop(double *sums_ms, long long *counts, int ncls) { retur
 int Nfft4GPB200HostPotrf(int n, double *A) { return b200_potrf_lower(n, A, n); }
 int Nfft4GPB200HostSyev(int n, double *A, double *w, int want_vectors) { return want_vectors ? b200_syev(n, A, w) : b200_syev_values(n, A, w); }
 
+/* host-only: symmetric tridiagonal eigen-decomposition used by the stochastic Lanczos quadrature (dense_small.c:b200_stev) */
+int Nfft4GPB200HostStev(int n, double *d, double *e, double *Z) { return b200_stev(n, d, e, Z); }
+
 int Nfft4GPB200Dgemm(char transa, char transb, int M, int N, int K, double alpha, const double *A, int lda, const double *B, int ldb,
                      double beta, double *C, int ldc)
 {

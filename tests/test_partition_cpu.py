@@ -59,3 +59,22 @@ def test_partition_degenerate_inputs():
     assert L.Nfft4GPB200DebugPartitionChunks(pkg.capi.iptr(ch), 0, 3, 2, pkg.capi.dptr(w), 24.0, pkg.capi.iptr(first)) == 0
     assert (first == 0).all()
     assert L.Nfft4GPB200DebugPartitionChunks(None, 1, 3, 2, pkg.capi.dptr(w), 24.0, pkg.capi.iptr(first)) == -1
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 40, 120])
+def test_host_tridiagonal_eigensolver(n):
+    """dense_small.c:b200_stev (the dstev of the stochastic Lanczos quadrature, lanczos.c:539) against NumPy."""
+    L = pkg.lib()
+    rng = np.random.default_rng(n)
+    d = rng.standard_normal(n) + 3.0
+    e = rng.standard_normal(max(n - 1, 1))
+    T = np.diag(d) + np.diag(e[:n - 1], 1) + np.diag(e[:n - 1], -1)
+    w = d.copy()
+    ee = e.copy()
+    Z = np.zeros((n, n))
+    assert L.Nfft4GPB200HostStev(n, pkg.capi.dptr(w), pkg.capi.dptr(ee), pkg.capi.dptr(Z)) == 0
+    Z = Z.T                                               # column-major eigenvectors
+    wr = np.linalg.eigvalsh(T)
+    assert np.abs(w - wr).max() <= 1e-13 * max(1.0, np.abs(wr).max())
+    assert np.abs(Z.T @ Z - np.eye(n)).max() <= 1e-12
+    assert np.abs(T @ Z - Z * w).max() <= 1e-12 * max(1.0, np.abs(wr).max())
