@@ -1,0 +1,54 @@
+"""bench.py contract checks that need no GPU: the reference arm prints exactly ONE JSON line with the agreed keys (C-level
+prints of the reference go to stderr), W >= 3 warm-up steps are enforced, and the product arm refuses to run without a CUDA
+device instead of falling back to anything."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, timeout=600):
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    env.pop("WORLD_SIZE", None)
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, timeout=timeout, cwd=ROOT,
+                          env=env)
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    p = _run(["--impl", "reference", "--n", "20000", "--steps", "2", "--warmup", "1"])
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, p.stdout[:2000]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "nfft_additive_matvecs_per_s" and d["unit"] == "matvecs/s"
+    for key in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["warmup"] >= 3 and d["steps"] == 2                      # W >= 3 is enforced whatever the caller asks for
+    assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1000.0) < 1e-6 * 1000.0
+    assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--n", "20000", "--steps", "1"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_product_arm_fails_loudly_without_a_gpu():
+    import preconditioned_additive_gaussian_processes_with_fourier_acceleration_b200 as pkg
+    if pkg.lib().Nfft4GPB200DeviceCount() > 0:
+        pytest.skip("a CUDA device is present")
+    p = _run(["--n", "20000", "--steps", "1", "--no-pcg", "--no-cpu"], timeout=300)
+    assert p.returncode != 0
+    assert not any(l.strip().startswith("{") for l in p.stdout.splitlines())      # no JSON line from a path that did not run
