@@ -165,3 +165,19 @@ def lanczos(matvec, n, x0, rhs, wsize, maxits, atol, tol, prec=None):
             y[k] = (y[k] - TLE[k] * y[k + 1]) / TLD[k]
         x = x + y @ V[:chol_size]
     return x, normr / normb, hist[:it + 1], it, TD[:it], TE[:max(it - 1, 0)]
+
+
+def slq_logdet(matvec, grad_matvec, n, maxits, probes):
+    """NumPy restatement of Nfft4GPLanczosQuadratureLogdet (SRC/solvers/lanczos.c:421-610) without a preconditioner:
+    logdet(K) / n ~ mean_z e1' log(T_z) e1 and its three derivatives ~ mean_z (dK_j z)' K^{-1} z / n, with K^{-1} z taken from
+    the same Lanczos run.  `grad_matvec(z)` returns the three stacked blocks.  TEST INFRASTRUCTURE (oracle)."""
+    eps = np.finfo(np.float64).eps
+    val, dval = 0.0, np.zeros(3)
+    for z in probes:
+        dAz = grad_matvec(z).reshape(3, n)
+        x, _, _, it, TD, TE = lanczos(matvec, n, np.zeros(n), z, maxits, maxits, 0, eps)
+        T = np.diag(TD) + np.diag(TE, 1) + np.diag(TE, -1)
+        w, Q = np.linalg.eigh(T)
+        val += float(np.sum(Q[0] ** 2 * np.log(np.abs(w))))
+        dval += dAz @ x
+    return val / len(probes), dval / len(probes) / n

@@ -34,3 +34,17 @@ def test_numpy_lanczos_matches_reference_golden():
         lead = min(m, 20)                       # the leading entries of T before rounding differences accumulate
         assert np.abs(TD[:lead] - g[f"{tag}_TD"][:lead]).max() <= 1e-8 * np.abs(g[f"{tag}_TD"][:lead]).max(), tag
         assert np.abs(TE[:lead - 1] - g[f"{tag}_TE"][:lead - 1]).max() <= 1e-8 * np.abs(g[f"{tag}_TD"][:lead]).max(), tag
+
+
+def test_numpy_slq_matches_reference_golden():
+    """log det / n and its gradient by stochastic Lanczos quadrature on the NFFT additive kernel (CPU oracle matvecs) with the
+    probe vectors of the reference run (lanczos.c:421-610)."""
+    from oracle import oracle_api as O
+    g = np.load(os.path.join(GOLD, "lanczos_dense300.npz"))
+    X, win = g["slq_X"], g["slq_windows"]
+    n = X.shape[1]
+    B = O.OracleAdditiveNFFT(X, win, 2, 3, "gaussian").build(float(g["slq_f"]), float(g["slq_l"]), float(g["slq_mu"]))
+    val, dval = S.slq_logdet(B.matvec, B.grad_matvec, n, int(g["slq_maxits"]), g["slq_probes"])
+    assert abs(val - float(g["slq_logdet"])) <= 1e-6 * abs(float(g["slq_logdet"]))
+    assert np.abs(dval - g["slq_dlogdet"]).max() <= 1e-6 * np.abs(g["slq_dlogdet"]).max()
+    B.free()
