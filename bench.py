@@ -157,6 +157,25 @@ def run_reference(args):
     return 0
 
 
+FP64_TENSOR_PEAK_TFLOPS = 37.1   # DMMA.8x8x4 rate measured on this pool's B200 (scripts/fp64_dmma.cu); MEASURED_PEAKS.json holds bf16 only
+
+
+def binding_roofline(roofline, dom, fp64_ach_tflops):
+    """The 3-D spread / gather are bound by the fp64 tensor pipe (62 flop per algorithmic byte): report THAT
+    roof at the top level (bound "tensor", TFLOP/s of algorithmic fp64 flops against the measured DMMA rate) and keep the HBM
+    view of the same launch next to it.  Kernels that are HBM-bound keep the HBM roof.  Pure function (tests/test_bench_contract.py)."""
+    if dom not in ("spread", "gather"):
+        return roofline
+    out = dict(roofline)
+    out["hbm"] = {k: roofline[k] for k in ("achieved", "peak", "unit", "frac", "peak_source") if k in roofline}
+    out.update({"bound": "tensor", "achieved": fp64_ach_tflops, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": fp64_ach_tflops / FP64_TENSOR_PEAK_TFLOPS,
+                "peak_source": "fp64 tensor-core (DMMA.8x8x4) rate measured on this pool's B200 with scripts/fp64_dmma.cu; "
+                               "MEASURED_PEAKS.json has no fp64 figure (its dense bf16 number does not apply to an fp64 kernel)",
+                "note": "algorithmic flops: 2 x 10^3 per point, window and direction (SURVEY.md 8(d)); the HBM view of the same launch is under 'hbm'"})
+    return out
+
+
 def run_pcg_section(pkg, L, A, X, rhs, windows, hp, args, hbm_peak, ranks=None):
     """Second half of BASELINE.json's metric: AFN-preconditioned CG on the NFFT additive matvec to 1e-6 relative residual
     (config C3, n = 10^6, d = 9, Gaussian).  Two landmark ranks: the one BASELINE.json names (500; too small for n = 10^6 at
@@ -401,6 +420,10 @@ def main():
                 "step_share": per_class[dom]["ms_per_step"] / (ms_prof_total / args.steps),
                 "per_class_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in per_class.items()},
                 "profiled_ms_per_step": ms_prof_total / args.steps}
+    try:
+        roofline = binding_roofline(roofline, dom, fp64_ach)
+    except Exception as exc:  # never lose the line over a reporting detail
+        print(f"bench.py: binding_roofline failed: {exc!r}", file=sys.stderr)
 
     # ---- CPU baseline on the host cores (bounded sample) + parity of this very run against it
     cpu = None

@@ -52,3 +52,19 @@ def test_product_arm_fails_loudly_without_a_gpu():
     p = _run(["--n", "20000", "--steps", "1", "--no-pcg", "--no-cpu"], timeout=300)
     assert p.returncode != 0
     assert not any(l.strip().startswith("{") for l in p.stdout.splitlines())      # no JSON line from a path that did not run
+
+
+def test_binding_roofline_reports_the_tensor_roof_for_the_3d_kernels():
+    sys.path.insert(0, ROOT)
+    import bench
+    base = {"bound": "hbm", "kernel": "spread", "achieved": 293.0, "peak": 6536.7, "unit": "GB/s", "frac": 293.0 / 6536.7,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)", "traffic": 7.5e8, "launch_ms": 0.327, "fp64": {"frac": 0.49}}
+    r = bench.binding_roofline(base, "spread", 18.3)
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["peak"] == bench.FP64_TENSOR_PEAK_TFLOPS
+    assert abs(r["frac"] - 18.3 / bench.FP64_TENSOR_PEAK_TFLOPS) < 1e-15 and abs(r["achieved"] - 18.3) < 1e-15
+    assert r["hbm"]["unit"] == "GB/s" and abs(r["hbm"]["frac"] - base["frac"]) < 1e-15 and r["traffic"] == 7.5e8
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in r
+    assert base["bound"] == "hbm"                                    # input untouched
+    same = bench.binding_roofline(dict(base, kernel="combine"), "combine", 0.1)
+    assert same["bound"] == "hbm" and "hbm" not in same
