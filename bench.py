@@ -30,9 +30,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "nfft_additive_matvecs_per_s"
 UNIT = "matvecs/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused three-window kernels at n = 10^6, from the one
-# `ncu --set full` capture of this command (profiles/r1_g_ncu_set_full_fused_spread_gather.csv); per-window launches: a third
-NCU_TRAFFIC_BYTES = {"spread": 752.503e6 + 4.831e6, "gather": 728.311e6 + 25.661e6}  # profiles/r1_k_ncu_set_full_fused_spread_gather.csv
+WORKLOAD = "C2: additive Gaussian NFFT matvec n={n} d=9 three 3-D windows N=32 n_os=64 m=4 (BASELINE.json configs[1])"
 PROF_CLASSES = ["prep", "spread", "fft_fwd", "fft_inv", "gather", "combine", "vec", "nys", "csr", "gemv", "other"]
 
 
@@ -46,6 +44,43 @@ def synthetic_problem(n, d=9, seed=906):
     side = n ** (1.0 / d)
     l = 0.25 * side  # resolved by the 32 Fourier modes: NFFT vs dense ~3e-8 rel. (tests/test_oracle.py)
     return X, x, windows, dict(f=1.0, l=l, mu=0.01)
+
+
+def ncu_traffic(kernel_class, n, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, looked up BY KEY in the committed summary of
+    the `ncu --set full` capture of this very command (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py from the raw-page
+    CSV it names).  None when no capture exists for this kernel / problem size / GPU count."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    try:
+        with open(p) as fh:
+            t = json.load(fh)
+        e = t.get(kernel_class)
+        if not e or int(e.get("n", -1)) != n or int(e.get("n_gpus", 1)) != world:
+            return None, None
+        return float(e["dram_bytes_read"]) + float(e["dram_bytes_write"]), e.get("source")
+    except Exception:
+        return None, None
+
+
+def host_cores():
+    """Host cores this process may use (the affinity mask: a container limit shows here, os.cpu_count() does not see it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def use_all_host_cores():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every worker, which made the N > 1 reference arm single-threaded in
+    round 1.  The CPU legs set their OpenMP team explicitly to the cores of the box and report the number they got."""
+    from oracle import oracle_api
+    want = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(want)
+    L = oracle_api.lib()
+    L.oracle_set_num_threads(want)
+    return int(L.oracle_num_threads())
 
 
 def peaks():
@@ -140,38 +175,44 @@ def run_reference(args):
     if rank != 0:
         return 0
     n = args.n
+    cores = use_all_host_cores()
     X, x, windows, hp = synthetic_problem(n)
     A, kind = cpu_reference_handle(X, windows, hp)
     val, _ = time_cpu(A, x, args.steps, args.warmup)
-    cores = cpu_cores()
+    if cores == 1 and host_cores() > 1:
+        print("bench.py: WARNING the CPU reference ran on 1 thread of a multi-core host", file=sys.stderr)
     sample = f"{args.steps} full additive matvecs at n={n}, d=9 (3x3-D windows) after {args.warmup} warm-up, {cores} OpenMP threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C2: additive Gaussian NFFT matvec n={n} d=9 three 3-D windows N=32 n_os=64 m=4"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": WORKLOAD.format(n=n), "l": hp["l"], "f": hp["f"], "mu": hp["mu"]},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "host_cores": host_cores(), "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
 
 
-FP64_TENSOR_PEAK_TFLOPS = 37.1   # DMMA.8x8x4 rate measured on this pool's B200 (scripts/fp64_dmma.cu); MEASURED_PEAKS.json holds bf16 only
+FP64_TENSOR_PEAK_FALLBACK_TFLOPS = 37.1   # DMMA.8x8x4 rate of this pool's B200 (scripts/fp64_dmma.cu), used only if the in-run measurement fails
 
 
-def binding_roofline(roofline, dom, fp64_ach_tflops):
+def binding_roofline(roofline, dom, fp64_ach_tflops, fp64_peak_tflops=None, peak_measured_in_run=False):
     """The 3-D spread / gather are bound by the fp64 tensor pipe (62 flop per algorithmic byte): report THAT
-    roof at the top level (bound "tensor", TFLOP/s of algorithmic fp64 flops against the measured DMMA rate) and keep the HBM
-    view of the same launch next to it.  Kernels that are HBM-bound keep the HBM roof.  Pure function (tests/test_bench_contract.py)."""
+    roof at the top level (bound "tensor", TFLOP/s of algorithmic fp64 flops against the DMMA rate measured in this run by
+    Nfft4GPB200MeasureFp64TensorPeak) and keep the HBM view of the same launch next to it.  Kernels that are HBM-bound keep the
+    HBM roof.  Pure function (tests/test_bench_contract.py)."""
     if dom not in ("spread", "gather"):
         return roofline
+    peak = fp64_peak_tflops if fp64_peak_tflops and fp64_peak_tflops > 0 else FP64_TENSOR_PEAK_FALLBACK_TFLOPS
     out = dict(roofline)
     out["hbm"] = {k: roofline[k] for k in ("achieved", "peak", "unit", "frac", "peak_source") if k in roofline}
-    out.update({"bound": "tensor", "achieved": fp64_ach_tflops, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": fp64_ach_tflops / FP64_TENSOR_PEAK_TFLOPS,
-                "peak_source": "fp64 tensor-core (DMMA.8x8x4) rate measured on this pool's B200 with scripts/fp64_dmma.cu; "
-                               "MEASURED_PEAKS.json has no fp64 figure (its dense bf16 number does not apply to an fp64 kernel)",
+    out.update({"bound": "tensor", "achieved": fp64_ach_tflops, "peak": peak, "unit": "TFLOP/s",
+                "frac": fp64_ach_tflops / peak,
+                "peak_source": ("fp64 tensor-core (mma.sync.m8n8k4.f64 = DMMA.8x8x4) rate measured IN THIS RUN on this GPU by "
+                                "Nfft4GPB200MeasureFp64TensorPeak (register operands, 16 warps/SM, best of 3)" if peak_measured_in_run else
+                                "fallback: DMMA.8x8x4 rate measured earlier on this pool's B200 with scripts/fp64_dmma.cu") +
+                               "; MEASURED_PEAKS.json has no fp64 figure (its dense bf16 number does not apply to an fp64 kernel)",
                 "note": "algorithmic flops: 2 x 10^3 per point, window and direction (SURVEY.md 8(d)); the HBM view of the same launch is under 'hbm'"})
     return out
 
@@ -225,11 +266,14 @@ def run_pcg_section(pkg, L, A, X, rhs, windows, hp, args, hbm_peak, ranks=None):
         sums = (C.c_double * len(PROF_CLASSES))()
         counts = (C.c_longlong * len(PROF_CLASSES))()
         L.Nfft4GPB200ProfileStop(sums, counts, len(PROF_CLASSES))
-        per_it = {PROF_CLASSES[i]: round(sums[i] / 51.0, 5) for i in range(len(PROF_CLASSES)) if counts[i] > 0}
+        # 50 iterations + the initial residual (one more matvec): matvec classes ran 51 times, everything else belongs to the 50 iterations
+        mv_cls = ("prep", "spread", "fft_fwd", "fft_inv", "gather", "combine")
+        per_it = {PROF_CLASSES[i]: round(sums[i] / (51.0 if PROF_CLASSES[i] in mv_cls else 50.0), 5) for i in range(len(PROF_CLASSES)) if counts[i] > 0}
         n2 = (n - lrank) / world
         gemv_bytes = 2.0 * (k12_bits / 8.0) * lrank * n2   # two passes over this rank's columns of K12 per apply
         csr_bytes = 2.0 * 12.0 * 100.0 * n2          # this rank's rows of G and G' (value + column index) per apply
-        run = {"precond": f"AFN rank {lrank} + FSAI(lfil 100) of the Schur complement" + (", K12 block stored in fp32 (fp64 vectors and sums)" if k12_bits == 32 else "")
+        run = {"landmark_rank": lrank, "baseline_config": bool(lrank == 500 and k12_bits == 64), "iteration_cap": maxits,
+               "precond": f"AFN rank {lrank} + FSAI(lfil 100) of the Schur complement" + (", K12 block stored in fp32 (fp64 vectors and sums)" if k12_bits == 32 else "")
                + (f", apply sharded over {world} GPUs (2 allreduces of k, 2 of n-k doubles)" if world > 1 else ""),
                "k12_storage_bits": k12_bits, "setup_s": setup_s, "solve_s": solve_s,
                "iters": its, "converged": bool(its > 0), "rel_res": rel, "ms_per_iter": 1000.0 * solve_s / max(done, 1),
@@ -241,10 +285,19 @@ def run_pcg_section(pkg, L, A, X, rhs, windows, hp, args, hbm_peak, ranks=None):
             P_keep = P
         else:
             P.free()
-    conv = [r for r in out["runs"] if r["converged"]]
-    best = min(conv, key=lambda r: r["solve_s"]) if conv else None
-    out["value"] = best["solve_s"] if best else None
-    out["value_run"] = best["precond"] if best else None
+    # Headline = fp64 storage only.  BASELINE's own rank (500) first; when it does not converge inside its cap the value is the
+    # fp64 run at the rank that does (off-config, labelled).  The fp32-K12 run is an extra and never the value.
+    base = next((r for r in out["runs"] if r["baseline_config"]), None)
+    fp64_conv = [r for r in out["runs"] if r["converged"] and r["k12_storage_bits"] == 64]
+    pick = base if (base and base["converged"]) else (min(fp64_conv, key=lambda r: r["solve_s"]) if fp64_conv else None)
+    out["value"] = pick["solve_s"] if pick else None
+    out["value_run"] = (pick["precond"] + ("" if pick.get("baseline_config") else " -- OFF-CONFIG rank: BASELINE's rank 500 does not converge (see runs[0])")) if pick else None
+    out["value_storage"] = "fp64"
+    out["baseline_config_converged"] = bool(base and base["converged"])
+    extra = next((r for r in out["runs"] if r["k12_storage_bits"] == 32), None)
+    if extra is not None:
+        out["extra_fp32_k12"] = {"solve_s": extra["solve_s"], "iters": extra["iters"], "converged": extra["converged"],
+                                 "note": "K12 block rounded to fp32 (narrower storage than the reference): reported for information, never the value"}
     D.free()
     A.build(hp["f"], hp["l"], hp["mu"])
     return out
@@ -356,30 +409,44 @@ def main():
     ms_per_step = ms_total / args.steps
     value = 1000.0 / ms_per_step
 
-    # ---- e2e through the reference-facing host-pointer call, pinned host vectors
+    # ---- e2e through the reference-facing host-pointer call.  Headline: PAGEABLE host vectors (plain malloc'd numpy arrays, what
+    # the reference's callers pass); the pinned-memory figure is kept next to it.
+    def time_host_calls(xp, yp):
+        def step_host():
+            assert L.Nfft4GPAdditiveNFFTMatSymv(A.K, n, 1.0, xp, 0.0, yp) == 0
+        for _ in range(3):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        L.Nfft4GPB200DeviceSynchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return args.steps / dt
+
     hx = L.Nfft4GPB200HostAlloc(8 * n)
     hy = L.Nfft4GPB200HostAlloc(8 * n)
     C.memmove(hx, x.ctypes.data, 8 * n)
     hxp = C.cast(hx, C.POINTER(C.c_double))
     hyp = C.cast(hy, C.POINTER(C.c_double))
+    e2e_pinned = time_host_calls(hxp, hyp)
+    x_pg = np.array(x, dtype=np.float64, copy=True)
+    y_pg = np.zeros(n)
+    e2e_val = time_host_calls(x_pg.ctypes.data_as(C.POINTER(C.c_double)), y_pg.ctypes.data_as(C.POINTER(C.c_double)))
+    y_host = y_pg.copy()
+    if dist is not None and mode == 2:
+        # every rank filled its block [lo, hi) of y: assemble the full vector (parity of the N-GPU result against the CPU below)
+        full = torch.zeros(n, device="cuda", dtype=torch.float64)
+        full[lo:hi] = torch.from_numpy(y_host[lo:hi]).cuda()
+        dist.all_reduce(full)
+        y_host = full.cpu().numpy()
 
-    def step_host():
-        assert L.Nfft4GPAdditiveNFFTMatSymv(A.K, n, 1.0, hxp, 0.0, hyp) == 0
-
-    for _ in range(3):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    L.Nfft4GPB200DeviceSynchronize()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_val = args.steps / e2e_s
-    y_host = np.ctypeslib.as_array(hyp, shape=(n,)).copy()
+    # fp64 tensor-core roof of THIS GPU, measured in this process (the binding roof of the 3-D kernels)
+    fp64_tensor_peak = float(L.Nfft4GPB200MeasureFp64TensorPeak())
 
     pcg_multi = None
     if world > 1 and mode == 2 and not args.no_pcg:
@@ -409,32 +476,38 @@ def main():
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp64_peak = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
     fp64_ach = 2000.0 * n_loc * win_per_launch / (dom_launch_ms * 1e-3) / 1e12
+    traffic, traffic_src = ncu_traffic(dom, n, world)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({pk_kind})",
-                "traffic": (NCU_TRAFFIC_BYTES.get(dom) * win_per_launch / 3.0) if (dom in NCU_TRAFFIC_BYTES and n == 1000000 and world == 1) else None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "launch_ms": dom_launch_ms, "algorithmic_bytes_per_launch": alg_bytes, "windows_per_launch": win_per_launch,
                 "note": "3-D windows are fp64-pipe-bound (62 flop/B, SURVEY.md finding 4): see fp64",
                 "fp64": {"achieved_tflops": fp64_ach, "peak_tflops": fp64_peak, "frac": fp64_ach / fp64_peak,
                          "peak_source": f"148 SM x 64 DFMA/clk x {sm_mhz:.0f} MHz (median SM clock under load)",
-                         "measured_unit_peaks_tflops": {"dmma_m8n8k4": 37.1, "dfma": 33.0, "source": "scripts/fp64_dmma.cu on this pool's B200: one shared unit, no overlap"}},
+                         "dmma_m8n8k4_measured_in_run_tflops": fp64_tensor_peak,
+                         "earlier_unit_peaks_tflops": {"dmma_m8n8k4": 37.1, "dfma": 33.0, "source": "scripts/fp64_dmma.cu on this pool's B200: one shared unit, no overlap"}},
                 "step_share": per_class[dom]["ms_per_step"] / (ms_prof_total / args.steps),
                 "per_class_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in per_class.items()},
                 "profiled_ms_per_step": ms_prof_total / args.steps}
     try:
-        roofline = binding_roofline(roofline, dom, fp64_ach)
+        roofline = binding_roofline(roofline, dom, fp64_ach, fp64_tensor_peak, fp64_tensor_peak > 0)
     except Exception as exc:  # never lose the line over a reporting detail
         print(f"bench.py: binding_roofline failed: {exc!r}", file=sys.stderr)
 
-    # ---- CPU baseline on the host cores (bounded sample) + parity of this very run against it
+    # ---- CPU baseline on the host cores (bounded sample, rank 0 at N = 1) + parity of THIS run's result against the CPU (every N)
     cpu = None
-    if world == 1 and not args.no_cpu:
+    parity = None
+    if not args.no_cpu:
+        cores = use_all_host_cores()
         Aref, kind = cpu_reference_handle(X, windows, hp)
-        cval, y_cpu = time_cpu(Aref, x, args.cpu_steps, 1)
-        cores = cpu_cores()
+        cval, y_cpu = time_cpu(Aref, x, args.cpu_steps if world == 1 else 1, 1)
         rel = float(np.linalg.norm(y_host - y_cpu) / np.linalg.norm(y_cpu))
-        cpu = {"value": cval, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": f"{args.cpu_steps} full additive matvecs at n={n} (same workload) after 1 warm-up, {cores} OpenMP threads",
-               "rel_l2_gpu_vs_cpu": rel}
+        parity = {"rel_l2_gpu_vs_cpu": rel, "n_gpus": world, "against": kind, "tolerance": 1e-10,
+                  "what": "y of the timed e2e call (all ranks' blocks assembled) vs one CPU matvec on the same inputs"}
+        if world == 1:
+            cpu = {"value": cval, "unit": UNIT, "cores": cores, "host_cores": host_cores(), "kind": kind,
+                   "sample": f"{args.cpu_steps} full additive matvecs at n={n} (same workload) after 1 warm-up, {cores} OpenMP threads",
+                   "rel_l2_gpu_vs_cpu": rel}
 
     pcg = None
     if world == 1 and not args.no_pcg:
@@ -448,15 +521,17 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"C2: additive Gaussian NFFT matvec n={n} d=9 three 3-D windows N=32 n_os=64 m=4 (BASELINE.json configs[1])",
+        "config": {"workload": WORKLOAD.format(n=n),
                    "parallelism": parallelism, "l": hp["l"], "f": hp["f"], "mu": hp["mu"],
                    "l2_policy": "inputs larger than L2: window tables streamed per step = 2 x 3 x 240 MB >> 126 MB"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 8 * nl * world, "d2h_bytes_per_step": 8 * nl * world,
-                "api": "Nfft4GPAdditiveNFFTMatSymv(host x, host y), pinned host memory"},
+                "api": "Nfft4GPAdditiveNFFTMatSymv(host x, host y), PAGEABLE host memory (malloc'd arrays, as the reference's callers pass)",
+                "pinned_value": e2e_pinned},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity": parity,
         "pcg": pcg if pcg is not None else pcg_multi,
     }
     print(json.dumps(line))

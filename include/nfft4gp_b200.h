@@ -303,6 +303,13 @@ int Nfft4GPB200PrecondAFNGetFactors(void *afn, int *n, int *k, int *k_est, int *
 /* AFN rank estimation (afn_setup.m:111-293): m sampled points (default 500), numests repetitions (default 5; 0 = skip the
  * estimation and use the maximum rank), noran != 0 = never switch to the Nystrom form, seed of the sub-sampling generator */
 int Nfft4GPB200PrecondAFNSetRankEstimation(void *afn, int m, int numests, int noran, unsigned long long seed);
+/* first stage of the rank estimation: 0 (default) = MATLAB afn_setup.m:163-228 (bisection on the 2-norm Nystrom error),
+ * 1 = the reference's compiled Nfft4GPRankestNysScaled (SRC/linearalg/rankest.c:354-391: 50-point scan, Frobenius norm) */
+int Nfft4GPB200PrecondAFNSetRankMethod(void *afn, int method);
+/* One sample of Nfft4GPRankestNysScaledEstimateRank (rankest.c:248-352) on given sample rows (the reference draws them with
+ * rand()); fkernel must be one of this library's dense kernels.  Returns the rank scaled to n, or -1. */
+int Nfft4GPB200RankestNysScaledSample(NFFT4GP_DOUBLE *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params,
+                                      const int *rows, int m, int max_rank);
 /* Storage of the AFN K12 block (k x (n-k), read twice by every apply and the dominant HBM traffic of a PCG iteration at
  * large rank): bits = 64 (default) or 32.  With 32 the block is kept in fp32 (k a multiple of 4), vectors and sums stay fp64
  * and the apply stays symmetric; the preconditioner changes by O(1e-7) relative, the solution PCG converges to does not. */
@@ -320,11 +327,17 @@ int Nfft4GPB200KnnPattern(const double *data, int n, int ldim, int d, int lfil, 
 
 /* Multi-GPU (one process per GPU).  The NCCL communicator is created from a unique id that the caller
  * broadcasts (128 bytes).  mode 0: replicate; 1: shard by feature window, allreduce(sum) of y per matvec;
- * 2: shard by point block, allreduce(sum) of the oversampled grids per matvec (y complete on every rank). */
+ * 2: shard by point block, allreduce(sum) of the oversampled grids per matvec; x and y stay sharded: the device entry points
+ *    take the rank's block, and the host-pointer calls read / fill the entries [n r / R, n (r + 1) / R) of the full-length
+ *    host vectors on rank r (the caller assembles y across ranks if it needs all of it on one rank). */
 int Nfft4GPB200CommGetUniqueId(void *id128);
 int Nfft4GPB200CommInit(int rank, int nranks, const void *id128);
 int Nfft4GPB200CommFinalize(void);
 int Nfft4GPB200SetSharding(void *additive_handle, int mode);
+
+/* fp64 tensor-core (mma.sync.m8n8k4.f64 = DMMA.8x8x4) throughput of the current GPU measured now, in TFLOP/s (a 2 ms kernel with
+ * register operands): the roof bench.py reports the 3-D spread / gather kernels against.  Negative on error. */
+double Nfft4GPB200MeasureFp64TensorPeak(void);
 
 /* Debug taps for the stage-by-stage parity tests (host output buffers). */
 int Nfft4GPB200DebugWindowInfo(void *additive_handle, int w, int *dim, double *scale, int *nseg);

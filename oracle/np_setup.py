@@ -2,9 +2,13 @@
 
 Rows N2 / G2 / A2 / K1 of SURVEY.md section 8(a).  Each function cites the reference lines it follows.  Pinned against the
 reference's own compiled code where the reference has one (tests/golden/nys_gauss300.npz, fsai_gauss300.npz,
-solver_dense300.npz were produced by oracle/_ref = the unmodified reference sources); the AFN setup has no compiled
-reference (SRC/preconds/afn.c is not built, SURVEY.md finding 2) and follows MATLAB afn_setup.m -- PARITY UNPINNED for
-that row, arbitrated by the pieces that are pinned (Cholesky block, FSAI rows, Nystrom) and by the solve it produces.
+solver_dense300.npz were produced by oracle/_ref = the unmodified reference sources).  SRC/preconds/afn.c itself is not
+built (SURVEY.md finding 2), but every part it calls is: afn_setup / afn_apply / fps / expand_perm are pinned on the chain
+Nfft4GPSortFps -> Nfft4GPExpandPerm -> Nfft4GPPrecondCholSetupWithKernel -> Nfft4GPKernelSchurCombineKernel ->
+Nfft4GPPrecondFsaiSetupWithKernel run by scripts/make_golden.py:afn_case (tests/golden/afn_ref_parts400.npz: landmarks and
+permutation identical, Cholesky factor 3e-15, FSAI pattern identical and values 5e-13, apply 1e-12), and
+rank_estimate_nys_scaled on the compiled Nfft4GPRankestNysScaled with its rand() sample rows replayed (identical ranks).
+rank_estimate (MATLAB afn_setup.m:111-293, a bisection in the 2-norm) has no compiled counterpart.
 Only tests/ may import this module.
 """
 import numpy as np
@@ -192,6 +196,39 @@ def rank_estimate(X, f, l, mu, max_k, m=500, numests=5, seed=906, kernel="gaussi
         sv = np.linalg.eigvalsh(K)
         r = max(r, int((sv > thr).sum()))
     return int(np.floor(r * mk / m))
+
+
+def rank_estimate_nys_scaled(X, rows, f, l, max_rank, kernel="gaussian", windows=None):
+    """One sample of Nfft4GPRankestNysScaledEstimateRank (rankest.c:248-352) on the given sample rows (the reference draws them
+    with rand()): scale the sample to the density of the full set, order it by farthest point sampling, K without noise plus
+    the shift nu = sqrt(n) ulp(||K||_F), then scan k = 0, ngap, 2 ngap, ... (ngap = n1 / 50) for the first scaled Nystrom error
+    ||K1' K11^{-1} K1 - (K + nu I)||_F / ||K + nu I||_F < 0.1 (K11 unshifted, rankest.c:196-246), stopping early once
+    (i - 1) ngap n / n1 > 2 max_rank; the result is scaled back by n / n1."""
+    d, n = X.shape
+    n1 = len(rows)
+    small = X[:, rows] * (n1 / n) ** (1.0 / d)
+    p = fps(small, n1)
+    K = dense_kernel(small, p, p, f, l, kernel, windows)
+    fro = np.linalg.norm(K, "fro")
+    nu = np.sqrt(n) * (np.nextafter(fro, fro + 1.0) - fro)
+    Ks = K + nu * np.eye(n1)
+    fro = np.linalg.norm(Ks, "fro")
+    ngap = max(n1 // 50, 1)
+    rank = n1
+    for i in range(50):
+        if i * ngap >= n1 or int(np.floor(((i - 1) * ngap) * n / n1)) > 2 * max_rank:
+            rank = (i - 1) * ngap
+            break
+        kk = i * ngap
+        if kk == 0:
+            err = 1.0
+        else:
+            B = np.linalg.solve(np.linalg.cholesky(K[:kk, :kk]), K[:kk, :])
+            err = np.linalg.norm(B.T @ B - Ks, "fro") / fro
+        if err < 0.1:
+            rank = kk
+            break
+    return int(np.floor(rank * n / n1))
 
 
 def afn_setup(X, k, lfil, f, l, mu, kernel="gaussian", windows=None):

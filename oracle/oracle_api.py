@@ -64,6 +64,8 @@ def lib():
         L.oracle_dense_symv.restype = C.c_int
         L.oracle_dense_symv.argtypes = [c_double_p, C.c_int, C.c_double, c_double_p, C.c_double, c_double_p]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.restype = None
+        L.oracle_set_num_threads.argtypes = [C.c_int]
         L.shim_kb_phi.restype = C.c_double
         L.shim_kb_phi.argtypes = [C.c_double, C.c_int, C.c_int]
         L.shim_kb_phi_hut.restype = C.c_double

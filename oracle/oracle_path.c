@@ -26,6 +26,18 @@ int oracle_num_threads(void)
 #endif
 }
 
+/* torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU baseline sets its thread count explicitly.  libgomp is one
+ * runtime per process, so this also governs oracle/_ref (the reference's own sources) loaded next to this library. */
+void oracle_set_num_threads(int nthreads)
+{
+#ifdef _OPENMP
+   if (nthreads > 0)
+      omp_set_num_threads(nthreads);
+#else
+   (void)nthreads;
+#endif
+}
+
 /* ------------------------------------------------------------------ */
 /* vector ops (SRC/linearalg/vecops.c:3-155)                            */
 /* ------------------------------------------------------------------ */

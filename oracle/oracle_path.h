@@ -59,6 +59,7 @@ int oracle_dense_additive(const double *data, int n, int ldim, int d, const int 
 int oracle_dense_symv(const double *K, int n, double alpha, const double *x, double beta, double *y);
 
 int oracle_num_threads(void);
+void oracle_set_num_threads(int nthreads);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,7 @@ from .capi import (  # noqa: F401
     solver_fgmres,
     solver_lanczos,
     solver_pcg,
+    rankest_nys_scaled_sample,
 )
 
-__all__ = ["LIB_PATH", "AdditiveNFFTKernel", "DenseAdditiveKernel", "DensePlainKernel", "NysPrecond", "FsaiPrecond", "AfnPrecond", "CholPrecond", "build_library", "lib", "solver_pcg", "solver_fgmres", "gp_predict", "solver_lanczos", "lanczos_quadrature_logdet"]
+__all__ = ["LIB_PATH", "AdditiveNFFTKernel", "DenseAdditiveKernel", "DensePlainKernel", "NysPrecond", "FsaiPrecond", "AfnPrecond", "CholPrecond", "build_library", "lib", "solver_pcg", "rankest_nys_scaled_sample", "solver_fgmres", "gp_predict", "solver_lanczos", "lanczos_quadrature_logdet"]

@@ -104,6 +104,8 @@ def lib():
                                                 c_int_p, c_int_p, c_double_p]),
         "Nfft4GPB200PrecondAFNSetRankEstimation": (i, [vp, i, i, i, C.c_ulonglong]),
         "Nfft4GPB200PrecondAFNSetK12Storage": (i, [vp, i]),
+        "Nfft4GPB200PrecondAFNSetRankMethod": (i, [vp, i]),
+        "Nfft4GPB200RankestNysScaledSample": (i, [c_double_p, i, i, i, vp, vp, c_int_p, i, i]),
         "Nfft4GPB200DebugPartitionChunks": (i, [c_int_p, i, i, i, c_double_p, d, c_int_p]),
         "Nfft4GPB200HostPotrf": (i, [i, c_double_p]), "Nfft4GPB200HostSyev": (i, [i, c_double_p, c_double_p, i]),
         "Nfft4GPB200HostStev": (i, [i, c_double_p, c_double_p, c_double_p]),
@@ -134,6 +136,7 @@ def lib():
         "Nfft4GPB200DebugCoeff": (i, [vp, i, i, c_double_p]),
         "Nfft4GPB200DebugGridAfterFFT": (i, [vp, i, d, c_double_p, c_double_p]),
         "Nfft4GPB200SetVariant": (i, [C.c_char_p, i]),
+        "Nfft4GPB200MeasureFp64TensorPeak": (d, []),
         "Nfft4GPB200ProfileStart": (None, []),
         "Nfft4GPB200ProfileStop": (i, [c_double_p, C.POINTER(C.c_longlong), i]),
     }
@@ -508,9 +511,11 @@ class AfnPrecond:
             raise RuntimeError("Nfft4GPB200PrecondAFNSetK12Storage failed")
         return self
 
-    def setup(self, kernel, max_k, lfil, est_m=500, numests=5, noran=0, seed=906):
-        """Nfft4GPPrecondAFNSetRank / SetLfil / SetupWithKernel (afn.h:65-132; MATLAB afn_setup.m:30-109)."""
+    def setup(self, kernel, max_k, lfil, est_m=500, numests=5, noran=0, seed=906, rank_method=0):
+        """Nfft4GPPrecondAFNSetRank / SetLfil / SetupWithKernel (afn.h:65-132; MATLAB afn_setup.m:30-109).
+        rank_method 1 = first stage of the rank estimation as the reference's compiled Nfft4GPRankestNysScaled."""
         L = lib()
+        assert L.Nfft4GPB200PrecondAFNSetRankMethod(self.h, rank_method) == 0
         L.Nfft4GPPrecondAFNSetRank(self.h, max_k)
         L.Nfft4GPPrecondAFNSetLfil(self.h, lfil)
         assert L.Nfft4GPB200PrecondAFNSetRankEstimation(self.h, est_m, numests, noran, seed) == 0
@@ -570,6 +575,14 @@ class AfnPrecond:
         if self.h:
             lib().Nfft4GPPrecondAFNFree(self.h)
             self.h = None
+
+
+def rankest_nys_scaled_sample(kernel, rows, max_rank):
+    """Nfft4GPB200RankestNysScaledSample: one sample of the reference's Nfft4GPRankestNysScaledEstimateRank (rankest.c:248-352)
+    on the given sample rows, for one of this library's dense kernel handles (DensePlainKernel / DenseAdditiveKernel)."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    return int(lib().Nfft4GPB200RankestNysScaledSample(dptr(kernel.X), kernel.n, kernel.n, kernel.d, kernel.fn(), kernel.h, iptr(rows),
+                                                       rows.size, max_rank))
 
 
 def solver_pcg(mat, n, matvec_fn, prec, solve_fn, x0, rhs, maxits, atol, tol, print_level=0):

@@ -30,6 +30,9 @@ float Nfft4GPB200EventElapsedMs(void *start, void *stop) { return b200_event_ela
 void Nfft4GPB200ProfileStart(void) { b200_prof_start(); }
 int Nfft4GPB200ProfileStop(double *sums_ms, long long *counts, int ncls) { return b200_prof_stop(sums_ms, counts, ncls); }
 
+/* fp64 tensor-core (DMMA.8x8x4) throughput of this GPU measured now, TFLOP/s: the roof of the 3-D spread / gather kernels */
+double Nfft4GPB200MeasureFp64TensorPeak(void) { return b200_init(-1) ? -1.0 : b200_fp64_tensor_peak_tflops(); }
+
 /* ------------------------------------------------------------------ setup building blocks for the parity tests */
 int Nfft4GPB200HostPotrf(int n, double *A) { return b200_potrf_lower(n, A, n); }
 int Nfft4GPB200HostSyev(int n, double *A, double *w, int want_vectors) { return want_vectors ? b200_syev(n, A, w) : b200_syev_values(n, A, w); }

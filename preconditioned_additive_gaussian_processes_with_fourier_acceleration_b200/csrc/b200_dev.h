@@ -76,6 +76,7 @@ void b200_graph_destroy(void *exec);
 void b200_outer_capture_set(int on);
 int b200_outer_capturing(void);
 int b200_d2h_async(void *dst, const void *src, size_t bytes);
+double b200_fp64_tensor_peak_tflops(void);
 void b200_prof_start(void);
 int b200_prof_stop(double *sums_ms, long long *counts, int ncls);
 

@@ -60,6 +60,7 @@ typedef struct
    int max_k, lfil;
    int est_m, est_num, noran; /* rank estimation: sample size (500), repetitions (5; 0 = use max_k), never switch to Nystrom */
    unsigned long long est_seed;
+   int est_method;            /* first stage of the rank estimation: 0 = MATLAB afn_setup.m:163-228, 1 = reference C rankest.c:354-391 */
    int k_est;                 /* last estimated rank (before the cap), -1 when the estimation was skipped */
    int n, k;
    int *d_perm;

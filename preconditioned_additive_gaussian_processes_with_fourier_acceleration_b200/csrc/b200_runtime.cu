@@ -309,4 +309,70 @@ void b200_launch_count_reset(void) { g_launches.store(0); }
 void b200_launch_count_add(long long k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
 void *b200_stream_handle(void) { return (void *)g_stream; }
 
+
+/* In-run measurement of the roof the 3-D spread / gather kernels are bound by: mma.sync.m8n8k4.f64 (DMMA.8x8x4) throughput of
+ * this GPU at its clocks of the moment -- 16 independent accumulator chains per warp, 16 warps per SM, operands in registers,
+ * no memory traffic (scripts/fp64_dmma.cu as a library entry, so that bench.py reports the fraction against a number measured
+ * in the same process instead of a constant).  Returns TFLOP/s (2 flop per FMA) or a negative value on error. */
+double b200_fp64_tensor_peak_tflops(void);
+} // extern "C"
+
+__global__ void __launch_bounds__(256) k_fp64_tensor_peak(double *out, int iters, double a, double b)
+{
+   double m[16][2];
+#pragma unroll
+   for (int i = 0; i < 16; i++)
+   {
+      m[i][0] = i + threadIdx.x;
+      m[i][1] = -i;
+   }
+   for (int it = 0; it < iters; it++)
+   {
+#pragma unroll
+      for (int i = 0; i < 16; i++)
+         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(m[i][0]), "+d"(m[i][1]) : "d"(a), "d"(b));
+   }
+   double s = 0.0;
+#pragma unroll
+   for (int i = 0; i < 16; i++)
+      s += m[i][0] + m[i][1];
+   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" {
+double b200_fp64_tensor_peak_tflops(void)
+{
+   int sm = 148, dev = 0;
+   const int iters = 4000, warps_per_sm = 16;
+   double *out = nullptr, best = -1.0;
+   cudaEvent_t e0, e1;
+   if (cudaGetDevice(&dev) != cudaSuccess)
+      return -1.0;
+   cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+   const int blocks = sm * warps_per_sm / 8;
+   if (cudaMalloc(&out, sizeof(double) * (size_t)blocks * 256) != cudaSuccess)
+      return -1.0;
+   cudaEventCreate(&e0);
+   cudaEventCreate(&e1);
+   k_fp64_tensor_peak<<<blocks, 256, 0, b200_stream()>>>(out, 200, 1.0000001, 1e-9); /* warm-up */
+   for (int rep = 0; rep < 3; rep++)
+   {
+      float ms = 0.f;
+      cudaEventRecord(e0, b200_stream());
+      k_fp64_tensor_peak<<<blocks, 256, 0, b200_stream()>>>(out, iters, 1.0000001, 1e-9);
+      cudaEventRecord(e1, b200_stream());
+      if (cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess || ms <= 0.f)
+      {
+         best = -1.0;
+         break;
+      }
+      const double tf = (double)blocks * 8.0 * 16.0 * iters * 512.0 / ((double)ms * 1e9); /* 8 x 8 x 4 x 2 flop per warp-level mma */
+      if (tf > best)
+         best = tf;
+   }
+   cudaEventDestroy(e0);
+   cudaEventDestroy(e1);
+   cudaFree(out);
+   return best;
+}
 } // extern "C"

@@ -645,6 +645,8 @@ int Nfft4GPNFFTKernelParamRemovePoints(void *kernel)
    b200_single *s = k ? (b200_single *)k->_external : NULL;
    if (!s || s->magic != B200_MAGIC_SINGLE)
       return -1;
+   /* the staging of the host-pointer API caches the window's device pointers (f, inv) and is sized for the old n */
+   single_free_device(s);
    window_free_device(s->win);
    free(s->win->h_perm);
    free(s->win->h_chunks);
@@ -777,6 +779,11 @@ static int single_host_call(void *data, int n, double alpha, double *x, double b
       return -1;
    }
    s = (b200_single *)w->owner;
+   if (!w->built || n != w->n) /* before the staging is sized with it */
+   {
+      printf("Error: NFFT matvec on a kernel that was not built for n = %d.\n", n);
+      return -1;
+   }
    if (!s || single_ensure_staging(s, n))
       return -1;
    if (b200_h2d(s->d_x, x, sizeof(double) * (size_t)n))

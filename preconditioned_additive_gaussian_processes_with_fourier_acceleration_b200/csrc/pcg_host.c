@@ -51,7 +51,9 @@ int b200_pcg_device(void *mat, int n, b200_dev_matvec mv, void *prec, b200_dev_s
                     int maxits, int atol, double tol, double *prel_res, double **prel_res_v, int *piter, int print_level)
 {
    int iter = 0, ii, rc = -1;
-   int use_graphs = !g_pcg_sharded && !b200_prof_active() && !getenv("NFFT4GP_B200_NO_GRAPH") && b200_dev_fn_is_native((void *)mv) &&
+   /* no iteration graph whenever a collective can sit inside mv / ps (window sharding allreduces y inside the matvec; a captured
+    * NCCL kernel next to the caller's own communicator deadlocked in a 2-GPU run, see nfft_host.c) */
+   int use_graphs = !g_pcg_sharded && b200_comm_size() == 1 && !b200_prof_active() && !getenv("NFFT4GP_B200_NO_GRAPH") && b200_dev_fn_is_native((void *)mv) &&
                     (!prec || b200_dev_fn_is_native((void *)ps));
    void *it_graph[2] = {NULL, NULL};
    long long it_launches[2] = {0, 0};
@@ -305,6 +307,10 @@ int Nfft4GPSolverPcg(void *mat_data, int n, func_symmatvec matvec, void *prec_da
          if (fmv.mv || fps.ps)
          {
             printf("Error: point-block-sharded PCG needs this library's own matvec and preconditioner.\n");
+            b200_host_free(fmv.hx);
+            b200_host_free(fmv.hy);
+            b200_host_free(fps.hx);
+            b200_host_free(fps.hy);
             return -1;
          }
          lo = A->blk_lo;

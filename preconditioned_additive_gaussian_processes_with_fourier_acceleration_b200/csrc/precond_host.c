@@ -442,6 +442,15 @@ int Nfft4GPB200PrecondAFNSetRankEstimation(void *str, int m, int numests, int no
    return 0;
 }
 
+int Nfft4GPB200PrecondAFNSetRankMethod(void *str, int method)
+{
+   b200_afn *s = (b200_afn *)str;
+   if (!s || s->magic != B200_MAGIC_AFN || method < 0 || method > 1)
+      return -1;
+   s->est_method = method;
+   return 0;
+}
+
 /* Storage of the K12 block (k x (n - k)): every apply reads it twice and nothing else of comparable size, so fp32 storage
  * halves the HBM traffic of a PCG iteration at large rank.  Products and vectors stay fp64; the preconditioner stays
  * symmetric (the same rounded block is used in both products).  Takes effect at the next setup / SetFactors, or

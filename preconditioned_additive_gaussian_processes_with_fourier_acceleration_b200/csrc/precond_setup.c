@@ -483,6 +483,130 @@ static int nystrom_error_rank(int m, double *K, double nrm, double tol, double *
    return m;
 }
 
+/* One sample of Nfft4GPRankestNysScaledEstimateRank (rankest.c:248-352) on the sample rows `rows` (the reference draws them
+ * with rand(), rankest.c:278): the sample is scaled to the density of the full set (:284), ordered by farthest point sampling
+ * (:287-294, here on the GPU), K without noise (:297-298, kernel block on the GPU) gets the shift nu = sqrt(n) ulp(||K||_F)
+ * (:301-318), and k = 0, ngap, 2 ngap, ... (ngap = m / 50) is scanned for the first scaled Nystrom error
+ * || K1' K11^{-1} K1 - (K + nu I) ||_F / || K + nu I ||_F < 0.1 (:330-345, error :196-246 with the unshifted K11), stopping early
+ * once (i - 1) ngap n / m > 2 max_rank.  The reference forms the error with potrf + trtrs + gemm per candidate; here ONE
+ * right-looking elimination sweep visits the candidates in order: after k columns the trailing block is the Schur complement
+ * S_k = K22 - K21 K11^{-1} K12, and the error matrix is -nu I (leading block) and -(S_k + nu I) (trailing block).
+ * Returns the rank scaled back by n / m (:347), or -1 on error. */
+#define RANKEST_NPOINTS 50 /* rankest.c:244-246 */
+static int nys_scaled_sample(const b200_dense_view *v, const double *h_Xw, size_t h_ld, const double *data, int n, int ldim, int d,
+                             const int *rows, int m, int max_rank)
+{
+   rank_sample rs = {NULL, NULL, 0};
+   b200_dense_view sv = *v;
+   int *d_permf = (int *)b200_malloc(sizeof(int) * (size_t)m), i, j, c, done = 0, rank = m, ngap, rc = -1;
+   double *d_K = (double *)b200_malloc(sizeof(double) * (size_t)m * m), *d_c = NULL;
+   double *K = (double *)b200_xmalloc(sizeof(double) * (size_t)m * m), fro = 0.0, nu, scale = pow((double)m / n, 1.0 / d);
+   if (!d_permf || !d_K || rank_sample_upload(v, h_Xw, h_ld, data, ldim, d, rows, m, scale, &rs) ||
+       centroid_to_device(data, m, ldim, d, rows, scale, &d_c) || b200k_fps(rs.d_X, m, m, d, d_c, m, d_permf))
+      goto out;
+   sv.d_Xw = rs.d_Xw;
+   sv.n = m;
+   if (b200_dense_view_block(&sv, 0.0, d_permf, m, d_permf, m, 0, d_K, m) || b200_d2h(K, d_K, sizeof(double) * (size_t)m * m))
+      goto out;
+   for (j = 0; j < m; j++)
+      for (i = 0; i < m; i++)
+         fro += K[(size_t)j * m + i] * K[(size_t)j * m + i];
+   fro = sqrt(fro);
+   nu = sqrt((double)n) * (nextafter(fro, fro + 1.0) - fro);
+   {
+      double t = 0.0; /* || K + nu I ||_F */
+      for (j = 0; j < m; j++)
+         for (i = 0; i < m; i++)
+         {
+            double e = K[(size_t)j * m + i] + (i == j ? nu : 0.0);
+            t += e * e;
+         }
+      fro = sqrt(t);
+   }
+   ngap = m / RANKEST_NPOINTS > 1 ? m / RANKEST_NPOINTS : 1;
+   for (i = 0; i < RANKEST_NPOINTS; i++)
+   {
+      int k = i * ngap;
+      double err2;
+      if (k >= m || (int)floor((double)((i - 1) * ngap) * (double)n / m) > 2 * max_rank)
+      {
+         rank = (i - 1) * ngap;
+         break;
+      }
+      /* eliminate the columns [done, k) of the lower triangle */
+      for (c = done; c < k; c++)
+      {
+         double piv = K[(size_t)c * m + c];
+         int a, b;
+         if (!(piv > 0.0))
+            break; /* numerically rank deficient: the error sits at the rounding level from here on */
+         for (b = c + 1; b < m; b++)
+         {
+            double fct = K[(size_t)c * m + b] / piv;
+            double *cb = K + (size_t)b * m;
+            const double *cc = K + (size_t)c * m;
+            for (a = b; a < m; a++)
+               cb[a] -= cc[a] * fct;
+         }
+      }
+      if (c < k)
+      {
+         rank = k;
+         break;
+      }
+      done = k;
+      if (k == 0)
+         err2 = 1.0; /* rankest.c:202-205 */
+      else
+      {
+         err2 = (double)k * nu * nu;
+         for (j = k; j < m; j++)
+         {
+            double dj = K[(size_t)j * m + j] + nu;
+            err2 += dj * dj;
+            for (c = j + 1; c < m; c++)
+               err2 += 2.0 * K[(size_t)j * m + c] * K[(size_t)j * m + c];
+         }
+         err2 = sqrt(err2) / fro;
+      }
+      if (err2 < 0.1)
+      {
+         rank = k;
+         break;
+      }
+   }
+   rc = (int)floor((double)rank * (double)n / m);
+out:
+   rank_sample_free(&rs);
+   b200_free(d_c);
+   b200_free(d_permf);
+   b200_free(d_K);
+   free(K);
+   return rc;
+}
+
+/* Nfft4GPRankestNysScaled (rankest.c:354-391) for ONE given sample: exported so that the estimate can be compared with the
+ * reference's compiled function on the very rows its rand() stream drew (tests/test_gpu_setup.py). */
+int Nfft4GPB200RankestNysScaledSample(double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params, const int *rows, int m,
+                                      int max_rank)
+{
+   b200_dense_view v;
+   size_t h_ld;
+   const double *h_Xw;
+   int rc;
+   if (!fkernel || !fkernel_params || !rows || m < 1 || m > n || d > 64 || b200_init(-1))
+      return -1;
+   if (b200_dense_view_acquire(fkernel, fkernel_params, data, n, ldim, d, &v))
+   {
+      printf("Error: the rank estimation needs one of this library's dense kernels.\n");
+      return -1;
+   }
+   h_Xw = view_host_features(fkernel, fkernel_params, data, n, ldim, &h_ld);
+   rc = nys_scaled_sample(&v, h_Xw, h_ld, data, n, ldim, d, rows, m, max_rank);
+   b200_dense_view_release(&v);
+   return rc;
+}
+
 /* afn_setup.m:111-293.  Returns the estimated rank (>= 0) or -1 on error. */
 static int afn_rank_estimate(b200_afn *s, const b200_dense_view *v, func_kernel fkernel, void *fkernel_params, const double *data, int n,
                              int ldim, int d, int max_k)
@@ -499,6 +623,33 @@ static int afn_rank_estimate(b200_afn *s, const b200_dense_view *v, func_kernel 
    rank_sample rs = {NULL, NULL, 0};
    if (!d_permf || !d_K)
       goto done;
+   if (s->est_method == 1)
+   {
+      /* first stage as the reference's compiled Nfft4GPRankestNysScaled (rankest.c:354-391): mean over the samples, and "0" when
+       * the estimate sits at the lower bound of the scan; the sub-samples come from this library's counter-based generator */
+      long long total = 0;
+      int ngap = m / RANKEST_NPOINTS > 1 ? m / RANKEST_NPOINTS : 1;
+      for (e = 0; e < numests; e++)
+      {
+         for (i = 0; i < n; i++)
+            pool[i] = i;
+         sample_without_replacement(pool, n, m, &st);
+         i = nys_scaled_sample(v, h_Xw, h_ld, data, n, ldim, d, pool, m, max_k);
+         if (i < 0)
+            goto done;
+         total += i;
+      }
+      k_scaled = (int)floor((double)total / numests);
+      if (k_scaled <= (int)floor((double)ngap * n / m))
+         k_scaled = 0;
+      printf("Estimate rank(scaled): %d/%d\n", k_scaled, n); /* rankest.c:386 */
+      if (k_scaled >= max_k) /* afn.c:193: "not low-rank, skip nonscaled rank estimation" */
+      {
+         rc = k_scaled;
+         goto done;
+      }
+      goto second_stage;
+   }
    /* ---- scaled Nystrom-error estimate (afn_setup.m:163-228) */
    for (e = 0; e < numests; e++)
    {
@@ -538,6 +689,7 @@ static int afn_rank_estimate(b200_afn *s, const b200_dense_view *v, func_kernel 
       rc = k_scaled;
       goto done;
    }
+second_stage:
    /* ---- numerical rank of sub-sampled kernel matrices (afn_setup.m:230-292) */
    {
       int mk = max_k < n ? max_k : n;

@@ -370,7 +370,143 @@ def lanczos_case():
     np.savez_compressed(os.path.join(OUT, "lanczos_dense300.npz"), **out)
 
 
+def afn_case():
+    """The AFN setup assembled from the reference's COMPILED parts in the order of SRC/preconds/afn.c:161-420 (afn.c itself is
+    not built, SURVEY.md finding 2): Nfft4GPSortFps (ordering.c:713, parallel algorithm :422) -> Nfft4GPExpandPerm (utils.c:208) ->
+    Nfft4GPPrecondCholSetupWithKernel on the landmark rows (chol.c:428, stable shift :439-466) ->
+    Nfft4GPKernelSchurCombineKernelParamCreate / Nfft4GPKernelSchurCombineKernel (kernels.c:3496-4009) ->
+    Nfft4GPPrecondFsaiSetupWithKernel on the non-landmark points (fsai.c:302), and the 5-step apply of afn.c:109-136 composed
+    from Nfft4GPPrecondCholSolve, the reference kernel's K12 block and Nfft4GPPrecondFsaiSolve.  Plain Gaussian kernel (the
+    reference's FSAI setup segfaults on its dense ADDITIVE kernel, see fsai_case).  Also: Nfft4GPRankestNysScaled
+    (rankest.c:248-391) with the sample rows replayed through srand()."""
+    libc = C.CDLL(None)
+    n, d, k, lfil = 400, 3, 60, 20
+    X = cloud(n, d, 91)
+    f, l, mu = 1.1, 1.0, 0.02
+    L.Nfft4GPKernelParamCreate.restype = C.c_void_p
+    L.Nfft4GPKernelParamCreate.argtypes = [C.c_int, C.c_int]
+    kh = L.Nfft4GPKernelParamCreate(n, 1)
+    R.set_hyper(kh, f, l, mu)
+    fk = C.cast(L.Nfft4GPKernelGaussianKernel, C.c_void_p)
+
+    class OrdFps(C.Structure):   # INC/_linearalg.h:820-841
+        _fields_ = [("_algorithm", C.c_int), ("_tol", C.c_double), ("_rho", C.c_double), ("_fdist", C.c_void_p), ("_fdist_params", C.c_void_p),
+                    ("_dist", C.c_void_p), ("_build_pattern", C.c_int), ("_pattern_lfil", C.c_int), ("_pattern_opt", C.c_int),
+                    ("_S_i", C.c_void_p), ("_S_j", C.c_void_p)]
+
+    L.Nfft4GPOrdFpsCreate.restype = C.c_void_p
+    L.Nfft4GPSortFps.argtypes = [C.c_void_p, R.c_double_p, C.c_int, C.c_int, C.c_int, R.c_int_p, C.POINTER(R.c_int_p)]
+    fps = L.Nfft4GPOrdFpsCreate()
+    o = OrdFps.from_address(fps)
+    o._algorithm, o._tol, o._build_pattern = 0, 0.0, 0      # afn.c:201-205
+    kk, pp = C.c_int(k), R.c_int_p()
+    assert L.Nfft4GPSortFps(fps, R.dptr(X), n, n, d, C.byref(kk), C.byref(pp)) == 0 and kk.value == k
+    sel = np.ctypeslib.as_array(pp, shape=(k,)).copy()
+    L.Nfft4GPExpandPerm.restype = R.c_int_p
+    L.Nfft4GPExpandPerm.argtypes = [R.c_int_p, C.c_int, C.c_int]
+    L.Nfft4GPSubData.restype = R.c_double_p
+    L.Nfft4GPSubData.argtypes = [R.c_double_p, C.c_int, C.c_int, C.c_int, R.c_int_p, C.c_int]
+    permp = L.Nfft4GPExpandPerm(pp, k, n)
+    perm = np.ctypeslib.as_array(permp, shape=(n,)).copy()
+    perm2p = C.cast(C.addressof(permp.contents) + 4 * k, R.c_int_p)
+    n2 = n - k
+    data1 = L.Nfft4GPSubData(R.dptr(X), n, n, d, permp, k)
+    ch = L.Nfft4GPPrecondCholCreate()
+    L.Nfft4GPPrecondCholSetStable.argtypes = [C.c_void_p, C.c_int]
+    L.Nfft4GPPrecondCholSetStable(ch, 1)
+    assert L.Nfft4GPPrecondCholSetupWithKernel(data1, k, k, d, fk, kh, 0, ch) == 0
+
+    class PChol(C.Structure):    # INC/_preconds.h:48-71
+        _fields_ = [("_stable", C.c_int), ("_chol_data", R.c_double_p), ("_GdKG_data", R.c_double_p), ("_dchol_data", R.c_double_p),
+                    ("_dK_data", R.c_double_p), ("_n", C.c_int)]
+
+    pc = PChol.from_address(ch)
+    Lc = np.tril(np.ctypeslib.as_array(pc._chol_data, shape=(k, k)).T.copy())
+    L.Nfft4GPKernelSchurCombineKernelParamCreate.restype = C.c_void_p
+    L.Nfft4GPKernelSchurCombineKernelParamCreate.argtypes = [R.c_double_p, C.c_int, C.c_int, C.c_int, R.c_int_p, C.c_int, R.c_double_p,
+                                                             R.c_double_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    sk = L.Nfft4GPKernelSchurCombineKernelParamCreate(R.dptr(X), n, n, d, permp, k, pc._chol_data, None, fk, kh, 1, 0)
+    data2 = L.Nfft4GPSubData(R.dptr(X), n, n, d, perm2p, n2)
+    fs = L.Nfft4GPPrecondFsaiCreate()
+    L.Nfft4GPPrecondFsaiSetLfil(fs, lfil)
+    assert L.Nfft4GPPrecondFsaiSetupWithKernel(data2, n2, n2, d, C.cast(L.Nfft4GPKernelSchurCombineKernel, C.c_void_p), sk, 0, fs) == 0
+
+    class PFsai(C.Structure):
+        _fields_ = [("_lfil", C.c_int), ("_n", C.c_int), ("_tits", C.c_int), ("_titt", C.c_double), ("_tset", C.c_double),
+                    ("_tlogdet", C.c_double), ("_tdvp", C.c_double), ("_L_i", R.c_int_p), ("_L_j", R.c_int_p),
+                    ("_L_a", R.c_double_p), ("_dL_a", R.c_double_p), ("_work", R.c_double_p)]
+
+    pf = PFsai.from_address(fs)
+    ia = np.ctypeslib.as_array(pf._L_i, shape=(n2 + 1,)).copy()
+    nnz = int(ia[-1])
+    ja = np.ctypeslib.as_array(pf._L_j, shape=(nnz,)).copy()
+    a = np.ctypeslib.as_array(pf._L_a, shape=(nnz,)).copy()
+    # one Schur block straight from the Schur kernel (rows 5..24 of the non-landmark points)
+    blk = np.arange(5, 25, dtype=np.int32)
+    gidx = np.ascontiguousarray(blk)                     # the Schur kernel looks its rows up through _ibufferp / _libufferp (fsai.c:377-381)
+    ks = R.Nfft4GPKernel.from_address(sk)
+    ipp = C.cast(ks._ibufferp, C.POINTER(R.c_int_p))
+    lpp = C.cast(ks._libufferp, C.POINTER(C.c_size_t))
+    ipp[0] = R.iptr(gidx)
+    lpp[0] = len(blk)
+    sub = L.Nfft4GPSubData(data2, n2, n2, d, R.iptr(gidx), len(blk))
+    Sb = C.c_void_p()
+    assert L.Nfft4GPKernelSchurCombineKernel(sk, sub, len(blk), len(blk), d, None, 0, None, 0, C.byref(Sb), None) == 0
+    Sblk = np.ctypeslib.as_array(C.cast(Sb, R.c_double_p), shape=(len(blk), len(blk))).T.copy()
+    Sblk = np.tril(Sblk) + np.tril(Sblk, -1).T
+    # apply (afn.c:109-136): rp = r(perm); y1 = A11^-1 rp1; rp2 -= A21 y1; y2 = FSAI(rp2); rp1 -= A12 y2; y1 = A11^-1 rp1; scatter
+    K12p = C.c_void_p()
+    assert L.Nfft4GPKernelGaussianKernel(kh, R.dptr(X), n, n, d, permp, k, perm2p, n2, C.byref(K12p), None) == 0
+    K12 = np.ctypeslib.as_array(C.cast(K12p, R.c_double_p), shape=(n2, k)).T.copy()
+    rhs = np.random.default_rng(92).random(n) - 0.5
+    rp = rhs[perm]
+    y1 = np.zeros(k)
+    r1 = np.ascontiguousarray(rp[:k])
+    L.Nfft4GPPrecondCholSolve(ch, k, R.dptr(y1), R.dptr(r1))
+    r2 = np.ascontiguousarray(rp[k:] - K12.T @ y1)
+    y2 = np.zeros(n2)
+    L.Nfft4GPPrecondFsaiSolve(fs, n2, R.dptr(y2), R.dptr(r2))
+    r1 = np.ascontiguousarray(rp[:k] - K12 @ y2)
+    L.Nfft4GPPrecondCholSolve(ch, k, R.dptr(y1), R.dptr(r1))
+    z = np.zeros(n)
+    z[perm] = np.concatenate([y1, y2])
+    out = {"X": X, "f": f, "l": l, "mu": mu, "k": k, "lfil": lfil, "fps_sel": sel, "perm": perm, "L": Lc, "K12": K12, "fsai_ia": ia,
+           "fsai_ja": ja, "fsai_a": a, "schur_rows": blk, "schur_block": Sblk, "rhs": rhs, "z": z}
+
+    # ---- rank estimation (rankest.c:248-391), one sample per call, rows replayed through srand()
+    class Rankest(C.Structure):  # INC/_linearalg.h:913-923
+        _fields_ = [("_nsample", C.c_int), ("_nsample_r", C.c_int), ("_max_rank", C.c_int), ("_full_tol", C.c_double),
+                    ("_kernel_func", C.c_void_p), ("_kernel_str", C.c_void_p), ("_ordering_str", C.c_void_p), ("_perm", C.c_void_p)]
+
+    L.Nfft4GPRankestStrCreate.restype = C.c_void_p
+    L.Nfft4GPRankestNysScaled.argtypes = [C.c_void_p, R.c_double_p, C.c_int, C.c_int, C.c_int]
+    L.Nfft4GPRandPerm.restype = R.c_int_p
+    L.Nfft4GPRandPerm.argtypes = [C.c_int, C.c_int]
+    cases = [(2000, 3, 1.0, 200, 300), (2000, 3, 4.0, 200, 300), (2000, 6, 1.5, 200, 2000), (1500, 3, 0.3, 150, 2000), (1200, 3, 2.0, 300, 500)]
+    rk_cfg, rk_rows, rk_out = [], [], []
+    for ci, (nn, dd, ll, m, maxr) in enumerate(cases):
+        Xr = cloud(nn, dd, 95)
+        kh2 = L.Nfft4GPKernelParamCreate(nn, 1)
+        R.set_hyper(kh2, 1.0, ll, 0.01)
+        rs = L.Nfft4GPRankestStrCreate()
+        r = Rankest.from_address(rs)
+        r._nsample, r._nsample_r, r._max_rank, r._kernel_str = m, 1, maxr, kh2
+        libc.srand(777 + ci)
+        rows = np.ctypeslib.as_array(L.Nfft4GPRandPerm(nn, m), shape=(m,)).copy()
+        libc.srand(777 + ci)
+        rk = L.Nfft4GPRankestNysScaled(rs, R.dptr(Xr), nn, nn, dd)
+        rk_cfg.append([nn, dd, ll, m, maxr])
+        rk_rows.append(np.pad(rows, (0, 300 - m), constant_values=-1))
+        rk_out.append(rk)
+    out.update(rankest_cfg=np.array(rk_cfg), rankest_rows=np.array(rk_rows, dtype=np.int32), rankest_rank=np.array(rk_out), rankest_seed=95)
+    np.savez_compressed(os.path.join(OUT, "afn_ref_parts400.npz"), **out)
+    print("wrote afn case: nnz", nnz, "ranks", rk_out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "afn":
+        afn_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "nysgrad":
         nys_grad_case()
         sys.exit(0)
@@ -400,3 +536,4 @@ if __name__ == "__main__":
     fgmres_case()
     predict_case()
     lanczos_case()
+    afn_case()

@@ -1,6 +1,8 @@
 """GPU parity of the NFFT additive matvec (rows M1, M2, M3, S1, S2 of SURVEY.md section 8(a)) against the CPU oracle,
 called through the C ABI exactly like the reference drivers call nfft4gp (TESTS/TEST1/foo.cpp:216-251).
 Tolerance: north_star -- <= 1e-10 relative l2 in fp64 (we observe ~1e-14)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -152,3 +154,50 @@ def test_stages_against_numpy(gpu):
     assert rel_l2(h, href) <= 1e-12
     A.free()
     B.free()
+
+
+# ------------------------------------------------------------------------------------------------ single-window entry points
+def _single_build(L, capi, h, X, kernel, f, l, mu):
+    k = capi.Nfft4GPKernel.from_address(h)
+    k._params[0], k._params[1], k._noise_level = f, l, mu
+    K, dK = C.c_void_p(), C.c_void_p()
+    fn = L.Nfft4GPNFFTKernelGaussianKernel if kernel == "gaussian" else L.Nfft4GPNFFTKernelMatern12Kernel
+    d, n = X.shape
+    assert fn(h, capi.dptr(X), n, n, d, None, 0, None, 0, C.byref(K), C.byref(dK)) == 0
+    return K, dK
+
+
+@pytest.mark.parametrize("dim,kernel,n", [(3, "gaussian", 2500), (2, "matern12", 1800), (1, "gaussian", 1500), (3, "matern12", 40000)])
+def test_single_window_entry_points(gpu, dim, kernel, n):
+    """Rows M1 / M3 through their own entry points (nfft_interface.c:3-161, 400-620): Nfft4GPNFFTKernelParamCreate,
+    Nfft4GPNFFTKernel{Gaussian,Matern12}Kernel, Nfft4GPNFFTMatSymv, Nfft4GPNFFTGradMatSymv against the oracle (an additive
+    kernel with ONE window is the same operator), for all (alpha, beta) branches of :428-494; then
+    Nfft4GPNFFTKernelParamRemovePoints + a rebuild on OTHER data of another size (nfft_interface.c:101-128)."""
+    L, capi = gpu.lib(), gpu.capi
+    f, l, mu = 1.1, 0.3 * n ** (1.0 / dim) / 4.0 + 0.5, 0.02
+    h = L.Nfft4GPNFFTKernelParamCreate(2 * n, dim)
+    win = np.arange(dim, dtype=np.int32)
+    for rebuild, nn in enumerate((n, n + n // 3)):
+        X = uniform_cloud(nn, dim, seed=40 + rebuild)
+        K, dK = _single_build(L, capi, h, X, kernel, f, l, mu)
+        B = O.OracleAdditiveNFFT(X, win, 1, dim, kernel).build(f, l, mu)
+        x = rand_vec(nn, 5)
+        y0, g0 = rand_vec(nn, 6), rand_vec(3 * nn, 7)
+        for al, be in ((1.0, 0.0), (-1.0, 1.0), (0.7, 0.3)):
+            y = y0.copy()
+            assert L.Nfft4GPNFFTMatSymv(K, nn, al, capi.dptr(x), be, capi.dptr(y)) == 0
+            assert rel_l2(y, B.matvec(x, al, be, y0)) <= 1e-10, (dim, kernel, al, be)
+            g = g0.copy()
+            assert L.Nfft4GPNFFTGradMatSymv(dK, nn, al, capi.dptr(x), be, capi.dptr(g)) == 0
+            assert rel_l2(g, B.grad_matvec(x, al, be, g0)) <= 1e-10, (dim, kernel, al, be)
+        # a new length scale on the same points: only the coefficient tables are rebuilt
+        K, dK = _single_build(L, capi, h, X, kernel, f, 1.7 * l, mu)
+        B.build(f, 1.7 * l, mu)
+        y = np.zeros(nn)
+        assert L.Nfft4GPNFFTMatSymv(K, nn, 1.0, capi.dptr(x), 0.0, capi.dptr(y)) == 0
+        assert rel_l2(y, B.matvec(x)) <= 1e-10
+        # a vector of the wrong length is refused (the handle was built for nn points)
+        assert L.Nfft4GPNFFTMatSymv(K, nn - 1, 1.0, capi.dptr(x), 0.0, capi.dptr(y)) == -1
+        B.free()
+        assert L.Nfft4GPNFFTKernelParamRemovePoints(h) == 0
+    L.Nfft4GPNFFTKernelParamFree(h)

@@ -205,6 +205,56 @@ def test_afn_setup_matches_numpy(gpu, kernel, n, k, lfil):
     D.free()
 
 
+def test_afn_setup_matches_reference_compiled_parts(gpu):
+    """Row A2 pinned on the reference's COMPILED code: the GPU AFN setup against the chain Nfft4GPSortFps (ordering.c:713) ->
+    Nfft4GPExpandPerm -> Nfft4GPPrecondCholSetupWithKernel (stable) -> Nfft4GPKernelSchurCombineKernel (kernels.c:3496-4009) ->
+    Nfft4GPPrecondFsaiSetupWithKernel, and its apply against afn.c:109-136 composed from the reference's Chol / FSAI solves
+    (tests/golden/afn_ref_parts400.npz, scripts/make_golden.py:afn_case)."""
+    z = np.load(os.path.join(GOLD, "afn_ref_parts400.npz"))
+    X, f, l, mu, k, lfil = z["X"], float(z["f"]), float(z["l"]), float(z["mu"]), int(z["k"]), int(z["lfil"])
+    n = X.shape[1]
+    P = gpu.DensePlainKernel(X, "gaussian").set_hyper(f, l, mu)
+    Af = gpu.AfnPrecond().setup(P, k, lfil, numests=0, noran=1)
+    F = Af.get_factors()
+    assert F["k"] == k and not F["is_nys"]
+    assert (F["perm"][:k] == z["fps_sel"]).all(), "landmarks differ from Nfft4GPSortFps"
+    assert (F["perm"] == z["perm"]).all()
+    Linv = np.linalg.inv(z["L"])
+    assert np.abs(F["Linv"] - Linv).max() <= 1e-9 * np.abs(Linv).max()
+    assert np.abs(F["K12"] - z["K12"]).max() <= 1e-13
+    assert (F["ia"] == z["fsai_ia"]).all() and (F["ja"] == z["fsai_ja"]).all(), "Schur FSAI pattern differs from the reference"
+    assert np.abs(F["a"] - z["fsai_a"]).max() <= 1e-8 * np.abs(z["fsai_a"]).max()
+    assert rel_l2(Af.solve(z["rhs"]), z["z"]) <= 1e-8
+    Af.free()
+    P.free()
+
+
+def test_rank_estimate_matches_reference_nys_scaled(gpu):
+    """Nfft4GPB200RankestNysScaledSample (FPS and kernel block on the GPU, one elimination sweep) against the reference's
+    compiled Nfft4GPRankestNysScaled (rankest.c:354) on the sample rows its rand() stream drew."""
+    z = np.load(os.path.join(GOLD, "afn_ref_parts400.npz"))
+    for cfg, rows, rk in zip(z["rankest_cfg"], z["rankest_rows"], z["rankest_rank"]):
+        nn, dd, ll, m, maxr = int(cfg[0]), int(cfg[1]), float(cfg[2]), int(cfg[3]), int(cfg[4])
+        X = np.random.default_rng(int(z["rankest_seed"])).random((dd, nn)) * nn ** (1.0 / dd)
+        P = gpu.DensePlainKernel(X, "gaussian").set_hyper(1.0, ll, 0.01)
+        got = gpu.rankest_nys_scaled_sample(P, rows[:m], maxr)
+        if got <= int(np.floor(max(m // 50, 1) * nn / m)):
+            got = 0                       # rankest.c:378-383
+        assert got == int(rk), (cfg, got, int(rk))
+        P.free()
+    # the same first stage inside the AFN setup (rank_method = 1), against the NumPy restatement with the product's sampler
+    n, d = 3000, 3
+    X = uniform_cloud(n, d, seed=12)
+    for l, expect_nys in ((40.0, True), (0.4, False)):
+        P = gpu.DensePlainKernel(X, "gaussian").set_hyper(1.0, l, 0.01)
+        Af = gpu.AfnPrecond().setup(P, 80, 20, est_m=300, numests=2, noran=0, seed=906, rank_method=1)
+        F = Af.get_factors()
+        assert F["is_nys"] == expect_nys, (l, F["k_est"])
+        assert np.isfinite(Af.solve(rand_vec(n, 2))).all()
+        Af.free()
+        P.free()
+
+
 def test_afn_k12_fp32_storage(gpu):
     """Optional fp32 storage of the K12 block (Nfft4GPB200PrecondAFNSetK12Storage): the apply agrees with the fp64 one to
     fp32 rounding, stays symmetric, returns the rounded block through GetFactors, and PCG needs the same iterations."""
