@@ -334,6 +334,10 @@ int Nfft4GPB200CommGetUniqueId(void *id128);
 int Nfft4GPB200CommInit(int rank, int nranks, const void *id128);
 int Nfft4GPB200CommFinalize(void);
 int Nfft4GPB200SetSharding(void *additive_handle, int mode);
+/* Stochastic Lanczos quadrature on several GPUs (BASELINE configs[4]): with on != 0, Nfft4GPLanczosQuadratureLogdet distributes its
+ * probe vectors over the ranks (probe i on rank i mod R; every rank holds the whole, unsharded operator) and completes the four
+ * sums with one allreduce of four doubles.  Same result as a single-process run, including the rand() stream of the probes. */
+int Nfft4GPB200SetProbeSharding(int on);
 
 /* fp64 tensor-core (mma.sync.m8n8k4.f64 = DMMA.8x8x4) throughput of the current GPU measured now, in TFLOP/s (a 2 ms kernel with
  * register operands): the roof bench.py reports the 3-D spread / gather kernels against.  Negative on error. */

@@ -131,6 +131,7 @@ def lib():
         "Nfft4GPB200PrecondFsaiGetFactors": (i, [vp, c_int_p, c_int_p, c_int_p, c_int_p, c_double_p]),
         "Nfft4GPB200CommGetUniqueId": (i, [vp]), "Nfft4GPB200CommInit": (i, [i, i, vp]), "Nfft4GPB200CommFinalize": (i, []),
         "Nfft4GPB200SetSharding": (i, [vp, i]),
+        "Nfft4GPB200SetProbeSharding": (i, [i]),
         "Nfft4GPB200DebugWindowInfo": (i, [vp, i, c_int_p, c_double_p, c_int_p]),
         "Nfft4GPB200DebugSpread": (i, [vp, i, d, c_double_p, c_double_p]),
         "Nfft4GPB200DebugCoeff": (i, [vp, i, i, c_double_p]),

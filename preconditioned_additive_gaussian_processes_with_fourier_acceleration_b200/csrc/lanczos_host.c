@@ -382,6 +382,14 @@ int Nfft4GPSolverLanczos(void *mat_data, int n, func_symmatvec matvec, void *pre
    return rc;
 }
 
+static int g_probe_sharding = 0;
+/* multi-GPU stochastic Lanczos quadrature: distribute the probe vectors over the ranks of the communicator (handles replicated) */
+int Nfft4GPB200SetProbeSharding(int on)
+{
+   g_probe_sharding = on ? 1 : 0;
+   return 0;
+}
+
 /* SRC/solvers/lanczos.c:421-610 (INC/_solvers.h:216): logdet(K) / n and its three derivatives by stochastic Lanczos quadrature */
 int Nfft4GPLanczosQuadratureLogdet(void *mat_data, void *dmat_data, int n, func_symmatvec matvec, func_symmatvec dmatvec, void *prec_data,
                                    func_solve precondfunc, func_trace tracefunc, func_logdet logdetfunc, func_dvp dvpfunc, int maxits, int nvecs,
@@ -389,6 +397,11 @@ int Nfft4GPLanczosQuadratureLogdet(void *mat_data, void *dmat_data, int n, func_
 {
    const double EPSILON = DBL_EPSILON;
    int i, j, rc = -1;
+   /* probe sharding (one process per GPU, every rank holds the whole operator): the probe vectors are independent, so rank r runs
+    * the probes i = r (mod R) and the four sums are completed by ONE allreduce of four doubles at the end -- no data-path
+    * collective inside the Lanczos runs.  Every rank still draws every probe, so the rand() stream (and with it the result) is
+    * the one of a single-process run. */
+   const int nranks = g_probe_sharding ? b200_comm_size() : 1, me = nranks > 1 ? b200_comm_rank() : 0;
    double val = 0.0, *dval, logdet_precond = 0.0, *traces_precond, *z, *dAz, *px = NULL, *x, *TV, scale;
    dval = *dlogdetp ? *dlogdetp : (double *)b200_xcalloc(3, sizeof(double));
    traces_precond = (double *)b200_xcalloc(3, sizeof(double));
@@ -414,6 +427,8 @@ int Nfft4GPLanczosQuadratureLogdet(void *mat_data, void *dmat_data, int n, func_
       else
          for (j = 0; j < n; j++) /* Nfft4GPVecRadamacher, vecops.c:27-45 */
             z[j] = ((double)rand() / (double)RAND_MAX) < 0.5 ? -1.0 : 1.0;
+      if (nranks > 1 && i % nranks != me)
+         continue;
       memset(x, 0, sizeof(double) * (size_t)n);
       if (dmatvec(dmat_data, n, 1.0, z, 0.0, dAz))
          goto done;
@@ -459,6 +474,18 @@ int Nfft4GPLanczosQuadratureLogdet(void *mat_data, void *dmat_data, int n, func_
       }
       free(TD);
       free(TE);
+   }
+   if (nranks > 1)
+   {
+      double h4[4] = {val, dval[0], dval[1], dval[2]}, *d4 = (double *)b200_malloc(sizeof(h4));
+      int bad = !d4 || b200_h2d(d4, h4, sizeof(h4)) || b200_comm_allreduce_sum(d4, 4) || b200_d2h(h4, d4, sizeof(h4));
+      b200_free(d4);
+      if (bad)
+         goto done;
+      val = h4[0];
+      dval[0] = h4[1];
+      dval[1] = h4[2];
+      dval[2] = h4[3];
    }
    scale = 1.0 / (double)nvecs;
    val *= scale;
