@@ -97,6 +97,22 @@ int b200k_gather3_warp(const b200_win_dev *w, double *d_f);
 /* nfft12_stream.cu: 1-D / 2-D windows, warp-per-range with the footprint in registers */
 int b200k_spread_stream(const b200_win_dev *w);
 int b200k_gather_stream(const b200_win_dev *w, double *d_f);
+/* nfft1d_poly.cu: ALL 1-D windows of an additive kernel without tap tables -- per-cell polynomial coefficients / moments.
+ * Points are sorted by cell inside blocks of T consecutive points of the original order (once per handle). */
+typedef struct
+{
+   int n, nblk, T, nw;          /* points of this rank, blocks of T points, windows handled by this rank */
+   const double *xt;            /* [nw][nblk * T] scaled coordinates, sorted by cell inside every block */
+   const unsigned short *lp;    /* [nw][nblk * T] position inside its block (original order) of the sorted point */
+   const unsigned short *rs;    /* [nw][nblk][65] run starts: the points of cell key c of a block are [rs[c], rs[c + 1]) */
+   double *mom;                 /* [nw][64][16] moments sum_i a_i v_i^k per cell (spread) */
+   double *ctab;                /* [2][nw][64][16] polynomial coefficients per cell (gather): kernel / derivative channel */
+} b200_poly1d_dev;
+int b200k_poly1d_max_block(void);
+int b200k_poly1d_spread(const b200_poly1d_dev *p, const double *d_x, double s, double *d_grids, size_t grid_stride);
+int b200k_poly1d_coef(const b200_poly1d_dev *p, int ch, const double *d_grids, size_t grid_stride, const double *d_wscale);
+int b200k_poly1d_gather(const b200_poly1d_dev *p, int nch, const double *d_x, double s, double c0, double mu, double ff, double beta,
+                        double *d_y, size_t ystride);
 /* nfft3d_mma.cu: the same streaming decomposition on the fp64 tensor cores (DMMA) */
 int b200k_mma_warp_ranges(void);
 int b200k_spread3_mma(const b200_win_dev *w);

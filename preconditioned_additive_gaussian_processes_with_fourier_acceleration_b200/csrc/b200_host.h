@@ -79,6 +79,11 @@ typedef struct b200_additive
       long long launches; /* kernels inside the graph (the launch counter is advanced by this on replay) */
    } graph[4];
    int graph_next, graph_off; /* graph_off: capture failed once or NFFT4GP_B200_NO_GRAPH is set */
+   /* all windows 1-D (config C4): table-free polynomial path (nfft1d_poly.cu) over the windows this rank owns */
+   int poly1d;              /* 0 = not examined, 1 = active, -1 = not applicable */
+   b200_poly1d_dev poly;
+   int *poly_win;           /* [poly.nw] window index of local slot li */
+   double *d_poly_wscale;   /* [poly.nw] per-window factor of the derivative channel (f^2 x gradient scale) */
    int nlocal;     /* windows owned by this rank under mode 1 */
    const double **d_fptr_local;
    const int **d_invptr_local;

@@ -1,0 +1,309 @@
+// 1-D feature windows (BASELINE config C4: additive kernel with many 1-D windows): spread (adjoint NFFT, B^T) and gather (NFFT
+// trafo, B) WITHOUT tap tables, atomics or a global permutation of the points.
+//
+// For a 1-D window the oversampled grid has 64 cells and a point with fractional offset u in [0, 1) inside its cell c touches
+// the ten taps psi_t(u) = phi(u + 4 - t).  On a cell every psi_t is one smooth piece of the Kaiser-Bessel window; its degree-14
+// interpolant p_t(v), v = 2u - 1, is exact to 4.6e-16 phi(0) in double (kb_window_coeffs.h, generated in 40-digit arithmetic).
+// Hence
+//   gather:  f_i = sum_t h[c_i - 4 + t] p_t(v_i) = C_{c_i}(v_i),  C_c = sum_t h[c - 4 + t] p_t   -- ONE Horner evaluation
+//            (14 FMAs) per point from a 64 x 15 coefficient table per window instead of ten taps;
+//   spread:  g[c - 4 + t] += sum_k p_t[k] M_c[k],  M_c[k] = sum_{i in cell c} a_i v_i^k            -- 15 moments per point.
+// Per point and window the kernels read the scaled coordinate (8 B) and a 2-byte index instead of 80 B of taps + 4 B key + 8 B of
+// permuted coefficient, and the prep / combine passes with their random 8-byte accesses disappear: points are sorted by cell
+// only INSIDE blocks of T consecutive points of the ORIGINAL order (done once per handle), so x and y are moved as coalesced
+// blocks through shared memory and the "permutation" is a shared-memory index.
+//   spread: CTA (g, w) walks the blocks b = g (mod G) of window w; a warp owns the runs of the cells c = warp (mod 16): lanes stride
+//           over the run accumulating 15 moments in registers, ONE transposing butterfly (16 values over 32 lanes in 16 shuffles)
+//           per run adds them to the CTA's 64 x 16 table in shared memory, which goes to the window's global table with fp64 REDs
+//           once per CTA.
+//   gather: CTA b keeps acc[T] for its block in shared memory and loops over the windows: coefficient table of the window to shared
+//           memory, a warp per run loads the cell's 15 coefficients into registers, Horner per point, acc[lp] += f; fused epilogue
+//           y = beta y + f^2 (acc + P mu a) for the block, coalesced.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#include "b200_dev.h"
+#include "b200_cuda_util.cuh"
+#include "kb_window_coeffs.h"
+
+#define TAPS B200_TAPS
+#define PNC (KB_POLY_DEG + 1) /* 15 coefficients */
+#define PLD 16                /* leading dimension of the per-cell rows (moments / coefficients) */
+#define PWARPS 16
+#define PTHREADS (PWARPS * 32)
+
+__constant__ double c_p1[TAPS][PNC] = KB_POLY_TABLE;
+
+__device__ __forceinline__ int p_tap_idx(int key, int t) { return (key + 28 + t) & 63; } // grid index of tap t of the cell with key c + 32
+__device__ __forceinline__ void p_red_add(double *p, double v)
+{
+   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+
+// sum of m[q] over the 32 lanes for q = 0..15 with 8 + 4 + 2 + 1 + 1 shuffles: afterwards every lane holds the total of the value
+// index q = 8 b4 + 4 b3 + 2 b2 + b1 (b_i = bit i of the lane id)
+__device__ __forceinline__ double p_transpose_reduce16(const double m[16], int lane, int &q)
+{
+   const unsigned full = 0xffffffffu;
+   const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+   double w8[8], w4[4], w2[2], w1;
+#pragma unroll
+   for (int i = 0; i < 8; i++)
+   {
+      const double send = b4 ? m[i] : m[i + 8], keep = b4 ? m[i + 8] : m[i];
+      w8[i] = keep + __shfl_xor_sync(full, send, 16);
+   }
+#pragma unroll
+   for (int i = 0; i < 4; i++)
+   {
+      const double send = b3 ? w8[i] : w8[i + 4], keep = b3 ? w8[i + 4] : w8[i];
+      w4[i] = keep + __shfl_xor_sync(full, send, 8);
+   }
+#pragma unroll
+   for (int i = 0; i < 2; i++)
+   {
+      const double send = b2 ? w4[i] : w4[i + 2], keep = b2 ? w4[i + 2] : w4[i];
+      w2[i] = keep + __shfl_xor_sync(full, send, 4);
+   }
+   {
+      const double send = b1 ? w2[0] : w2[1], keep = b1 ? w2[1] : w2[0];
+      w1 = keep + __shfl_xor_sync(full, send, 2);
+   }
+   w1 += __shfl_xor_sync(full, w1, 1);
+   q = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+   return w1;
+}
+
+// ---------------------------------------------------------------------------------------------------- spread: moments
+__global__ void __launch_bounds__(PTHREADS)
+k_poly1d_spread(b200_poly1d_dev p, const double *__restrict__ x, double s)
+{
+   extern __shared__ __align__(16) double psm[];
+   double *xs = psm, *msm = psm + p.T;
+   unsigned short *rs = reinterpret_cast<unsigned short *>(msm + 64 * PLD);
+   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, w = blockIdx.y;
+   const size_t wbase = (size_t)w * p.nblk * p.T;
+   const double *__restrict__ xt = p.xt + wbase;
+   const unsigned short *__restrict__ lp = p.lp + wbase;
+   for (int e = tid; e < 64 * PLD; e += PTHREADS)
+      msm[e] = 0.0;
+   for (int b = blockIdx.x; b < p.nblk; b += gridDim.x)
+   {
+      const int base = b * p.T, cnt = min(p.T, p.n - base);
+      __syncthreads(); // the previous block's runs are done with xs / rs
+      for (int j = tid; j < p.T; j += PTHREADS)
+         xs[j] = j < cnt ? s * __ldg(x + base + j) : 0.0;
+      if (tid < 65)
+         rs[tid] = p.rs[((size_t)w * p.nblk + b) * 65 + tid];
+      __syncthreads();
+      for (int c = wid; c < 64; c += PWARPS)
+      {
+         const int j0 = rs[c], j1 = rs[c + 1];
+         if (j0 == j1) // warp-uniform
+            continue;
+         double m[16];
+#pragma unroll
+         for (int k = 0; k < 16; k++)
+            m[k] = 0.0;
+         for (int j = j0 + lane; j < j1; j += 32)
+         {
+            const double t = __ldg(xt + base + j) * 64.0;
+            const double v = 2.0 * (t - floor(t)) - 1.0;
+            double pw = xs[lp[base + j]];
+#pragma unroll
+            for (int k = 0; k < PNC; k++)
+            {
+               m[k] += pw;
+               pw *= v;
+            }
+         }
+         int q;
+         const double tot = p_transpose_reduce16(m, lane, q);
+         if (!(lane & 1) && q < PNC)
+            msm[c * PLD + q] += tot; // this warp is the only one that touches cell c of this CTA
+      }
+   }
+   __syncthreads();
+   double *mg = p.mom + (size_t)w * 64 * PLD;
+   for (int e = tid; e < 64 * PLD; e += PTHREADS)
+      if (msm[e] != 0.0)
+         p_red_add(mg + e, msm[e]);
+}
+
+// moments -> oversampled grid: g[l] = sum_t sum_k p_t[k] M[cell with tap t at l][k]; one CTA per window, one thread per grid cell
+__global__ void k_poly1d_mom2grid(const double *__restrict__ mom, double *__restrict__ grid, size_t grid_stride)
+{
+   const int w = blockIdx.x, l = threadIdx.x;
+   const double *m = mom + (size_t)w * 64 * PLD;
+   double g = 0.0;
+#pragma unroll
+   for (int t = 0; t < TAPS; t++)
+   {
+      const double *mc = m + ((l - 28 - t) & 63) * PLD;
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < PNC; k++)
+         acc = fma(c_p1[t][k], mc[k], acc);
+      g += acc;
+   }
+   grid[(size_t)w * grid_stride + l] = g;
+}
+
+// Re h (64 values per window) -> polynomial coefficients per cell: C[c][k] = scale_w * sum_t h[tap t of cell c] p_t[k]
+__global__ void k_poly1d_grid2coef(const double *__restrict__ grid, size_t grid_stride, const double *__restrict__ wscale, double *__restrict__ ctab)
+{
+   const int w = blockIdx.x, c = threadIdx.x >> 4, k = threadIdx.x & 15;
+   const double *h = grid + (size_t)w * grid_stride;
+   double acc = 0.0;
+   if (k < PNC)
+   {
+#pragma unroll
+      for (int t = 0; t < TAPS; t++)
+         acc = fma(h[p_tap_idx(c, t)], c_p1[t][k], acc);
+   }
+   ctab[(size_t)w * 64 * PLD + c * PLD + k] = (wscale ? wscale[w] : 1.0) * acc;
+}
+
+// ---------------------------------------------------------------------------------------------------- gather: Horner + epilogue
+// NCH = 1: y = beta y + c0 (sum_w f_w + nw mu a)                                     (nfft_interface.c:428-494, 803-814)
+// NCH = 2: gradient blocks y0 = beta y0 + f2 (sum_w f_w + nw mu a), y1 = beta y1 + sum_w c1_w fd_w (c1_w folded into the table),
+//          y2 = beta y2 + nw ff a                                                       (nfft_interface.c:539-617, 826-837)
+template <int NCH>
+__global__ void __launch_bounds__(PTHREADS)
+k_poly1d_gather(b200_poly1d_dev p, const double *__restrict__ x, double s, double c0, double mu, double ff, double beta, double *__restrict__ y,
+                size_t ystride)
+{
+   extern __shared__ __align__(16) double psm[];
+   double *acc = psm;                        // [NCH][T]
+   double *ct = psm + (size_t)NCH * p.T;     // [NCH][64][PLD]
+   unsigned short *rs = reinterpret_cast<unsigned short *>(ct + NCH * 64 * PLD);
+   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.x;
+   const int base = b * p.T, cnt = min(p.T, p.n - base);
+   for (int j = tid; j < NCH * p.T; j += PTHREADS)
+      acc[j] = 0.0;
+   for (int w = 0; w < p.nw; w++)
+   {
+      const size_t wbase = (size_t)w * p.nblk * p.T + base;
+      const double *__restrict__ xt = p.xt + wbase;
+      const unsigned short *__restrict__ lp = p.lp + wbase;
+      __syncthreads(); // the previous window's runs are done with ct / rs (and acc is zeroed)
+#pragma unroll
+      for (int ch = 0; ch < NCH; ch++)
+         for (int e = tid; e < 64 * PLD; e += PTHREADS)
+            ct[ch * 64 * PLD + e] = __ldg(p.ctab + ((size_t)ch * p.nw + w) * 64 * PLD + e);
+      if (tid < 65)
+         rs[tid] = p.rs[((size_t)w * p.nblk + b) * 65 + tid];
+      __syncthreads();
+      for (int c = wid; c < 64; c += PWARPS)
+      {
+         const int j0 = rs[c], j1 = rs[c + 1];
+         if (j0 == j1) // warp-uniform
+            continue;
+         double cf[NCH][PNC];
+#pragma unroll
+         for (int ch = 0; ch < NCH; ch++)
+#pragma unroll
+            for (int k = 0; k < PNC; k++)
+               cf[ch][k] = ct[ch * 64 * PLD + c * PLD + k];
+         for (int j = j0 + lane; j < j1; j += 32)
+         {
+            const double t = __ldg(xt + j) * 64.0;
+            const double v = 2.0 * (t - floor(t)) - 1.0;
+            const int l = lp[j];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++)
+            {
+               double f = cf[ch][PNC - 1];
+#pragma unroll
+               for (int k = PNC - 2; k >= 0; k--)
+                  f = fma(f, v, cf[ch][k]);
+               acc[ch * p.T + l] += f; // every point of the block belongs to exactly one run of this window
+            }
+         }
+      }
+   }
+   __syncthreads();
+   const double nwmu = (double)p.nw * mu;
+   for (int j = tid; j < cnt; j += PTHREADS)
+   {
+      const size_t i = (size_t)base + j;
+      const double ai = s * __ldg(x + i);
+      if (NCH == 1)
+         y[i] = (beta == 0.0 ? 0.0 : beta * y[i]) + c0 * (acc[j] + nwmu * ai);
+      else
+      {
+         double *y0 = y, *y1 = y + ystride, *y2 = y + 2 * ystride;
+         const double a0 = c0 * (acc[j] + nwmu * ai), a1 = acc[p.T + j], a2 = (double)p.nw * ff * ai;
+         y0[i] = (beta == 0.0 ? 0.0 : beta * y0[i]) + a0;
+         y1[i] = (beta == 0.0 ? 0.0 : beta * y1[i]) + a1;
+         y2[i] = (beta == 0.0 ? 0.0 : beta * y2[i]) + a2;
+      }
+   }
+}
+
+// ---------------------------------------------------------------------------------------------------- launch layer
+extern "C" {
+
+static size_t poly_smem_spread(int T) { return sizeof(double) * ((size_t)T + 64 * PLD) + 2 * 80; }
+static size_t poly_smem_gather(int T, int nch) { return sizeof(double) * (size_t)nch * ((size_t)T + 64 * PLD) + 2 * 80; }
+
+// largest block size (points per locally sorted block) the gather kernel of the gradient matvec still fits into shared memory with
+int b200k_poly1d_max_block(void) { return 8192; }
+
+// x (n values, original order) -> oversampled grids of the nw local windows (64 doubles each, stride grid_stride)
+int b200k_poly1d_spread(const b200_poly1d_dev *p, const double *d_x, double s, double *d_grids, size_t grid_stride)
+{
+   B200ProfScope prof_scope_(PC_SPREAD);
+   static bool attr_set = false;
+   if (!attr_set)
+   {
+      B200_CHECK(cudaFuncSetAttribute(k_poly1d_spread, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)poly_smem_spread(b200k_poly1d_max_block())));
+      attr_set = true;
+   }
+   int sm = 148, dev = 0;
+   if (cudaGetDevice(&dev) == cudaSuccess)
+      cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+   int G = (2 * sm + p->nw - 1) / p->nw; // about two CTAs per SM over all windows
+   if (G > p->nblk)
+      G = p->nblk;
+   if (G < 1)
+      G = 1;
+   B200_CHECK(cudaMemsetAsync(p->mom, 0, sizeof(double) * (size_t)p->nw * 64 * PLD, b200_stream()));
+   k_poly1d_spread<<<dim3(G, p->nw), PTHREADS, poly_smem_spread(p->T), b200_stream()>>>(*p, d_x, s);
+   B200_LAUNCHED();
+   k_poly1d_mom2grid<<<p->nw, 64, 0, b200_stream()>>>(p->mom, d_grids, grid_stride);
+   B200_LAUNCHED();
+   return 0;
+}
+
+// channel ch (0 kernel, 1 derivative kernel) of the coefficient tables from Re h of the nw local windows; d_wscale: optional per-window factor
+int b200k_poly1d_coef(const b200_poly1d_dev *p, int ch, const double *d_grids, size_t grid_stride, const double *d_wscale)
+{
+   B200ProfScope prof_scope_(PC_GATHER);
+   k_poly1d_grid2coef<<<p->nw, 64 * PLD, 0, b200_stream()>>>(d_grids, grid_stride, d_wscale, p->ctab + (size_t)ch * p->nw * 64 * PLD);
+   B200_LAUNCHED();
+   return 0;
+}
+
+// nch = 1: matvec epilogue into y (n values); nch = 2: gradient epilogue into y (3 blocks of ystride values)
+int b200k_poly1d_gather(const b200_poly1d_dev *p, int nch, const double *d_x, double s, double c0, double mu, double ff, double beta, double *d_y,
+                        size_t ystride)
+{
+   B200ProfScope prof_scope_(PC_GATHER);
+   static bool attr_set = false;
+   if (!attr_set)
+   {
+      B200_CHECK(cudaFuncSetAttribute(k_poly1d_gather<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)poly_smem_gather(b200k_poly1d_max_block(), 1)));
+      B200_CHECK(cudaFuncSetAttribute(k_poly1d_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)poly_smem_gather(b200k_poly1d_max_block(), 2)));
+      attr_set = true;
+   }
+   if (nch == 1)
+      k_poly1d_gather<1><<<p->nblk, PTHREADS, poly_smem_gather(p->T, 1), b200_stream()>>>(*p, d_x, s, c0, mu, ff, beta, d_y, ystride);
+   else
+      k_poly1d_gather<2><<<p->nblk, PTHREADS, poly_smem_gather(p->T, 2), b200_stream()>>>(*p, d_x, s, c0, mu, ff, beta, d_y, ystride);
+   B200_LAUNCHED();
+   return 0;
+}
+
+} // extern "C"

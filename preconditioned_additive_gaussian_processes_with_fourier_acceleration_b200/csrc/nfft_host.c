@@ -299,26 +299,13 @@ static void window_free(b200_window *w)
  * r_max is already in [0.125, 0.25]), point-major transpose -- same sequential fp64 arithmetic as the reference
  * so that `scale` is bit-identical -- followed by this library's own bin sort by oversampled-grid cell.
  * `cols` holds the window's d feature columns, n contiguous values each (feature-major, ldim = n). */
-static int window_setup_points(b200_window *w, const double *cols, int n_all, int lo, int hi)
+/* centre, r_max and scale of a window in the reference's sequential fp64 arithmetic (nfft_interface.c:162-196): returns the centred,
+ * scaled feature columns (feature-major, n_all values each; caller frees) and sets w->scale */
+static double *window_scale_points(b200_window *w, const double *cols, int n_all)
 {
-   /* n_all points define centre and scale (identical on every rank); this rank tabulates the block [lo, hi) only
-    * (the whole range unless the handle is sharded by point block, SURVEY.md 8(e)) */
-   const int n = hi - lo;
-   int d = w->d, i, j, t;
-   size_t nbins = ipow(B200_NOS, d);
+   int d = w->d, i, j;
    double radius = 0.0;
-   double *tmp, *xs;
-   int *keys, *binstart, *perm, *inv;
-   b200_win_dev *v = &w->dev;
-
-   if (d < 1 || d > 3)
-   {
-      printf("Error: nfft4gp_b200 supports window dimensions 1..3, got %d.\n", d);
-      return -1;
-   }
-   if (b200_init(-1))
-      return -1;
-   tmp = (double *)b200_xmalloc(sizeof(double) * (size_t)n_all * d);
+   double *tmp = (double *)b200_xmalloc(sizeof(double) * (size_t)n_all * d);
    memcpy(tmp, cols, sizeof(double) * (size_t)n_all * d);
    for (i = 0; i < d; i++)
    {
@@ -346,6 +333,28 @@ static int window_setup_points(b200_window *w, const double *cols, int n_all, in
    }
    else
       w->scale = 1.0;
+   return tmp;
+}
+
+static int window_setup_points(b200_window *w, const double *cols, int n_all, int lo, int hi)
+{
+   /* n_all points define centre and scale (identical on every rank); this rank tabulates the block [lo, hi) only
+    * (the whole range unless the handle is sharded by point block, SURVEY.md 8(e)) */
+   const int n = hi - lo;
+   int d = w->d, i, j, t;
+   size_t nbins = ipow(B200_NOS, d);
+   double *tmp, *xs;
+   int *keys, *binstart, *perm, *inv;
+   b200_win_dev *v = &w->dev;
+
+   if (d < 1 || d > 3)
+   {
+      printf("Error: nfft4gp_b200 supports window dimensions 1..3, got %d.\n", d);
+      return -1;
+   }
+   if (b200_init(-1))
+      return -1;
+   tmp = window_scale_points(w, cols, n_all);
 
    /* cell keys, stable counting sort */
    keys = (int *)b200_xmalloc(sizeof(int) * (size_t)n);
@@ -891,6 +900,160 @@ static int additive_ensure_device(b200_additive *A)
 
 static void additive_graphs_release(b200_additive *A);
 
+/* ------------------------------------------------------------------ 1-D windows without tap tables (nfft1d_poly.cu)
+ * An additive kernel whose windows are all 1-D (BASELINE config C4) takes the polynomial path: per window the handle keeps the
+ * scaled coordinates sorted by cell INSIDE blocks of T consecutive points (8 B + a 2-byte block-local index per point and
+ * window, against 80 B of taps + key + permutations of the table path), the spread accumulates 15 moments per cell and the
+ * gather evaluates one degree-14 polynomial per point.  Under window sharding a rank builds only the windows it owns. */
+#define POLY1D_MIN_N 32768 /* below this the per-window kernels are launch-bound either way and the debug taps stay available */
+static int additive_wants_poly1d(const b200_additive *A, int n)
+{
+   const char *e = getenv("NFFT4GP_B200_POLY1D");
+   int i;
+   if (e && atoi(e) == 0)
+      return 0;
+   if (A->shard_mode == 2 && b200_comm_size() > 1)
+      return 0; /* point-block sharding keeps the table path */
+   for (i = 0; i < A->P; i++)
+      if (A->win[i]->d != 1)
+         return 0;
+   return (e && atoi(e) > 0) || n >= POLY1D_MIN_N;
+}
+
+static void additive_poly_release(b200_additive *A)
+{
+   b200_free((void *)A->poly.xt);
+   b200_free((void *)A->poly.lp);
+   b200_free((void *)A->poly.rs);
+   b200_free(A->poly.mom);
+   b200_free(A->poly.ctab);
+   b200_free(A->d_poly_wscale);
+   free(A->poly_win);
+   memset(&A->poly, 0, sizeof(A->poly));
+   A->poly_win = NULL;
+   A->d_poly_wscale = NULL;
+   A->poly1d = 0;
+}
+
+/* small per-window device state of the polynomial path: grid / band / coefficient slots only (no point tables) */
+static int window_setup_small(b200_window *w, int n)
+{
+   b200_win_dev *v = &w->dev;
+   size_t gsz = ipow(B200_NOS, w->d), bsz = ipow(B200_NBAND, w->d);
+   window_free_device(w);
+   v->d = w->d;
+   v->n = n;
+   v->grid = w->ext_grid ? w->ext_grid : (double *)b200_malloc(sizeof(double) * gsz);
+   v->specA = w->ext_specA ? w->ext_specA : (double *)b200_malloc(sizeof(double) * gsz);
+   v->specB = w->ext_specB ? w->ext_specB : (double *)b200_malloc(sizeof(double) * gsz);
+   v->band = w->ext_band ? w->ext_band : (double *)b200_malloc(sizeof(double) * 2 * bsz);
+   v->coef = w->ext_coef ? w->ext_coef : (double *)b200_malloc(sizeof(double) * 2 * bsz);
+   v->dcoef = w->ext_dcoef ? w->ext_dcoef : (double *)b200_malloc(sizeof(double) * 2 * bsz);
+   w->n = w->n_global = n;
+   return (v->grid && v->specA && v->specB && v->band && v->coef && v->dcoef) ? 0 : -1;
+}
+
+/* first kernel build of a polynomial-path handle: contiguous work-array slots for the owned windows, scaling of every owned
+ * window in the reference's arithmetic, block-local counting sort by cell, upload */
+static int additive_poly_setup(b200_additive *A, const double *cols_all, int n)
+{
+   const int P = A->P;
+   int i, li, nw = 0, T, nblk, b, j, rc = -1;
+   size_t per_w, gsz = B200_NOS, bsz = B200_NBAND;
+   double *h_xt = NULL;
+   unsigned short *h_lp = NULL, *h_rs = NULL;
+   if (b200_init(-1))
+      return -1;
+   A->poly_win = (int *)b200_xcalloc((size_t)P, sizeof(int));
+   for (i = 0; i < P; i++)
+      if (b200_comm_owns_window(A, i))
+         A->poly_win[nw++] = i;
+   /* block size: a power of two in [1024, max] giving at least ~ 2 blocks per SM */
+   T = b200k_poly1d_max_block();
+   while (T > 1024 && (long long)n / T < 296)
+      T >>= 1;
+   nblk = (n + T - 1) / T;
+   per_w = (size_t)nblk * T;
+   A->poly.n = n;
+   A->poly.T = T;
+   A->poly.nblk = nblk;
+   A->poly.nw = nw;
+   A->nbatch = nw;
+   A->grids_doubles = gsz * (size_t)(nw ? nw : 1);
+   A->d_grids = (double *)b200_malloc(sizeof(double) * A->grids_doubles);
+   A->d_specA = (double *)b200_malloc(sizeof(double) * gsz * (size_t)(nw ? nw : 1));
+   A->d_specB = (double *)b200_malloc(sizeof(double) * gsz * (size_t)(nw ? nw : 1));
+   A->d_band = (double *)b200_malloc(sizeof(double) * 2 * bsz * (size_t)(nw ? nw : 1));
+   A->d_coef = (double *)b200_malloc(sizeof(double) * 2 * bsz * (size_t)(nw ? nw : 1));
+   A->d_dcoef = (double *)b200_malloc(sizeof(double) * 2 * bsz * (size_t)(nw ? nw : 1));
+   if (!A->d_grids || !A->d_specA || !A->d_specB || !A->d_band || !A->d_coef || !A->d_dcoef)
+      return -1;
+   if (nw == 0)
+   {
+      A->poly1d = 1;
+      return 0;
+   }
+   A->poly.xt = (const double *)b200_malloc(sizeof(double) * per_w * nw);
+   A->poly.lp = (const unsigned short *)b200_malloc(sizeof(unsigned short) * per_w * nw);
+   A->poly.rs = (const unsigned short *)b200_malloc(sizeof(unsigned short) * 65 * (size_t)nblk * nw);
+   A->poly.mom = (double *)b200_malloc(sizeof(double) * 64 * 16 * (size_t)nw);
+   A->poly.ctab = (double *)b200_malloc(sizeof(double) * 2 * 64 * 16 * (size_t)nw);
+   A->d_poly_wscale = (double *)b200_malloc(sizeof(double) * (size_t)nw);
+   if (!A->poly.xt || !A->poly.lp || !A->poly.rs || !A->poly.mom || !A->poly.ctab || !A->d_poly_wscale)
+      return -1;
+   h_xt = (double *)b200_xcalloc(per_w, sizeof(double));
+   h_lp = (unsigned short *)b200_xcalloc(per_w, sizeof(unsigned short));
+   h_rs = (unsigned short *)b200_xcalloc(65 * (size_t)nblk, sizeof(unsigned short));
+   for (li = 0; li < nw; li++)
+   {
+      b200_window *w = A->win[A->poly_win[li]];
+      double *xt = window_scale_points(w, cols_all + (size_t)A->poly_win[li] * n * A->dw, n);
+      w->ext_grid = A->d_grids + gsz * (size_t)li;
+      w->ext_specA = A->d_specA + gsz * (size_t)li;
+      w->ext_specB = A->d_specB + gsz * (size_t)li;
+      w->ext_band = A->d_band + 2 * bsz * (size_t)li;
+      w->ext_coef = A->d_coef + 2 * bsz * (size_t)li;
+      w->ext_dcoef = A->d_dcoef + 2 * bsz * (size_t)li;
+      if (window_setup_small(w, n))
+      {
+         free(xt);
+         goto done;
+      }
+      for (b = 0; b < nblk; b++)
+      {
+         const int base = b * T, cnt = n - base < T ? n - base : T;
+         unsigned short *rs = h_rs + 65 * (size_t)b;
+         int count[65], c;
+         memset(count, 0, sizeof(count));
+         for (j = 0; j < cnt; j++)
+            count[(((int)floor(xt[base + j] * (double)B200_NOS) + 32) & 63) + 1]++;
+         for (c = 0; c < 64; c++)
+            count[c + 1] += count[c];
+         for (c = 0; c <= 64; c++)
+            rs[c] = (unsigned short)count[c];
+         for (j = 0; j < cnt; j++) /* stable: a cell's points keep their original order, so every sum has a fixed order */
+         {
+            int pos = count[((int)floor(xt[base + j] * (double)B200_NOS) + 32) & 63]++;
+            h_xt[base + pos] = xt[base + j];
+            h_lp[base + pos] = (unsigned short)j;
+         }
+      }
+      free(xt);
+      if (b200_h2d((void *)(A->poly.xt + per_w * li), h_xt, sizeof(double) * per_w) ||
+          b200_h2d((void *)(A->poly.lp + per_w * li), h_lp, sizeof(unsigned short) * per_w) ||
+          b200_h2d((void *)(A->poly.rs + 65 * (size_t)nblk * li), h_rs, sizeof(unsigned short) * 65 * (size_t)nblk) || b200_sync())
+         goto done;
+   }
+   A->poly1d = 1;
+   rc = 0;
+done:
+   free(h_xt);
+   free(h_lp);
+   free(h_rs);
+   return rc;
+}
+
+
 static int additive_kernel_build(void *str, int kernel, double *data, int n, int ldim, int d, double **Kp, double **dKp)
 {
    nfft4gp_kernel *k = (nfft4gp_kernel *)str;
@@ -907,6 +1070,55 @@ static int additive_kernel_build(void *str, int kernel, double *data, int n, int
    {
       printf("Error: NFFT kernel requires n == ldim.\n");
       return -1;
+   }
+   if (!A->d_grids && A->poly1d == 0)
+      A->poly1d = additive_wants_poly1d(A, n) ? 2 : -1; /* 2 = wanted, set up below */
+   if (A->poly1d == 2)
+   {
+      A->blk_lo = 0;
+      A->blk_hi = n;
+      if (additive_poly_setup(A, cols, n))
+      {
+         printf("Error: set-up of the 1-D polynomial path failed.\n");
+         return -1;
+      }
+   }
+   if (A->poly1d == 1)
+   {
+      double *c1 = (double *)b200_xmalloc(sizeof(double) * (size_t)(A->poly.nw ? A->poly.nw : 1));
+      double ff = k->_params[0] * k->_params[0];
+      for (i = 0; i < A->poly.nw; i++)
+      {
+         b200_window *w = A->win[A->poly_win[i]];
+         if (window_build(w, kernel, k->_params[0], k->_params[1], k->_noise_level))
+         {
+            free(c1);
+            return -1;
+         }
+         c1[i] = ff * window_grad_scale(w);
+      }
+      if (A->poly.nw && (b200_h2d(A->d_poly_wscale, c1, sizeof(double) * (size_t)A->poly.nw) || b200_sync()))
+      {
+         free(c1);
+         return -1;
+      }
+      free(c1);
+      /* the hyper-parameters of the epilogue are read from any built window */
+      for (i = 0; i < A->P; i++)
+      {
+         A->win[i]->kernel_scale = k->_params[0];
+         A->win[i]->mu = k->_noise_level;
+      }
+      A->kernel = kernel;
+      A->built = 1;
+      additive_graphs_release(A);
+      if (additive_ensure_device(A))
+         return -1;
+      if (A->shard_mode == 1 && b200_comm_size() > 1 && !A->d_ypart)
+         A->d_ypart = (double *)b200_malloc(sizeof(double) * (size_t)A->n);
+      *Kp = (double *)str;
+      *dKp = (double *)str;
+      return 0;
    }
    if (!A->d_grids)
    {
@@ -1360,6 +1572,42 @@ static void additive_graphs_release(b200_additive *A)
    A->graph_next = 0;
 }
 
+/* all windows 1-D: spread (moments) -> batched FFTs -> coefficient tables -> gather with the fused epilogue */
+static int additive_poly_matvec(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y, int grad)
+{
+   const double s = 1.0 / (double)A->P * alpha, f = A->win[0]->kernel_scale, ff = f * f, mu = A->win[0]->mu;
+   const int sharded = (A->shard_mode == 1 && b200_comm_size() > 1);
+   const b200_poly1d_dev *p = &A->poly;
+   double *out = sharded ? A->d_ypart : d_y;
+   if (grad && sharded)
+   {
+      printf("Error: the gradient matvec is not available under window sharding; use point-block sharding (mode 2).\n");
+      return -1;
+   }
+   if (p->nw > 0)
+   {
+      const b200_win_dev *v0 = &A->win[A->poly_win[0]]->dev;
+      if (b200k_poly1d_spread(p, d_x, s, A->d_grids, B200_NOS) || b200k_forward_fft_batch(v0, p->nw) || b200k_backward_fft_batch(v0, p->nw, 0) ||
+          b200k_poly1d_coef(p, 0, A->d_grids, B200_NOS, NULL))
+         return -1;
+      if (grad && (b200k_backward_fft_batch(v0, p->nw, 1) || b200k_poly1d_coef(p, 1, A->d_grids, B200_NOS, A->d_poly_wscale)))
+         return -1;
+      if (b200k_poly1d_gather(p, grad ? 2 : 1, d_x, s, grad ? 2.0 * f : ff, mu, ff, sharded ? 0.0 : beta, out, (size_t)n))
+         return -1;
+   }
+   else if (b200_memset(out, 0, sizeof(double) * (size_t)n)) /* a rank without windows contributes zero */
+      return -1;
+   if (!sharded)
+      return 0;
+   if (b200_comm_allreduce_sum(A->d_ypart, (size_t)n))
+      return -1;
+   if (beta == 0.0)
+      return b200_d2d(d_y, A->d_ypart, sizeof(double) * (size_t)n);
+   if (beta != 1.0 && b200k_scale(n, beta, d_y))
+      return -1;
+   return b200k_axpy(n, 1.0, A->d_ypart, d_y);
+}
+
 static int additive_matvec_body(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y, int phases)
 {
    double s = 1.0 / (double)A->P * alpha; /* :806 */
@@ -1379,6 +1627,8 @@ int b200_additive_matvec_dev(b200_additive *A, int n, double alpha, const double
       printf("Error: additive NFFT matvec on a kernel that was not built for n = %d.\n", n);
       return -1;
    }
+   if (A->poly1d == 1)
+      return additive_poly_matvec(A, n, alpha, d_x, beta, d_y, 0);
    /* CUDA graph of the launch sequence (fused tensor-core path only), one per argument signature.  Under point-block
     * sharding the collective is NOT captured: two graphs around a plainly enqueued allreduce (a captured NCCL kernel next
     * to the caller's own communicator deadlocked in a 2-GPU bench run). */
@@ -1465,6 +1715,8 @@ int b200_additive_grad_matvec_dev(b200_additive *A, int n, double alpha, const d
       printf("Error: additive NFFT matvec on a kernel that was not built for n = %d.\n", n);
       return -1;
    }
+   if (A->poly1d == 1)
+      return additive_poly_matvec(A, n, alpha, d_x, beta, d_y, 1);
    if (A->shard_mode == 1 && b200_comm_size() > 1)
    {
       printf("Error: the gradient matvec is not available under window sharding; use point-block sharding (mode 2).\n");
@@ -1583,6 +1835,7 @@ void Nfft4GPAdditiveNFFTKernelFree(void *str)
       b200_free((void *)A->d_invptr_local);
       additive_fused_release(A);
       additive_graphs_release(A);
+      additive_poly_release(A);
       free(A);
    }
    if (k->_own_buffer)
@@ -1614,6 +1867,11 @@ static int debug_stage(void *h, int wi, double alpha, const double *x, double *o
    size_t gsz;
    if (!A || wi < 0 || wi >= A->P || !A->built || additive_ensure_device(A))
       return -1;
+   if (A->poly1d == 1)
+   {
+      printf("Error: the stage taps need the tap tables; this handle takes the table-free 1-D path (NFFT4GP_B200_POLY1D=0 disables it).\n");
+      return -1;
+   }
    w = A->win[wi];
    v = &w->dev;
    gsz = ipow(B200_NOS, w->d);

@@ -97,4 +97,15 @@ def test_c4_style_windows_at_full_size(gpu, dw):
     for name in (b"spread3d", b"gather3d"):
         assert L.Nfft4GPB200SetVariant(name, -1) == 0
     assert rel_l2(Kx, K0) <= 1e-12
+    if dw == 1:
+        # the 1-D handle above took the table-free polynomial path (nfft1d_poly.cu); the tap-table kernels on the same data agree
+        import os
+        os.environ["NFFT4GP_B200_POLY1D"] = "0"
+        try:
+            B = gpu.AdditiveNFFTKernel(X, np.arange(d, dtype=np.int32), d // dw, dw, "matern12").build(1.1, 0.5 * n ** (1.0 / d), 0.02)
+        finally:
+            del os.environ["NFFT4GP_B200_POLY1D"]
+        assert rel_l2(Kx, B.matvec(x)) <= 1e-12
+        assert rel_l2(A.grad_matvec(x), B.grad_matvec(x)) <= 1e-12
+        B.free()
     A.free()

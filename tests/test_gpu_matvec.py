@@ -201,3 +201,42 @@ def test_single_window_entry_points(gpu, dim, kernel, n):
         B.free()
         assert L.Nfft4GPNFFTKernelParamRemovePoints(h) == 0
     L.Nfft4GPNFFTKernelParamFree(h)
+
+
+# ------------------------------------------------------------------------------------------------ 1-D windows: table-free path
+@pytest.mark.parametrize("n,d,kernel,force", [(40000, 5, "gaussian", False), (50000, 3, "matern12", False), (3000, 4, "gaussian", True),
+                                              (700, 2, "matern12", True), (8192 * 3 + 1, 2, "gaussian", True)])
+def test_poly1d_path_matches_oracle(gpu, n, d, kernel, force):
+    """BASELINE config C4's kernel class -- an additive kernel of 1-D windows -- on the polynomial path (nfft1d_poly.cu: moments per
+    cell in the spread, one degree-14 Horner evaluation per point in the gather, points sorted by cell inside blocks of the original
+    order): matvec and gradient matvec against the oracle for all (alpha, beta) branches, and against the tap-table kernels."""
+    import os
+    X = uniform_cloud(n, d, seed=50 + d)
+    win = np.arange(d, dtype=np.int32)
+    f, l, mu = 1.2, 0.4 * n ** (1.0 / d), 0.03
+    if force:
+        os.environ["NFFT4GP_B200_POLY1D"] = "1"
+    try:
+        A = gpu.AdditiveNFFTKernel(X, win, d, 1, kernel).build(f, l, mu)
+    finally:
+        os.environ.pop("NFFT4GP_B200_POLY1D", None)
+    assert gpu.lib().Nfft4GPB200DebugSpread(A.h, 0, 1.0, gpu.capi.dptr(np.zeros(n)), gpu.capi.dptr(np.zeros(64))) == -1   # no tap tables on this path
+    B = O.OracleAdditiveNFFT(X, win, d, 1, kernel).build(f, l, mu)
+    x = rand_vec(n, 5)
+    y0, g0 = rand_vec(n, 6), rand_vec(3 * n, 7)
+    for al, be in ((1.0, 0.0), (-1.0, 1.0), (0.7, 0.3)):
+        assert rel_l2(A.matvec(x, al, be, y0), B.matvec(x, al, be, y0)) <= TOL, (al, be)
+        assert rel_l2(A.grad_matvec(x, al, be, g0), B.grad_matvec(x, al, be, g0)) <= TOL, (al, be)
+    # new hyper-parameters on the same points
+    A.build(0.8, 1.9 * l, 0.2)
+    B.build(0.8, 1.9 * l, 0.2)
+    assert rel_l2(A.matvec(x), B.matvec(x)) <= TOL
+    os.environ["NFFT4GP_B200_POLY1D"] = "0"
+    try:
+        T = gpu.AdditiveNFFTKernel(X, win, d, 1, kernel).build(0.8, 1.9 * l, 0.2)
+    finally:
+        os.environ.pop("NFFT4GP_B200_POLY1D", None)
+    assert rel_l2(A.matvec(x), T.matvec(x)) <= 1e-12
+    assert T.debug_spread(0, x).shape == (64,)      # the table path keeps its stage taps
+    for h in (A, B, T):
+        h.free()
