@@ -1168,6 +1168,14 @@ static int additive_kernel_build(void *str, int kernel, double *data, int n, int
    for (i = 0; i < A->P; i++)
    {
       b200_window *w = A->win[i];
+      if (!b200_comm_owns_window(A, i))
+      {
+         /* window sharding: another rank tabulates and applies this window; the epilogue reads f and mu from window 0 */
+         w->kernel_scale = k->_params[0];
+         w->mu = k->_noise_level;
+         cols += (size_t)n * A->dw;
+         continue;
+      }
       if (w->scale < 0.0)
       {
          if (window_setup_points(w, cols, n, A->blk_lo, A->blk_hi))
