@@ -243,12 +243,19 @@ def run_pcg_section(pkg, L, A, X, rhs, windows, hp, args, hbm_peak, ranks=None):
     D = pkg.DenseAdditiveKernel(X, windows, 3, 3, "gaussian").set_hyper(hp["f"], hp["l"], mu)
     out = {"config": f"C3: AFN-PCG to 1e-6 rel. residual, n={n}, d=9, Gaussian, f={hp['f']}, l={hp['l']:.4f}, mu={mu}, lfil=100, rhs=U(0,1)-0.5",
            "unit": "s", "runs": []}
-    for lrank, maxits, k12_bits in ((500, 300, 64), (args.pcg_rank, 3000, 64), (args.pcg_rank, 3000, 32)):
+    variants = [(500, 300, 64), (args.pcg_rank, 3000, 64)]
+    if world == 1:
+        variants.append((args.pcg_rank, 3000, "nfft"))   # labelled extra: K12 products of the apply through the NFFT operator (fp64)
+    variants.append((args.pcg_rank, 3000, 32))           # labelled extra: K12 block stored in fp32
+    for lrank, maxits, k12_bits in variants:
         sync_all()
         t0 = time.perf_counter()
         if k12_bits == 64:
             P = pkg.AfnPrecond().setup(D, lrank, 100, numests=0, noran=1)   # N > 1: replicated on every rank; the apply is sharded
+        elif k12_bits == "nfft":
+            P = P_keep.set_k12_operator(A)       # same factors; the dense block stays (the fp32 run below converts it)
         else:
+            P_keep.set_k12_operator(None)
             P = P_keep.set_k12_storage(32)       # same factors, K12 block rounded to fp32 in place (conversion time = "setup_s")
         sync_all()
         setup_s = max_over_ranks(time.perf_counter() - t0)
@@ -270,30 +277,42 @@ def run_pcg_section(pkg, L, A, X, rhs, windows, hp, args, hbm_peak, ranks=None):
         mv_cls = ("prep", "spread", "fft_fwd", "fft_inv", "gather", "combine")
         per_it = {PROF_CLASSES[i]: round(sums[i] / (51.0 if PROF_CLASSES[i] in mv_cls else 50.0), 5) for i in range(len(PROF_CLASSES)) if counts[i] > 0}
         n2 = (n - lrank) / world
+        k12_label = k12_bits
+        if k12_bits == "nfft":
+            k12_bits = 0                                    # no dense block is read
         gemv_bytes = 2.0 * (k12_bits / 8.0) * lrank * n2   # two passes over this rank's columns of K12 per apply
         csr_bytes = 2.0 * 12.0 * 100.0 * n2          # this rank's rows of G and G' (value + column index) per apply
         run = {"landmark_rank": lrank, "baseline_config": bool(lrank == 500 and k12_bits == 64), "iteration_cap": maxits,
                "precond": f"AFN rank {lrank} + FSAI(lfil 100) of the Schur complement" + (", K12 block stored in fp32 (fp64 vectors and sums)" if k12_bits == 32 else "")
+               + (", K12 products of the apply through the NFFT operator (two fast matvecs, fp64; Nfft4GPB200PrecondAFNSetK12Operator)" if k12_label == "nfft" else "")
                + (f", apply sharded over {world} GPUs (2 allreduces of k, 2 of n-k doubles)" if world > 1 else ""),
-               "k12_storage_bits": k12_bits, "setup_s": setup_s, "solve_s": solve_s,
+               "k12_storage_bits": 64 if k12_label == "nfft" else k12_bits, "k12_form": "nfft-operator" if k12_label == "nfft" else "dense-block", "setup_s": setup_s, "solve_s": solve_s,
                "iters": its, "converged": bool(its > 0), "rel_res": rel, "ms_per_iter": 1000.0 * solve_s / max(done, 1),
                "gpu_launches": launches, "per_class_ms_per_iter": per_it,
                "afn_apply_hbm": {"gemv_GBs": gemv_bytes / (per_it.get("gemv", float("nan")) * 1e-3) / 1e9,
                                  "spmv_GBs": csr_bytes / (per_it.get("csr", float("nan")) * 1e-3) / 1e9, "peak_GBs": hbm_peak}}
         out["runs"].append(run)
-        if lrank == args.pcg_rank and k12_bits == 64:
+        if lrank == args.pcg_rank and k12_label == 64:
             P_keep = P
+        elif k12_label == "nfft":
+            pass                                   # P is P_keep
         else:
             P.free()
     # Headline = fp64 storage only.  BASELINE's own rank (500) first; when it does not converge inside its cap the value is the
     # fp64 run at the rank that does (off-config, labelled).  The fp32-K12 run is an extra and never the value.
     base = next((r for r in out["runs"] if r["baseline_config"]), None)
-    fp64_conv = [r for r in out["runs"] if r["converged"] and r["k12_storage_bits"] == 64]
+    fp64_conv = [r for r in out["runs"] if r["converged"] and r["k12_storage_bits"] == 64 and r["k12_form"] == "dense-block"]
     pick = base if (base and base["converged"]) else (min(fp64_conv, key=lambda r: r["solve_s"]) if fp64_conv else None)
     out["value"] = pick["solve_s"] if pick else None
     out["value_run"] = (pick["precond"] + ("" if pick.get("baseline_config") else " -- OFF-CONFIG rank: BASELINE's rank 500 does not converge (see runs[0])")) if pick else None
     out["value_storage"] = "fp64"
     out["baseline_config_converged"] = bool(base and base["converged"])
+    op = next((r for r in out["runs"] if r["k12_form"] == "nfft-operator"), None)
+    if op is not None:
+        out["extra_nfft_k12"] = {"solve_s": op["solve_s"], "iters": op["iters"], "converged": op["converged"], "ms_per_iter": op["ms_per_iter"],
+                                 "note": "same AFN factors, fp64 throughout; the two K12 products of every apply are NFFT matvecs instead of passes "
+                                         "over the dense block (the reference's afn.h keeps A12 behind a function pointer).  Reported for "
+                                         "information, never the value"}
     extra = next((r for r in out["runs"] if r["k12_storage_bits"] == 32), None)
     if extra is not None:
         out["extra_fp32_k12"] = {"solve_s": extra["solve_s"], "iters": extra["iters"], "converged": extra["converged"],

@@ -314,6 +314,13 @@ int Nfft4GPB200RankestNysScaledSample(NFFT4GP_DOUBLE *data, int n, int ldim, int
  * large rank): bits = 64 (default) or 32.  With 32 the block is kept in fp32 (k a multiple of 4), vectors and sums stay fp64
  * and the apply stays symmetric; the preconditioner changes by O(1e-7) relative, the solution PCG converges to does not. */
 int Nfft4GPB200PrecondAFNSetK12Storage(void *afn, int bits);
+/* The two K12 products of every AFN apply through the NFFT operator instead of the dense k x (n-k) block: K21 y and K12 y2 are
+ * rows of K applied to vectors that vanish on the other block, i.e. two fast O(n) matvecs (afn.h:27-58 keeps A12 behind a function
+ * pointer, _fA12_matvec).  nfft_kernel: the *Kp of an additive NFFT kernel built on the same data and hyper-parameters (NULL: back to
+ * the dense block); release_block != 0 frees the dense block after the setup.  fp64 throughout; K12 is then the NFFT approximation
+ * of the kernel block (3e-8 relative at a resolved length scale) -- the preconditioner changes at that level, the solution PCG
+ * converges to does not.  Default: dense block (the reference's form). */
+int Nfft4GPB200PrecondAFNSetK12Operator(void *afn, void *nfft_kernel, int release_block);
 /* setup building blocks, exposed for the parity tests (host in / host out; the device ones need a GPU) */
 int Nfft4GPB200DebugPartitionChunks(const int *chunks /* int4 per chunk */, int nchunk, int wcnt, int rounds, const double *weight,
                                     double flush, int *first /* rounds * wcnt + 1 */);

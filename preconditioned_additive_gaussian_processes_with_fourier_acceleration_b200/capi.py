@@ -105,6 +105,7 @@ def lib():
         "Nfft4GPB200PrecondAFNSetRankEstimation": (i, [vp, i, i, i, C.c_ulonglong]),
         "Nfft4GPB200PrecondAFNSetK12Storage": (i, [vp, i]),
         "Nfft4GPB200PrecondAFNSetRankMethod": (i, [vp, i]),
+        "Nfft4GPB200PrecondAFNSetK12Operator": (i, [vp, vp, i]),
         "Nfft4GPB200RankestNysScaledSample": (i, [c_double_p, i, i, i, vp, vp, c_int_p, i, i]),
         "Nfft4GPB200DebugPartitionChunks": (i, [c_int_p, i, i, i, c_double_p, d, c_int_p]),
         "Nfft4GPB200HostPotrf": (i, [i, c_double_p]), "Nfft4GPB200HostSyev": (i, [i, c_double_p, c_double_p, i]),
@@ -510,6 +511,13 @@ class AfnPrecond:
         """Nfft4GPB200PrecondAFNSetK12Storage: 32 = keep the K12 block in fp32 (halves the HBM traffic of the apply)."""
         if lib().Nfft4GPB200PrecondAFNSetK12Storage(self.h, bits) != 0:
             raise RuntimeError("Nfft4GPB200PrecondAFNSetK12Storage failed")
+        return self
+
+    def set_k12_operator(self, nfft_kernel, release_block=False):
+        """Nfft4GPB200PrecondAFNSetK12Operator: the K12 products of the apply through the NFFT operator `nfft_kernel`
+        (an AdditiveNFFTKernel built with the hyper-parameters of the setup) instead of the dense block; None = dense block."""
+        if lib().Nfft4GPB200PrecondAFNSetK12Operator(self.h, nfft_kernel.K if nfft_kernel is not None else None, int(release_block)) != 0:
+            raise RuntimeError("Nfft4GPB200PrecondAFNSetK12Operator failed")
         return self
 
     def setup(self, kernel, max_k, lfil, est_m=500, numests=5, noran=0, seed=906, rank_method=0):

@@ -69,6 +69,9 @@ typedef struct
    float *d_K12f;  /* the same block in fp32 when k12_bits == 32 (then d_K12 is released after the setup) */
    int k12_bits;   /* 64 (default) or 32: storage of K12 for the two HBM-bound products of every apply */
    b200_fsai schur;
+   /* optional: the two products with K12 of every apply through the NFFT operator instead of the dense block (precond_host.c) */
+   void *k12_op;        /* b200_additive* of an NFFT kernel handle built with the hyper-parameters of the setup, or NULL */
+   double *d_opz, *d_opt; /* two vectors of length n */
    void *nys;      /* set when the estimated rank is below max_k: Nystrom on the FPS ordering */
    double *d_work; /* 2n + 2k */
    double *d_x, *d_rhs;

@@ -403,6 +403,10 @@ void b200_afn_release(b200_afn *s)
    b200_free(s->d_lm_idx);
    b200_free(s->d_sc_idx);
    b200_free(s->d_sh_work);
+   b200_free(s->d_opz);
+   b200_free(s->d_opt);
+   s->d_opz = s->d_opt = NULL;
+   s->k12_op = NULL; /* a new setup starts from the dense block */
    s->d_perm = NULL;
    s->d_lm_idx = s->d_sc_idx = NULL;
    s->d_Linv = s->d_K12 = s->d_work = s->d_sh_work = NULL;
@@ -439,6 +443,58 @@ int Nfft4GPB200PrecondAFNSetRankEstimation(void *str, int m, int numests, int no
    s->est_num = numests;
    s->noran = noran;
    s->est_seed = seed;
+   return 0;
+}
+
+/* K12 products of the apply through the NFFT operator (see b200_afn_solve_dev).  nfft_kernel = the pointer an NFFT additive kernel
+ * function returned in *Kp for the SAME data and hyper-parameters as the dense kernel of the setup (NULL switches back to the dense
+ * block).  release_block != 0 frees the dense K12 block (8 k (n - k) bytes; the setup needs it, the apply then does not).  The
+ * operator approximates K12 to the NFFT accuracy (3e-8 relative at a resolved length scale), in fp64; the preconditioner stays
+ * symmetric because the NFFT matvec is (spread = adjoint of the gather).  Single-GPU apply only. */
+int Nfft4GPB200PrecondAFNSetK12Operator(void *str, void *nfft_kernel, int release_block)
+{
+   b200_afn *s = (b200_afn *)str;
+   b200_additive *op = nfft_kernel ? b200_additive_from_handle(nfft_kernel) : NULL;
+   if (!s || s->magic != B200_MAGIC_AFN || (nfft_kernel && !op))
+   {
+      printf("Error: Nfft4GPB200PrecondAFNSetK12Operator needs an AFN handle and an additive NFFT kernel handle.\n");
+      return -1;
+   }
+   if (!op)
+   {
+      if (!s->d_K12 && !s->d_K12f && s->d_Linv && s->n > s->k)
+      {
+         printf("Error: the dense K12 block was released; run the setup again.\n");
+         return -1;
+      }
+      s->k12_op = NULL;
+      return 0;
+   }
+   if (!s->d_Linv || s->nys)
+   {
+      printf("Error: Nfft4GPB200PrecondAFNSetK12Operator follows the setup (block form of the AFN preconditioner).\n");
+      return -1;
+   }
+   if (!op->built || op->n != s->n || (op->shard_mode == 2 && b200_comm_size() > 1))
+   {
+      printf("Error: the NFFT kernel handle is not built for the %d points of the preconditioner (unsharded).\n", s->n);
+      return -1;
+   }
+   if (!s->d_opz)
+   {
+      s->d_opz = (double *)b200_malloc(sizeof(double) * (size_t)s->n);
+      s->d_opt = (double *)b200_malloc(sizeof(double) * (size_t)s->n);
+      if (!s->d_opz || !s->d_opt)
+         return -1;
+   }
+   s->k12_op = op;
+   if (release_block)
+   {
+      b200_free(s->d_K12);
+      b200_free(s->d_K12f);
+      s->d_K12 = NULL;
+      s->d_K12f = NULL;
+   }
    return 0;
 }
 
@@ -686,7 +742,14 @@ int b200_afn_solve_dev(void *va, int n, double *d_x, const double *d_rhs)
    if (s->nys) /* rank < max rank: Nystrom on the FPS ordering (afn_setup.m:80-100, afn_solve.m:41-44) */
       return b200_nys_solve_dev(s->nys, n, d_x, d_rhs);
    if (s->d_Linv && n != s->n && b200_comm_size() > 1)
+   {
+      if (!s->d_K12 && !s->d_K12f)
+      {
+         printf("Error: the sharded AFN apply needs the dense K12 block (released by Nfft4GPB200PrecondAFNSetK12Operator).\n");
+         return -1;
+      }
       return afn_solve_sharded(s, n, d_x, d_rhs);
+   }
    if (!s->d_Linv || n != s->n)
    {
       printf("Error: AFN preconditioner is not set up for n = %d.\n", n);
@@ -705,7 +768,21 @@ int b200_afn_solve_dev(void *va, int n, double *d_x, const double *d_rhs)
    /* y = A11 \ rp = L^{-T} (L^{-1} rp) */
    if (b200k_gemv('N', k, k, 1.0, s->d_Linv, rp, 0.0, t) || b200k_gemv('T', k, k, 1.0, s->d_Linv, t, 0.0, y))
       return -1;
-   if (n2 > 0)
+   if (n2 > 0 && s->k12_op)
+   {
+      /* The same four steps with the K12 products done by the NFFT operator: K21 y = (K z)(perm2) for z = y scattered to the landmark
+       * positions (z vanishes on the other rows, so the noise term of the operator does not reach them), and K12 y2 = (K z)(perm1)
+       * for z = y2 scattered to the non-landmark positions.  Two fast matvecs (O(n)) replace two passes over the k x (n - k) block. */
+      b200_additive *op = (b200_additive *)s->k12_op;
+      double *z = s->d_opz, *tt = s->d_opt;
+      if (b200k_fill(n, 0.0, z) || b200k_scatter_perm(k, s->d_perm, y, z) || b200_additive_matvec_dev(op, n, 1.0, z, 0.0, tt) ||
+          b200k_gather_perm(n2, s->d_perm + k, tt, z) || b200k_axpy(n2, -1.0, z, rp2) || b200_fsai_solve_dev(&s->schur, n2, y2, rp2) ||
+          b200k_fill(n, 0.0, z) || b200k_scatter_perm(n2, s->d_perm + k, y2, z) || b200_additive_matvec_dev(op, n, 1.0, z, 0.0, tt) ||
+          b200k_gather_perm(k, s->d_perm, tt, z) || b200k_axpy(k, -1.0, z, rp) || b200k_gemv('N', k, k, 1.0, s->d_Linv, rp, 0.0, t) ||
+          b200k_gemv('T', k, k, 1.0, s->d_Linv, t, 0.0, y))
+         return -1;
+   }
+   else if (n2 > 0)
    {
       /* rp2 -= A21 y ; y2 = S^{-1} rp2 ; rp -= A12 y2 ; y = A11 \ rp */
       if (afn_k12_gemv(s, 'T', n2, 0, -1.0, y, 1.0, rp2) || b200_fsai_solve_dev(&s->schur, n2, y2, rp2) ||

@@ -136,8 +136,10 @@ k_csr_mv(int nrows, const int *__restrict__ ia, const int *__restrict__ ja, cons
       return;
    int j1 = ia[row], j2 = ia[row + 1];
    double s = 0.0;
+   // values and column indices are read once per product (streaming, evict-first: 12 B per entry that must not push the 8 n bytes of
+   // x out of L2); the gathers x[ja] are the reusable part (__ldg: L1 / L2 resident)
    for (int j = j1 + lane; j < j2; j += 32)
-      s = fma(a[j], __ldg(x + ja[j]), s);
+      s = fma(__ldcs(a + j), __ldg(x + __ldcs(ja + j)), s);
    s = b200_warp_sum(s);
    if (lane == 0)
       y[row] = s;

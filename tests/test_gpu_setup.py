@@ -290,6 +290,40 @@ def test_afn_k12_fp32_storage(gpu):
         h.free()
 
 
+def test_afn_k12_through_the_nfft_operator(gpu):
+    """Nfft4GPB200PrecondAFNSetK12Operator: the two K12 products of the AFN apply as NFFT matvecs (rows of K applied to vectors that
+    vanish on the other block).  The apply agrees with the dense-block apply to the NFFT accuracy, stays symmetric, PCG needs the
+    same number of iterations and reaches the same solution; the dense block can be released afterwards."""
+    n, d, k, lfil = 3000, 6, 300, 100
+    X = uniform_cloud(n, d)
+    win = np.arange(6, dtype=np.int32)
+    f, l, mu = 1.0, 1.0, 0.01
+    D = gpu.DenseAdditiveKernel(X, win, 2, 3, "gaussian").set_hyper(f, l, mu)
+    A = gpu.AdditiveNFFTKernel(X, win, 2, 3, "gaussian").build(f, l, mu)
+    P = gpu.AfnPrecond().setup(D, k, lfil, numests=0, noran=1)
+    r, q = rand_vec(n, 8), rand_vec(n, 9)
+    z_dense = P.solve(r)
+    rhs = rand_vec(n, 4)
+    x1, rel1, _, it1 = gpu.solver_pcg(A.K, n, A.matvec_fn(), P.h, P.solve_fn(), np.zeros(n), rhs, 800, 0, 1e-6)
+    P.set_k12_operator(A)
+    z_op = P.solve(r)
+    err = rel_l2(z_op, z_dense)
+    assert 0 < err <= 1e-5, err                     # the NFFT approximation of the kernel block (measured below 1e-6 at this length scale)
+    assert abs(q @ z_op - r @ P.solve(q)) <= 1e-9 * np.linalg.norm(q) * np.linalg.norm(z_op)    # symmetric apply
+    x2, rel2, _, it2 = gpu.solver_pcg(A.K, n, A.matvec_fn(), P.h, P.solve_fn(), np.zeros(n), rhs, 800, 0, 1e-6)
+    assert it1 > 0 and abs(it2 - it1) <= 1 and rel2 <= 1e-6, (it1, it2)
+    assert rel_l2(x2, x1) <= 1e-5
+    # back to the dense block, then release it for good
+    P.set_k12_operator(None)
+    assert rel_l2(P.solve(r), z_dense) <= 1e-14
+    P.set_k12_operator(A, release_block=True)
+    assert rel_l2(P.solve(r), z_op) <= 1e-12
+    with pytest.raises(RuntimeError):
+        P.set_k12_operator(None)
+    for h in (A, P, D):
+        h.free()
+
+
 def test_afn_rank_estimate_and_branches(gpu):
     n, d = 3000, 3
     X = uniform_cloud(n, d, seed=12)

@@ -167,3 +167,49 @@ def test_sharded_preconditioner_algebra_two_ranks():
     for rank, e_afn, e_nys in res:
         assert e_afn <= 1e-10, (rank, e_afn)
         assert e_nys <= 1e-10, (rank, e_nys)
+
+
+def _probe_sharding_worker(rank, world, port, q):
+    """Probe sharding of the stochastic Lanczos quadrature (lanczos_host.c: Nfft4GPB200SetProbeSharding; BASELINE configs[4]): probe i
+    on rank i (mod R), every rank keeps the whole operator, ONE allreduce of the four sums.  NumPy restatement of the quadrature
+    (oracle/np_solvers.py) with gloo, against the single-process run over all probes."""
+    sys.path.insert(0, ROOT)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    from oracle import np_setup as S
+    from oracle import np_solvers as NS
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    n, d, nv, maxits = 200, 6, 6, 30
+    rng = np.random.default_rng(9)
+    X = rng.random((d, n)) * n ** (1.0 / d)
+    wins = [[0, 1, 2], [3, 4, 5]]
+    f, l, mu = 1.1, 0.9, 0.05
+    K = S.dense_matrix(X, f, l, mu, "gaussian", wins)
+    h = 1e-6
+    dKl = (S.dense_matrix(X, f, l + h, mu, "gaussian", wins) - S.dense_matrix(X, f, l - h, mu, "gaussian", wins)) / (2 * h)
+    mv = lambda v: K @ v
+    gmv = lambda v: np.concatenate([2.0 / f * (K @ v), dKl @ v, f * f * v])
+    probes = np.where(np.random.default_rng(10).random((nv, n)) < 0.5, -1.0, 1.0)      # every rank draws every probe
+    mine = [probes[i] for i in range(nv) if i % world == rank]
+    val, dval = NS.slq_logdet(mv, gmv, n, maxits, mine)
+    sums = np.concatenate([[val * len(mine)], dval * len(mine) * n])                   # un-normalised local sums
+    t = torch.from_numpy(sums)
+    dist.all_reduce(t)                                                                  # the one collective
+    val_sh, dval_sh = t.numpy()[0] / nv, t.numpy()[1:] / nv / n
+    val_1, dval_1 = NS.slq_logdet(mv, gmv, n, maxits, probes)
+    q.put((rank, abs(val_sh - val_1) / abs(val_1), float(np.abs(dval_sh - dval_1).max() / np.abs(dval_1).max())))
+    dist.destroy_process_group()
+
+
+def test_probe_sharded_lanczos_quadrature_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_probe_sharding_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, e_val, e_dval in res:
+        assert e_val <= 1e-12 and e_dval <= 1e-12, (rank, e_val, e_dval)
