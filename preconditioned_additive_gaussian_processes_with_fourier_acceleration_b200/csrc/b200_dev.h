@@ -109,6 +109,7 @@ typedef struct
    double *ctab;                /* [2][nw][64][16] polynomial coefficients per cell (gather): kernel / derivative channel */
 } b200_poly1d_dev;
 int b200k_poly1d_max_block(void);
+int b200k_poly1d_wave_slots(void);
 int b200k_poly1d_spread(const b200_poly1d_dev *p, const double *d_x, double s, double *d_grids, size_t grid_stride);
 int b200k_poly1d_coef(const b200_poly1d_dev *p, int ch, const double *d_grids, size_t grid_stride, const double *d_wscale);
 int b200k_poly1d_gather(const b200_poly1d_dev *p, int nch, const double *d_x, double s, double c0, double mu, double ff, double beta,

@@ -12,7 +12,7 @@
 // permuted coefficient, and the prep / combine passes with their random 8-byte accesses disappear: points are sorted by cell
 // only INSIDE blocks of T consecutive points of the ORIGINAL order (done once per handle), so x and y are moved as coalesced
 // blocks through shared memory and the "permutation" is a shared-memory index.
-//   spread: CTA (g, w) walks the blocks b = g (mod G) of window w; a warp owns the runs of the cells c = warp (mod 16): lanes stride
+//   spread: the (window, block) items are cut into one wave of equal CTA ranges; a warp owns the runs of the cells c = warp (mod 16): lanes stride
 //           over the run accumulating 15 moments in registers, ONE transposing butterfly (16 values over 32 lanes in 16 shuffles)
 //           per run adds them to the CTA's 64 x 16 table in shared memory, which goes to the window's global table with fp64 REDs
 //           once per CTA.
@@ -76,22 +76,63 @@ __device__ __forceinline__ double p_transpose_reduce16(const double m[16], int l
 }
 
 // ---------------------------------------------------------------------------------------------------- spread: moments
+// moments of one point: m[k] += a v^k, k = 0..14, as two independent chains in v^2 (even / odd powers)
+__device__ __forceinline__ void p_moments(double m[16], double a, double v)
+{
+   const double v2 = v * v;
+   double e = a, o = a * v;
+#pragma unroll
+   for (int k = 0; k < PNC; k += 2)
+   {
+      m[k] += e;
+      e *= v2;
+      if (k + 1 < PNC)
+      {
+         m[k + 1] += o;
+         o *= v2;
+      }
+   }
+}
+__device__ __forceinline__ double p_offset(double xt) // v = 2 u - 1, u = fractional part of 64 x
+{
+   const double t = xt * 64.0;
+   return 2.0 * (t - floor(t)) - 1.0;
+}
+
+// The work items (window w, block b), w-major, are cut into gridDim.x equal consecutive ranges: ONE wave of CTAs whatever the
+// number of windows (a grid of G x nw CTAs left a second, nearly empty wave behind: 304 CTAs on 296 slots doubled the time).
+// A CTA keeps the moments of its current window in shared memory and adds them to the window's global table when it moves on.
 __global__ void __launch_bounds__(PTHREADS)
 k_poly1d_spread(b200_poly1d_dev p, const double *__restrict__ x, double s)
 {
    extern __shared__ __align__(16) double psm[];
    double *xs = psm, *msm = psm + p.T;
    unsigned short *rs = reinterpret_cast<unsigned short *>(msm + 64 * PLD);
-   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, w = blockIdx.y;
-   const size_t wbase = (size_t)w * p.nblk * p.T;
-   const double *__restrict__ xt = p.xt + wbase;
-   const unsigned short *__restrict__ lp = p.lp + wbase;
-   for (int e = tid; e < 64 * PLD; e += PTHREADS)
-      msm[e] = 0.0;
-   for (int b = blockIdx.x; b < p.nblk; b += gridDim.x)
+   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+   const long long items = (long long)p.nw * p.nblk;
+   const long long it0 = items * blockIdx.x / gridDim.x, it1 = items * (blockIdx.x + 1) / gridDim.x;
+   int wcur = -1;
+   for (long long it = it0; it < it1; it++)
    {
+      const int w = (int)(it / p.nblk), b = (int)(it - (long long)w * p.nblk);
+      const size_t wbase = (size_t)w * p.nblk * p.T;
+      const double *__restrict__ xt = p.xt + wbase;
+      const unsigned short *__restrict__ lp = p.lp + wbase;
       const int base = b * p.T, cnt = min(p.T, p.n - base);
-      __syncthreads(); // the previous block's runs are done with xs / rs
+      __syncthreads(); // the previous item's runs are done with xs / rs / msm
+      if (w != wcur)
+      {
+         if (wcur >= 0)
+         {
+            double *mg = p.mom + (size_t)wcur * 64 * PLD;
+            for (int e = tid; e < 64 * PLD; e += PTHREADS)
+               if (msm[e] != 0.0)
+                  p_red_add(mg + e, msm[e]);
+         }
+         for (int e = tid; e < 64 * PLD; e += PTHREADS)
+            msm[e] = 0.0;
+         wcur = w;
+      }
       for (int j = tid; j < p.T; j += PTHREADS)
          xs[j] = j < cnt ? s * __ldg(x + base + j) : 0.0;
       if (tid < 65)
@@ -106,18 +147,17 @@ k_poly1d_spread(b200_poly1d_dev p, const double *__restrict__ x, double s)
 #pragma unroll
          for (int k = 0; k < 16; k++)
             m[k] = 0.0;
-         for (int j = j0 + lane; j < j1; j += 32)
+         int j = j0 + lane;
+         for (; j + 32 < j1; j += 64) // two points per lane and step: four independent dependency chains
          {
-            const double t = __ldg(xt + base + j) * 64.0;
-            const double v = 2.0 * (t - floor(t)) - 1.0;
-            double pw = xs[lp[base + j]];
-#pragma unroll
-            for (int k = 0; k < PNC; k++)
-            {
-               m[k] += pw;
-               pw *= v;
-            }
+            const double xa = __ldg(xt + base + j), xb = __ldg(xt + base + j + 32);
+            const int la = lp[base + j], lb = lp[base + j + 32];
+            const double aa = xs[la], ab = xs[lb];
+            p_moments(m, aa, p_offset(xa));
+            p_moments(m, ab, p_offset(xb));
          }
+         if (j < j1)
+            p_moments(m, xs[lp[base + j]], p_offset(__ldg(xt + base + j)));
          int q;
          const double tot = p_transpose_reduce16(m, lane, q);
          if (!(lane & 1) && q < PNC)
@@ -125,10 +165,13 @@ k_poly1d_spread(b200_poly1d_dev p, const double *__restrict__ x, double s)
       }
    }
    __syncthreads();
-   double *mg = p.mom + (size_t)w * 64 * PLD;
-   for (int e = tid; e < 64 * PLD; e += PTHREADS)
-      if (msm[e] != 0.0)
-         p_red_add(mg + e, msm[e]);
+   if (wcur >= 0)
+   {
+      double *mg = p.mom + (size_t)wcur * 64 * PLD;
+      for (int e = tid; e < 64 * PLD; e += PTHREADS)
+         if (msm[e] != 0.0)
+            p_red_add(mg + e, msm[e]);
+   }
 }
 
 // moments -> oversampled grid: g[l] = sum_t sum_k p_t[k] M[cell with tap t at l][k]; one CTA per window, one thread per grid cell
@@ -166,6 +209,21 @@ __global__ void k_poly1d_grid2coef(const double *__restrict__ grid, size_t grid_
 }
 
 // ---------------------------------------------------------------------------------------------------- gather: Horner + epilogue
+// degree-14 polynomial as E(v^2) + v O(v^2): two independent FMA chains of 7 instead of one of 14
+__device__ __forceinline__ double p_horner(const double cf[PNC], double v)
+{
+   const double v2 = v * v;
+   double e = cf[14], o = cf[13];
+#pragma unroll
+   for (int k = 12; k >= 0; k -= 2)
+   {
+      e = fma(e, v2, cf[k]);
+      if (k - 1 >= 0)
+         o = fma(o, v2, cf[k - 1]);
+   }
+   return fma(o, v, e);
+}
+
 // NCH = 1: y = beta y + c0 (sum_w f_w + nw mu a)                                     (nfft_interface.c:428-494, 803-814)
 // NCH = 2: gradient blocks y0 = beta y0 + f2 (sum_w f_w + nw mu a), y1 = beta y1 + sum_w c1_w fd_w (c1_w folded into the table),
 //          y2 = beta y2 + nw ff a                                                       (nfft_interface.c:539-617, 826-837)
@@ -206,20 +264,25 @@ k_poly1d_gather(b200_poly1d_dev p, const double *__restrict__ x, double s, doubl
 #pragma unroll
             for (int k = 0; k < PNC; k++)
                cf[ch][k] = ct[ch * 64 * PLD + c * PLD + k];
-         for (int j = j0 + lane; j < j1; j += 32)
+         int j = j0 + lane;
+         for (; j + 32 < j1; j += 64) // two points per lane and step, each polynomial as two chains in v^2
          {
-            const double t = __ldg(xt + j) * 64.0;
-            const double v = 2.0 * (t - floor(t)) - 1.0;
-            const int l = lp[j];
+            const double va = p_offset(__ldg(xt + j)), vb = p_offset(__ldg(xt + j + 32));
+            const int la = lp[j], lb = lp[j + 32];
 #pragma unroll
             for (int ch = 0; ch < NCH; ch++)
             {
-               double f = cf[ch][PNC - 1];
-#pragma unroll
-               for (int k = PNC - 2; k >= 0; k--)
-                  f = fma(f, v, cf[ch][k]);
-               acc[ch * p.T + l] += f; // every point of the block belongs to exactly one run of this window
+               acc[ch * p.T + la] += p_horner(cf[ch], va); // every point of the block belongs to exactly one run of this window
+               acc[ch * p.T + lb] += p_horner(cf[ch], vb);
             }
+         }
+         if (j < j1)
+         {
+            const double v = p_offset(__ldg(xt + j));
+            const int l = lp[j];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch++)
+               acc[ch * p.T + l] += p_horner(cf[ch], v);
          }
       }
    }
@@ -250,6 +313,14 @@ static size_t poly_smem_gather(int T, int nch) { return sizeof(double) * (size_t
 
 // largest block size (points per locally sorted block) the gather kernel of the gradient matvec still fits into shared memory with
 int b200k_poly1d_max_block(void) { return 8192; }
+// CTAs of one resident wave of the spread / gather kernels (two per SM: registers and shared memory)
+int b200k_poly1d_wave_slots(void)
+{
+   int sm = 148, dev = 0;
+   if (cudaGetDevice(&dev) == cudaSuccess)
+      cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+   return 2 * sm;
+}
 
 // x (n values, original order) -> oversampled grids of the nw local windows (64 doubles each, stride grid_stride)
 int b200k_poly1d_spread(const b200_poly1d_dev *p, const double *d_x, double s, double *d_grids, size_t grid_stride)
@@ -264,13 +335,14 @@ int b200k_poly1d_spread(const b200_poly1d_dev *p, const double *d_x, double s, d
    int sm = 148, dev = 0;
    if (cudaGetDevice(&dev) == cudaSuccess)
       cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
-   int G = (2 * sm + p->nw - 1) / p->nw; // about two CTAs per SM over all windows
-   if (G > p->nblk)
-      G = p->nblk;
+   long long items = (long long)p->nw * p->nblk;
+   int G = 2 * sm; // one wave: two CTAs per SM (registers and shared memory allow exactly two)
+   if (G > items)
+      G = (int)items;
    if (G < 1)
       G = 1;
    B200_CHECK(cudaMemsetAsync(p->mom, 0, sizeof(double) * (size_t)p->nw * 64 * PLD, b200_stream()));
-   k_poly1d_spread<<<dim3(G, p->nw), PTHREADS, poly_smem_spread(p->T), b200_stream()>>>(*p, d_x, s);
+   k_poly1d_spread<<<G, PTHREADS, poly_smem_spread(p->T), b200_stream()>>>(*p, d_x, s);
    B200_LAUNCHED();
    k_poly1d_mom2grid<<<p->nw, 64, 0, b200_stream()>>>(p->mom, d_grids, grid_stride);
    B200_LAUNCHED();

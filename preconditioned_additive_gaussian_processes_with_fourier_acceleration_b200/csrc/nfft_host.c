@@ -968,10 +968,18 @@ static int additive_poly_setup(b200_additive *A, const double *cols_all, int n)
    for (i = 0; i < P; i++)
       if (b200_comm_owns_window(A, i))
          A->poly_win[nw++] = i;
-   /* block size: a power of two in [1024, max] giving at least ~ 2 blocks per SM */
-   T = b200k_poly1d_max_block();
-   while (T > 1024 && (long long)n / T < 296)
-      T >>= 1;
+   /* block size: the gather runs one CTA per block, two CTAs per SM, so the number of blocks should fill whole waves of
+    * `slots` CTAs: T = n / (slots m) for the smallest m that brings T under the shared-memory limit (a multiple of 32, >= 1024) */
+   {
+      const int slots = b200k_poly1d_wave_slots(), tmax = b200k_poly1d_max_block();
+      int m = 1;
+      while (((long long)n + (long long)slots * m - 1) / ((long long)slots * m) > tmax - 31)
+         m++;
+      T = (int)(((long long)n + (long long)slots * m - 1) / ((long long)slots * m));
+      T = (T + 31) & ~31;
+      if (T < 1024)
+         T = 1024;
+   }
    nblk = (n + T - 1) / T;
    per_w = (size_t)nblk * T;
    A->poly.n = n;

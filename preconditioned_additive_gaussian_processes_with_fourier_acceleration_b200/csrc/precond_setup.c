@@ -94,8 +94,8 @@ static int nys_setup_perm(b200_nys *s, double *data, int n, int ldim, int d, fun
                           const int *perm_in, int k, int require_grad)
 {
    nfft4gp_kernel *pk = (nfft4gp_kernel *)fkernel_params;
-   b200_dense_view v;
-   int own, rc = -1, i, j, *perm = NULL, *d_perm = NULL;
+   b200_dense_view v, v11;
+   int own, rc = -1, i, j, *perm = NULL, *d_perm = NULL, quirk = 0;
    double *K11 = NULL, *AA = NULL, *w = NULL, *sv = NULL, *Vs = NULL;
    double *d_K1 = NULL, *d_U = NULL, *d_small = NULL, *d_small2 = NULL;
    double noise_level, f2, eta;
@@ -134,8 +134,19 @@ static int nys_setup_perm(b200_nys *s, double *data, int n, int ldim, int d, fun
    {
       /* K1 = K(perm, perm[0:k]) (n x k, no noise: nys.c:597) and K11 = its leading block (noise 0: nys.c:562) */
       d_perm = upload_ints(perm, (size_t)n);
+      /* Reference quirk, reproduced on request (NFFT4GP_B200_REFERENCE_QUIRKS=1) so that the reference's own drivers print what they
+       * print on the reference's code: nys.c:549-566 forms K11 by calling the kernel on the k sub-sampled points with n = k, and the
+       * reference's dense ADDITIVE kernel ignores its data argument and strides its own feature copy with that n (kernels.c:3160),
+       * i.e. it reads the FIRST P dw k values of the copy as a [P dw] x k feature table.  The same view here: stride k, rows 0..k-1. */
+      if (fkernel == Nfft4GPKernelAdditiveKernel && getenv("NFFT4GP_B200_REFERENCE_QUIRKS") && atoi(getenv("NFFT4GP_B200_REFERENCE_QUIRKS")) > 0)
+      {
+         v11 = v;
+         v11.n = k;
+         v11.owns = 0;
+         quirk = 1;
+      }
       if (!d_perm || b200_dense_view_block(&v, 0.0, d_perm, n, d_perm, k, 0, d_K1, n) ||
-          b200_dense_view_block(&v, 0.0, d_perm, k, d_perm, k, 1, d_small2, k))
+          b200_dense_view_block(quirk ? &v11 : &v, 0.0, quirk ? NULL : d_perm, k, quirk ? NULL : d_perm, k, 1, d_small2, k))
          goto done;
    }
    else
@@ -182,10 +193,10 @@ static int nys_setup_perm(b200_nys *s, double *data, int n, int ldim, int d, fun
           b200_d2d(g_K1, d_K1, sizeof(double) * (size_t)n * k) || b200_d2d(g_Linv, d_small, sizeof(double) * kk) ||
           b200_dense_view_block_dl(&v, d_perm, n, d_perm, k, 0, g_dK1l, n) ||
           /* dK11/df = (2/f) K11 (noise 0, no shift): G_0 = (2/f) L^{-1} K11 L^{-T} */
-          b200_dense_view_block(&v, 0.0, d_perm, k, d_perm, k, 0, t1, k) ||
+          b200_dense_view_block(quirk ? &v11 : &v, 0.0, quirk ? NULL : d_perm, k, quirk ? NULL : d_perm, k, 0, t1, k) ||
           b200k_dgemm('N', 'N', k, k, k, 2.0 / pk->_params[0], d_small, k, t1, k, 0.0, t2, k) ||
           b200k_dgemm('N', 'T', k, k, k, 1.0, t2, k, d_small, k, 0.0, g_G0, k) ||
-          b200_dense_view_block_dl(&v, d_perm, k, d_perm, k, 0, t1, k) ||
+          b200_dense_view_block_dl(quirk ? &v11 : &v, quirk ? NULL : d_perm, k, quirk ? NULL : d_perm, k, 0, t1, k) ||
           b200k_dgemm('N', 'N', k, k, k, 1.0, d_small, k, t1, k, 0.0, t2, k) ||
           b200k_dgemm('N', 'T', k, k, k, 1.0, t2, k, d_small, k, 0.0, g_G1, k) || b200_sync();
       b200_free(t1);

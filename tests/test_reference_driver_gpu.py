@@ -81,8 +81,12 @@ def test_reference_test3_test4_drivers_run_on_the_gpu_library(tmp_path, test, ex
     work = str(tmp_path)
     os.symlink(os.path.join(d, "data"), os.path.join(work, "data"))
     args = str(gold["args"]).split()
+    # TEST3 factors a Nystrom preconditioner of the dense ADDITIVE kernel, where the reference reads the wrong rows of its feature copy
+    # (nys.c:549-566 + kernels.c:3160; DESIGN.md "deliberate deviations"): the library's intended-semantics default gives another
+    # (better) preconditioner and therefore another optimisation path; NFFT4GP_B200_REFERENCE_QUIRKS=1 reproduces the reference's block
+    env = dict(os.environ, OMP_NUM_THREADS="1", NFFT4GP_B200_REFERENCE_QUIRKS="1")
     try:
-        p = subprocess.run([exe] + args, capture_output=True, text=True, timeout=timeout, cwd=work, env=dict(os.environ, OMP_NUM_THREADS="1"))
+        p = subprocess.run([exe] + args, capture_output=True, text=True, timeout=timeout, cwd=work, env=env)
     except (OSError, subprocess.TimeoutExpired) as exc:
         pytest.skip(f"the prebuilt reference driver could not be started here: {exc!r}")
     name = args[0]
@@ -95,7 +99,5 @@ def test_reference_test3_test4_drivers_run_on_the_gpu_library(tmp_path, test, ex
     dl, dp, dq = np.abs(loss - gold["loss"]).max(), np.abs(params - gold["final_params"]).max(), np.abs(pred - gold["pred"]).max()
     print(f"{test}: max |loss - ref| {dl:.2e}, max |params - ref| {dp:.2e}, max |pred - ref| {dq:.2e} (printed precision 1e-10)")
     assert loss.shape == gold["loss"].shape and pred.shape == gold["pred"].shape
-    # TEST3 factors a Nystrom preconditioner of the dense ADDITIVE kernel, where the reference reads the wrong rows of its feature copy
-    # (DESIGN.md "deliberate deviations"): the preconditioner differs, the preconditioned SOLUTIONS agree to the solver tolerance
-    tol = 5e-4 if test == "TEST3" else 1e-6
-    assert dl <= tol and dp <= tol and dq <= 50 * tol
+    tol = 1e-6
+    assert dl <= tol and dp <= tol and dq <= tol
