@@ -99,5 +99,5 @@ def test_reference_test3_test4_drivers_run_on_the_gpu_library(tmp_path, test, ex
     dl, dp, dq = np.abs(loss - gold["loss"]).max(), np.abs(params - gold["final_params"]).max(), np.abs(pred - gold["pred"]).max()
     print(f"{test}: max |loss - ref| {dl:.2e}, max |params - ref| {dp:.2e}, max |pred - ref| {dq:.2e} (printed precision 1e-10)")
     assert loss.shape == gold["loss"].shape and pred.shape == gold["pred"].shape
-    tol = 1e-6
+    tol = 2e-9       # the printed precision; measured on a B200: every printed digit identical (profiles/r2_c_reference_drivers_test3_test4_on_gpu.txt)
     assert dl <= tol and dp <= tol and dq <= tol
