@@ -97,6 +97,50 @@ def fsai_rows(Kfun, pattern):
     return vals
 
 
+def dense_kernel_dl(X, rows, cols, f, l, kernel="gaussian", windows=None):
+    """dK/dl of dense_kernel: Gaussian f^2 exp(-r^2 / 2 l^2) r^2 / l^3 (kernels.c:522), Matern-1/2 f^2 exp(-r / l) r / l^2 (:2220)."""
+    X = np.asarray(X, dtype=np.float64)
+    wins = [list(range(X.shape[0]))] if windows is None else windows
+    out = np.zeros((len(rows), len(cols)))
+    for feats in wins:
+        A = X[np.ix_(feats, rows)].T
+        B = X[np.ix_(feats, cols)].T
+        r2 = ((A[:, None, :] - B[None, :, :]) ** 2).sum(-1)
+        out += np.exp(-r2 / (2.0 * l * l)) * r2 / l ** 3 if kernel == "gaussian" else np.exp(-np.sqrt(r2) / l) * np.sqrt(r2) / l ** 2
+    return f * f * out / len(wins)
+
+
+def fsai_rows_grad(Kfun, dKfuns, pattern):
+    """fsai.c:495-560 (require_grad): per row g = K^{-1} e / sqrt(e' K^{-1} e) and, for every hyper-parameter, w = -K^{-1} dK g,
+    dg = w - 0.5 w_last dd g with dd = 1 / sqrt(e' K^{-1} e).  dKfuns: three callables J -> dK_theta(J, J).  Returns (vals, dvals[3])."""
+    vals, dvals = [], [[], [], []]
+    for J in pattern:
+        J = np.asarray(J)
+        Kb = Kfun(J)
+        e = np.zeros(len(J))
+        e[-1] = 1.0
+        u = np.linalg.solve(Kb, e)
+        dd = 1.0 / np.sqrt(u[-1])
+        g = u * dd
+        vals.append(g)
+        for t in range(3):
+            w = -np.linalg.solve(Kb, dKfuns[t](J) @ g)
+            dvals[t].append(w - 0.5 * w[-1] * dd * g)
+    return vals, dvals
+
+
+def fsai_trace(vals, dvals):
+    """fsai.c:221-276: 2 sum_i dG_ii / G_ii per hyper-parameter (the diagonal is the last entry of a row)."""
+    return np.array([2.0 * sum(dg[-1] / g[-1] for g, dg in zip(vals, dvals[t])) for t in range(3)])
+
+
+def fsai_dvp(G, dG, x):
+    """fsai.c:125-219 for one hyper-parameter: y = G' ( G^{-T} dG' G^{-T} x + dG G^{-1} G^{-T} x )."""
+    w1 = np.linalg.solve(G.T, x)
+    w2 = np.linalg.solve(G.T, dG.T @ w1) + dG @ np.linalg.solve(G, w1)
+    return G.T @ w2
+
+
 def csr_to_dense(n, ia, ja, a):
     G = np.zeros((n, n))
     for i in range(n):

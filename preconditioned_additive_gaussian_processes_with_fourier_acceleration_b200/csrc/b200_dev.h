@@ -209,6 +209,12 @@ int b200k_knn_pattern(const double *d_X, int n, int ld, int d, int lfil, int *d_
 int b200k_fsai_rows(const double *d_Xw, const int *d_dims, int n_points, int P, int dw, int kernel, double ff, double l,
                     double noise_diag, int nrows, const int *d_ia, const int *d_ja, const int *d_rowmap, const double *d_Z, int kz,
                     int kmax, double *d_a, int *breakdown_out);
+int b200k_fsai_rows_grad(const double *d_Xw, const int *d_dims, int n_points, int P, int dw, int kernel, double ff, double l,
+                         double noise_diag, int nrows, const int *d_ia, const int *d_ja, int kmax, double *d_a, double *d_da, size_t da_stride,
+                         int *breakdown_out);
+/* sparse triangular solves with the FSAI factor: upper = 0: G x = rhs (rows of G, diagonal last); 1: G' x = rhs (rows of G', diagonal first) */
+int b200k_sptrsv(int upper, int n, const int *d_ia, const int *d_ja, const double *d_a, const double *d_rhs, double *d_x);
+int b200k_fsai_trace(int n, const int *d_ia, const double *d_a, const double *d_da, size_t stride, double *d_out3);
 int b200k_csr_transpose(int nrows, int ncols, int nnz, const int *d_ia, const int *d_ja, const double *d_a, int *d_iat, int *d_jat,
                         double *d_at);
 int b200k_gather_rows(int n, int ncol, const int *d_perm, const double *d_src, int lds, double *d_dst, int ldd);

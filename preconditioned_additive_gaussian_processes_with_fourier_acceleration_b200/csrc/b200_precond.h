@@ -51,6 +51,11 @@ typedef struct
    double *d_x, *d_rhs;
    int cap;
    double tset;
+   /* setup with require_grad (fsai.c:495-560): derivatives of the factor values in f, l, mu on the pattern of G and on the pattern
+    * of G' (the reference's _dL_a, and its transpose so that dG' x needs no scatter), and 4 n doubles of work for Dvp */
+   double *d_da;  /* [3][nnz] */
+   double *d_dat; /* [3][nnz] */
+   double *d_gwork;
 } b200_fsai;
 
 /* AFN (afn.h:27-58 design; MATLAB afn_setup.m / afn_solve.m). */
@@ -88,6 +93,8 @@ int b200_nys_set_device_factors(b200_nys *s, int n, int k, const int *h_perm, do
 int b200_fsai_set_host_factors(b200_fsai *s, int n, const int *ia, const int *ja, const double *a);
 /* takes ownership of the device CSR arrays and builds the explicit transpose on the device */
 int b200_fsai_set_device_factors(b200_fsai *s, int n, int nnz, int *d_ia, int *d_ja, double *d_a);
+/* takes ownership of d_da = [3][nnz] derivative values (require_grad) and builds their transposes */
+int b200_fsai_set_device_grad(b200_fsai *s, double *d_da);
 int b200_afn_set_device_factors(b200_afn *s, int n, int k, const int *h_perm, const double *h_L, double *d_K12_owned,
                                 const int *ia, const int *ja, const double *a);
 void b200_fsai_release(b200_fsai *s);

@@ -236,8 +236,12 @@ void b200_fsai_release(b200_fsai *s)
    b200_free(s->d_jat);
    b200_free(s->d_at);
    b200_free(s->d_work);
+   b200_free(s->d_da);
+   b200_free(s->d_dat);
+   b200_free(s->d_gwork);
    s->d_ia = s->d_ja = s->d_iat = s->d_jat = NULL;
    s->d_a = s->d_at = s->d_work = NULL;
+   s->d_da = s->d_dat = s->d_gwork = NULL;
    s->n = s->nnz = 0;
 }
 
@@ -277,6 +281,141 @@ int b200_fsai_set_device_factors(b200_fsai *s, int n, int nnz, int *d_ia, int *d
    if (!s->d_iat || !s->d_jat || !s->d_at || !s->d_work)
       return -1;
    return b200k_csr_transpose(n, n, nnz, d_ia, d_ja, d_a, s->d_iat, s->d_jat, s->d_at) || b200_sync();
+}
+
+int b200_fsai_set_device_grad(b200_fsai *s, double *d_da)
+{
+   int t, *iat_tmp, *jat_tmp;
+   size_t nnz = (size_t)(s->nnz ? s->nnz : 1);
+   s->d_da = d_da;
+   s->d_dat = (double *)b200_malloc(sizeof(double) * 3 * nnz);
+   s->d_gwork = (double *)b200_malloc(sizeof(double) * 4 * (size_t)(s->n ? s->n : 1));
+   iat_tmp = (int *)b200_malloc(sizeof(int) * ((size_t)s->n + 1));
+   jat_tmp = (int *)b200_malloc(sizeof(int) * nnz);
+   t = !s->d_dat || !s->d_gwork || !iat_tmp || !jat_tmp;
+   /* same pattern, same ordering rule: the transposed values land where the entries of G' are */
+   for (int q = 0; !t && q < 3; q++)
+      t = b200k_csr_transpose(s->n, s->n, s->nnz, s->d_ia, s->d_ja, s->d_da + q * (size_t)s->nnz, iat_tmp, jat_tmp, s->d_dat + q * (size_t)s->nnz);
+   t = t || b200_sync();
+   b200_free(iat_tmp);
+   b200_free(jat_tmp);
+   return t ? -1 : 0;
+}
+
+/* ---- gradient side of the FSAI preconditioner M = (G'G)^{-1} (fsai.c:125-276, 675-721), device resident */
+static int fsai_has_grad(const b200_fsai *s, const char *who)
+{
+   if (!s || s->magic != B200_MAGIC_FSAI || !s->d_a)
+      return 0;
+   if (!s->d_da)
+   {
+      printf("Setup FSAI without gradient, %s not supported.\n", who); /* fsai.c:141-145, 229-233 */
+      return 0;
+   }
+   return 1;
+}
+
+/* fsai.c:675-698 */
+int Nfft4GPPrecondFsaiInvL(void *vfsai_mat, int n, double *x, double *rhs)
+{
+   b200_fsai *s = (b200_fsai *)vfsai_mat;
+   if (!s || s->magic != B200_MAGIC_FSAI || !s->d_a || n != s->n || stage_vectors(&s->d_x, &s->d_rhs, &s->cap, n))
+      return -1;
+   if (b200_h2d(s->d_rhs, rhs, sizeof(double) * (size_t)n) || b200k_sptrsv(0, n, s->d_ia, s->d_ja, s->d_a, s->d_rhs, s->d_x))
+      return -1;
+   return b200_d2h(x, s->d_x, sizeof(double) * (size_t)n);
+}
+
+/* fsai.c:700-721 */
+int Nfft4GPPrecondFsaiInvLT(void *vfsai_mat, int n, double *x, double *rhs)
+{
+   b200_fsai *s = (b200_fsai *)vfsai_mat;
+   if (!s || s->magic != B200_MAGIC_FSAI || !s->d_a || n != s->n || stage_vectors(&s->d_x, &s->d_rhs, &s->cap, n))
+      return -1;
+   if (b200_h2d(s->d_rhs, rhs, sizeof(double) * (size_t)n) || b200k_sptrsv(1, n, s->d_iat, s->d_jat, s->d_at, s->d_rhs, s->d_x))
+      return -1;
+   return b200_d2h(x, s->d_x, sizeof(double) * (size_t)n);
+}
+
+/* fsai.c:221-276: tr(M^{-1} dM/dtheta) = 2 sum_i (dG_ii / dtheta) / G_ii for theta = f, l, mu */
+int Nfft4GPPrecondFsaiTrace(void *vfsai_mat, double **tracesp)
+{
+   b200_fsai *s = (b200_fsai *)vfsai_mat;
+   double *tr, *d3;
+   int rc;
+   if (!fsai_has_grad(s, "trace"))
+      return -1;
+   if (!tracesp)
+   {
+      printf("Trace pointer cannot be NULL\n");
+      return -1;
+   }
+   d3 = (double *)b200_malloc(sizeof(double) * 3);
+   tr = *tracesp ? *tracesp : (double *)b200_xcalloc(3, sizeof(double));
+   {
+      double h3[3];
+      rc = !d3 || b200k_fsai_trace(s->n, s->d_ia, s->d_a, s->d_da, (size_t)s->nnz, d3) || b200_d2h(h3, d3, sizeof(h3));
+      if (!rc)
+      {
+         tr[0] += h3[0]; /* the reference accumulates into the caller's array (fsai.c:257-259) */
+         tr[1] += h3[1];
+         tr[2] += h3[2];
+      }
+   }
+   b200_free(d3);
+   if (rc)
+   {
+      if (!*tracesp)
+         free(tr);
+      return -1;
+   }
+   *tracesp = tr;
+   return 0;
+}
+
+/* fsai.c:125-219: y_theta = G' ( G^{-T} dG' G^{-T} x + dG G^{-1} G^{-T} x ) for the selected hyper-parameters, stacked [f; l; mu] */
+int Nfft4GPPrecondFsaiDvp(void *vfsai_mat, int n, int *mask, double *x, double **yp)
+{
+   b200_fsai *s = (b200_fsai *)vfsai_mat;
+   double *y, *w1, *w2, *t1, *t2;
+   int q, rc = 0;
+   size_t nb = sizeof(double) * (size_t)n;
+   if (!fsai_has_grad(s, "trace"))
+      return -1;
+   if (!yp)
+   {
+      printf("output pointer cannot be NULL\n");
+      return -1;
+   }
+   if (n != s->n || stage_vectors(&s->d_x, &s->d_rhs, &s->cap, n))
+      return -1;
+   y = *yp ? *yp : (double *)b200_xcalloc(3 * (size_t)n, sizeof(double));
+   w1 = s->d_gwork;
+   w2 = w1 + n;
+   t1 = w2 + n;
+   t2 = t1 + n;
+   rc = b200_h2d(s->d_rhs, x, nb) || b200k_sptrsv(1, n, s->d_iat, s->d_jat, s->d_at, s->d_rhs, w1); /* w1 = G^{-T} x */
+   rc = rc || b200k_sptrsv(0, n, s->d_ia, s->d_ja, s->d_a, w1, t2);                                /* t2 = G^{-1} w1 */
+   for (q = 0; !rc && q < 3; q++)
+   {
+      const double *da = s->d_da + (size_t)q * s->nnz, *dat = s->d_dat + (size_t)q * s->nnz;
+      if (mask && !mask[q])
+         continue;
+      rc = b200k_csr_mv(n, s->d_iat, s->d_jat, dat, w1, t1) ||            /* t1 = dG' w1            */
+           b200k_sptrsv(1, n, s->d_iat, s->d_jat, s->d_at, t1, w2) ||      /* w2 = G^{-T} t1         */
+           b200k_csr_mv(n, s->d_ia, s->d_ja, da, t2, t1) ||                /* t1 = dG G^{-1} G^{-T} x */
+           b200k_axpy(n, 1.0, t1, w2) ||                                   /* w2 += t1               */
+           b200k_csr_mv(n, s->d_iat, s->d_jat, s->d_at, w2, s->d_x) ||     /* y = G' w2              */
+           b200_d2h(y + (size_t)q * n, s->d_x, nb);
+   }
+   if (rc)
+   {
+      if (!*yp)
+         free(y);
+      return -1;
+   }
+   *yp = y;
+   return 0;
 }
 
 /* upload G (CSR, rows as given) */

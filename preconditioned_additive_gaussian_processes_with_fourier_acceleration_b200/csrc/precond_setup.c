@@ -296,17 +296,17 @@ int Nfft4GPPrecondNysSetupWithKernel(double *data, int n, int ldim, int d, func_
 }
 
 /* ================================================================== FSAI (fsai.c:302-673) */
-int Nfft4GPPrecondFsaiSetupWithKernel(double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params, int require_grad,
-                                      void *vfsai_mat)
+/* fsai.c:302-673.  pattern_i / pattern_j: the caller's CSR pattern (host, lower triangular, diagonal last in every row; NULL = the
+ * KNN pattern of Nfft4GPDistanceEuclidKnn built on the GPU).  require_grad also builds the derivative factors (fsai.c:495-560). */
+static int fsai_setup_impl(const int *pattern_i, const int *pattern_j, double *data, int n, int ldim, int d, func_kernel fkernel,
+                           void *fkernel_params, int require_grad, b200_fsai *s)
 {
-   b200_fsai *s = (b200_fsai *)vfsai_mat;
    b200_dense_view v;
-   double t0 = wtime(), *d_X = NULL, *d_a = NULL;
-   int own, rc = -1, lfil, kmax, bad = 0, *d_ia = NULL, *d_ja = NULL;
+   double t0 = wtime(), *d_X = NULL, *d_a = NULL, *d_da = NULL;
+   int own, rc = -1, lfil, kmax, bad = 0, *d_ia = NULL, *d_ja = NULL, i;
    long long nnz;
    if (!s || s->magic != B200_MAGIC_FSAI || !fkernel || !fkernel_params || b200_init(-1))
       return -1;
-   (void)require_grad; /* accepted: the derivative factors only serve Dvp / Trace / Logdet, which this library does not export */
    own = b200_dense_view_acquire(fkernel, fkernel_params, data, n, ldim, d, &v);
    if (own)
    {
@@ -314,23 +314,47 @@ int Nfft4GPPrecondFsaiSetupWithKernel(double *data, int n, int ldim, int d, func
          printf("Error: the FSAI setup needs one of this library's dense kernels (Nfft4GPKernel{Additive,Gaussian,Matern12}Kernel).\n");
       return -1;
    }
-   lfil = s->lfil < 1 ? 1 : s->lfil;
-   kmax = lfil < n ? lfil : n;
-   nnz = b200k_knn_nnz(n, lfil);
+   if (pattern_i)
+   {
+      nnz = pattern_i[n];
+      kmax = 1;
+      for (i = 0; i < n; i++)
+         if (pattern_i[i + 1] - pattern_i[i] > kmax)
+            kmax = pattern_i[i + 1] - pattern_i[i];
+   }
+   else
+   {
+      lfil = s->lfil < 1 ? 1 : s->lfil;
+      kmax = lfil < n ? lfil : n;
+      nnz = b200k_knn_nnz(n, lfil);
+   }
    if (nnz > 2147483647LL)
    {
       printf("Error: FSAI pattern with %lld entries exceeds the 32-bit index range of the reference's CSR format.\n", nnz);
       goto done;
    }
-   d_X = upload_features(data, n, ldim, d);
    d_ia = (int *)b200_malloc(sizeof(int) * ((size_t)n + 1));
-   d_ja = (int *)b200_malloc(sizeof(int) * (size_t)nnz);
-   d_a = (double *)b200_malloc(sizeof(double) * (size_t)nnz);
-   if (!d_X || !d_ia || !d_ja || !d_a)
+   d_ja = (int *)b200_malloc(sizeof(int) * (size_t)(nnz ? nnz : 1));
+   d_a = (double *)b200_malloc(sizeof(double) * (size_t)(nnz ? nnz : 1));
+   if (require_grad)
+      d_da = (double *)b200_malloc(sizeof(double) * 3 * (size_t)(nnz ? nnz : 1));
+   if (!d_ia || !d_ja || !d_a || (require_grad && !d_da))
       goto done;
-   if (b200k_knn_pattern(d_X, n, n, d, lfil, d_ia, d_ja) ||
-       b200k_fsai_rows(v.d_Xw, v.d_dims, v.n, v.P, v.dw, v.kernel, v.f * v.f, v.l, v.mu * v.f * v.f, n, d_ia, d_ja, NULL, NULL, 0, kmax, d_a,
-                       &bad))
+   if (pattern_i)
+   {
+      if (b200_h2d(d_ia, pattern_i, sizeof(int) * ((size_t)n + 1)) || b200_h2d(d_ja, pattern_j, sizeof(int) * (size_t)nnz) || b200_sync())
+         goto done;
+   }
+   else
+   {
+      d_X = upload_features(data, n, ldim, d);
+      if (!d_X || b200k_knn_pattern(d_X, n, n, d, s->lfil < 1 ? 1 : s->lfil, d_ia, d_ja))
+         goto done;
+   }
+   if (require_grad ? b200k_fsai_rows_grad(v.d_Xw, v.d_dims, v.n, v.P, v.dw, v.kernel, v.f * v.f, v.l, v.mu * v.f * v.f, n, d_ia, d_ja, kmax, d_a,
+                                           d_da, (size_t)nnz, &bad)
+                    : b200k_fsai_rows(v.d_Xw, v.d_dims, v.n, v.P, v.dw, v.kernel, v.f * v.f, v.l, v.mu * v.f * v.f, n, d_ia, d_ja, NULL, NULL, 0,
+                                      kmax, d_a, &bad))
       goto done;
    if (bad)
    {
@@ -340,13 +364,38 @@ int Nfft4GPPrecondFsaiSetupWithKernel(double *data, int n, int ldim, int d, func
    rc = b200_fsai_set_device_factors(s, n, (int)nnz, d_ia, d_ja, d_a);
    d_ia = d_ja = NULL;
    d_a = NULL;
+   if (!rc && require_grad)
+   {
+      rc = b200_fsai_set_device_grad(s, d_da);
+      d_da = NULL;
+   }
 done:
    b200_free(d_X);
    b200_free(d_ia);
    b200_free(d_ja);
    b200_free(d_a);
+   b200_free(d_da);
    b200_dense_view_release(&v);
    s->tset = wtime() - t0;
+   return rc;
+}
+
+int Nfft4GPPrecondFsaiSetupWithKernel(double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params, int require_grad,
+                                      void *vfsai_mat)
+{
+   return fsai_setup_impl(NULL, NULL, data, n, ldim, d, fkernel, fkernel_params, require_grad, (b200_fsai *)vfsai_mat);
+}
+
+/* fsai.c:314-673: the caller's pattern; as in the reference the preconditioner takes ownership of A_i / A_j (malloc'd by the caller) */
+int Nfft4GPPrecondFsaiSetupWithKernelPattern(int *A_i, int *A_j, double *data, int n, int ldim, int d, func_kernel fkernel, void *fkernel_params,
+                                             int require_grad, void *vfsai_mat)
+{
+   int rc;
+   if (!A_i || !A_j)
+      return -1;
+   rc = fsai_setup_impl(A_i, A_j, data, n, ldim, d, fkernel, fkernel_params, require_grad, (b200_fsai *)vfsai_mat);
+   free(A_i);
+   free(A_j);
    return rc;
 }
 

@@ -579,13 +579,64 @@ __device__ __forceinline__ double additive_kernel_value(const double *pa, const 
    return ff * (acc / (double)P);
 }
 
+// d/dl of additive_kernel_value (kernels.c:522, 2220): Gauss exp(-r^2 / 2 l^2) r^2 / l^3, Matern-1/2 exp(-r / l) r / l^2
+__device__ __forceinline__ double additive_kernel_dl_value(const double *pa, const double *pb, int P, int dw, const int *sdims, int kernel,
+                                                           double l, double ff)
+{
+   double acc = 0.0;
+   for (int w = 0; w < P; w++)
+   {
+      double r2 = 0.0;
+      int dd = sdims[w];
+      for (int t = 0; t < dd; t++)
+      {
+         double df = pa[w * dw + t] - pb[w * dw + t];
+         r2 = fma(df, df, r2);
+      }
+      const double r = sqrt(r2);
+      acc += (kernel == 0) ? exp(-r2 / (2.0 * l * l)) * r2 / (l * l * l) : exp(-r / l) * r / (l * l);
+   }
+   return ff * (acc / (double)P);
+}
+
+// v <- (L L')^{-1} v with the Cholesky factor in A (lower, element (r, c) at A[c * lda + r]); all 128 threads of the CTA call it
+__device__ __forceinline__ void fs_chol_solve(const double *A, int lda, int k, double *v, int tid)
+{
+   for (int b = 0; b < k; b++) // L y = v, column oriented
+   {
+      __syncthreads();
+      const double yb = v[b] / A[b * lda + b];
+      __syncthreads();
+      if (tid == 0)
+         v[b] = yb;
+      for (int r = b + 1 + tid; r < k; r += 128)
+         v[r] -= A[b * lda + r] * yb;
+   }
+   for (int b = k - 1; b >= 0; b--) // L' x = y
+   {
+      __syncthreads();
+      const double xb = v[b] / A[b * lda + b];
+      __syncthreads();
+      if (tid == 0)
+         v[b] = xb;
+      for (int r = tid; r < b; r += 128)
+         v[r] -= A[r * lda + b] * xb;
+   }
+   __syncthreads();
+}
+
 #define FS_CH 16 /* rows of Z staged per pass of the Schur Gram */
 
-template <bool SCHUR>
+// GRAD (plain rows only): additionally the derivatives of the row in f, l and mu (fsai.c:495-560): with g the scaled row,
+// w = -K^{-1} dK g and dg = w - 0.5 w_last dd g, dd = 1 / sqrt(e' K^{-1} e); dK/df = (2 / f) K gives dg = -g / f in closed form,
+// dK/dmu = f^2 I, dK/dl from the points that are still in shared memory.  da = [3][da_stride].
+template <bool SCHUR, bool GRAD>
 __global__ void __launch_bounds__(128)
 k_fsai_rows(DenseDesc D, int nrows, const int *__restrict__ ia, const int *__restrict__ ja, const int *__restrict__ rowmap,
-            const double *__restrict__ Z, int kz, double *__restrict__ a, int *__restrict__ breakdown, int kmax)
+            const double *__restrict__ Z, int kz, double *__restrict__ a, int *__restrict__ breakdown, int kmax, double *__restrict__ da,
+            size_t da_stride)
 {
+   static_assert(!(SCHUR && GRAD), "the derivative rows are built for plain kernels");
    extern __shared__ double sm[];
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int row = blockIdx.x;
@@ -743,8 +794,110 @@ k_fsai_rows(DenseDesc D, int nrows, const int *__restrict__ ia, const int *__res
    double sc = 1.0 / sqrt(x[k - 1]);
    for (int e = tid; e < k; e += 128)
       a[j1 + e] = x[e] * sc;
+   if (GRAD)
+   {
+      double *g = x, *tv = zc; // zc: [kmax] work vector behind x (the Schur staging area is not used by plain rows)
+      __syncthreads();
+      for (int e = tid; e < k; e += 128)
+      {
+         g[e] *= sc;
+         da[j1 + e] = -g[e] / sqrt(D.ff);            // d/df
+         tv[e] = -D.ff * g[e];                       // -dK/dmu g
+      }
+      __syncthreads();
+      fs_chol_solve(A, lda, k, tv, tid);
+      {
+         const double half = 0.5 * tv[k - 1] * sc;
+         for (int e = tid; e < k; e += 128)
+            da[2 * da_stride + j1 + e] = tv[e] - half * g[e];
+      }
+      __syncthreads();
+      for (int r = tid; r < k; r += 128)            // -dK/dl g
+      {
+         double acc = 0.0;
+         for (int c = 0; c < k; c++)
+            acc = fma(additive_kernel_dl_value(pts + r * dtot, pts + c * dtot, D.P, D.dw, sdims, D.kernel, D.l, D.ff), g[c], acc);
+         tv[r] = -acc;
+      }
+      __syncthreads();
+      fs_chol_solve(A, lda, k, tv, tid);
+      {
+         const double half = 0.5 * tv[k - 1] * sc;
+         for (int e = tid; e < k; e += 128)
+            da[da_stride + j1 + e] = tv[e] - half * g[e];
+      }
+   }
    if (tid == 0 && bad)
       atomicAdd(breakdown, 1);
+}
+
+// ---- sparse triangular solves with the FSAI factor (fsai.c:675-721), synchronisation-free: a warp takes the next row from a ticket
+// counter, waits for the rows it depends on (their flags) and publishes its own.  Warps get their tickets in row order and a warp
+// that holds a ticket is resident, so the lowest unfinished row always makes progress.
+// lower: rows of G in CSR, diagonal LAST in every row; x_i = (rhs_i - sum_{j<i} G_ij x_j) / G_ii, tickets ascending.
+// upper: rows of G' in CSR (columns ascending, so the diagonal comes FIRST); x_i = (rhs_i - sum_{j>i} G'_ij x_j) / G'_ii, descending.
+template <bool UPPER>
+__global__ void __launch_bounds__(256)
+k_sptrsv(int n, const int *__restrict__ ia, const int *__restrict__ ja, const double *__restrict__ a, const double *__restrict__ rhs,
+         volatile double *x, volatile int *ready, int *ticket)
+{
+   const int lane = threadIdx.x & 31;
+   for (;;)
+   {
+      int tk = 0;
+      if (lane == 0)
+         tk = atomicAdd(ticket, 1);
+      tk = __shfl_sync(0xffffffffu, tk, 0);
+      if (tk >= n)
+         return;
+      const int row = UPPER ? n - 1 - tk : tk;
+      const int j1 = ia[row], j2 = ia[row + 1];
+      const int jd = UPPER ? j1 : j2 - 1;            // position of the diagonal
+      double s = 0.0;
+      for (int j = (UPPER ? j1 + 1 : j1) + lane; j < (UPPER ? j2 : j2 - 1); j += 32)
+      {
+         const int c = ja[j];
+         while (ready[c] == 0)
+         {
+         }
+         __threadfence();
+         s = fma(a[j], x[c], s);
+      }
+      s = b200_warp_sum(s);
+      if (lane == 0)
+      {
+         x[row] = (rhs[row] - s) / a[jd];
+         __threadfence();
+         ready[row] = 1;
+      }
+   }
+}
+
+__global__ void k_fsai_trace(int n, const int *__restrict__ ia, const double *__restrict__ a, const double *__restrict__ da, size_t stride,
+                             double *__restrict__ out3)
+{
+   // 2 sum_i dG_ii / G_ii for the three hyper-parameters (fsai.c:255-263); one CTA, deterministic order
+   __shared__ double sh[3][256];
+   double acc[3] = {0.0, 0.0, 0.0};
+   for (int i = threadIdx.x; i < n; i += 256)
+   {
+      const int jd = ia[i + 1] - 1;
+      const double inv = 1.0 / a[jd];
+      for (int t = 0; t < 3; t++)
+         acc[t] += da[t * stride + jd] * inv;
+   }
+   for (int t = 0; t < 3; t++)
+      sh[t][threadIdx.x] = acc[t];
+   __syncthreads();
+   for (int o = 128; o > 0; o >>= 1)
+   {
+      if (threadIdx.x < o)
+         for (int t = 0; t < 3; t++)
+            sh[t][threadIdx.x] += sh[t][threadIdx.x + o];
+      __syncthreads();
+   }
+   if (threadIdx.x < 3)
+      out3[threadIdx.x] = 2.0 * sh[threadIdx.x][0];
 }
 
 // =====================================================================================================================
@@ -1086,9 +1239,59 @@ int b200k_knn_pattern(const double *d_X, int n, int ld, int d, int lfil, int *d_
 // FSAI values for the rows of a pattern.  rowmap (device, may be NULL): pattern index -> original point (AFN: perm2).
 // d_Z (may be NULL): kz x nrows column-major L^{-1} K12 of the Schur complement.  *breakdown_out = rows whose Cholesky hit
 // a non-positive pivot.
+static int fsai_rows_impl(const double *d_Xw, const int *d_dims, int n_points, int P, int dw, int kernel, double ff, double l,
+                          double noise_diag, int nrows, const int *d_ia, const int *d_ja, const int *d_rowmap, const double *d_Z, int kz,
+                          int kmax, double *d_a, int *breakdown_out, double *d_da, size_t da_stride);
+
 int b200k_fsai_rows(const double *d_Xw, const int *d_dims, int n_points, int P, int dw, int kernel, double ff, double l,
                     double noise_diag, int nrows, const int *d_ia, const int *d_ja, const int *d_rowmap, const double *d_Z, int kz,
                     int kmax, double *d_a, int *breakdown_out)
+{
+   return fsai_rows_impl(d_Xw, d_dims, n_points, P, dw, kernel, ff, l, noise_diag, nrows, d_ia, d_ja, d_rowmap, d_Z, kz, kmax, d_a, breakdown_out,
+                         nullptr, 0);
+}
+
+// the same rows with their derivatives in f, l, mu: d_da = [3][da_stride] (plain kernels, no Schur term)
+int b200k_fsai_rows_grad(const double *d_Xw, const int *d_dims, int n_points, int P, int dw, int kernel, double ff, double l,
+                         double noise_diag, int nrows, const int *d_ia, const int *d_ja, int kmax, double *d_a, double *d_da, size_t da_stride,
+                         int *breakdown_out)
+{
+   return fsai_rows_impl(d_Xw, d_dims, n_points, P, dw, kernel, ff, l, noise_diag, nrows, d_ia, d_ja, nullptr, nullptr, 0, kmax, d_a, breakdown_out,
+                         d_da, da_stride);
+}
+
+// x = G^{-1} rhs (upper = 0: rows of G, diagonal last) or x = G^{-T} rhs (upper = 1: rows of G', diagonal first)
+int b200k_sptrsv(int upper, int n, const int *d_ia, const int *d_ja, const double *d_a, const double *d_rhs, double *d_x)
+{
+   B200ProfScope prof_scope_(PC_CSR);
+   int *flags = nullptr;
+   B200_CHECK(cudaMalloc(&flags, sizeof(int) * ((size_t)n + 1)));
+   B200_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)n + 1), b200_stream()));
+   int sm = 148, dev = 0;
+   if (cudaGetDevice(&dev) == cudaSuccess)
+      cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+   int blocks = b200_cdiv(n, 8) < sm * 4 ? b200_cdiv(n, 8) : sm * 4; // all resident: a waiting warp must never block an unscheduled one
+   if (upper)
+      k_sptrsv<true><<<blocks, 256, 0, b200_stream()>>>(n, d_ia, d_ja, d_a, d_rhs, d_x, flags, flags + n);
+   else
+      k_sptrsv<false><<<blocks, 256, 0, b200_stream()>>>(n, d_ia, d_ja, d_a, d_rhs, d_x, flags, flags + n);
+   B200_LAUNCHED();
+   B200_CHECK(cudaStreamSynchronize(b200_stream()));
+   cudaFree(flags);
+   return 0;
+}
+
+int b200k_fsai_trace(int n, const int *d_ia, const double *d_a, const double *d_da, size_t stride, double *d_out3)
+{
+   B200ProfScope prof_scope_(PC_OTHER);
+   k_fsai_trace<<<1, 256, 0, b200_stream()>>>(n, d_ia, d_a, d_da, stride, d_out3);
+   B200_LAUNCHED();
+   return 0;
+}
+
+static int fsai_rows_impl(const double *d_Xw, const int *d_dims, int n_points, int P, int dw, int kernel, double ff, double l,
+                          double noise_diag, int nrows, const int *d_ia, const int *d_ja, const int *d_rowmap, const double *d_Z, int kz,
+                          int kmax, double *d_a, int *breakdown_out, double *d_da, size_t da_stride)
 {
    B200ProfScope prof_scope_(PC_OTHER);
    if (kmax > 128 || P > 64)
@@ -1108,7 +1311,7 @@ int b200k_fsai_rows(const double *d_Xw, const int *d_dims, int n_points, int P, 
    D.noise_diag = noise_diag;
    int lda = kmax | 1;
    int T = (kmax + 7) >> 3, kpad = (T << 3) + 4;
-   size_t smem = sizeof(double) * ((size_t)kmax * lda + (size_t)kmax * P * dw + kmax + (d_Z ? (size_t)FS_CH * kpad : 0));
+   size_t smem = sizeof(double) * ((size_t)kmax * lda + (size_t)kmax * P * dw + kmax + (d_Z ? (size_t)FS_CH * kpad : (d_da ? (size_t)kmax : 0)));
    if (smem > 220 * 1024)
    {
       fprintf(stderr, "nfft4gp_b200: FSAI row block does not fit shared memory (%zu bytes)\n", smem);
@@ -1119,13 +1322,18 @@ int b200k_fsai_rows(const double *d_Xw, const int *d_dims, int n_points, int P, 
    B200_CHECK(cudaMemsetAsync(d_bad, 0, sizeof(int), b200_stream()));
    if (d_Z)
    {
-      B200_CHECK(cudaFuncSetAttribute(k_fsai_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_fsai_rows<true><<<nrows, 128, smem, b200_stream()>>>(D, nrows, d_ia, d_ja, d_rowmap, d_Z, kz, d_a, d_bad, kmax);
+      B200_CHECK(cudaFuncSetAttribute(k_fsai_rows<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_fsai_rows<true, false><<<nrows, 128, smem, b200_stream()>>>(D, nrows, d_ia, d_ja, d_rowmap, d_Z, kz, d_a, d_bad, kmax, nullptr, 0);
+   }
+   else if (d_da)
+   {
+      B200_CHECK(cudaFuncSetAttribute(k_fsai_rows<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_fsai_rows<false, true><<<nrows, 128, smem, b200_stream()>>>(D, nrows, d_ia, d_ja, d_rowmap, d_Z, kz, d_a, d_bad, kmax, d_da, da_stride);
    }
    else
    {
-      B200_CHECK(cudaFuncSetAttribute(k_fsai_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_fsai_rows<false><<<nrows, 128, smem, b200_stream()>>>(D, nrows, d_ia, d_ja, d_rowmap, d_Z, kz, d_a, d_bad, kmax);
+      B200_CHECK(cudaFuncSetAttribute(k_fsai_rows<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_fsai_rows<false, false><<<nrows, 128, smem, b200_stream()>>>(D, nrows, d_ia, d_ja, d_rowmap, d_Z, kz, d_a, d_bad, kmax, nullptr, 0);
    }
    B200_LAUNCHED();
    int bad = 0;

@@ -127,7 +127,8 @@ for dw in dims:
     line = {"config": f"C4: additive Matern-1/2 NFFT matvec, n={n}, d={d}, {P} windows of dimension {dw}", "n_gpus": world,
             "parallelism": "single" if world == 1 else f"window-sharded x{world} + 1 allreduce(y, {8 * n / 1e6:.0f} MB) per matvec",
             "ms_per_matvec": ms, "matvecs_per_s": 1000.0 / ms, "plan_build_s": plan_s,
-            "algorithmic_bytes": alg, "algorithmic_GBs": alg / ms / 1e6, "hbm_peak_GBs": hbm_peak, "hbm_frac_algorithmic": alg / ms / 1e6 / hbm_peak,
+            "algorithmic_bytes": alg, "algorithmic_GBs": alg / ms / 1e6, "hbm_peak_GBs_per_gpu": hbm_peak,
+            "hbm_frac_algorithmic": alg / ms / 1e6 / (hbm_peak * world),   # against the aggregate roof of the GPUs used
             "per_class_us_rank0": {names[i]: round(sums[i] / reps * 1000, 1) for i in range(11) if cnts[i]},
             "launches_per_matvec_rank0": int(sum(cnts[i] for i in range(11)) / reps),
             "path": "table-free polynomial path (nfft1d_poly.cu)" if dw == 1 and n >= 32768 else "tap-table streaming kernels (nfft12_stream.cu)",

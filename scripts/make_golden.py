@@ -503,7 +503,52 @@ def afn_case():
     print("wrote afn case: nnz", nnz, "ranks", rk_out)
 
 
+def fsai_grad_case():
+    """Reference FSAI set up with require_grad (fsai.c:302-673 gradient branch :495-560) on the reference's plain Gaussian kernel, the
+    problem of fsai_case: derivative factor values dG/df, dG/dl, dG/dmu, Nfft4GPPrecondFsaiTrace (:221-276), Nfft4GPPrecondFsaiDvp
+    (:125-219) and the two sparse triangular solves Nfft4GPPrecondFsaiInvL / InvLT (:675-721)."""
+    z = np.load(os.path.join(OUT, "fsai_gauss300.npz"))
+    X, f, l, mu, rhs, lfil = z["X"], float(z["f"]), float(z["l"]), float(z["mu"]), z["rhs"], int(z["fsai_lfil"])
+    n, d = X.shape[1], X.shape[0]
+    L.Nfft4GPKernelParamCreate.restype = C.c_void_p
+    L.Nfft4GPKernelParamCreate.argtypes = [C.c_int, C.c_int]
+    kh = L.Nfft4GPKernelParamCreate(n, 1)
+    R.set_hyper(kh, f, l, mu)
+    fs = L.Nfft4GPPrecondFsaiCreate()
+    L.Nfft4GPPrecondFsaiSetLfil(fs, lfil)
+    assert L.Nfft4GPPrecondFsaiSetupWithKernel(R.dptr(X), n, n, d, C.cast(L.Nfft4GPKernelGaussianKernel, C.c_void_p), kh, 1, fs) == 0
+
+    class PFsai(C.Structure):
+        _fields_ = [("_lfil", C.c_int), ("_n", C.c_int), ("_tits", C.c_int), ("_titt", C.c_double), ("_tset", C.c_double),
+                    ("_tlogdet", C.c_double), ("_tdvp", C.c_double), ("_L_i", R.c_int_p), ("_L_j", R.c_int_p),
+                    ("_L_a", R.c_double_p), ("_dL_a", R.c_double_p), ("_work", R.c_double_p)]
+
+    pf = PFsai.from_address(fs)
+    ia = np.ctypeslib.as_array(pf._L_i, shape=(n + 1,)).copy()
+    nnz = int(ia[-1])
+    assert (ia == z["fsai_ia"]).all()
+    dL = np.ctypeslib.as_array(pf._dL_a, shape=(3, nnz)).copy()
+    tr = np.zeros(3)
+    trp = R.dptr(tr)
+    L.Nfft4GPPrecondFsaiTrace.argtypes = [C.c_void_p, C.POINTER(R.c_double_p)]
+    assert L.Nfft4GPPrecondFsaiTrace(fs, C.byref(trp)) == 0
+    y = np.zeros(3 * n)
+    yp = R.dptr(y)
+    L.Nfft4GPPrecondFsaiDvp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, R.c_double_p, C.POINTER(R.c_double_p)]
+    assert L.Nfft4GPPrecondFsaiDvp(fs, n, None, R.dptr(rhs), C.byref(yp)) == 0
+    xl, xlt = np.zeros(n), np.zeros(n)
+    for nm in ("Nfft4GPPrecondFsaiInvL", "Nfft4GPPrecondFsaiInvLT"):
+        getattr(L, nm).argtypes = [C.c_void_p, C.c_int, R.c_double_p, R.c_double_p]
+    L.Nfft4GPPrecondFsaiInvL(fs, n, R.dptr(xl), R.dptr(rhs))
+    L.Nfft4GPPrecondFsaiInvLT(fs, n, R.dptr(xlt), R.dptr(rhs))
+    np.savez_compressed(os.path.join(OUT, "fsai_grad_gauss300.npz"), dL=dL, trace=tr, dvp=y, invl=xl, invlt=xlt)
+    print("wrote fsai grad case: traces", tr)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "fsaigrad":
+        fsai_grad_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "afn":
         afn_case()
         sys.exit(0)
@@ -537,3 +582,4 @@ if __name__ == "__main__":
     predict_case()
     lanczos_case()
     afn_case()
+    fsai_grad_case()

@@ -39,6 +39,30 @@ def test_fsai_setup_matches_reference():
     assert np.linalg.norm(zf - z["fsai_z"]) <= 1e-10 * np.linalg.norm(z["fsai_z"])
 
 
+def test_fsai_gradient_side_matches_reference():
+    """np_setup.fsai_rows_grad / fsai_trace / fsai_dvp against the reference's compiled fsai.c with require_grad
+    (tests/golden/fsai_grad_gauss300.npz: derivative factors, Nfft4GPPrecondFsaiTrace, Nfft4GPPrecondFsaiDvp, InvL / InvLT)."""
+    z, g = _load("fsai_gauss300.npz"), _load("fsai_grad_gauss300.npz")
+    X, f, l, mu = z["X"], float(z["f"]), float(z["l"]), float(z["mu"])
+    n = X.shape[1]
+    pattern = S.knn_pattern(X, int(z["fsai_lfil"]))
+    K = z["K"]
+    dKl = S.dense_kernel_dl(X, np.arange(n), np.arange(n), f, l)
+    funs = [lambda J: 2.0 / f * K[np.ix_(J, J)], lambda J: dKl[np.ix_(J, J)], lambda J: f * f * np.eye(len(J))]
+    vals, dvals = S.fsai_rows_grad(lambda J: K[np.ix_(J, J)], funs, pattern)
+    G = S.rows_to_dense(n, pattern, vals)
+    ia, ja = z["fsai_ia"], z["fsai_ja"]
+    for t in range(3):
+        dG = S.rows_to_dense(n, pattern, dvals[t])
+        dGref = S.csr_to_dense(n, ia, ja, g["dL"][t])
+        assert np.abs(dG - dGref).max() <= 1e-9 * max(np.abs(dGref).max(), 1.0), t
+        y = S.fsai_dvp(G, dG, z["rhs"])
+        assert np.linalg.norm(y - g["dvp"][t * n:(t + 1) * n]) <= 1e-9 * np.linalg.norm(g["dvp"][t * n:(t + 1) * n]), t
+    assert np.abs(S.fsai_trace(vals, dvals) - g["trace"]).max() <= 1e-9 * np.abs(g["trace"]).max()
+    assert np.linalg.norm(np.linalg.solve(G, z["rhs"]) - g["invl"]) <= 1e-10 * np.linalg.norm(g["invl"])
+    assert np.linalg.norm(np.linalg.solve(G.T, z["rhs"]) - g["invlt"]) <= 1e-10 * np.linalg.norm(g["invlt"])
+
+
 def test_nystrom_setup_matches_reference():
     z = _load("nys_gauss300.npz")
     U, s, eta = S.nys_setup(z["X"], z["perm"], int(z["k"]), float(z["f"]), float(z["l"]), float(z["mu"]))
