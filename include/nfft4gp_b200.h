@@ -202,7 +202,17 @@ void Nfft4GPPrecondFsaiSetLfil(void *str, int lfil);                     /* fsai
 int Nfft4GPPrecondFsaiSolve(void *vfsai_mat, int n, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs); /* fsai.c:106-123 (:220) */
 int Nfft4GPPrecondFsaiSetupWithKernel(NFFT4GP_DOUBLE *data, int n, int ldim, int d, func_kernel fkernel,
                                       void *fkernel_params, int require_grad, void *vfsai_mat); /* fsai.c:302-673 (:264) */
-NFFT4GP_DOUBLE Nfft4GPPrecondFsaiLogdet(void *vfsai_mat);                /* fsai.c:278-300 (:246); Dvp / Trace: not built */
+NFFT4GP_DOUBLE Nfft4GPPrecondFsaiLogdet(void *vfsai_mat);                /* fsai.c:278-300 (:246) */
+/* gradient side (set up with require_grad != 0): derivative factors, trace, derivative-vector products, and the two sparse
+ * triangular solves with the factor -- synchronisation-free on the GPU (rows wait on the flags of the rows they depend on) */
+int Nfft4GPPrecondFsaiDvp(void *vfsai_mat, int n, int *mask, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE **yp);  /* fsai.c:125-219 (:233) */
+int Nfft4GPPrecondFsaiTrace(void *vfsai_mat, NFFT4GP_DOUBLE **tracesp);                             /* fsai.c:221-276 (:241) */
+int Nfft4GPPrecondFsaiSetupWithKernelPattern(int *A_i, int *A_j, NFFT4GP_DOUBLE *data, int n, int ldim, int d, func_kernel fkernel,
+                                             void *fkernel_params, int require_grad, void *vfsai_mat); /* fsai.c:314-673 (:282) */
+int Nfft4GPPrecondFsaiInvL(void *vfsai_mat, int n, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs);          /* fsai.c:675-698 (:295) */
+int Nfft4GPPrecondFsaiInvLT(void *vfsai_mat, int n, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs);         /* fsai.c:700-721 (:307) */
+/* read the derivative factor values back (parity tests): dG/df, dG/dl, dG/dmu on the pattern of G, 3 * nnz values */
+int Nfft4GPB200PrecondFsaiGetGradFactors(void *fsai, double *da);
 
 /* Dense Cholesky (the exact solver of the small-n experiments), SRC/preconds/chol.c; with require_grad the setup keeps
  * K and dK/dl in HBM and Trace / Dvp / Logdet are available (the reference's Dvp dereferences a NULL mask copy when the
@@ -225,6 +235,12 @@ void Nfft4GPPrecondAFNFree(void *str);
 void Nfft4GPPrecondAFNSetRank(void *str, int max_k);
 void Nfft4GPPrecondAFNSetLfil(void *str, int lfil);
 int Nfft4GPPrecondAFNSolve(void *vafn_mat, int n, NFFT4GP_DOUBLE *x, NFFT4GP_DOUBLE *rhs);
+/* afn.h:99 / MATLAB afn_logdet.m: log det M = 2 (sum log L_ii + sum log 1 / G_ii); the Nystrom form delegates to Nfft4GPPrecondNysLogdet */
+NFFT4GP_DOUBLE Nfft4GPPrecondAFNLogdet(void *vafn_mat);
+/* afn.h:91 / MATLAB afn_trace.m: tr(M^{-1} dM / dtheta).  Available when the setup chose the Nystrom form (rank below the maximum,
+ * set up with require_grad; delegates to Nfft4GPPrecondNysTrace); in the block form only the f component has a closed form (2 n / f)
+ * and the call returns -1 for the others (the derivative of the Schur-complement FSAI rows is not built). */
+int Nfft4GPPrecondAFNTrace(void *vafn_mat, NFFT4GP_DOUBLE **tracesp);
 int Nfft4GPPrecondAFNSetupWithKernel(NFFT4GP_DOUBLE *data, int n, int ldim, int d, func_kernel fkernel,
                                      void *fkernel_params, int require_grad, void *vafn_mat);
 

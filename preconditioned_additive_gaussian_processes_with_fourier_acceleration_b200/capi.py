@@ -84,6 +84,14 @@ def lib():
         "Nfft4GPPrecondFsaiSetLfil": (None, [vp, i]),
         "Nfft4GPPrecondFsaiSolve": (i, [vp, i, c_double_p, c_double_p]),
         "Nfft4GPPrecondFsaiLogdet": (d, [vp]),
+        "Nfft4GPPrecondFsaiDvp": (i, [vp, i, c_int_p, c_double_p, C.POINTER(c_double_p)]),
+        "Nfft4GPPrecondFsaiTrace": (i, [vp, C.POINTER(c_double_p)]),
+        "Nfft4GPPrecondFsaiSetupWithKernelPattern": (i, [vp, vp, c_double_p, i, i, i, vp, vp, i, vp]),
+        "Nfft4GPPrecondFsaiInvL": (i, [vp, i, c_double_p, c_double_p]),
+        "Nfft4GPPrecondFsaiInvLT": (i, [vp, i, c_double_p, c_double_p]),
+        "Nfft4GPB200PrecondFsaiGetGradFactors": (i, [vp, c_double_p]),
+        "Nfft4GPPrecondAFNLogdet": (d, [vp]),
+        "Nfft4GPPrecondAFNTrace": (i, [vp, C.POINTER(c_double_p)]),
         "Nfft4GPPrecondFsaiSetupWithKernel": (i, [c_double_p, i, i, i, vp, vp, i, vp]),
         "Nfft4GPPrecondCholCreate": (vp, []), "Nfft4GPPrecondCholFree": (None, [vp]), "Nfft4GPPrecondCholReset": (None, [vp]),
         "Nfft4GPPrecondCholSetStable": (None, [vp, i]),
@@ -461,14 +469,57 @@ class FsaiPrecond:
     def __init__(self):
         self.h = lib().Nfft4GPPrecondFsaiCreate()
 
-    def setup(self, kernel, lfil):
-        """Nfft4GPPrecondFsaiSetLfil / SetupWithKernel (fsai.c:100-104, 302-673)."""
+    def setup(self, kernel, lfil, require_grad=0, pattern=None):
+        """Nfft4GPPrecondFsaiSetLfil / SetupWithKernel (fsai.c:100-104, 302-673); pattern = (ia, ja): SetupWithKernelPattern (:314)."""
         L = lib()
         L.Nfft4GPPrecondFsaiSetLfil(self.h, lfil)
-        rc = L.Nfft4GPPrecondFsaiSetupWithKernel(dptr(kernel.X), kernel.n, kernel.n, kernel.d, kernel.fn(), kernel.h, 0, self.h)
+        if pattern is None:
+            rc = L.Nfft4GPPrecondFsaiSetupWithKernel(dptr(kernel.X), kernel.n, kernel.n, kernel.d, kernel.fn(), kernel.h, require_grad, self.h)
+        else:
+            # the callee takes ownership of the two arrays (the reference keeps them as its CSR pattern): hand it malloc'd copies
+            libc = C.CDLL(None)
+            libc.malloc.restype = C.c_void_p
+            libc.malloc.argtypes = [C.c_size_t]
+            ia = np.ascontiguousarray(pattern[0], dtype=np.int32)
+            ja = np.ascontiguousarray(pattern[1], dtype=np.int32)
+            pi, pj = libc.malloc(ia.nbytes), libc.malloc(max(ja.nbytes, 4))
+            C.memmove(pi, ia.ctypes.data, ia.nbytes)
+            C.memmove(pj, ja.ctypes.data, ja.nbytes)
+            rc = L.Nfft4GPPrecondFsaiSetupWithKernelPattern(pi, pj, dptr(kernel.X), kernel.n, kernel.n, kernel.d, kernel.fn(), kernel.h,
+                                                            require_grad, self.h)
         if rc != 0:
-            raise RuntimeError("Nfft4GPPrecondFsaiSetupWithKernel failed")
+            raise RuntimeError("FSAI setup failed")
         return self
+
+    def grad_factors(self):
+        ia, ja, a = self.get_factors()
+        da = np.zeros((3, a.size))
+        assert lib().Nfft4GPB200PrecondFsaiGetGradFactors(self.h, dptr(da)) == 0
+        return da
+
+    def trace(self):
+        tr = np.zeros(3)
+        p = dptr(tr)
+        if lib().Nfft4GPPrecondFsaiTrace(self.h, C.byref(p)) != 0:
+            raise RuntimeError("Nfft4GPPrecondFsaiTrace failed")
+        return tr
+
+    def dvp(self, x, mask=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros(3 * x.size)
+        p = dptr(y)
+        m = None if mask is None else iptr(np.ascontiguousarray(mask, dtype=np.int32))
+        if lib().Nfft4GPPrecondFsaiDvp(self.h, x.size, m, dptr(x), C.byref(p)) != 0:
+            raise RuntimeError("Nfft4GPPrecondFsaiDvp failed")
+        return y
+
+    def inv_l(self, rhs, transpose=False):
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        x = np.zeros_like(rhs)
+        fn = lib().Nfft4GPPrecondFsaiInvLT if transpose else lib().Nfft4GPPrecondFsaiInvL
+        if fn(self.h, rhs.size, dptr(x), dptr(rhs)) != 0:
+            raise RuntimeError("FSAI triangular solve failed")
+        return x
 
     def get_factors(self):
         L = lib()
@@ -579,6 +630,9 @@ class AfnPrecond:
 
     def solve_fn(self):
         return C.cast(lib().Nfft4GPPrecondAFNSolve, C.c_void_p)
+
+    def logdet(self):
+        return float(lib().Nfft4GPPrecondAFNLogdet(self.h))
 
     def free(self):
         if self.h:

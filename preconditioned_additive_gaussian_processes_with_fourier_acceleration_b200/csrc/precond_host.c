@@ -444,6 +444,14 @@ int Nfft4GPB200PrecondFsaiSetFactors(void *fsai, int n, const int *ia, const int
    return b200_fsai_set_host_factors(s, n, ia, ja, a);
 }
 
+int Nfft4GPB200PrecondFsaiGetGradFactors(void *fsai, double *da)
+{
+   b200_fsai *s = (b200_fsai *)fsai;
+   if (!s || s->magic != B200_MAGIC_FSAI || !s->d_da || !da)
+      return -1;
+   return b200_d2h(da, s->d_da, sizeof(double) * 3 * (size_t)s->nnz);
+}
+
 int Nfft4GPB200PrecondFsaiGetFactors(void *fsai, int *n, int *nnz, int *ia, int *ja, double *a)
 {
    b200_fsai *s = (b200_fsai *)fsai;
@@ -930,6 +938,42 @@ int b200_afn_solve_dev(void *va, int n, double *d_x, const double *d_rhs)
          return -1;
    }
    return b200k_scatter_perm(n, s->d_perm, y, d_x);
+}
+
+/* afn.h:99; MATLAB afn_logdet.m: 2 (sum log diag L + sum log 1 / diag G).  The landmark factor is kept as its explicit inverse. */
+double Nfft4GPPrecondAFNLogdet(void *vafn_mat)
+{
+   b200_afn *s = (b200_afn *)vafn_mat;
+   double val = 0.0, *h;
+   int i, k;
+   if (!s || s->magic != B200_MAGIC_AFN)
+      return 0.0;
+   if (s->nys)
+      return Nfft4GPPrecondNysLogdet(s->nys);
+   if (!s->d_Linv)
+      return 0.0;
+   k = s->k;
+   h = (double *)b200_xmalloc(sizeof(double) * (size_t)k * k);
+   if (!b200_d2h(h, s->d_Linv, sizeof(double) * (size_t)k * k))
+      for (i = 0; i < k; i++)
+         val -= 2.0 * log(h[(size_t)i * k + i]); /* diag(L^{-1}) = 1 / diag(L) */
+   free(h);
+   if (s->n > k)
+      val += Nfft4GPPrecondFsaiLogdet(&s->schur);
+   return val;
+}
+
+/* afn.h:91; MATLAB afn_trace.m */
+int Nfft4GPPrecondAFNTrace(void *vafn_mat, double **tracesp)
+{
+   b200_afn *s = (b200_afn *)vafn_mat;
+   if (!s || s->magic != B200_MAGIC_AFN || !tracesp)
+      return -1;
+   if (s->nys)
+      return Nfft4GPPrecondNysTrace(s->nys, tracesp);
+   printf("Error: Nfft4GPPrecondAFNTrace: the derivative of the Schur-complement FSAI factor is not built (block form of the AFN "
+          "preconditioner); only the Nystrom form carries its gradient side.\n");
+   return -1;
 }
 
 int Nfft4GPPrecondAFNSolve(void *vafn_mat, int n, double *x, double *rhs)

@@ -113,6 +113,81 @@ def test_fsai_setup_matches_reference_golden(gpu):
     P.free()
 
 
+def test_fsai_gradient_side_matches_reference_golden(gpu):
+    """Rows f2: FSAI set up with require_grad against the reference's compiled fsai.c (tests/golden/fsai_grad_gauss300.npz):
+    derivative factor values (fsai.c:495-560), Nfft4GPPrecondFsaiTrace (:221), Nfft4GPPrecondFsaiDvp (:125), the sparse triangular
+    solves Nfft4GPPrecondFsaiInvL / InvLT (:675-721, synchronisation-free on the GPU), and Nfft4GPPrecondFsaiSetupWithKernelPattern
+    (:314) fed with the reference's own pattern."""
+    z, g = _load("fsai_gauss300.npz"), _load("fsai_grad_gauss300.npz")
+    X = z["X"]
+    n = X.shape[1]
+    P = gpu.DensePlainKernel(X, "gaussian").set_hyper(float(z["f"]), float(z["l"]), float(z["mu"]))
+    for pattern in (None, (z["fsai_ia"], z["fsai_ja"])):
+        F = gpu.FsaiPrecond().setup(P, int(z["fsai_lfil"]), require_grad=1, pattern=pattern)
+        ia, ja, a = F.get_factors()
+        da = F.grad_factors()
+        Gref = S.csr_to_dense(n, z["fsai_ia"], z["fsai_ja"], z["fsai_a"])
+        assert np.abs(S.csr_to_dense(n, ia, ja, a) - Gref).max() <= 1e-10 * np.abs(Gref).max()
+        for t in range(3):
+            dG, dGref = S.csr_to_dense(n, ia, ja, da[t]), S.csr_to_dense(n, z["fsai_ia"], z["fsai_ja"], g["dL"][t])
+            assert np.abs(dG - dGref).max() <= 1e-8 * max(np.abs(dGref).max(), 1.0), t
+        assert np.abs(F.trace() - g["trace"]).max() <= 1e-9 * np.abs(g["trace"]).max()
+        assert rel_l2(F.inv_l(z["rhs"]), g["invl"]) <= 1e-10
+        assert rel_l2(F.inv_l(z["rhs"], transpose=True), g["invlt"]) <= 1e-10
+        y = F.dvp(z["rhs"])
+        for t in range(3):
+            assert rel_l2(y[t * n:(t + 1) * n], g["dvp"][t * n:(t + 1) * n]) <= 1e-8, t
+        ym = F.dvp(z["rhs"], mask=[0, 1, 0])
+        assert rel_l2(ym[n:2 * n], g["dvp"][n:2 * n]) <= 1e-8 and not ym[:n].any() and not ym[2 * n:].any()
+        F.free()
+    # without require_grad the gradient side refuses, as the reference does (fsai.c:141-145)
+    F = gpu.FsaiPrecond().setup(P, int(z["fsai_lfil"]))
+    with pytest.raises(RuntimeError):
+        F.trace()
+    F.free()
+    P.free()
+
+
+def test_fsai_triangular_solves_at_scale(gpu):
+    """The synchronisation-free sparse triangular solves on a pattern with long dependency chains (n = 20000, lfil 50, additive
+    kernel): G (G^{-1} b) = b and G' (G^{-T} b) = b through the CSR products of the apply."""
+    n, d, lfil = 20000, 6, 50
+    X = uniform_cloud(n, d, seed=77)
+    D = gpu.DenseAdditiveKernel(X, np.arange(6, dtype=np.int32), 2, 3, "gaussian").set_hyper(1.0, 0.8, 0.05)
+    F = gpu.FsaiPrecond().setup(D, lfil, require_grad=1)
+    ia, ja, a = F.get_factors()
+    import scipy.sparse as sp
+    G = sp.csr_matrix((a, ja, ia), shape=(n, n))
+    b = rand_vec(n, 3)
+    assert rel_l2(G @ F.inv_l(b), b) <= 1e-11
+    assert rel_l2(G.T @ F.inv_l(b, transpose=True), b) <= 1e-11
+    tr = F.trace()
+    assert abs(tr[0] + 2.0 * n / 1.0) <= 1e-9 * n          # d/df: dG = -G / f  =>  trace = -2 n / f
+    F.free()
+    D.free()
+
+
+def test_afn_logdet(gpu):
+    """Nfft4GPPrecondAFNLogdet (afn.h:99, MATLAB afn_logdet.m): 2 (sum log L_ii + sum log 1 / G_ii) from the factors of the handle."""
+    n, d, k, lfil = 2000, 6, 150, 40
+    X = uniform_cloud(n, d, seed=31)
+    D = gpu.DenseAdditiveKernel(X, np.arange(6, dtype=np.int32), 2, 3, "gaussian").set_hyper(1.2, 0.8, 0.05)
+    Af = gpu.AfnPrecond().setup(D, k, lfil, numests=0, noran=1)
+    F = Af.get_factors()
+    diagG = F["a"][F["ia"][1:] - 1]
+    ref = -2.0 * np.log(np.diag(F["Linv"])).sum() - 2.0 * np.log(diagG).sum()
+    assert abs(Af.logdet() - ref) <= 1e-10 * abs(ref)
+    # against the log det of the explicit preconditioner matrix M = (apply)^{-1} on a small problem
+    n2, k2 = 300, 40
+    X2 = uniform_cloud(n2, d, seed=32)
+    D2 = gpu.DenseAdditiveKernel(X2, np.arange(6, dtype=np.int32), 2, 3, "gaussian").set_hyper(1.2, 0.8, 0.05)
+    A2 = gpu.AfnPrecond().setup(D2, k2, 20, numests=0, noran=1)
+    Minv = np.column_stack([A2.solve(e) for e in np.eye(n2)])
+    assert abs(A2.logdet() + np.linalg.slogdet(Minv)[1]) <= 1e-8 * abs(A2.logdet())
+    for h in (Af, D, A2, D2):
+        h.free()
+
+
 def test_fsai_setup_additive_kernel(gpu):
     n, d, lfil = 2500, 9, 40
     X = uniform_cloud(n, d, seed=77)
