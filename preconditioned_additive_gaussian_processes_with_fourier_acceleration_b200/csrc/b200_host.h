@@ -88,6 +88,11 @@ typedef struct b200_additive
    const double **d_fptr_local;
    const int **d_invptr_local;
    double *d_ypart;
+   /* gradient matvec: per-window pointer / factor tables are uploaded once per kernel build, not per call */
+   int grad_tables_ready;
+   const double **d_f2ptr_local; /* mode 1: derivative-channel results of the owned windows */
+   double *d_c1w_local;
+   double *d_ypart3;             /* mode 1: partial gradient blocks (3 n) */
 } b200_additive;
 
 void *b200_xmalloc(size_t bytes);

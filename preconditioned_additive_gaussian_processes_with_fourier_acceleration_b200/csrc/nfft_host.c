@@ -1196,6 +1196,7 @@ static int additive_kernel_build(void *str, int kernel, double *data, int n, int
    }
    A->kernel = kernel;
    A->built = 1;
+   A->grad_tables_ready = 0;   /* the gradient factors depend on the length scale */
    additive_graphs_release(A); /* hyper-parameters are baked into the captured kernel arguments */
    if (additive_ensure_device(A) || b200_comm_build_local_windows(A))
       return -1;
@@ -1594,11 +1595,15 @@ static int additive_poly_matvec(b200_additive *A, int n, double alpha, const dou
    const double s = 1.0 / (double)A->P * alpha, f = A->win[0]->kernel_scale, ff = f * f, mu = A->win[0]->mu;
    const int sharded = (A->shard_mode == 1 && b200_comm_size() > 1);
    const b200_poly1d_dev *p = &A->poly;
-   double *out = sharded ? A->d_ypart : d_y;
-   if (grad && sharded)
+   const size_t ny = grad ? 3 * (size_t)n : (size_t)n;
+   double *out = d_y;
+   if (sharded)
    {
-      printf("Error: the gradient matvec is not available under window sharding; use point-block sharding (mode 2).\n");
-      return -1;
+      if (grad && !A->d_ypart3)
+         A->d_ypart3 = (double *)b200_malloc(sizeof(double) * 3 * (size_t)A->n);
+      out = grad ? A->d_ypart3 : A->d_ypart;
+      if (!out)
+         return -1;
    }
    if (p->nw > 0)
    {
@@ -1611,17 +1616,18 @@ static int additive_poly_matvec(b200_additive *A, int n, double alpha, const dou
       if (b200k_poly1d_gather(p, grad ? 2 : 1, d_x, s, grad ? 2.0 * f : ff, mu, ff, sharded ? 0.0 : beta, out, (size_t)n))
          return -1;
    }
-   else if (b200_memset(out, 0, sizeof(double) * (size_t)n)) /* a rank without windows contributes zero */
+   else if (b200_memset(out, 0, sizeof(double) * ny)) /* a rank without windows contributes zero */
       return -1;
    if (!sharded)
       return 0;
-   if (b200_comm_allreduce_sum(A->d_ypart, (size_t)n))
+   /* window sharding: ONE allreduce of the partial result (n values, 3 n for the gradient blocks), then y = beta y + sum */
+   if (b200_comm_allreduce_sum(out, ny))
       return -1;
    if (beta == 0.0)
-      return b200_d2d(d_y, A->d_ypart, sizeof(double) * (size_t)n);
-   if (beta != 1.0 && b200k_scale(n, beta, d_y))
+      return b200_d2d(d_y, out, sizeof(double) * ny);
+   if (beta != 1.0 && b200k_scale((int)ny, beta, d_y))
       return -1;
-   return b200k_axpy(n, 1.0, A->d_ypart, d_y);
+   return b200k_axpy((int)ny, 1.0, out, d_y);
 }
 
 static int additive_matvec_body(b200_additive *A, int n, double alpha, const double *d_x, double beta, double *d_y, int phases)
@@ -1733,25 +1739,66 @@ int b200_additive_grad_matvec_dev(b200_additive *A, int n, double alpha, const d
    }
    if (A->poly1d == 1)
       return additive_poly_matvec(A, n, alpha, d_x, beta, d_y, 1);
-   if (A->shard_mode == 1 && b200_comm_size() > 1)
+   if (!A->grad_tables_ready)
    {
-      printf("Error: the gradient matvec is not available under window sharding; use point-block sharding (mode 2).\n");
-      return -1;
+      /* once per kernel build: derivative-channel buffers, their pointer table and the factors c1_w = f^2 x gradient scale of the
+       * window (nfft_interface.c:536-537) -- not per call (the allocation and the synchronous upload used to sit in every matvec) */
+      const int sharded = (A->shard_mode == 1 && b200_comm_size() > 1);
+      int nl = 0;
+      c1 = (double *)b200_xmalloc(sizeof(double) * 2 * (size_t)A->P);
+      fp = (const double **)b200_xmalloc(sizeof(double *) * 2 * (size_t)A->P);
+      for (i = 0; i < A->P; i++)
+      {
+         b200_window *w = A->win[i];
+         if (!b200_comm_owns_window(A, i))
+         {
+            c1[i] = 0.0;
+            fp[i] = NULL;
+            continue;
+         }
+         if (!w->dev.f2)
+            w->dev.f2 = (double *)b200_malloc(sizeof(double) * (size_t)(w->dev.n ? w->dev.n : 1));
+         c1[i] = ff * window_grad_scale(w);
+         fp[i] = w->dev.f2;
+         c1[A->P + nl] = c1[i];
+         fp[A->P + nl] = fp[i];
+         nl++;
+      }
+      rc = b200_h2d((void *)A->d_f2ptr, fp, sizeof(double *) * (size_t)A->P) || b200_h2d(A->d_c1w, c1, sizeof(double) * (size_t)A->P);
+      if (!rc && sharded)
+      {
+         if (!A->d_f2ptr_local)
+         {
+            A->d_f2ptr_local = (const double **)b200_malloc(sizeof(double *) * (size_t)(nl ? nl : 1));
+            A->d_c1w_local = (double *)b200_malloc(sizeof(double) * (size_t)(nl ? nl : 1));
+            A->d_ypart3 = (double *)b200_malloc(sizeof(double) * 3 * (size_t)A->n);
+         }
+         rc = !A->d_f2ptr_local || !A->d_c1w_local || !A->d_ypart3 ||
+              b200_h2d((void *)A->d_f2ptr_local, fp + A->P, sizeof(double *) * (size_t)nl) || b200_h2d(A->d_c1w_local, c1 + A->P, sizeof(double) * (size_t)nl);
+      }
+      rc = rc || b200_sync();
+      free(c1);
+      free(fp);
+      if (rc)
+         return -1;
+      A->grad_tables_ready = 1;
    }
    if (additive_apply_windows(A, d_x, s, 1, PHASE_ALL))
       return -1;
-   c1 = (double *)b200_xmalloc(sizeof(double) * (size_t)A->P);
-   fp = (const double **)b200_xmalloc(sizeof(double *) * (size_t)A->P);
-   for (i = 0; i < A->P; i++)
+   if (A->shard_mode == 1 && b200_comm_size() > 1)
    {
-      c1[i] = ff * window_grad_scale(A->win[i]);
-      fp[i] = A->win[i]->dev.f2;
+      /* window sharding: partial gradient blocks of the owned windows, ONE allreduce of 3 n doubles, y = beta y + sum */
+      const size_t n3 = 3 * (size_t)n;
+      if (b200k_combine_grad(n, A->nlocal, A->d_fptr_local, A->d_f2ptr_local, A->d_invptr_local, d_x, s, 2.0 * f, ff, A->d_c1w_local,
+                             A->win[0]->mu, 0.0, A->d_ypart3) ||
+          b200_comm_allreduce_sum(A->d_ypart3, n3))
+         return -1;
+      if (beta == 0.0)
+         return b200_d2d(d_y, A->d_ypart3, sizeof(double) * n3);
+      if (beta != 1.0 && b200k_scale((int)n3, beta, d_y))
+         return -1;
+      return b200k_axpy((int)n3, 1.0, A->d_ypart3, d_y);
    }
-   rc = b200_h2d((void *)A->d_f2ptr, fp, sizeof(double *) * (size_t)A->P) || b200_h2d(A->d_c1w, c1, sizeof(double) * (size_t)A->P) || b200_sync();
-   free(c1);
-   free(fp);
-   if (rc)
-      return -1;
    return b200k_combine_grad(n, A->P, A->d_fptr, A->d_f2ptr, A->d_invptr, d_x, s, 2.0 * f, ff, A->d_c1w, A->win[0]->mu, beta, d_y);
 }
 
@@ -1849,6 +1896,9 @@ void Nfft4GPAdditiveNFFTKernelFree(void *str)
       b200_free(A->d_dcoef);
       b200_free((void *)A->d_fptr_local);
       b200_free((void *)A->d_invptr_local);
+      b200_free((void *)A->d_f2ptr_local);
+      b200_free(A->d_c1w_local);
+      b200_free(A->d_ypart3);
       additive_fused_release(A);
       additive_graphs_release(A);
       additive_poly_release(A);

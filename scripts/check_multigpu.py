@@ -53,6 +53,40 @@ for mode in (1, 2):
         print(f"mode {mode} on {world} GPUs: rel l2 vs oracle {err:.2e}")
         ok = ok and err <= 1e-10
     A.free()
+# ---- window sharding: gradient matvec (ONE allreduce of 3 n doubles), 3-D windows on the table path and 1-D windows on the polynomial path
+g0 = rng.random(3 * n) - 0.5
+for tag, dd, nw, dw, env in (("3-D windows", 9, 3, 3, None), ("1-D windows, polynomial path", 5, 5, 1, "1")):
+    Xg = np.ascontiguousarray(X[:dd])
+    wing = np.arange(dd, dtype=np.int32)
+    if env:
+        os.environ["NFFT4GP_B200_POLY1D"] = env
+    A = pkg.AdditiveNFFTKernel(Xg, wing, nw, dw, "gaussian")
+    assert L.Nfft4GPB200SetSharding(A.h, 1) == 0
+    A.build(f, l, mu)
+    os.environ.pop("NFFT4GP_B200_POLY1D", None)
+    g = A.grad_matvec(x, 0.7, 0.3, g0)
+    y = A.matvec(x, 0.7, 0.3, y0)
+    if rank == 0:
+        B = O.OracleAdditiveNFFT(Xg, wing, nw, dw, "gaussian").build(f, l, mu)
+        eg = float(np.linalg.norm(g - B.grad_matvec(x, 0.7, 0.3, g0)) / np.linalg.norm(B.grad_matvec(x, 0.7, 0.3, g0)))
+        ey = float(np.linalg.norm(y - B.matvec(x, 0.7, 0.3, y0)) / np.linalg.norm(B.matvec(x, 0.7, 0.3, y0)))
+        print(f"mode 1 on {world} GPUs, {tag}: matvec {ey:.2e}, gradient matvec {eg:.2e} (rel l2 vs oracle)")
+        ok = ok and eg <= 1e-10 and ey <= 1e-10
+        B.free()
+    A.free()
+# ---- window sharding: PCG with the allreduce inside the matvec (no CUDA-graph capture of the iteration: pcg_host.c)
+A = pkg.AdditiveNFFTKernel(X, win, 3, 3, "gaussian")
+assert L.Nfft4GPB200SetSharding(A.h, 1) == 0
+A.build(1.0, 0.12 * n ** (1 / 9), 1.0)
+xs, rel, hist, its = pkg.solver_pcg(A.K, n, A.matvec_fn(), None, None, np.zeros(n), x, 400, 0, 1e-8)
+if rank == 0:
+    Bo = O.OracleAdditiveNFFT(X, win, 3, 3, "gaussian").build(1.0, 0.12 * n ** (1 / 9), 1.0)
+    mv, h = Bo.matvec_cb()
+    xo, relo, histo, ito = O.pcg(h, n, mv, None, None, np.zeros(n), x, 400, 0, 1e-8)
+    ex = float(np.linalg.norm(xs - xo) / np.linalg.norm(xo))
+    print(f"mode 1 on {world} GPUs, PCG: iterations {its} (oracle {ito}), rel res {rel:.2e}, solution vs oracle {ex:.2e}")
+    ok = ok and its > 0 and abs(its - ito) <= 1 and ex <= 1e-6
+A.free()
 dist.barrier()
 L.Nfft4GPB200CommFinalize()
 dist.destroy_process_group()
