@@ -117,6 +117,7 @@ int b200_additive_epilogue(b200_additive *A, int n, const double *d_x, double s,
 typedef int (*b200_dev_solve)(void *prec, int n, double *d_x, const double *d_rhs);
 typedef int (*b200_dev_matvec)(void *mat, int n, double alpha, const double *d_x, double beta, double *d_y);
 b200_dev_solve b200_lookup_dev_solve(void *host_fn);
+void b200_note_foreign_fn_on_native_handle(const void *prec_data);
 int b200_dev_fn_is_native(void *fn);
 b200_dev_matvec b200_lookup_dev_matvec(void *host_fn, void *mat_data, void **dev_handle);
 

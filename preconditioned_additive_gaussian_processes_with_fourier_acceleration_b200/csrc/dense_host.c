@@ -12,7 +12,8 @@
  *    copy with the caller's n, which breaks every call made with a sub-sampled `data` (nys.c:549, fsai.c:374);
  *  - a short LAST window is detected from its trailing -1 entries (the reference tests windows[w * dwindows - 1] of the
  *    wrong windows, kernels.c:3054-3060).
- * Gradient blocks (dKp) belong to the GP optimizer and are not built: dKp != NULL returns -1. */
+ * Gradient blocks: dKp != NULL returns the three stacked blocks [d/df; d/dl; d/dmu] of the same call shape (kernels.c:495-549,
+ * 2218-2222), which the preconditioners' gradient sides and the GP optimizer use. */
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>

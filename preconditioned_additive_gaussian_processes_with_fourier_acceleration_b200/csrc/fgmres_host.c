@@ -265,6 +265,7 @@ int Nfft4GPSolverFgmres(void *mat_data, int n, func_symmatvec matvec, void *prec
    }
    if (prec_data && !ps)
    {
+      b200_note_foreign_fn_on_native_handle(prec_data);
       fps.ps = precondfunc;
       fps.data = prec_data;
       fps.hx = (double *)b200_host_alloc(bytes);

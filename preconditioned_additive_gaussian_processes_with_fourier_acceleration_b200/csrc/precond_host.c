@@ -1027,6 +1027,26 @@ int b200_dev_fn_is_native(void *fn)
           fn == (void *)b200_fsai_solve_dev || fn == (void *)b200_afn_solve_dev || fn == (void *)b200_chol_solve_dev;
 }
 
+/* A solver was handed one of THIS library's preconditioner handles together with a function pointer that is none of this library's
+ * entry points: in a non-PIE executable the address of an imported function is the executable's PLT stub, which differs from the
+ * address the library (linked -Bsymbolic) compares with.  The solve still works through the host-callback path (one D2H + H2D per
+ * apply); say so once instead of being silently slow. */
+void b200_note_foreign_fn_on_native_handle(const void *prec_data)
+{
+   static int warned = 0;
+   int magic;
+   if (warned || !prec_data)
+      return;
+   memcpy(&magic, prec_data, sizeof(int));
+   if (magic == B200_MAGIC_NYS || magic == B200_MAGIC_FSAI || magic == B200_MAGIC_AFN)
+   {
+      warned = 1;
+      printf("Warning: nfft4gp_b200: a preconditioner handle of this library is applied through a function pointer that is not the "
+             "library's own entry point (non-PIE executable? link with -fPIE / -fPIC so that &Nfft4GPPrecond*Solve is the library's "
+             "address): using the host-callback path with one device-host round trip per apply.\n");
+   }
+}
+
 b200_dev_solve b200_lookup_dev_solve(void *host_fn)
 {
    if (host_fn == (void *)Nfft4GPPrecondNysSolve)
