@@ -114,6 +114,9 @@ int b200k_poly1d_spread(const b200_poly1d_dev *p, const double *d_x, double s, d
 int b200k_poly1d_coef(const b200_poly1d_dev *p, int ch, const double *d_grids, size_t grid_stride, const double *d_wscale);
 int b200k_poly1d_gather(const b200_poly1d_dev *p, int nch, const double *d_x, double s, double c0, double mu, double ff, double beta,
                         double *d_y, size_t ystride);
+/* nfft2d_mma.cu: 2-D windows on the fp64 tensor cores (same data as the stream kernels) */
+int b200k_spread2_mma(const b200_win_dev *w);
+int b200k_gather2_mma(const b200_win_dev *w, double *d_f);
 /* nfft3d_mma.cu: the same streaming decomposition on the fp64 tensor cores (DMMA) */
 int b200k_mma_warp_ranges(void);
 int b200k_spread3_mma(const b200_win_dev *w);

@@ -570,11 +570,13 @@ int b200k_spread(const b200_win_dev *w, int variant)
    B200ProfScope prof_scope_(PC_SPREAD);
    B200_CHECK(cudaMemsetAsync(w->grid, 0, sizeof(double) * grid_elems(w->d), b200_stream()));
    if (variant < 0) // automatic: tensor-core kernels for dense cells, DFMA kernels with register-tile shifting for sparse ones
-      variant = (w->nseg > 0 && w->n / w->nseg >= B200_MMA_MIN_POINTS_PER_CELL) ? 5 : 1;
+      variant = (w->d == 2 || (w->nseg > 0 && w->n / w->nseg >= B200_MMA_MIN_POINTS_PER_CELL)) ? 5 : 1;
    if (w->d == 3 && variant == 5) // fp64 tensor-core kernels (nfft3d_mma.cu)
       return b200k_spread3_mma(w);
    if (w->d == 3 && variant != 0) // DFMA kernels (nfft3d_warp.cu); variant 0 = generic kernel (cross-check)
       return b200k_spread3_warp(w);
+   if (w->d == 2 && variant != 0 && variant != 1 && !w->xs) // 2-D: fp64 tensor-core kernels (nfft2d_mma.cu); variant 1 = DFMA stream kernels
+      return b200k_spread2_mma(w);
    if (w->d < 3 && variant != 0) // 1-D / 2-D: streaming warp-per-range kernels (nfft12_stream.cu)
       return b200k_spread_stream(w);
    int grid = b200_cdiv(w->n, 128);
@@ -592,11 +594,13 @@ int b200k_gather(const b200_win_dev *w, double *d_f, int variant)
 {
    B200ProfScope prof_scope_(PC_GATHER);
    if (variant < 0)
-      variant = (w->nseg > 0 && w->n / w->nseg >= B200_MMA_MIN_POINTS_PER_CELL) ? 5 : 1;
+      variant = (w->d == 2 || (w->nseg > 0 && w->n / w->nseg >= B200_MMA_MIN_POINTS_PER_CELL)) ? 5 : 1;
    if (w->d == 3 && variant == 5)
       return b200k_gather3_mma(w, d_f);
    if (w->d == 3 && variant != 0)
       return b200k_gather3_warp(w, d_f);
+   if (w->d == 2 && variant != 0 && variant != 1 && !w->xs) // 2-D: fp64 tensor-core kernel (nfft2d_mma.cu); variant 1 = DFMA stream kernel
+      return b200k_gather2_mma(w, d_f);
    if (w->d == 2 && variant != 0) // 1-D stays thread-per-point: 10 taps per point need no cross-lane reduction (measured 62 vs 152 us)
       return b200k_gather_stream(w, d_f);
    int grid = b200_cdiv(w->n, 128);

@@ -131,7 +131,8 @@ for dw in dims:
             "hbm_frac_algorithmic": alg / ms / 1e6 / (hbm_peak * world),   # against the aggregate roof of the GPUs used
             "per_class_us_rank0": {names[i]: round(sums[i] / reps * 1000, 1) for i in range(11) if cnts[i]},
             "launches_per_matvec_rank0": int(sum(cnts[i] for i in range(11)) / reps),
-            "path": "table-free polynomial path (nfft1d_poly.cu)" if dw == 1 and n >= 32768 else "tap-table streaming kernels (nfft12_stream.cu)",
+            "path": ("table-free polynomial path (nfft1d_poly.cu)" if dw == 1 and n >= 32768 and os.environ.get("NFFT4GP_B200_POLY1D") != "0" else
+                     "tap tables, fp64 tensor-core kernels (nfft2d_mma.cu)" if dw == 2 else "tap tables, streaming kernels (nfft12_stream.cu)"),
             "parity_rel_l2_vs_oracle_on_first_20000_points": rel, "parity_rel_l2_sharded_vs_one_gpu": rel_1gpu}
     if rank == 0:
         print(json.dumps(line), flush=True)
