@@ -60,6 +60,17 @@ static int lz_mgs2(double *z, int n, const double *V, const double *Z, double *T
    return 0;
 }
 
+static double *g_lz_bases[2] = {NULL, NULL};
+static size_t g_lz_bases_bytes = 0;
+static int g_lz_keep = 0;
+static void lz_release_bases(void)
+{
+   b200_free(g_lz_bases[0]);
+   b200_free(g_lz_bases[1]);
+   g_lz_bases[0] = g_lz_bases[1] = NULL;
+   g_lz_bases_bytes = 0;
+}
+
 static int lz_apply_prec(void *prec, b200_dev_solve ps, int n, double *v, const double *z)
 {
    if (prec)
@@ -103,8 +114,21 @@ static int lanczos_device(void *mat, int n, b200_dev_matvec mv, void *prec, b200
       rc = b200_sync();
       goto done;
    }
-   V = (double *)b200_malloc(bytes * ((size_t)maxits + 1));
-   Z = (double *)b200_malloc(bytes * ((size_t)maxits + 1));
+   /* the two Krylov bases: (maxits + 1) n doubles each -- 1.3 GB at n = 4 10^6, maxits = 20.  The stochastic quadrature calls this
+    * once per probe; allocating and releasing them every time cost more than a probe's kernels (cudaFree of that size), so inside
+    * its probe loop the buffers are kept (g_lz_keep) and reused while they are large enough. */
+   if (g_lz_keep && g_lz_bases[0] && g_lz_bases_bytes >= bytes * ((size_t)maxits + 1))
+   {
+      V = g_lz_bases[0];
+      Z = g_lz_bases[1];
+      g_lz_bases[0] = g_lz_bases[1] = NULL;
+   }
+   else
+   {
+      lz_release_bases();
+      V = (double *)b200_malloc(bytes * ((size_t)maxits + 1));
+      Z = (double *)b200_malloc(bytes * ((size_t)maxits + 1));
+   }
    if (!V || !Z)
    {
       printf("Error: Lanczos could not allocate the bases (2 x %d x %d doubles) on the device.\n", n, maxits + 1);
@@ -279,8 +303,17 @@ static int lanczos_device(void *mat, int n, b200_dev_matvec mv, void *prec, b200
    rc = 0;
 done:
    b200_sync();
-   b200_free(V);
-   b200_free(Z);
+   if (g_lz_keep && V && Z && !g_lz_bases[0])
+   {
+      g_lz_bases[0] = V;
+      g_lz_bases[1] = Z;
+      g_lz_bases_bytes = bytes * ((size_t)maxits + 1);
+   }
+   else
+   {
+      b200_free(V);
+      b200_free(Z);
+   }
    b200_free(d_h);
    free(h);
    free(hrand);
@@ -438,6 +471,7 @@ int Nfft4GPLanczosQuadratureLogdet(void *mat_data, void *dmat_data, int n, func_
    dAz = (double *)b200_xmalloc(sizeof(double) * (size_t)n * 3);
    TV = (double *)b200_xmalloc(sizeof(double) * (size_t)maxits * (size_t)maxits);
    dval[0] = dval[1] = dval[2] = 0.0;
+   g_lz_keep = 1; /* the probes reuse the Krylov bases (released at `done`) */
    for (i = 0; i < nvecs; i++)
    {
       double rel_res, *rel_res_v = NULL, *TD = NULL, *TE = NULL;
@@ -539,6 +573,8 @@ int Nfft4GPLanczosQuadratureLogdet(void *mat_data, void *dmat_data, int n, func_
    *dlogdetp = dval;
    rc = 0;
 done:
+   g_lz_keep = 0;
+   lz_release_bases();
    b200_free(d_z);
    b200_free(d_xs);
    b200_free(d_dAz);
