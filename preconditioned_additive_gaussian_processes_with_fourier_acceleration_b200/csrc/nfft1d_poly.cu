@@ -32,6 +32,9 @@
 #define PLD 16                /* leading dimension of the per-cell rows (moments / coefficients) */
 #define PWARPS 16
 #define PTHREADS (PWARPS * 32)
+#ifndef PU
+#define PU 4 /* points per lane whose loads are issued together */
+#endif
 
 __constant__ double c_p1[TAPS][PNC] = KB_POLY_TABLE;
 
@@ -147,17 +150,25 @@ k_poly1d_spread(b200_poly1d_dev p, const double *__restrict__ x, double s)
 #pragma unroll
          for (int k = 0; k < 16; k++)
             m[k] = 0.0;
-         int j = j0 + lane;
-         for (; j + 32 < j1; j += 64) // two points per lane and step: four independent dependency chains
+         // all loads of (a chunk of) the run first -- up to PU points per lane in flight, so the latency of the coordinate / index loads is
+         // paid once per run instead of once per point -- then the arithmetic, PU independent chains
+         for (int jc = j0; jc < j1; jc += 32 * PU)
          {
-            const double xa = __ldg(xt + base + j), xb = __ldg(xt + base + j + 32);
-            const int la = lp[base + j], lb = lp[base + j + 32];
-            const double aa = xs[la], ab = xs[lb];
-            p_moments(m, aa, p_offset(xa));
-            p_moments(m, ab, p_offset(xb));
+            double xv[PU];
+            int lv[PU];
+#pragma unroll
+            for (int u = 0; u < PU; u++)
+            {
+               const int j = jc + lane + 32 * u;
+               const bool ok = j < j1;
+               xv[u] = ok ? __ldg(xt + base + j) : 0.0;
+               lv[u] = ok ? (int)lp[base + j] : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < PU; u++)
+               if (lv[u] >= 0)
+                  p_moments(m, xs[lv[u]], p_offset(xv[u]));
          }
-         if (j < j1)
-            p_moments(m, xs[lp[base + j]], p_offset(__ldg(xt + base + j)));
          int q;
          const double tot = p_transpose_reduce16(m, lane, q);
          if (!(lane & 1) && q < PNC)
@@ -264,25 +275,28 @@ k_poly1d_gather(b200_poly1d_dev p, const double *__restrict__ x, double s, doubl
 #pragma unroll
             for (int k = 0; k < PNC; k++)
                cf[ch][k] = ct[ch * 64 * PLD + c * PLD + k];
-         int j = j0 + lane;
-         for (; j + 32 < j1; j += 64) // two points per lane and step, each polynomial as two chains in v^2
+         // all loads of (a chunk of) the run first, then the polynomials (PU independent pairs of chains in v^2 per lane)
+         for (int jc = j0; jc < j1; jc += 32 * PU)
          {
-            const double va = p_offset(__ldg(xt + j)), vb = p_offset(__ldg(xt + j + 32));
-            const int la = lp[j], lb = lp[j + 32];
+            double xv[PU];
+            int lv[PU];
 #pragma unroll
-            for (int ch = 0; ch < NCH; ch++)
+            for (int u = 0; u < PU; u++)
             {
-               acc[ch * p.T + la] += p_horner(cf[ch], va); // every point of the block belongs to exactly one run of this window
-               acc[ch * p.T + lb] += p_horner(cf[ch], vb);
+               const int j = jc + lane + 32 * u;
+               const bool ok = j < j1;
+               xv[u] = ok ? __ldg(xt + j) : 0.0;
+               lv[u] = ok ? (int)lp[j] : -1;
             }
-         }
-         if (j < j1)
-         {
-            const double v = p_offset(__ldg(xt + j));
-            const int l = lp[j];
 #pragma unroll
-            for (int ch = 0; ch < NCH; ch++)
-               acc[ch * p.T + l] += p_horner(cf[ch], v);
+            for (int u = 0; u < PU; u++)
+               if (lv[u] >= 0)
+               {
+                  const double v = p_offset(xv[u]);
+#pragma unroll
+                  for (int ch = 0; ch < NCH; ch++)
+                     acc[ch * p.T + lv[u]] += p_horner(cf[ch], v); // every point of the block belongs to exactly one run of this window
+               }
          }
       }
    }

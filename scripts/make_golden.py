@@ -545,7 +545,33 @@ def fsai_grad_case():
     print("wrote fsai grad case: traces", tr)
 
 
+def nys_additive_quirk_case():
+    """The reference's Nystrom setup handed the dense ADDITIVE kernel (what TESTS/TEST3/foo3.cpp does): nys.c:549-566 forms K11 by calling
+    the kernel on k sub-sampled points with n = k, and kernels.c:3160 strides the handle's feature copy with that n, so the factored
+    landmark block belongs to the first P dw k values of the copy read as a [P dw] x k table.  Recorded so that the library's
+    NFFT4GP_B200_REFERENCE_QUIRKS=1 mode is pinned on the compiled reference (its default uses the intended block)."""
+    n, d, k = 300, 6, 40
+    X = np.random.default_rng(3).random((d, n)) * n ** (1.0 / d)
+    win = np.arange(6, dtype=np.int32)
+    f, l, mu = 1.1, 0.9, 0.05
+    D = R.RefAdditiveDense(X, win, 2, 3, "gaussian")
+    R.set_hyper(D.h, f, l, mu)
+    perm = np.random.default_rng(4).permutation(n).astype(np.int32)
+    nys = L.Nfft4GPPrecondNysCreate()
+    L.Nfft4GPPrecondNysSetRank(nys, k)
+    L.Nfft4GPPrecondNysSetPerm(nys, R.iptr(perm), 0)
+    assert L.Nfft4GPPrecondNysSetupWithKernel(R.dptr(D.X), n, n, d, C.cast(L.Nfft4GPKernelAdditiveKernel, C.c_void_p), D.h, 0, nys) == 0
+    rhs = np.random.default_rng(5).random(n) - 0.5
+    z = np.zeros(n)
+    L.Nfft4GPPrecondNysSolve(nys, n, R.dptr(z), R.dptr(rhs))
+    np.savez_compressed(os.path.join(OUT, "nys_additive_quirk300.npz"), X=X, windows=win, f=f, l=l, mu=mu, k=k, perm=perm, rhs=rhs, z=z)
+    print("wrote nys additive quirk case")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "quirk":
+        nys_additive_quirk_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fsaigrad":
         fsai_grad_case()
         sys.exit(0)
@@ -583,3 +609,4 @@ if __name__ == "__main__":
     lanczos_case()
     afn_case()
     fsai_grad_case()
+    nys_additive_quirk_case()

@@ -365,6 +365,22 @@ def test_afn_k12_fp32_storage(gpu):
         h.free()
 
 
+def test_nystrom_reference_quirk_mode(gpu, monkeypatch):
+    """NFFT4GP_B200_REFERENCE_QUIRKS=1: the Nystrom setup on the dense additive kernel reproduces the landmark block the REFERENCE
+    factors (tests/golden/nys_additive_quirk300.npz, compiled nys.c + kernels.c); the default (intended rows) differs from it."""
+    z = _load("nys_additive_quirk300.npz")
+    X, f, l, mu, k, perm = z["X"], float(z["f"]), float(z["l"]), float(z["mu"]), int(z["k"]), z["perm"]
+    D = gpu.DenseAdditiveKernel(X, z["windows"], 2, 3, "gaussian").set_hyper(f, l, mu)
+    monkeypatch.setenv("NFFT4GP_B200_REFERENCE_QUIRKS", "1")
+    Nq = gpu.NysPrecond().setup(D, perm, k)
+    assert rel_l2(Nq.solve(z["rhs"]), z["z"]) <= 1e-6          # eig(U'U) conditioning, as test_nystrom_setup_matches_reference_golden
+    monkeypatch.delenv("NFFT4GP_B200_REFERENCE_QUIRKS")
+    Ni = gpu.NysPrecond().setup(D, perm, k)
+    assert rel_l2(Ni.solve(z["rhs"]), z["z"]) >= 1e-3
+    for h in (Nq, Ni, D):
+        h.free()
+
+
 def test_afn_k12_through_the_nfft_operator(gpu):
     """Nfft4GPB200PrecondAFNSetK12Operator: the two K12 products of the AFN apply as NFFT matvecs (rows of K applied to vectors that
     vanish on the other block).  The apply agrees with the dense-block apply to the NFFT accuracy, stays symmetric, PCG needs the

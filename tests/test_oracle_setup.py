@@ -74,6 +74,26 @@ def test_nystrom_setup_matches_reference():
     assert np.linalg.norm(x - z["z"]) <= 1e-6 * np.linalg.norm(z["z"])
 
 
+def test_reference_quirk_of_the_additive_nystrom_block():
+    """The reference's Nystrom setup with its dense ADDITIVE kernel factors the landmark block of the wrong rows (nys.c:549-566 +
+    kernels.c:3160): the compiled reference's apply (tests/golden/nys_additive_quirk300.npz) equals the NumPy setup whose K11 is the
+    kernel of the first P dw k values of the window-major feature copy read as a [P dw] x k table -- and differs from the intended one."""
+    z = _load("nys_additive_quirk300.npz")
+    X, f, l, mu, k, perm = z["X"], float(z["f"]), float(z["l"]), float(z["mu"]), int(z["k"]), z["perm"]
+    wins = S.window_dims(z["windows"], 2, 3)
+    K1 = S.dense_kernel(X, perm, perm[:k], f, l, "gaussian", wins)
+    Xq = X[z["windows"]].reshape(-1)[: 6 * k].reshape(6, k)
+    K11 = S.dense_kernel(Xq, np.arange(k), np.arange(k), f, l, "gaussian", wins)
+    K11 = K11 + S.chol_shift(K11) * np.eye(k)
+    B = np.linalg.solve(np.linalg.cholesky(K11), K1.T).T
+    U, sig, _ = np.linalg.svd(B, full_matrices=False)
+    eta = mu * f * f
+    zq = S.nys_apply(perm, U, 1.0 / (sig ** 2 + eta), eta, z["rhs"])
+    assert np.linalg.norm(zq - z["z"]) <= 1e-10 * np.linalg.norm(z["z"])
+    U2, s2, eta2 = S.nys_setup(X, perm, k, f, l, mu, "gaussian", wins)
+    assert np.linalg.norm(S.nys_apply(perm, U2, s2, eta2, z["rhs"]) - z["z"]) >= 1e-3 * np.linalg.norm(z["z"])
+
+
 def test_afn_setup_matches_reference_compiled_parts():
     """np_setup.fps / expand_perm / afn_setup / afn_apply against the AFN chain assembled from the reference's compiled functions
     (Nfft4GPSortFps ordering.c:713, Nfft4GPExpandPerm, Nfft4GPPrecondCholSetupWithKernel, Nfft4GPKernelSchurCombineKernel
