@@ -60,6 +60,21 @@ static int lz_mgs2(double *z, int n, const double *V, const double *Z, double *T
    return 0;
 }
 
+#include <time.h>
+static double lz_now(void)
+{
+   struct timespec ts;
+   clock_gettime(CLOCK_MONOTONIC, &ts);
+   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+static int lz_timing(void)
+{
+   static int on = -1;
+   if (on < 0)
+      on = getenv("NFFT4GP_B200_SLQ_TIMING") ? 1 : 0; /* development aid: wall-clock split of a probe, printed per probe */
+   return on;
+}
+
 static double *g_lz_bases[2] = {NULL, NULL};
 static size_t g_lz_bases_bytes = 0;
 static int g_lz_keep = 0;
@@ -87,6 +102,7 @@ static int lanczos_device(void *mat, int n, b200_dev_matvec mv, void *prec, b200
    double normb, normr, normz, beta, le, ls = 0.0, tolr, t = 1.0, dotvz = 0.0, idotvz, td, te, tmp;
    double *V = NULL, *Z = NULL, *TD = NULL, *TE = NULL, *TLD = NULL, *TLE = NULL, *y = NULL, *rel_res_v = NULL, *d_h = NULL, *h = NULL, *hrand = NULL;
    double *v, *z, *w;
+   double tl0 = 0.0, tl1 = 0.0, tl2 = 0.0;
    size_t bytes = sizeof(double) * (size_t)n, ld = (size_t)n;
 
    if (wsize <= 0)
@@ -117,6 +133,7 @@ static int lanczos_device(void *mat, int n, b200_dev_matvec mv, void *prec, b200
    /* the two Krylov bases: (maxits + 1) n doubles each -- 1.3 GB at n = 4 10^6, maxits = 20.  The stochastic quadrature calls this
     * once per probe; allocating and releasing them every time cost more than a probe's kernels (cudaFree of that size), so inside
     * its probe loop the buffers are kept (g_lz_keep) and reused while they are large enough. */
+   tl0 = lz_now();
    if (g_lz_keep && g_lz_bases[0] && g_lz_bases_bytes >= bytes * ((size_t)maxits + 1))
    {
       V = g_lz_bases[0];
@@ -153,6 +170,7 @@ static int lanczos_device(void *mat, int n, b200_dev_matvec mv, void *prec, b200
    }
    z = Z;
    v = V;
+   tl1 = lz_now();
    if (b200_d2d(z, d_rhs, bytes) || mv(mat, n, -1.0, d_x, 1.0, z) || lz_apply_prec(prec, ps, n, v, z) || lz_dot(n, z, z, d_h, &tmp))
       goto done;
    normr = sqrt(tmp);
@@ -303,6 +321,9 @@ static int lanczos_device(void *mat, int n, b200_dev_matvec mv, void *prec, b200
    rc = 0;
 done:
    b200_sync();
+   tl2 = lz_now();
+   if (lz_timing())
+      printf("[slq timing] lanczos_device: bases %.1f ms, iteration + tail %.1f ms\n", 1e3 * (tl1 - tl0), 1e3 * (tl2 - tl1));
    if (g_lz_keep && V && Z && !g_lz_bases[0])
    {
       g_lz_bases[0] = V;
@@ -485,11 +506,20 @@ int Nfft4GPLanczosQuadratureLogdet(void *mat_data, void *dmat_data, int n, func_
          continue;
       if (fast_A)
       {
-         if (b200_h2d(d_z, z, sizeof(double) * (size_t)n) || b200_additive_grad_matvec_dev(fast_A, n, 1.0, d_z, 0.0, d_dAz) ||
-             b200k_fill(n, 0.0, d_xs) ||
-             lanczos_device(fast_mat, n, fast_mv, NULL, NULL, d_xs, d_z, maxits, maxits, 0, EPSILON, &rel_res, &rel_res_v, &niter, &tsize, &TD, &TE,
+         double t0 = lz_now(), t1, t2, t3;
+         if (b200_h2d(d_z, z, sizeof(double) * (size_t)n) || b200_sync())
+            goto done;
+         t1 = lz_now();
+         if (b200_additive_grad_matvec_dev(fast_A, n, 1.0, d_z, 0.0, d_dAz) || b200k_fill(n, 0.0, d_xs) || (lz_timing() && b200_sync()))
+            goto done;
+         t2 = lz_now();
+         if (lanczos_device(fast_mat, n, fast_mv, NULL, NULL, d_xs, d_z, maxits, maxits, 0, EPSILON, &rel_res, &rel_res_v, &niter, &tsize, &TD, &TE,
                             print_level))
             goto done;
+         t3 = lz_now();
+         if (lz_timing())
+            printf("[slq timing] probe %d: upload %.1f ms, gradient matvec %.1f ms, Lanczos %.1f ms\n", i, 1e3 * (t1 - t0), 1e3 * (t2 - t1),
+                   1e3 * (t3 - t2));
       }
       else
       {
