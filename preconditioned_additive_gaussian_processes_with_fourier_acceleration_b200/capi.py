@@ -116,6 +116,7 @@ def lib():
         "Nfft4GPB200PrecondAFNSetK12Operator": (i, [vp, vp, i]),
         "Nfft4GPB200RankestNysScaledSample": (i, [c_double_p, i, i, i, vp, vp, c_int_p, i, i]),
         "Nfft4GPB200DebugPartitionChunks": (i, [c_int_p, i, i, i, c_double_p, d, c_int_p]),
+        "Nfft4GPB200DebugPoly1dBlockSort": (i, [c_double_p, i, i, c_double_p, C.POINTER(C.c_ushort), C.POINTER(C.c_ushort)]),
         "Nfft4GPB200HostPotrf": (i, [i, c_double_p]), "Nfft4GPB200HostSyev": (i, [i, c_double_p, c_double_p, i]),
         "Nfft4GPB200HostStev": (i, [i, c_double_p, c_double_p, c_double_p]),
         "Nfft4GPB200Dgemm": (i, [C.c_char, C.c_char, i, i, i, d, c_double_p, i, c_double_p, i, d, c_double_p, i]),

@@ -953,12 +953,49 @@ static int window_setup_small(b200_window *w, int n)
    return (v->grid && v->specA && v->specB && v->band && v->coef && v->dcoef) ? 0 : -1;
 }
 
+/* Order the scaled coordinates xt[0..n) of one 1-D window by grid cell INSIDE blocks of T consecutive points (pure host code, exported
+ * for the CPU tests as Nfft4GPB200DebugPoly1dBlockSort): out_xt / out_lp [nblk * T] = coordinate and position inside its block of
+ * the sorted point, out_rs [nblk][65] = run starts per cell key (c + 32) & 63.  Stable: a cell's points keep their original order, so
+ * every sum the kernels form has a fixed order. */
+void b200_poly1d_block_sort(const double *xt, int n, int T, double *out_xt, unsigned short *out_lp, unsigned short *out_rs)
+{
+   const int nblk = (n + T - 1) / T;
+   int b, j;
+   for (b = 0; b < nblk; b++)
+   {
+      const int base = b * T, cnt = n - base < T ? n - base : T;
+      unsigned short *rs = out_rs + 65 * (size_t)b;
+      int count[65], c;
+      memset(count, 0, sizeof(count));
+      for (j = 0; j < cnt; j++)
+         count[(((int)floor(xt[base + j] * (double)B200_NOS) + 32) & 63) + 1]++;
+      for (c = 0; c < 64; c++)
+         count[c + 1] += count[c];
+      for (c = 0; c <= 64; c++)
+         rs[c] = (unsigned short)count[c];
+      for (j = 0; j < cnt; j++)
+      {
+         int pos = count[((int)floor(xt[base + j] * (double)B200_NOS) + 32) & 63]++;
+         out_xt[base + pos] = xt[base + j];
+         out_lp[base + pos] = (unsigned short)j;
+      }
+   }
+}
+
+int Nfft4GPB200DebugPoly1dBlockSort(const double *xt, int n, int T, double *out_xt, unsigned short *out_lp, unsigned short *out_rs)
+{
+   if (!xt || n < 1 || T < 32 || T > 65535 || !out_xt || !out_lp || !out_rs)
+      return -1;
+   b200_poly1d_block_sort(xt, n, T, out_xt, out_lp, out_rs);
+   return 0;
+}
+
 /* first kernel build of a polynomial-path handle: contiguous work-array slots for the owned windows, scaling of every owned
  * window in the reference's arithmetic, block-local counting sort by cell, upload */
 static int additive_poly_setup(b200_additive *A, const double *cols_all, int n)
 {
    const int P = A->P;
-   int i, li, nw = 0, T, nblk, b, j, rc = -1;
+   int i, li, nw = 0, T, nblk, rc = -1;
    size_t per_w, gsz = B200_NOS, bsz = B200_NBAND;
    double *h_xt = NULL;
    unsigned short *h_lp = NULL, *h_rs = NULL;
@@ -1027,25 +1064,7 @@ static int additive_poly_setup(b200_additive *A, const double *cols_all, int n)
          free(xt);
          goto done;
       }
-      for (b = 0; b < nblk; b++)
-      {
-         const int base = b * T, cnt = n - base < T ? n - base : T;
-         unsigned short *rs = h_rs + 65 * (size_t)b;
-         int count[65], c;
-         memset(count, 0, sizeof(count));
-         for (j = 0; j < cnt; j++)
-            count[(((int)floor(xt[base + j] * (double)B200_NOS) + 32) & 63) + 1]++;
-         for (c = 0; c < 64; c++)
-            count[c + 1] += count[c];
-         for (c = 0; c <= 64; c++)
-            rs[c] = (unsigned short)count[c];
-         for (j = 0; j < cnt; j++) /* stable: a cell's points keep their original order, so every sum has a fixed order */
-         {
-            int pos = count[((int)floor(xt[base + j] * (double)B200_NOS) + 32) & 63]++;
-            h_xt[base + pos] = xt[base + j];
-            h_lp[base + pos] = (unsigned short)j;
-         }
-      }
+      b200_poly1d_block_sort(xt, n, T, h_xt, h_lp, h_rs);
       free(xt);
       if (b200_h2d((void *)(A->poly.xt + per_w * li), h_xt, sizeof(double) * per_w) ||
           b200_h2d((void *)(A->poly.lp + per_w * li), h_lp, sizeof(unsigned short) * per_w) ||

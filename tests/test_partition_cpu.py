@@ -78,3 +78,32 @@ def test_host_tridiagonal_eigensolver(n):
     assert np.abs(w - wr).max() <= 1e-13 * max(1.0, np.abs(wr).max())
     assert np.abs(Z.T @ Z - np.eye(n)).max() <= 1e-12
     assert np.abs(T @ Z - Z * w).max() <= 1e-12 * max(1.0, np.abs(wr).max())
+
+
+def test_poly1d_block_local_cell_sort():
+    """Plan build of the table-free 1-D path (nfft_host.c:b200_poly1d_block_sort, host only): inside every block of T consecutive points
+    the points are ordered by grid cell, stably; lp is a permutation of the block, rs the run starts per cell key."""
+    import ctypes as C
+    import preconditioned_additive_gaussian_processes_with_fourier_acceleration_b200 as pkg
+    L = pkg.lib()
+    rng = np.random.default_rng(3)
+    for n, T in ((1000, 256), (8192 * 2 + 77, 8192), (50, 64), (6784 * 3, 6784)):
+        xt = np.clip((rng.random(n) - 0.5) * 0.5, -0.25, 0.25)
+        xt[0], xt[-1] = 0.25, -0.25                      # the two extreme cells (keys 48 and 16)
+        nblk = (n + T - 1) // T
+        oxt, olp, ors = np.zeros(nblk * T), np.zeros(nblk * T, dtype=np.uint16), np.zeros(nblk * 65, dtype=np.uint16)
+        assert L.Nfft4GPB200DebugPoly1dBlockSort(pkg.capi.dptr(xt), n, T, pkg.capi.dptr(oxt), olp.ctypes.data_as(C.POINTER(C.c_ushort)),
+                                                 ors.ctypes.data_as(C.POINTER(C.c_ushort))) == 0
+        key = (np.floor(xt * 64).astype(int) + 32) & 63
+        for b in range(nblk):
+            base, cnt = b * T, min(T, n - b * T)
+            lp, rs = olp[base:base + cnt].astype(int), ors[b * 65:(b + 1) * 65].astype(int)
+            assert sorted(lp.tolist()) == list(range(cnt))                       # a permutation of the block
+            assert (oxt[base:base + cnt] == xt[base + lp]).all()                 # coordinates follow it
+            kb = key[base + lp]
+            assert (np.diff(kb) >= 0).all()                                      # ordered by cell
+            assert rs[0] == 0 and rs[64] == cnt and (np.diff(rs) >= 0).all()
+            for c in np.unique(kb):
+                seg = lp[rs[c]:rs[c + 1]]
+                assert (kb[rs[c]:rs[c + 1]] == c).all() and (np.diff(seg) > 0).all()   # the run of cell c, original order kept
+    assert L.Nfft4GPB200DebugPoly1dBlockSort(pkg.capi.dptr(np.zeros(4)), 4, 16, None, None, None) == -1
