@@ -342,7 +342,7 @@ int Nfft4GPB200DebugPartitionChunks(const int *chunks /* int4 per chunk */, int 
                                     double flush, int *first /* rounds * wcnt + 1 */);
 /* plan build of the table-free 1-D path (host only): cell sort inside blocks of T consecutive points of the original order */
 int Nfft4GPB200DebugPoly1dBlockSort(const double *xt, int n, int T, double *out_xt /* nblk*T */, unsigned short *out_lp /* nblk*T */,
-                                    unsigned short *out_rs /* nblk*65 */);
+                                    unsigned short *out_rs /* nblk*80: 65 run starts per block, rows padded to 160 bytes */);
 int Nfft4GPB200HostPotrf(int n, double *A /* lower, column-major, in place */);
 int Nfft4GPB200HostSyev(int n, double *A /* in: symmetric; out: eigenvectors */, double *w /* ascending */, int want_vectors);
 int Nfft4GPB200HostStev(int n, double *d /* diagonal -> eigenvalues */, double *e /* sub-diagonal, destroyed */, double *Z /* n x n */);

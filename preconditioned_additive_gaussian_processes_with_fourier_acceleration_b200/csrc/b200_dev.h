@@ -99,12 +99,13 @@ int b200k_spread_stream(const b200_win_dev *w);
 int b200k_gather_stream(const b200_win_dev *w, double *d_f);
 /* nfft1d_poly.cu: ALL 1-D windows of an additive kernel without tap tables -- per-cell polynomial coefficients / moments.
  * Points are sorted by cell inside blocks of T consecutive points of the original order (once per handle). */
+#define B200_POLY_RS 80 /* 65 run starts per block, padded to 160 bytes so that a row is 16-byte aligned (bulk staging) */
 typedef struct
 {
    int n, nblk, T, nw;          /* points of this rank, blocks of T points, windows handled by this rank */
    const double *xt;            /* [nw][nblk * T] scaled coordinates, sorted by cell inside every block */
    const unsigned short *lp;    /* [nw][nblk * T] position inside its block (original order) of the sorted point */
-   const unsigned short *rs;    /* [nw][nblk][65] run starts: the points of cell key c of a block are [rs[c], rs[c + 1]) */
+   const unsigned short *rs;    /* [nw][nblk][B200_POLY_RS] run starts: the points of cell key c of a block are [rs[c], rs[c + 1]) */
    double *mom;                 /* [nw][64][16] moments sum_i a_i v_i^k per cell (spread) */
    double *ctab;                /* [2][nw][64][16] polynomial coefficients per cell (gather): kernel / derivative channel */
 } b200_poly1d_dev;

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "b200_dev.h"
 #include "b200_cuda_util.cuh"
@@ -139,7 +140,7 @@ k_poly1d_spread(b200_poly1d_dev p, const double *__restrict__ x, double s)
       for (int j = tid; j < p.T; j += PTHREADS)
          xs[j] = j < cnt ? s * __ldg(x + base + j) : 0.0;
       if (tid < 65)
-         rs[tid] = p.rs[((size_t)w * p.nblk + b) * 65 + tid];
+         rs[tid] = p.rs[((size_t)w * p.nblk + b) * B200_POLY_RS + tid];
       __syncthreads();
       for (int c = wid; c < 64; c += PWARPS)
       {
@@ -262,7 +263,7 @@ k_poly1d_gather(b200_poly1d_dev p, const double *__restrict__ x, double s, doubl
          for (int e = tid; e < 64 * PLD; e += PTHREADS)
             ct[ch * 64 * PLD + e] = __ldg(p.ctab + ((size_t)ch * p.nw + w) * 64 * PLD + e);
       if (tid < 65)
-         rs[tid] = p.rs[((size_t)w * p.nblk + b) * 65 + tid];
+         rs[tid] = p.rs[((size_t)w * p.nblk + b) * B200_POLY_RS + tid];
       __syncthreads();
       for (int c = wid; c < 64; c += PWARPS)
       {
@@ -319,14 +320,211 @@ k_poly1d_gather(b200_poly1d_dev p, const double *__restrict__ x, double s, doubl
    }
 }
 
+// ---------------------------------------------------------------------------------------------------- asynchronously staged variants
+// The kernels above read a run's coordinates / indices straight from global memory: their top stall is that dependent chain (ncu:
+// long scoreboard), with 2 CTAs x 16 warps per SM for cover.  Here ONE CTA per SM streams the next (window, block) item -- coordinates,
+// indices, run starts, coefficient table: 76 KB -- into shared memory with cp.async while the current one is processed from shared
+// memory, so the HBM stream is decoupled from the arithmetic (double buffer; one barrier pair per item as before).
+__device__ __forceinline__ void p_cpa16(void *smem, const void *gmem)
+{
+   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void p_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void p_wait()
+{
+   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+// bytes (a multiple of 16, both sides 16-byte aligned) global -> shared, all threads of the CTA
+__device__ __forceinline__ void p_stage(void *dst, const void *src, int bytes, int tid)
+{
+   for (int o = tid * 16; o < bytes; o += PTHREADS * 16)
+      p_cpa16((char *)dst + o, (const char *)src + o);
+}
+
+// shared-memory layout of the staged kernels (doubles first, then the 16-bit arrays); T is a multiple of 32
+struct PStage
+{
+   double *xt0;             // [2][T]
+   unsigned short *lp0, *rs0; // [2][T], [2][B200_POLY_RS]
+   int T;
+   __device__ __forceinline__ double *xt(int buf) const { return xt0 + (size_t)buf * T; }
+   __device__ __forceinline__ unsigned short *lp(int buf) const { return lp0 + (size_t)buf * T; }
+   __device__ __forceinline__ unsigned short *rs(int buf) const { return rs0 + buf * B200_POLY_RS; }
+};
+__device__ __forceinline__ void p_stage_item(const b200_poly1d_dev &p, const PStage &st, int buf, int w, int b, int tid)
+{
+   const size_t off = (size_t)w * p.nblk * p.T + (size_t)b * p.T;
+   p_stage(st.xt(buf), p.xt + off, p.T * 8, tid);
+   p_stage(st.lp(buf), p.lp + off, p.T * 2, tid);
+   p_stage(st.rs(buf), p.rs + ((size_t)w * p.nblk + b) * B200_POLY_RS, B200_POLY_RS * 2, tid);
+}
+
+__global__ void __launch_bounds__(PTHREADS, 1)
+k_poly1d_gather_async(b200_poly1d_dev p, const double *__restrict__ x, double s, double c0, double mu, double beta, double *__restrict__ y)
+{
+   extern __shared__ __align__(16) double psm[];
+   double *acc = psm;                                  // [T]
+   double *ctb = acc + p.T;                            // [2][64][PLD]
+   PStage st;
+   st.T = p.T;
+   st.xt0 = ctb + 2 * 64 * PLD;
+   st.lp0 = reinterpret_cast<unsigned short *>(st.xt0 + 2 * (size_t)p.T);
+   st.rs0 = st.lp0 + 2 * (size_t)p.T;
+   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.x;
+   const int base = b * p.T, cnt = min(p.T, p.n - base);
+   for (int j = tid; j < p.T; j += PTHREADS)
+      acc[j] = 0.0;
+   p_stage_item(p, st, 0, 0, b, tid);
+   p_stage(ctb, p.ctab, 64 * PLD * 8, tid);
+   p_commit();
+   for (int w = 0; w < p.nw; w++)
+   {
+      const int buf = w & 1;
+      if (w + 1 < p.nw) // the other buffer was released by the barrier that ended the previous window
+      {
+         p_stage_item(p, st, buf ^ 1, w + 1, b, tid);
+         p_stage(ctb + (buf ^ 1) * 64 * PLD, p.ctab + (size_t)(w + 1) * 64 * PLD, 64 * PLD * 8, tid);
+      }
+      p_commit();
+      p_wait<1>(); // everything but the group just committed has landed (this thread's copies; the barrier makes it everybody's)
+      __syncthreads();
+      const double *xt = st.xt(buf);
+      const unsigned short *lp = st.lp(buf), *rs = st.rs(buf);
+      const double *ct = ctb + buf * 64 * PLD;
+      for (int c = wid; c < 64; c += PWARPS)
+      {
+         const int j0 = rs[c], j1 = rs[c + 1];
+         if (j0 == j1) // warp-uniform
+            continue;
+         double cf[PNC];
+#pragma unroll
+         for (int k = 0; k < PNC; k++)
+            cf[k] = ct[c * PLD + k];
+         for (int jc = j0; jc < j1; jc += 32 * PU)
+         {
+#pragma unroll
+            for (int u = 0; u < PU; u++)
+            {
+               const int j = jc + lane + 32 * u;
+               if (j < j1)
+                  acc[lp[j]] += p_horner(cf, p_offset(xt[j]));
+            }
+         }
+      }
+      __syncthreads(); // the runs are done with this buffer (and acc is complete for this window)
+   }
+   const double nwmu = (double)p.nw * mu;
+   for (int j = tid; j < cnt; j += PTHREADS)
+   {
+      const size_t i = (size_t)base + j;
+      const double ai = s * __ldg(x + i);
+      y[i] = (beta == 0.0 ? 0.0 : beta * y[i]) + c0 * (acc[j] + nwmu * ai);
+   }
+}
+
+__global__ void __launch_bounds__(PTHREADS, 1)
+k_poly1d_spread_async(b200_poly1d_dev p, const double *__restrict__ x, double s)
+{
+   extern __shared__ __align__(16) double psm[];
+   double *xs = psm, *msm = psm + p.T;
+   PStage st;
+   st.T = p.T;
+   st.xt0 = msm + 64 * PLD;
+   st.lp0 = reinterpret_cast<unsigned short *>(st.xt0 + 2 * (size_t)p.T);
+   st.rs0 = st.lp0 + 2 * (size_t)p.T;
+   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+   const long long items = (long long)p.nw * p.nblk;
+   const long long it0 = items * blockIdx.x / gridDim.x, it1 = items * (blockIdx.x + 1) / gridDim.x;
+   int wcur = -1;
+   if (it0 < it1)
+      p_stage_item(p, st, 0, (int)(it0 / p.nblk), (int)(it0 % p.nblk), tid);
+   p_commit();
+   for (long long it = it0; it < it1; it++)
+   {
+      const int buf = (int)((it - it0) & 1);
+      const int w = (int)(it / p.nblk), b = (int)(it - (long long)w * p.nblk);
+      const int base = b * p.T, cnt = min(p.T, p.n - base);
+      if (it + 1 < it1)
+         p_stage_item(p, st, buf ^ 1, (int)((it + 1) / p.nblk), (int)((it + 1) % p.nblk), tid);
+      p_commit();
+      if (w != wcur) // the previous item's runs ended with a barrier: msm is quiescent
+      {
+         if (wcur >= 0)
+         {
+            double *mg = p.mom + (size_t)wcur * 64 * PLD;
+            for (int e = tid; e < 64 * PLD; e += PTHREADS)
+               if (msm[e] != 0.0)
+                  p_red_add(mg + e, msm[e]);
+         }
+         for (int e = tid; e < 64 * PLD; e += PTHREADS)
+            msm[e] = 0.0;
+         wcur = w;
+      }
+      for (int j = tid; j < p.T; j += PTHREADS)
+         xs[j] = j < cnt ? s * __ldg(x + base + j) : 0.0;
+      p_wait<1>();
+      __syncthreads();
+      const double *xt = st.xt(buf);
+      const unsigned short *lp = st.lp(buf), *rs = st.rs(buf);
+      for (int c = wid; c < 64; c += PWARPS)
+      {
+         const int j0 = rs[c], j1 = rs[c + 1];
+         if (j0 == j1) // warp-uniform
+            continue;
+         double m[16];
+#pragma unroll
+         for (int k = 0; k < 16; k++)
+            m[k] = 0.0;
+         for (int jc = j0; jc < j1; jc += 32 * PU)
+         {
+#pragma unroll
+            for (int u = 0; u < PU; u++)
+            {
+               const int j = jc + lane + 32 * u;
+               if (j < j1)
+                  p_moments(m, xs[lp[j]], p_offset(xt[j]));
+            }
+         }
+         int q;
+         const double tot = p_transpose_reduce16(m, lane, q);
+         if (!(lane & 1) && q < PNC)
+            msm[c * PLD + q] += tot;
+      }
+      __syncthreads(); // the runs are done with xs / this buffer / msm
+   }
+   if (wcur >= 0)
+   {
+      double *mg = p.mom + (size_t)wcur * 64 * PLD;
+      for (int e = tid; e < 64 * PLD; e += PTHREADS)
+         if (msm[e] != 0.0)
+            p_red_add(mg + e, msm[e]);
+   }
+}
+
 // ---------------------------------------------------------------------------------------------------- launch layer
 extern "C" {
 
 static size_t poly_smem_spread(int T) { return sizeof(double) * ((size_t)T + 64 * PLD) + 2 * 80; }
+// staged variants: xs / acc [T] + tables + two buffers of (T doubles + T + B200_POLY_RS shorts)
+static size_t poly_smem_spread_async(int T) { return sizeof(double) * ((size_t)T + 64 * PLD + 2 * (size_t)T) + 2 * 2 * ((size_t)T + B200_POLY_RS); }
+static size_t poly_smem_gather_async(int T) { return sizeof(double) * ((size_t)T + 2 * 64 * PLD + 2 * (size_t)T) + 2 * 2 * ((size_t)T + B200_POLY_RS); }
+static bool poly_async_enabled(void)
+{
+   static int on = -1;
+   if (on < 0)
+   {
+      const char *e = getenv("NFFT4GP_B200_POLY1D_ASYNC"); // 0: the direct-load kernels (A/B, cross-check)
+      on = (e && atoi(e) == 0) ? 0 : 1;
+   }
+   return on != 0;
+}
 static size_t poly_smem_gather(int T, int nch) { return sizeof(double) * (size_t)nch * ((size_t)T + 64 * PLD) + 2 * 80; }
 
 // largest block size (points per locally sorted block) the gather kernel of the gradient matvec still fits into shared memory with
-int b200k_poly1d_max_block(void) { return 8192; }
+// largest block the kernels hold in shared memory: 7680 points is where the staged (double-buffered) gather still fits 227 KB
+int b200k_poly1d_max_block(void) { return poly_async_enabled() ? 7680 : 8192; }
 // CTAs of one resident wave of the spread / gather kernels (two per SM: registers and shared memory)
 int b200k_poly1d_wave_slots(void)
 {
@@ -356,7 +554,19 @@ int b200k_poly1d_spread(const b200_poly1d_dev *p, const double *d_x, double s, d
    if (G < 1)
       G = 1;
    B200_CHECK(cudaMemsetAsync(p->mom, 0, sizeof(double) * (size_t)p->nw * 64 * PLD, b200_stream()));
-   k_poly1d_spread<<<G, PTHREADS, poly_smem_spread(p->T), b200_stream()>>>(*p, d_x, s);
+   if (poly_async_enabled() && poly_smem_spread_async(p->T) <= 227 * 1024)
+   {
+      static bool attr2 = false;
+      if (!attr2)
+      {
+         B200_CHECK(cudaFuncSetAttribute(k_poly1d_spread_async, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+         attr2 = true;
+      }
+      int G1 = sm < items ? sm : (int)items; // one CTA per SM
+      k_poly1d_spread_async<<<G1, PTHREADS, poly_smem_spread_async(p->T), b200_stream()>>>(*p, d_x, s);
+   }
+   else
+      k_poly1d_spread<<<G, PTHREADS, poly_smem_spread(p->T), b200_stream()>>>(*p, d_x, s);
    B200_LAUNCHED();
    k_poly1d_mom2grid<<<p->nw, 64, 0, b200_stream()>>>(p->mom, d_grids, grid_stride);
    B200_LAUNCHED();
@@ -384,7 +594,17 @@ int b200k_poly1d_gather(const b200_poly1d_dev *p, int nch, const double *d_x, do
       B200_CHECK(cudaFuncSetAttribute(k_poly1d_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)poly_smem_gather(b200k_poly1d_max_block(), 2)));
       attr_set = true;
    }
-   if (nch == 1)
+   if (nch == 1 && poly_async_enabled() && poly_smem_gather_async(p->T) <= 227 * 1024)
+   {
+      static bool attr2 = false;
+      if (!attr2)
+      {
+         B200_CHECK(cudaFuncSetAttribute(k_poly1d_gather_async, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+         attr2 = true;
+      }
+      k_poly1d_gather_async<<<p->nblk, PTHREADS, poly_smem_gather_async(p->T), b200_stream()>>>(*p, d_x, s, c0, mu, beta, d_y);
+   }
+   else if (nch == 1)
       k_poly1d_gather<1><<<p->nblk, PTHREADS, poly_smem_gather(p->T, 1), b200_stream()>>>(*p, d_x, s, c0, mu, ff, beta, d_y, ystride);
    else
       k_poly1d_gather<2><<<p->nblk, PTHREADS, poly_smem_gather(p->T, 2), b200_stream()>>>(*p, d_x, s, c0, mu, ff, beta, d_y, ystride);

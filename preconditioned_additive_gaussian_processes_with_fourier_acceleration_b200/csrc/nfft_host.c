@@ -955,7 +955,7 @@ static int window_setup_small(b200_window *w, int n)
 
 /* Order the scaled coordinates xt[0..n) of one 1-D window by grid cell INSIDE blocks of T consecutive points (pure host code, exported
  * for the CPU tests as Nfft4GPB200DebugPoly1dBlockSort): out_xt / out_lp [nblk * T] = coordinate and position inside its block of
- * the sorted point, out_rs [nblk][65] = run starts per cell key (c + 32) & 63.  Stable: a cell's points keep their original order, so
+ * the sorted point, out_rs [nblk][B200_POLY_RS] = the 65 run starts per cell key (c + 32) & 63.  Stable: a cell's points keep their original order, so
  * every sum the kernels form has a fixed order. */
 void b200_poly1d_block_sort(const double *xt, int n, int T, double *out_xt, unsigned short *out_lp, unsigned short *out_rs)
 {
@@ -964,7 +964,7 @@ void b200_poly1d_block_sort(const double *xt, int n, int T, double *out_xt, unsi
    for (b = 0; b < nblk; b++)
    {
       const int base = b * T, cnt = n - base < T ? n - base : T;
-      unsigned short *rs = out_rs + 65 * (size_t)b;
+      unsigned short *rs = out_rs + B200_POLY_RS * (size_t)b;
       int count[65], c;
       memset(count, 0, sizeof(count));
       for (j = 0; j < cnt; j++)
@@ -1040,7 +1040,7 @@ static int additive_poly_setup(b200_additive *A, const double *cols_all, int n)
    }
    A->poly.xt = (const double *)b200_malloc(sizeof(double) * per_w * nw);
    A->poly.lp = (const unsigned short *)b200_malloc(sizeof(unsigned short) * per_w * nw);
-   A->poly.rs = (const unsigned short *)b200_malloc(sizeof(unsigned short) * 65 * (size_t)nblk * nw);
+   A->poly.rs = (const unsigned short *)b200_malloc(sizeof(unsigned short) * B200_POLY_RS * (size_t)nblk * nw);
    A->poly.mom = (double *)b200_malloc(sizeof(double) * 64 * 16 * (size_t)nw);
    A->poly.ctab = (double *)b200_malloc(sizeof(double) * 2 * 64 * 16 * (size_t)nw);
    A->d_poly_wscale = (double *)b200_malloc(sizeof(double) * (size_t)nw);
@@ -1048,7 +1048,7 @@ static int additive_poly_setup(b200_additive *A, const double *cols_all, int n)
       return -1;
    h_xt = (double *)b200_xcalloc(per_w, sizeof(double));
    h_lp = (unsigned short *)b200_xcalloc(per_w, sizeof(unsigned short));
-   h_rs = (unsigned short *)b200_xcalloc(65 * (size_t)nblk, sizeof(unsigned short));
+   h_rs = (unsigned short *)b200_xcalloc(B200_POLY_RS * (size_t)nblk, sizeof(unsigned short));
    for (li = 0; li < nw; li++)
    {
       b200_window *w = A->win[A->poly_win[li]];
@@ -1068,7 +1068,7 @@ static int additive_poly_setup(b200_additive *A, const double *cols_all, int n)
       free(xt);
       if (b200_h2d((void *)(A->poly.xt + per_w * li), h_xt, sizeof(double) * per_w) ||
           b200_h2d((void *)(A->poly.lp + per_w * li), h_lp, sizeof(unsigned short) * per_w) ||
-          b200_h2d((void *)(A->poly.rs + 65 * (size_t)nblk * li), h_rs, sizeof(unsigned short) * 65 * (size_t)nblk) || b200_sync())
+          b200_h2d((void *)(A->poly.rs + B200_POLY_RS * (size_t)nblk * li), h_rs, sizeof(unsigned short) * B200_POLY_RS * (size_t)nblk) || b200_sync())
          goto done;
    }
    A->poly1d = 1;

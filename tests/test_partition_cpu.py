@@ -91,13 +91,13 @@ def test_poly1d_block_local_cell_sort():
         xt = np.clip((rng.random(n) - 0.5) * 0.5, -0.25, 0.25)
         xt[0], xt[-1] = 0.25, -0.25                      # the two extreme cells (keys 48 and 16)
         nblk = (n + T - 1) // T
-        oxt, olp, ors = np.zeros(nblk * T), np.zeros(nblk * T, dtype=np.uint16), np.zeros(nblk * 65, dtype=np.uint16)
+        oxt, olp, ors = np.zeros(nblk * T), np.zeros(nblk * T, dtype=np.uint16), np.zeros(nblk * 80, dtype=np.uint16)
         assert L.Nfft4GPB200DebugPoly1dBlockSort(pkg.capi.dptr(xt), n, T, pkg.capi.dptr(oxt), olp.ctypes.data_as(C.POINTER(C.c_ushort)),
                                                  ors.ctypes.data_as(C.POINTER(C.c_ushort))) == 0
         key = (np.floor(xt * 64).astype(int) + 32) & 63
         for b in range(nblk):
             base, cnt = b * T, min(T, n - b * T)
-            lp, rs = olp[base:base + cnt].astype(int), ors[b * 65:(b + 1) * 65].astype(int)
+            lp, rs = olp[base:base + cnt].astype(int), ors[b * 80:b * 80 + 65].astype(int)
             assert sorted(lp.tolist()) == list(range(cnt))                       # a permutation of the block
             assert (oxt[base:base + cnt] == xt[base + lp]).all()                 # coordinates follow it
             kb = key[base + lp]
