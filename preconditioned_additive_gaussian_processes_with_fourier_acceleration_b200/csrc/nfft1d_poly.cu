@@ -80,28 +80,27 @@ __device__ __forceinline__ double p_transpose_reduce16(const double m[16], int l
 }
 
 // ---------------------------------------------------------------------------------------------------- spread: moments
-// moments of one point: m[k] += a v^k, k = 0..14, as two independent chains in v^2 (even / odd powers)
+// moments of one point: m[k] += a v^k, k = 0..14, from ONE chain in v^4: e = a v^(4q); m[4q] += e, m[4q+r] = fma(e, v^r, m[4q+r]) --
+// 21 fp64 instructions per point (3 + 3 products, 4 additions, 11 FMAs) instead of 30 with separate power and sum steps
 __device__ __forceinline__ void p_moments(double m[16], double a, double v)
 {
-   const double v2 = v * v;
-   double e = a, o = a * v;
+   const double v2 = v * v, v3 = v2 * v, v4 = v2 * v2;
+   double e = a;
 #pragma unroll
-   for (int k = 0; k < PNC; k += 2)
+   for (int k = 0; k < PNC; k += 4)
    {
       m[k] += e;
-      e *= v2;
-      if (k + 1 < PNC)
+      m[k + 1] = fma(e, v, m[k + 1]);
+      m[k + 2] = fma(e, v2, m[k + 2]);
+      if (k + 3 < PNC)
       {
-         m[k + 1] += o;
-         o *= v2;
+         m[k + 3] = fma(e, v3, m[k + 3]);
+         e *= v4;
       }
    }
 }
-__device__ __forceinline__ double p_offset(double xt) // v = 2 u - 1, u = fractional part of 64 x
-{
-   const double t = xt * 64.0;
-   return 2.0 * (t - floor(t)) - 1.0;
-}
+// the stored coordinate IS v = 2 u - 1 (u = offset of the point inside its cell; the cell is the run the point stands in)
+__device__ __forceinline__ double p_offset(double xt) { return xt; }
 
 // The work items (window w, block b), w-major, are cut into gridDim.x equal consecutive ranges: ONE wave of CTAs whatever the
 // number of windows (a grid of G x nw CTAs left a second, nearly empty wave behind: 304 CTAs on 296 slots doubled the time).
@@ -320,80 +319,122 @@ k_poly1d_gather(b200_poly1d_dev p, const double *__restrict__ x, double s, doubl
    }
 }
 
-// ---------------------------------------------------------------------------------------------------- asynchronously staged variants
-// The kernels above read a run's coordinates / indices straight from global memory: their top stall is that dependent chain (ncu:
-// long scoreboard), with 2 CTAs x 16 warps per SM for cover.  Here ONE CTA per SM streams the next (window, block) item -- coordinates,
-// indices, run starts, coefficient table: 76 KB -- into shared memory with cp.async while the current one is processed from shared
-// memory, so the HBM stream is decoupled from the arithmetic (double buffer; one barrier pair per item as before).
-__device__ __forceinline__ void p_cpa16(void *smem, const void *gmem)
+// ---------------------------------------------------------------------------------------------------- staged variants (bulk copies)
+// The kernels above read a run's offsets / indices straight from global memory and reduce the lanes' moments once per run.  ncu of
+// that structure (profiles/r2_l_*): DP instructions are only 25 % of the instructions issued -- 35 % go into the per-run butterfly,
+// 22 % into per-item address arithmetic and staging, the rest into per-slot branches that also keep the compiler from interleaving
+// the points' dependent chains.  The staged kernels remove all three:
+//  * ONE CTA per SM; one thread streams the whole NEXT (window, block) item -- offsets, indices, run starts, the vector block (spread)
+//    or the coefficient table (gather) -- into the other half of a double buffer with four bulk copies (cp.async.bulk -> UBLKCP,
+//    completion on an mbarrier) while the CTA works on the current one from shared memory;
+//  * runs are walked in full chunks of 32 PU points without any predicate (PU independent chains per lane) plus one clamped tail;
+//  * spread: the scaled points lie in [-1/4, 1/4], i.e. in the 32 cells with keys 16..47 (key 48 only for a point exactly on the
+//    upper end).  Warp w owns the cells 16 + w + PAW h for the whole kernel and keeps their lane-private moments in REGISTERS across
+//    the items of a window: the butterfly runs once per window and CTA instead of once per run.  Any other key takes the old path.
+#ifndef PAW
+#define PAW 32 /* warps of the staged kernels */
+#endif
+#ifndef PUA
+#define PUA 2 /* points per lane and chunk of the staged kernels */
+#endif
+#define PATHREADS (PAW * 32)
+#define PNH (32 / PAW) /* home cells per warp */
+
+__device__ __forceinline__ unsigned p_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void p_mbar_init(unsigned long long *bar)
 {
-   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(p_saddr(bar)) : "memory");
 }
-__device__ __forceinline__ void p_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void p_wait()
+__device__ __forceinline__ void p_mbar_expect(unsigned long long *bar, unsigned bytes)
 {
-   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(p_saddr(bar)), "r"(bytes) : "memory");
 }
-// bytes (a multiple of 16, both sides 16-byte aligned) global -> shared, all threads of the CTA
-__device__ __forceinline__ void p_stage(void *dst, const void *src, int bytes, int tid)
+__device__ __forceinline__ void p_mbar_wait(unsigned long long *bar, unsigned parity)
 {
-   for (int o = tid * 16; o < bytes; o += PTHREADS * 16)
-      p_cpa16((char *)dst + o, (const char *)src + o);
+   asm volatile("{\n"
+                ".reg .pred ok;\n"
+                "PWAIT_%=:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 ok, [%0], %1;\n"
+                "@ok bra PDONE_%=;\n"
+                "bra PWAIT_%=;\n"
+                "PDONE_%=:\n"
+                "}\n" ::"r"(p_saddr(bar)),
+                "r"(parity)
+                : "memory");
+}
+// bytes: a multiple of 16; both addresses 16-byte aligned
+__device__ __forceinline__ void p_bulk(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(p_saddr(dst)), "l"(src), "r"(bytes),
+                "r"(p_saddr(bar))
+                : "memory");
 }
 
-// shared-memory layout of the staged kernels (doubles first, then the 16-bit arrays); T is a multiple of 32
+// double-buffered part of the shared memory of the staged kernels; T is a multiple of 32
 struct PStage
 {
-   double *xt0;             // [2][T]
+   double *xt0;               // [2][T]
    unsigned short *lp0, *rs0; // [2][T], [2][B200_POLY_RS]
+   unsigned long long *bar;   // [2]
    int T;
    __device__ __forceinline__ double *xt(int buf) const { return xt0 + (size_t)buf * T; }
    __device__ __forceinline__ unsigned short *lp(int buf) const { return lp0 + (size_t)buf * T; }
    __device__ __forceinline__ unsigned short *rs(int buf) const { return rs0 + buf * B200_POLY_RS; }
 };
-__device__ __forceinline__ void p_stage_item(const b200_poly1d_dev &p, const PStage &st, int buf, int w, int b, int tid)
+#define PSTAGE_ITEM_BYTES(T) ((unsigned)(T) * 10u + B200_POLY_RS * 2u)
+// issued by ONE thread after the mbarrier of the buffer was armed with the byte count of everything that goes into it
+__device__ __forceinline__ void p_stage_item(const b200_poly1d_dev &p, const PStage &st, int buf, int w, int b)
 {
    const size_t off = (size_t)w * p.nblk * p.T + (size_t)b * p.T;
-   p_stage(st.xt(buf), p.xt + off, p.T * 8, tid);
-   p_stage(st.lp(buf), p.lp + off, p.T * 2, tid);
-   p_stage(st.rs(buf), p.rs + ((size_t)w * p.nblk + b) * B200_POLY_RS, B200_POLY_RS * 2, tid);
+   p_bulk(st.xt(buf), p.xt + off, (unsigned)p.T * 8u, st.bar + buf);
+   p_bulk(st.lp(buf), p.lp + off, (unsigned)p.T * 2u, st.bar + buf);
+   p_bulk(st.rs(buf), p.rs + ((size_t)w * p.nblk + b) * B200_POLY_RS, B200_POLY_RS * 2u, st.bar + buf);
 }
 
-__global__ void __launch_bounds__(PTHREADS, 1)
+__global__ void __launch_bounds__(PATHREADS, 1)
 k_poly1d_gather_async(b200_poly1d_dev p, const double *__restrict__ x, double s, double c0, double mu, double beta, double *__restrict__ y)
 {
    extern __shared__ __align__(16) double psm[];
-   double *acc = psm;                                  // [T]
-   double *ctb = acc + p.T;                            // [2][64][PLD]
+   double *acc = psm;       // [T]
+   double *ctb = acc + p.T; // [2][64][PLD]
    PStage st;
    st.T = p.T;
    st.xt0 = ctb + 2 * 64 * PLD;
    st.lp0 = reinterpret_cast<unsigned short *>(st.xt0 + 2 * (size_t)p.T);
    st.rs0 = st.lp0 + 2 * (size_t)p.T;
+   st.bar = reinterpret_cast<unsigned long long *>(st.rs0 + 2 * B200_POLY_RS);
    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.x;
    const int base = b * p.T, cnt = min(p.T, p.n - base);
-   for (int j = tid; j < p.T; j += PTHREADS)
+   const unsigned item_bytes = PSTAGE_ITEM_BYTES(p.T) + 64 * PLD * 8;
+   if (tid == 0)
+   {
+      p_mbar_init(st.bar);
+      p_mbar_init(st.bar + 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+   }
+   for (int j = tid; j < p.T; j += PATHREADS)
       acc[j] = 0.0;
-   p_stage_item(p, st, 0, 0, b, tid);
-   p_stage(ctb, p.ctab, 64 * PLD * 8, tid);
-   p_commit();
+   __syncthreads();
+   if (tid == 0)
+   {
+      p_mbar_expect(st.bar, item_bytes);
+      p_stage_item(p, st, 0, 0, b);
+      p_bulk(ctb, p.ctab, 64 * PLD * 8, st.bar);
+   }
    for (int w = 0; w < p.nw; w++)
    {
       const int buf = w & 1;
-      if (w + 1 < p.nw) // the other buffer was released by the barrier that ended the previous window
+      if (tid == 0 && w + 1 < p.nw) // the other buffer was released by the barrier that ended the previous window
       {
-         p_stage_item(p, st, buf ^ 1, w + 1, b, tid);
-         p_stage(ctb + (buf ^ 1) * 64 * PLD, p.ctab + (size_t)(w + 1) * 64 * PLD, 64 * PLD * 8, tid);
+         p_mbar_expect(st.bar + (buf ^ 1), item_bytes);
+         p_stage_item(p, st, buf ^ 1, w + 1, b);
+         p_bulk(ctb + (buf ^ 1) * 64 * PLD, p.ctab + (size_t)(w + 1) * 64 * PLD, 64 * PLD * 8, st.bar + (buf ^ 1));
       }
-      p_commit();
-      p_wait<1>(); // everything but the group just committed has landed (this thread's copies; the barrier makes it everybody's)
-      __syncthreads();
+      p_mbar_wait(st.bar + buf, (unsigned)(w >> 1) & 1u);
       const double *xt = st.xt(buf);
       const unsigned short *lp = st.lp(buf), *rs = st.rs(buf);
       const double *ct = ctb + buf * 64 * PLD;
-      for (int c = wid; c < 64; c += PWARPS)
+      for (int c = wid; c < 64; c += PAW)
       {
          const int j0 = rs[c], j1 = rs[c + 1];
          if (j0 == j1) // warp-uniform
@@ -402,21 +443,36 @@ k_poly1d_gather_async(b200_poly1d_dev p, const double *__restrict__ x, double s,
 #pragma unroll
          for (int k = 0; k < PNC; k++)
             cf[k] = ct[c * PLD + k];
-         for (int jc = j0; jc < j1; jc += 32 * PU)
+         int jc = j0;
+         for (; jc + 32 * PUA <= j1; jc += 32 * PUA) // full chunks: no predicate, PUA independent Horner chains per lane
          {
+            double v[PUA], f[PUA];
+            int l[PUA];
 #pragma unroll
-            for (int u = 0; u < PU; u++)
+            for (int u = 0; u < PUA; u++)
             {
-               const int j = jc + lane + 32 * u;
-               if (j < j1)
-                  acc[lp[j]] += p_horner(cf, p_offset(xt[j]));
+               v[u] = xt[jc + lane + 32 * u];
+               l[u] = lp[jc + lane + 32 * u];
             }
+#pragma unroll
+            for (int u = 0; u < PUA; u++)
+               f[u] = p_horner(cf, v[u]);
+#pragma unroll
+            for (int u = 0; u < PUA; u++)
+               acc[l[u]] += f[u]; // every point of the block belongs to exactly one run of this window
+         }
+         for (; jc < j1; jc += 32) // tail: clamped loads, one predicated update
+         {
+            const int j = jc + lane, jj = min(j, j1 - 1);
+            const double f = p_horner(cf, xt[jj]);
+            if (j < j1)
+               acc[lp[jj]] += f;
          }
       }
       __syncthreads(); // the runs are done with this buffer (and acc is complete for this window)
    }
    const double nwmu = (double)p.nw * mu;
-   for (int j = tid; j < cnt; j += PTHREADS)
+   for (int j = tid; j < cnt; j += PATHREADS)
    {
       const size_t i = (size_t)base + j;
       const double ai = s * __ldg(x + i);
@@ -424,82 +480,141 @@ k_poly1d_gather_async(b200_poly1d_dev p, const double *__restrict__ x, double s,
    }
 }
 
-__global__ void __launch_bounds__(PTHREADS, 1)
+// moments of the run [j0, j1) of one cell into the lane-private m
+__device__ __forceinline__ void p_run_moments(double m[16], const double *xs, const double *xt, const unsigned short *lp, int j0, int j1, int lane)
+{
+   int jc = j0;
+   for (; jc + 32 * PUA <= j1; jc += 32 * PUA)
+   {
+      double v[PUA], a[PUA];
+#pragma unroll
+      for (int u = 0; u < PUA; u++)
+      {
+         v[u] = xt[jc + lane + 32 * u];
+         a[u] = xs[lp[jc + lane + 32 * u]];
+      }
+#pragma unroll
+      for (int u = 0; u < PUA; u++)
+         p_moments(m, a[u], v[u]);
+   }
+   for (; jc < j1; jc += 32)
+   {
+      const int j = jc + lane, jj = min(j, j1 - 1);
+      const double a = xs[lp[jj]];
+      p_moments(m, j < j1 ? a : 0.0, xt[jj]);
+   }
+}
+// lanes' moments of cell `key` -> the CTA's table (the calling warp is the only one that touches this cell)
+__device__ __forceinline__ void p_flush_moments(double m[16], double *msm, int key, int lane)
+{
+   int q;
+   const double tot = p_transpose_reduce16(m, lane, q);
+   if (!(lane & 1) && q < PNC)
+      msm[key * PLD + q] += tot;
+#pragma unroll
+   for (int k = 0; k < 16; k++)
+      m[k] = 0.0;
+}
+
+// the block of the vector is staged raw (x has to be 16-byte aligned: checked at launch); the factor s goes onto the moments
+__global__ void __launch_bounds__(PATHREADS, 1)
 k_poly1d_spread_async(b200_poly1d_dev p, const double *__restrict__ x, double s)
 {
    extern __shared__ __align__(16) double psm[];
-   double *xs = psm, *msm = psm + p.T;
+   double *xs0 = psm, *msm = psm + 2 * (size_t)p.T; // xs [2][T]
    PStage st;
    st.T = p.T;
    st.xt0 = msm + 64 * PLD;
    st.lp0 = reinterpret_cast<unsigned short *>(st.xt0 + 2 * (size_t)p.T);
    st.rs0 = st.lp0 + 2 * (size_t)p.T;
+   st.bar = reinterpret_cast<unsigned long long *>(st.rs0 + 2 * B200_POLY_RS);
    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
    const long long items = (long long)p.nw * p.nblk;
    const long long it0 = items * blockIdx.x / gridDim.x, it1 = items * (blockIdx.x + 1) / gridDim.x;
    int wcur = -1;
-   if (it0 < it1)
-      p_stage_item(p, st, 0, (int)(it0 / p.nblk), (int)(it0 % p.nblk), tid);
-   p_commit();
+   double m[PNH][16];
+#pragma unroll
+   for (int h = 0; h < PNH; h++)
+#pragma unroll
+      for (int k = 0; k < 16; k++)
+         m[h][k] = 0.0;
+   if (tid == 0)
+   {
+      p_mbar_init(st.bar);
+      p_mbar_init(st.bar + 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+   }
+   __syncthreads();
+   // one thread: everything of item `it` into buffer `buf`
+   auto stage = [&](long long it, int buf)
+   {
+      const int w = (int)(it / p.nblk), b = (int)(it - (long long)w * p.nblk);
+      const int cnt = min(p.T, p.n - b * p.T), even = cnt & ~1;
+      double *xs = xs0 + (size_t)buf * p.T;
+      if (cnt & 1)
+         xs[cnt - 1] = __ldg(x + (size_t)b * p.T + cnt - 1); // released to the CTA by the arrive below
+      p_mbar_expect(st.bar + buf, PSTAGE_ITEM_BYTES(p.T) + (unsigned)even * 8u);
+      p_stage_item(p, st, buf, w, b);
+      if (even)
+         p_bulk(xs, x + (size_t)b * p.T, (unsigned)even * 8u, st.bar + buf);
+   };
+   if (tid == 0 && it0 < it1)
+      stage(it0, 0);
    for (long long it = it0; it < it1; it++)
    {
-      const int buf = (int)((it - it0) & 1);
-      const int w = (int)(it / p.nblk), b = (int)(it - (long long)w * p.nblk);
-      const int base = b * p.T, cnt = min(p.T, p.n - base);
-      if (it + 1 < it1)
-         p_stage_item(p, st, buf ^ 1, (int)((it + 1) / p.nblk), (int)((it + 1) % p.nblk), tid);
-      p_commit();
-      if (w != wcur) // the previous item's runs ended with a barrier: msm is quiescent
+      const int k = (int)(it - it0), buf = k & 1;
+      const int w = (int)(it / p.nblk);
+      if (tid == 0 && it + 1 < it1) // the other buffers were released by the barrier that ended the previous item
+         stage(it + 1, buf ^ 1);
+      if (w != wcur) // uniform over the CTA
       {
          if (wcur >= 0)
          {
+#pragma unroll
+            for (int h = 0; h < PNH; h++)
+               p_flush_moments(m[h], msm, 16 + wid + PAW * h, lane);
+            __syncthreads();
             double *mg = p.mom + (size_t)wcur * 64 * PLD;
-            for (int e = tid; e < 64 * PLD; e += PTHREADS)
+            for (int e = tid; e < 64 * PLD; e += PATHREADS)
                if (msm[e] != 0.0)
-                  p_red_add(mg + e, msm[e]);
+                  p_red_add(mg + e, s * msm[e]);
          }
-         for (int e = tid; e < 64 * PLD; e += PTHREADS)
+         for (int e = tid; e < 64 * PLD; e += PATHREADS)
             msm[e] = 0.0;
          wcur = w;
+         __syncthreads();
       }
-      for (int j = tid; j < p.T; j += PTHREADS)
-         xs[j] = j < cnt ? s * __ldg(x + base + j) : 0.0;
-      p_wait<1>();
-      __syncthreads();
-      const double *xt = st.xt(buf);
+      p_mbar_wait(st.bar + buf, (unsigned)(k >> 1) & 1u);
+      const double *xs = xs0 + (size_t)buf * p.T, *xt = st.xt(buf);
       const unsigned short *lp = st.lp(buf), *rs = st.rs(buf);
-      for (int c = wid; c < 64; c += PWARPS)
+#pragma unroll
+      for (int h = 0; h < PNH; h++) // the warp's home cells: moments stay in registers
       {
-         const int j0 = rs[c], j1 = rs[c + 1];
+         const int c = 16 + wid + PAW * h;
+         p_run_moments(m[h], xs, xt, lp, rs[c], rs[c + 1], lane);
+      }
+      for (int c = wid; c < 32; c += PAW) // keys 0..15 and 48..63: empty unless a point sits exactly on the upper end
+      {
+         const int key = c < 16 ? c : c + 32;
+         const int j0 = rs[key], j1 = rs[key + 1];
          if (j0 == j1) // warp-uniform
             continue;
-         double m[16];
-#pragma unroll
-         for (int k = 0; k < 16; k++)
-            m[k] = 0.0;
-         for (int jc = j0; jc < j1; jc += 32 * PU)
-         {
-#pragma unroll
-            for (int u = 0; u < PU; u++)
-            {
-               const int j = jc + lane + 32 * u;
-               if (j < j1)
-                  p_moments(m, xs[lp[j]], p_offset(xt[j]));
-            }
-         }
-         int q;
-         const double tot = p_transpose_reduce16(m, lane, q);
-         if (!(lane & 1) && q < PNC)
-            msm[c * PLD + q] += tot;
+         p_flush_moments(m[0], msm, 16 + wid, lane);
+         p_run_moments(m[0], xs, xt, lp, j0, j1, lane);
+         p_flush_moments(m[0], msm, key, lane);
       }
-      __syncthreads(); // the runs are done with xs / this buffer / msm
+      __syncthreads(); // the runs are done with these buffers
    }
    if (wcur >= 0)
    {
+#pragma unroll
+      for (int h = 0; h < PNH; h++)
+         p_flush_moments(m[h], msm, 16 + wid + PAW * h, lane);
+      __syncthreads();
       double *mg = p.mom + (size_t)wcur * 64 * PLD;
-      for (int e = tid; e < 64 * PLD; e += PTHREADS)
+      for (int e = tid; e < 64 * PLD; e += PATHREADS)
          if (msm[e] != 0.0)
-            p_red_add(mg + e, msm[e]);
+            p_red_add(mg + e, s * msm[e]);
    }
 }
 
@@ -507,9 +622,9 @@ k_poly1d_spread_async(b200_poly1d_dev p, const double *__restrict__ x, double s)
 extern "C" {
 
 static size_t poly_smem_spread(int T) { return sizeof(double) * ((size_t)T + 64 * PLD) + 2 * 80; }
-// staged variants: xs / acc [T] + tables + two buffers of (T doubles + T + B200_POLY_RS shorts)
-static size_t poly_smem_spread_async(int T) { return sizeof(double) * ((size_t)T + 64 * PLD + 2 * (size_t)T) + 2 * 2 * ((size_t)T + B200_POLY_RS); }
-static size_t poly_smem_gather_async(int T) { return sizeof(double) * ((size_t)T + 2 * 64 * PLD + 2 * (size_t)T) + 2 * 2 * ((size_t)T + B200_POLY_RS); }
+// staged variants: acc [T] (gather) or the vector block [2][T] (spread) + tables + two buffers of (T doubles + T + B200_POLY_RS shorts) + 2 mbarriers
+static size_t poly_smem_spread_async(int T) { return sizeof(double) * (2 * (size_t)T + 64 * PLD + 2 * (size_t)T) + 2 * 2 * ((size_t)T + B200_POLY_RS) + 16; }
+static size_t poly_smem_gather_async(int T) { return sizeof(double) * ((size_t)T + 2 * 64 * PLD + 2 * (size_t)T) + 2 * 2 * ((size_t)T + B200_POLY_RS) + 16; }
 static bool poly_async_enabled(void)
 {
    static int on = -1;
@@ -523,15 +638,15 @@ static bool poly_async_enabled(void)
 static size_t poly_smem_gather(int T, int nch) { return sizeof(double) * (size_t)nch * ((size_t)T + 64 * PLD) + 2 * 80; }
 
 // largest block size (points per locally sorted block) the gather kernel of the gradient matvec still fits into shared memory with
-// largest block the kernels hold in shared memory: 7680 points is where the staged (double-buffered) gather still fits 227 KB
-int b200k_poly1d_max_block(void) { return poly_async_enabled() ? 7680 : 8192; }
-// CTAs of one resident wave of the spread / gather kernels (two per SM: registers and shared memory)
+// largest block the kernels hold in shared memory: 6208 points is where the staged (double-buffered) spread still fits 227 KB
+int b200k_poly1d_max_block(void) { return poly_async_enabled() ? 6208 : 8192; }
+// CTAs of one resident wave of the spread / gather kernels (staged: one per SM; direct: two per SM, registers and shared memory)
 int b200k_poly1d_wave_slots(void)
 {
    int sm = 148, dev = 0;
    if (cudaGetDevice(&dev) == cudaSuccess)
       cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
-   return 2 * sm;
+   return poly_async_enabled() ? sm : 2 * sm;
 }
 
 // x (n values, original order) -> oversampled grids of the nw local windows (64 doubles each, stride grid_stride)
@@ -554,7 +669,7 @@ int b200k_poly1d_spread(const b200_poly1d_dev *p, const double *d_x, double s, d
    if (G < 1)
       G = 1;
    B200_CHECK(cudaMemsetAsync(p->mom, 0, sizeof(double) * (size_t)p->nw * 64 * PLD, b200_stream()));
-   if (poly_async_enabled() && poly_smem_spread_async(p->T) <= 227 * 1024)
+   if (poly_async_enabled() && poly_smem_spread_async(p->T) <= 227 * 1024 && ((uintptr_t)d_x & 15) == 0)
    {
       static bool attr2 = false;
       if (!attr2)
@@ -563,7 +678,7 @@ int b200k_poly1d_spread(const b200_poly1d_dev *p, const double *d_x, double s, d
          attr2 = true;
       }
       int G1 = sm < items ? sm : (int)items; // one CTA per SM
-      k_poly1d_spread_async<<<G1, PTHREADS, poly_smem_spread_async(p->T), b200_stream()>>>(*p, d_x, s);
+      k_poly1d_spread_async<<<G1, PATHREADS, poly_smem_spread_async(p->T), b200_stream()>>>(*p, d_x, s);
    }
    else
       k_poly1d_spread<<<G, PTHREADS, poly_smem_spread(p->T), b200_stream()>>>(*p, d_x, s);
@@ -602,7 +717,7 @@ int b200k_poly1d_gather(const b200_poly1d_dev *p, int nch, const double *d_x, do
          B200_CHECK(cudaFuncSetAttribute(k_poly1d_gather_async, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
          attr2 = true;
       }
-      k_poly1d_gather_async<<<p->nblk, PTHREADS, poly_smem_gather_async(p->T), b200_stream()>>>(*p, d_x, s, c0, mu, beta, d_y);
+      k_poly1d_gather_async<<<p->nblk, PATHREADS, poly_smem_gather_async(p->T), b200_stream()>>>(*p, d_x, s, c0, mu, beta, d_y);
    }
    else if (nch == 1)
       k_poly1d_gather<1><<<p->nblk, PTHREADS, poly_smem_gather(p->T, 1), b200_stream()>>>(*p, d_x, s, c0, mu, ff, beta, d_y, ystride);

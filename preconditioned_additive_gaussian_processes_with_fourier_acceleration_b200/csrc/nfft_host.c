@@ -954,13 +954,19 @@ static int window_setup_small(b200_window *w, int n)
 }
 
 /* Order the scaled coordinates xt[0..n) of one 1-D window by grid cell INSIDE blocks of T consecutive points (pure host code, exported
- * for the CPU tests as Nfft4GPB200DebugPoly1dBlockSort): out_xt / out_lp [nblk * T] = coordinate and position inside its block of
- * the sorted point, out_rs [nblk][B200_POLY_RS] = the 65 run starts per cell key (c + 32) & 63.  Stable: a cell's points keep their original order, so
- * every sum the kernels form has a fixed order. */
+ * for the CPU tests as Nfft4GPB200DebugPoly1dBlockSort): out_xt / out_lp [nblk * T] = offset v = 2 u - 1 in [-1, 1) inside its cell
+ * (u = fractional part of 64 x: exact in double, so is v) and position inside its block of the sorted point -- the cell itself is
+ * the run the point stands in --, out_rs [nblk][B200_POLY_RS] = the 65 run starts per cell key (c + 32) & 63.
+ * Inside a run the points are dealt out by shared-memory bank: the kernels index acc[lp] / xs[lp] (8-byte words, 16 per wavefront)
+ * with 16 consecutive entries of a run per half-warp, so the run is emitted in rounds over the 16 classes lp mod 16 (each class in
+ * original order): as long as all classes have points left, every group of 16 is conflict-free (ncu of the unordered runs: 3.0
+ * wavefronts per ideal one, the shared-memory pipe 70 % busy).  Deterministic: every sum the kernels form has a fixed order. */
 void b200_poly1d_block_sort(const double *xt, int n, int T, double *out_xt, unsigned short *out_lp, unsigned short *out_rs)
 {
    const int nblk = (n + T - 1) / T;
    int b, j;
+   unsigned short *tmp = (unsigned short *)b200_xcalloc((size_t)T, sizeof(unsigned short));
+   unsigned char *key = (unsigned char *)b200_xcalloc((size_t)T, 1);
    for (b = 0; b < nblk; b++)
    {
       const int base = b * T, cnt = n - base < T ? n - base : T;
@@ -968,18 +974,56 @@ void b200_poly1d_block_sort(const double *xt, int n, int T, double *out_xt, unsi
       int count[65], c;
       memset(count, 0, sizeof(count));
       for (j = 0; j < cnt; j++)
-         count[(((int)floor(xt[base + j] * (double)B200_NOS) + 32) & 63) + 1]++;
+      {
+         key[j] = (unsigned char)(((int)floor(xt[base + j] * (double)B200_NOS) + 32) & 63);
+         count[key[j] + 1]++;
+      }
       for (c = 0; c < 64; c++)
          count[c + 1] += count[c];
       for (c = 0; c <= 64; c++)
          rs[c] = (unsigned short)count[c];
+      for (j = 0; j < cnt; j++) /* stable counting sort by cell */
+         tmp[count[key[j]]++] = (unsigned short)j;
+      for (c = 0; c < 64; c++)
+      {
+         const int r0 = rs[c], r1 = rs[c + 1];
+         int len[16], start[16], q, r, pos = r0, longest = 0;
+         if (r0 == r1)
+            continue;
+         memset(len, 0, sizeof(len));
+         for (j = r0; j < r1; j++)
+            len[tmp[j] & 15]++;
+         start[0] = 0;
+         for (q = 0; q < 16; q++)
+         {
+            if (q)
+               start[q] = start[q - 1] + len[q - 1];
+            if (len[q] > longest)
+               longest = len[q];
+         }
+         {
+            /* bucket the run by bank class; this run's slice of out_lp serves as scratch (it is written for good further down) */
+            unsigned short *bucket = out_lp + base + r0;
+            int fill[16];
+            memcpy(fill, start, sizeof(fill));
+            for (j = r0; j < r1; j++)
+               bucket[fill[tmp[j] & 15]++] = tmp[j];
+            /* emit round r: the r-th point of every class that still has one; tmp[r0..r1) receives the final order */
+            for (r = 0; r < longest; r++)
+               for (q = 0; q < 16; q++)
+                  if (r < len[q])
+                     tmp[pos++] = bucket[start[q] + r];
+         }
+      }
       for (j = 0; j < cnt; j++)
       {
-         int pos = count[((int)floor(xt[base + j] * (double)B200_NOS) + 32) & 63]++;
-         out_xt[base + pos] = xt[base + j];
-         out_lp[base + pos] = (unsigned short)j;
+         const double t = xt[base + tmp[j]] * (double)B200_NOS;
+         out_xt[base + j] = 2.0 * (t - floor(t)) - 1.0;
+         out_lp[base + j] = tmp[j];
       }
    }
+   free(tmp);
+   free(key);
 }
 
 int Nfft4GPB200DebugPoly1dBlockSort(const double *xt, int n, int T, double *out_xt, unsigned short *out_lp, unsigned short *out_rs)
@@ -1016,6 +1060,11 @@ static int additive_poly_setup(b200_additive *A, const double *cols_all, int n)
       T = (T + 31) & ~31;
       if (T < 1024)
          T = 1024;
+      {
+         const char *e = getenv("NFFT4GP_B200_POLY1D_T"); /* tuning aid: block size, a multiple of 32 */
+         if (e && atoi(e) >= 32 && atoi(e) <= tmax)
+            T = atoi(e) & ~31;
+      }
    }
    nblk = (n + T - 1) / T;
    per_w = (size_t)nblk * T;

@@ -82,7 +82,8 @@ def test_host_tridiagonal_eigensolver(n):
 
 def test_poly1d_block_local_cell_sort():
     """Plan build of the table-free 1-D path (nfft_host.c:b200_poly1d_block_sort, host only): inside every block of T consecutive points
-    the points are ordered by grid cell, stably; lp is a permutation of the block, rs the run starts per cell key."""
+    the points are ordered by grid cell (inside a cell: dealt out by bank class); lp is a permutation of the block, rs the run starts per cell key, and the stored
+    coordinate is the offset 2 u - 1 of the point inside its cell (exact)."""
     import ctypes as C
     import preconditioned_additive_gaussian_processes_with_fourier_acceleration_b200 as pkg
     L = pkg.lib()
@@ -99,11 +100,18 @@ def test_poly1d_block_local_cell_sort():
             base, cnt = b * T, min(T, n - b * T)
             lp, rs = olp[base:base + cnt].astype(int), ors[b * 80:b * 80 + 65].astype(int)
             assert sorted(lp.tolist()) == list(range(cnt))                       # a permutation of the block
-            assert (oxt[base:base + cnt] == xt[base + lp]).all()                 # coordinates follow it
+            t = xt[base + lp] * 64
+            assert (oxt[base:base + cnt] == 2.0 * (t - np.floor(t)) - 1.0).all()  # in-cell offsets follow it
             kb = key[base + lp]
             assert (np.diff(kb) >= 0).all()                                      # ordered by cell
             assert rs[0] == 0 and rs[64] == cnt and (np.diff(rs) >= 0).all()
             for c in np.unique(kb):
                 seg = lp[rs[c]:rs[c + 1]]
-                assert (kb[rs[c]:rs[c + 1]] == c).all() and (np.diff(seg) > 0).all()   # the run of cell c, original order kept
+                assert (kb[rs[c]:rs[c + 1]] == c).all()                          # the run of cell c
+                # dealt out by shared-memory bank class (lp mod 16), every class in original order: while all classes have points
+                # left, each group of 16 consecutive entries of the run holds 16 different classes
+                full = 16 * np.bincount(seg % 16, minlength=16).min()
+                assert all(len(set((seg[g:g + 16] % 16).tolist())) == 16 for g in range(0, full, 16))
+                for q in range(16):
+                    assert (np.diff(seg[seg % 16 == q]) > 0).all()
     assert L.Nfft4GPB200DebugPoly1dBlockSort(pkg.capi.dptr(np.zeros(4)), 4, 16, None, None, None) == -1
