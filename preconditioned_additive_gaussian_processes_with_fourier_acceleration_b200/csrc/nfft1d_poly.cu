@@ -223,6 +223,13 @@ __global__ void k_poly1d_grid2coef(const double *__restrict__ grid, size_t grid_
 // degree-14 polynomial as E(v^2) + v O(v^2): two independent FMA chains of 7 instead of one of 14
 __device__ __forceinline__ double p_horner(const double cf[PNC], double v)
 {
+#ifdef PESTRIN /* Estrin's scheme: 14 FMAs + 3 products, dependency depth 5 instead of 8 (A/B aid) */
+   const double v2 = v * v, v4 = v2 * v2, v8 = v4 * v4;
+   const double p0 = fma(cf[1], v, cf[0]), p1 = fma(cf[3], v, cf[2]), p2 = fma(cf[5], v, cf[4]), p3 = fma(cf[7], v, cf[6]);
+   const double p4 = fma(cf[9], v, cf[8]), p5 = fma(cf[11], v, cf[10]), p6 = fma(cf[13], v, cf[12]);
+   const double q0 = fma(p1, v2, p0), q1 = fma(p3, v2, p2), q2 = fma(p5, v2, p4), q3 = fma(cf[14], v2, p6);
+   return fma(fma(q3, v4, q2), v8, fma(q1, v4, q0));
+#else
    const double v2 = v * v;
    double e = cf[14], o = cf[13];
 #pragma unroll
@@ -233,6 +240,7 @@ __device__ __forceinline__ double p_horner(const double cf[PNC], double v)
          o = fma(o, v2, cf[k - 1]);
    }
    return fma(o, v, e);
+#endif
 }
 
 // NCH = 1: y = beta y + c0 (sum_w f_w + nw mu a)                                     (nfft_interface.c:428-494, 803-814)
@@ -330,7 +338,10 @@ k_poly1d_gather(b200_poly1d_dev p, const double *__restrict__ x, double s, doubl
 //  * runs are walked in full chunks of 32 PU points without any predicate (PU independent chains per lane) plus one clamped tail;
 //  * spread: the scaled points lie in [-1/4, 1/4], i.e. in the 32 cells with keys 16..47 (key 48 only for a point exactly on the
 //    upper end).  Warp w owns the cells 16 + w + PAW h for the whole kernel and keeps their lane-private moments in REGISTERS across
-//    the items of a window: the butterfly runs once per window and CTA instead of once per run.  Any other key takes the old path.
+//    the items of a window: the butterfly runs once per window and warp instead of once per run, and its 15 totals go straight to
+//    the window's global table as fp64 REDs.  Any other key is flushed around its run.
+//  * no CTA barrier per item: the last warp to finish an item re-arms its buffer with the item after the next, so warps drift up
+//    to one item apart (the gather therefore accumulates even and odd windows in two arrays).
 #ifndef PAW
 #define PAW 32 /* warps of the staged kernels */
 #endif
@@ -362,12 +373,26 @@ __device__ __forceinline__ void p_mbar_wait(unsigned long long *bar, unsigned pa
                 "r"(parity)
                 : "memory");
 }
-// bytes: a multiple of 16; both addresses 16-byte aligned
-__device__ __forceinline__ void p_bulk(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+// bytes: a multiple of 16; both addresses 16-byte aligned.  policy: L2 eviction class of the lines read -- the offsets / indices stream
+// through once per matvec (evict first), the vector block is read again by every window (evict last; without the hints 25 % of the
+// vector reads of the spread came from DRAM: ncu r2_o)
+__device__ __forceinline__ void p_bulk(void *dst, const void *src, unsigned bytes, unsigned long long *bar, unsigned long long policy)
 {
-   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(p_saddr(dst)), "l"(src), "r"(bytes),
-                "r"(p_saddr(bar))
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(p_saddr(dst)),
+                "l"(src), "r"(bytes), "r"(p_saddr(bar)), "l"(policy)
                 : "memory");
+}
+__device__ __forceinline__ unsigned long long p_policy_stream()
+{
+   unsigned long long pol;
+   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+   return pol;
+}
+__device__ __forceinline__ unsigned long long p_policy_keep()
+{
+   unsigned long long pol;
+   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+   return pol;
 }
 
 // double-buffered part of the shared memory of the staged kernels; T is a multiple of 32
@@ -386,63 +411,84 @@ struct PStage
 __device__ __forceinline__ void p_stage_item(const b200_poly1d_dev &p, const PStage &st, int buf, int w, int b)
 {
    const size_t off = (size_t)w * p.nblk * p.T + (size_t)b * p.T;
-   p_bulk(st.xt(buf), p.xt + off, (unsigned)p.T * 8u, st.bar + buf);
-   p_bulk(st.lp(buf), p.lp + off, (unsigned)p.T * 2u, st.bar + buf);
-   p_bulk(st.rs(buf), p.rs + ((size_t)w * p.nblk + b) * B200_POLY_RS, B200_POLY_RS * 2u, st.bar + buf);
+   const unsigned long long pol = p_policy_stream();
+   p_bulk(st.xt(buf), p.xt + off, (unsigned)p.T * 8u, st.bar + buf, pol);
+   p_bulk(st.lp(buf), p.lp + off, (unsigned)p.T * 2u, st.bar + buf, pol);
+   p_bulk(st.rs(buf), p.rs + ((size_t)w * p.nblk + b) * B200_POLY_RS, B200_POLY_RS * 2u, st.bar + buf, pol);
+}
+
+// A warp that has finished an item counts itself off; the LAST one re-arms the buffer with the item after the next.  No CTA barrier per
+// item: a fast warp runs up to one item ahead of a slow one (run lengths differ), the data of item k + 2 cannot overwrite item k
+// before every warp is done with it.
+__device__ __forceinline__ bool p_last_finisher(unsigned *done, int lane)
+{
+   unsigned old = 0;
+   __syncwarp();
+   if (lane == 0)
+   {
+      old = atomicAdd(done, 1u);
+      if (old == PAW - 1)
+         *done = 0; // nobody counts on this buffer again before it has been refilled and consumed
+   }
+   return lane == 0 && old == PAW - 1;
 }
 
 __global__ void __launch_bounds__(PATHREADS, 1)
 k_poly1d_gather_async(b200_poly1d_dev p, const double *__restrict__ x, double s, double c0, double mu, double beta, double *__restrict__ y)
 {
    extern __shared__ __align__(16) double psm[];
-   double *acc = psm;       // [T]
-   double *ctb = acc + p.T; // [2][64][PLD]
+   double *acc = psm;           // [2][T]: windows of even / odd number (neighbouring windows may be in flight together)
+   double *ctb = acc + 2 * (size_t)p.T; // [2][64][PLD]
    PStage st;
    st.T = p.T;
    st.xt0 = ctb + 2 * 64 * PLD;
    st.lp0 = reinterpret_cast<unsigned short *>(st.xt0 + 2 * (size_t)p.T);
    st.rs0 = st.lp0 + 2 * (size_t)p.T;
    st.bar = reinterpret_cast<unsigned long long *>(st.rs0 + 2 * B200_POLY_RS);
+   unsigned *done = reinterpret_cast<unsigned *>(st.bar + 2);
    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.x;
    const int base = b * p.T, cnt = min(p.T, p.n - base);
    const unsigned item_bytes = PSTAGE_ITEM_BYTES(p.T) + 64 * PLD * 8;
+   auto stage = [&](int w, int buf) // one thread
+   {
+      p_mbar_expect(st.bar + buf, item_bytes);
+      p_stage_item(p, st, buf, w, b);
+      p_bulk(ctb + buf * 64 * PLD, p.ctab + (size_t)w * 64 * PLD, 64 * PLD * 8, st.bar + buf, p_policy_keep());
+   };
    if (tid == 0)
    {
       p_mbar_init(st.bar);
       p_mbar_init(st.bar + 1);
+      done[0] = done[1] = 0;
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      stage(0, 0);
+      if (p.nw > 1)
+         stage(1, 1);
    }
-   for (int j = tid; j < p.T; j += PATHREADS)
+   for (int j = tid; j < 2 * p.T; j += PATHREADS)
       acc[j] = 0.0;
    __syncthreads();
-   if (tid == 0)
-   {
-      p_mbar_expect(st.bar, item_bytes);
-      p_stage_item(p, st, 0, 0, b);
-      p_bulk(ctb, p.ctab, 64 * PLD * 8, st.bar);
-   }
    for (int w = 0; w < p.nw; w++)
    {
       const int buf = w & 1;
-      if (tid == 0 && w + 1 < p.nw) // the other buffer was released by the barrier that ended the previous window
-      {
-         p_mbar_expect(st.bar + (buf ^ 1), item_bytes);
-         p_stage_item(p, st, buf ^ 1, w + 1, b);
-         p_bulk(ctb + (buf ^ 1) * 64 * PLD, p.ctab + (size_t)(w + 1) * 64 * PLD, 64 * PLD * 8, st.bar + (buf ^ 1));
-      }
       p_mbar_wait(st.bar + buf, (unsigned)(w >> 1) & 1u);
       const double *xt = st.xt(buf);
       const unsigned short *lp = st.lp(buf), *rs = st.rs(buf);
       const double *ct = ctb + buf * 64 * PLD;
+      double *ac = acc + (size_t)buf * p.T;
       for (int c = wid; c < 64; c += PAW)
       {
          const int j0 = rs[c], j1 = rs[c + 1];
          if (j0 == j1) // warp-uniform
             continue;
-         double cf[PNC];
+         double cf[PLD]; // the row is 128 bytes, aligned: 8 x LDS.128 (entry 15 is padding)
 #pragma unroll
-         for (int k = 0; k < PNC; k++)
-            cf[k] = ct[c * PLD + k];
+         for (int k = 0; k < PLD; k += 2)
+         {
+            const double2 t = *reinterpret_cast<const double2 *>(ct + c * PLD + k);
+            cf[k] = t.x;
+            cf[k + 1] = t.y;
+         }
          int jc = j0;
          for (; jc + 32 * PUA <= j1; jc += 32 * PUA) // full chunks: no predicate, PUA independent Horner chains per lane
          {
@@ -459,24 +505,26 @@ k_poly1d_gather_async(b200_poly1d_dev p, const double *__restrict__ x, double s,
                f[u] = p_horner(cf, v[u]);
 #pragma unroll
             for (int u = 0; u < PUA; u++)
-               acc[l[u]] += f[u]; // every point of the block belongs to exactly one run of this window
+               ac[l[u]] += f[u]; // every point of the block belongs to exactly one run of this window
          }
          for (; jc < j1; jc += 32) // tail: clamped loads, one predicated update
          {
             const int j = jc + lane, jj = min(j, j1 - 1);
             const double f = p_horner(cf, xt[jj]);
             if (j < j1)
-               acc[lp[jj]] += f;
+               ac[lp[jj]] += f;
          }
       }
-      __syncthreads(); // the runs are done with this buffer (and acc is complete for this window)
+      if (p_last_finisher(done + buf, lane) && w + 2 < p.nw)
+         stage(w + 2, buf);
    }
+   __syncthreads();
    const double nwmu = (double)p.nw * mu;
    for (int j = tid; j < cnt; j += PATHREADS)
    {
       const size_t i = (size_t)base + j;
       const double ai = s * __ldg(x + i);
-      y[i] = (beta == 0.0 ? 0.0 : beta * y[i]) + c0 * (acc[j] + nwmu * ai);
+      y[i] = (beta == 0.0 ? 0.0 : beta * y[i]) + c0 * (acc[j] + acc[p.T + j] + nwmu * ai);
    }
 }
 
@@ -504,13 +552,13 @@ __device__ __forceinline__ void p_run_moments(double m[16], const double *xs, co
       p_moments(m, j < j1 ? a : 0.0, xt[jj]);
    }
 }
-// lanes' moments of cell `key` -> the CTA's table (the calling warp is the only one that touches this cell)
-__device__ __forceinline__ void p_flush_moments(double m[16], double *msm, int key, int lane)
+// lanes' moments of one cell -> the window's global table (fp64 REDs: 15 per warp), scaled; m is cleared
+__device__ __forceinline__ void p_flush_moments(double m[16], double *mom_w, int key, double s, int lane)
 {
    int q;
    const double tot = p_transpose_reduce16(m, lane, q);
-   if (!(lane & 1) && q < PNC)
-      msm[key * PLD + q] += tot;
+   if (!(lane & 1) && q < PNC && tot != 0.0)
+      p_red_add(mom_w + key * PLD + q, s * tot);
 #pragma unroll
    for (int k = 0; k < 16; k++)
       m[k] = 0.0;
@@ -521,68 +569,76 @@ __global__ void __launch_bounds__(PATHREADS, 1)
 k_poly1d_spread_async(b200_poly1d_dev p, const double *__restrict__ x, double s)
 {
    extern __shared__ __align__(16) double psm[];
-   double *xs0 = psm, *msm = psm + 2 * (size_t)p.T; // xs [2][T]
+   double *xs0 = psm; // [2][T]
    PStage st;
    st.T = p.T;
-   st.xt0 = msm + 64 * PLD;
+   st.xt0 = xs0 + 2 * (size_t)p.T;
    st.lp0 = reinterpret_cast<unsigned short *>(st.xt0 + 2 * (size_t)p.T);
    st.rs0 = st.lp0 + 2 * (size_t)p.T;
    st.bar = reinterpret_cast<unsigned long long *>(st.rs0 + 2 * B200_POLY_RS);
+   unsigned *done = reinterpret_cast<unsigned *>(st.bar + 2);
    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
    const long long items = (long long)p.nw * p.nblk;
    const long long it0 = items * blockIdx.x / gridDim.x, it1 = items * (blockIdx.x + 1) / gridDim.x;
-   int wcur = -1;
+   const int nit = (int)(it1 - it0);
+   int w = (int)(it0 / p.nblk), b = (int)(it0 - (long long)w * p.nblk), wcur = -1;
    double m[PNH][16];
 #pragma unroll
    for (int h = 0; h < PNH; h++)
 #pragma unroll
       for (int k = 0; k < 16; k++)
          m[h][k] = 0.0;
+   // one thread: everything of the item (w, b) into buffer `buf`
+   auto stage = [&](int sw, int sb, int buf)
+   {
+      const int cnt = min(p.T, p.n - sb * p.T), even = cnt & ~1;
+      double *xs = xs0 + (size_t)buf * p.T;
+      if (cnt & 1)
+         xs[cnt - 1] = __ldg(x + (size_t)sb * p.T + cnt - 1); // released to the CTA by the arrive below
+      p_mbar_expect(st.bar + buf, PSTAGE_ITEM_BYTES(p.T) + (unsigned)even * 8u);
+      p_stage_item(p, st, buf, sw, sb);
+      if (even)
+         p_bulk(xs, x + (size_t)sb * p.T, (unsigned)even * 8u, st.bar + buf, p_policy_keep());
+   };
+   // the item `ahead` places after (w, b)
+   auto item_after = [&](int ahead, int &sw, int &sb)
+   {
+      sw = w;
+      sb = b + ahead;
+      while (sb >= p.nblk)
+      {
+         sb -= p.nblk;
+         sw++;
+      }
+   };
    if (tid == 0)
    {
       p_mbar_init(st.bar);
       p_mbar_init(st.bar + 1);
+      done[0] = done[1] = 0;
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      if (nit > 0)
+         stage(w, b, 0);
+      if (nit > 1)
+      {
+         int sw, sb;
+         item_after(1, sw, sb);
+         stage(sw, sb, 1);
+      }
    }
    __syncthreads();
-   // one thread: everything of item `it` into buffer `buf`
-   auto stage = [&](long long it, int buf)
+   for (int k = 0; k < nit; k++)
    {
-      const int w = (int)(it / p.nblk), b = (int)(it - (long long)w * p.nblk);
-      const int cnt = min(p.T, p.n - b * p.T), even = cnt & ~1;
-      double *xs = xs0 + (size_t)buf * p.T;
-      if (cnt & 1)
-         xs[cnt - 1] = __ldg(x + (size_t)b * p.T + cnt - 1); // released to the CTA by the arrive below
-      p_mbar_expect(st.bar + buf, PSTAGE_ITEM_BYTES(p.T) + (unsigned)even * 8u);
-      p_stage_item(p, st, buf, w, b);
-      if (even)
-         p_bulk(xs, x + (size_t)b * p.T, (unsigned)even * 8u, st.bar + buf);
-   };
-   if (tid == 0 && it0 < it1)
-      stage(it0, 0);
-   for (long long it = it0; it < it1; it++)
-   {
-      const int k = (int)(it - it0), buf = k & 1;
-      const int w = (int)(it / p.nblk);
-      if (tid == 0 && it + 1 < it1) // the other buffers were released by the barrier that ended the previous item
-         stage(it + 1, buf ^ 1);
-      if (w != wcur) // uniform over the CTA
+      const int buf = k & 1;
+      if (w != wcur) // per warp: its home cells' moments of the finished window go to the global table
       {
          if (wcur >= 0)
          {
 #pragma unroll
             for (int h = 0; h < PNH; h++)
-               p_flush_moments(m[h], msm, 16 + wid + PAW * h, lane);
-            __syncthreads();
-            double *mg = p.mom + (size_t)wcur * 64 * PLD;
-            for (int e = tid; e < 64 * PLD; e += PATHREADS)
-               if (msm[e] != 0.0)
-                  p_red_add(mg + e, s * msm[e]);
+               p_flush_moments(m[h], p.mom + (size_t)wcur * 64 * PLD, 16 + wid + PAW * h, s, lane);
          }
-         for (int e = tid; e < 64 * PLD; e += PATHREADS)
-            msm[e] = 0.0;
          wcur = w;
-         __syncthreads();
       }
       p_mbar_wait(st.bar + buf, (unsigned)(k >> 1) & 1u);
       const double *xs = xs0 + (size_t)buf * p.T, *xt = st.xt(buf);
@@ -599,22 +655,28 @@ k_poly1d_spread_async(b200_poly1d_dev p, const double *__restrict__ x, double s)
          const int j0 = rs[key], j1 = rs[key + 1];
          if (j0 == j1) // warp-uniform
             continue;
-         p_flush_moments(m[0], msm, 16 + wid, lane);
+         double *mom_w = p.mom + (size_t)w * 64 * PLD;
+         p_flush_moments(m[0], mom_w, 16 + wid, s, lane);
          p_run_moments(m[0], xs, xt, lp, j0, j1, lane);
-         p_flush_moments(m[0], msm, key, lane);
+         p_flush_moments(m[0], mom_w, key, s, lane);
       }
-      __syncthreads(); // the runs are done with these buffers
+      if (p_last_finisher(done + buf, lane) && k + 2 < nit)
+      {
+         int sw, sb;
+         item_after(2, sw, sb);
+         stage(sw, sb, buf);
+      }
+      if (++b == p.nblk)
+      {
+         b = 0;
+         w++;
+      }
    }
    if (wcur >= 0)
    {
 #pragma unroll
       for (int h = 0; h < PNH; h++)
-         p_flush_moments(m[h], msm, 16 + wid + PAW * h, lane);
-      __syncthreads();
-      double *mg = p.mom + (size_t)wcur * 64 * PLD;
-      for (int e = tid; e < 64 * PLD; e += PATHREADS)
-         if (msm[e] != 0.0)
-            p_red_add(mg + e, s * msm[e]);
+         p_flush_moments(m[h], p.mom + (size_t)wcur * 64 * PLD, 16 + wid + PAW * h, s, lane);
    }
 }
 
@@ -622,9 +684,10 @@ k_poly1d_spread_async(b200_poly1d_dev p, const double *__restrict__ x, double s)
 extern "C" {
 
 static size_t poly_smem_spread(int T) { return sizeof(double) * ((size_t)T + 64 * PLD) + 2 * 80; }
-// staged variants: acc [T] (gather) or the vector block [2][T] (spread) + tables + two buffers of (T doubles + T + B200_POLY_RS shorts) + 2 mbarriers
-static size_t poly_smem_spread_async(int T) { return sizeof(double) * (2 * (size_t)T + 64 * PLD + 2 * (size_t)T) + 2 * 2 * ((size_t)T + B200_POLY_RS) + 16; }
-static size_t poly_smem_gather_async(int T) { return sizeof(double) * ((size_t)T + 2 * 64 * PLD + 2 * (size_t)T) + 2 * 2 * ((size_t)T + B200_POLY_RS) + 16; }
+// staged variants: acc [2][T] and the coefficient tables [2] (gather) or the vector block [2][T] (spread) + two buffers of (T doubles + T + B200_POLY_RS
+// shorts) + 2 mbarriers + 2 counters
+static size_t poly_smem_spread_async(int T) { return sizeof(double) * (2 * (size_t)T + 2 * (size_t)T) + 2 * 2 * ((size_t)T + B200_POLY_RS) + 16 + 8; }
+static size_t poly_smem_gather_async(int T) { return sizeof(double) * (2 * (size_t)T + 2 * 64 * PLD + 2 * (size_t)T) + 2 * 2 * ((size_t)T + B200_POLY_RS) + 16 + 8; }
 static bool poly_async_enabled(void)
 {
    static int on = -1;
@@ -638,8 +701,8 @@ static bool poly_async_enabled(void)
 static size_t poly_smem_gather(int T, int nch) { return sizeof(double) * (size_t)nch * ((size_t)T + 64 * PLD) + 2 * 80; }
 
 // largest block size (points per locally sorted block) the gather kernel of the gradient matvec still fits into shared memory with
-// largest block the kernels hold in shared memory: 6208 points is where the staged (double-buffered) spread still fits 227 KB
-int b200k_poly1d_max_block(void) { return poly_async_enabled() ? 6208 : 8192; }
+// largest block the kernels hold in shared memory: 5984 points is where the staged gather (36 B per point + tables) still fits 227 KB
+int b200k_poly1d_max_block(void) { return poly_async_enabled() ? 5984 : 8192; }
 // CTAs of one resident wave of the spread / gather kernels (staged: one per SM; direct: two per SM, registers and shared memory)
 int b200k_poly1d_wave_slots(void)
 {

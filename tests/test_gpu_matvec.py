@@ -240,3 +240,48 @@ def test_poly1d_path_matches_oracle(gpu, n, d, kernel, force):
     assert T.debug_spread(0, x).shape == (64,)      # the table path keeps its stage taps
     for h in (A, B, T):
         h.free()
+
+
+def test_poly1d_upper_end_point_and_direct_kernels(gpu):
+    """(1) A point whose scaled coordinate is exactly +1/4 (cell key 48: outside the 32 home cells whose moments the staged spread keeps in
+    registers, nfft1d_poly.cu) in every window and in the last, odd-sized block.  (2) The direct-load kernels -- the fallback of the
+    staged ones for an unaligned vector, and the gradient gather -- in a fresh process (the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n, d = 3 * 1024 + 1, 3
+    rng = np.random.default_rng(77)
+    a = rng.random((d, (n - 1) // 2)) * 0.49
+    X = np.zeros((d, n))
+    X[:, 0:n - 1:2], X[:, 1:n - 1:2] = a, -a            # mean exactly 0 (the last point is 0)
+    X[:, 0], X[:, 1] = 0.5, -0.5                        # radius 1/2 -> scale 1/2 -> scaled coordinates exactly +-1/4
+    X[:, n - 3], X[:, n - 2] = 0.5, -0.5                # ... also next to the last block
+    win = np.arange(d, dtype=np.int32)
+    os.environ["NFFT4GP_B200_POLY1D"] = "1"
+    try:
+        A = gpu.AdditiveNFFTKernel(X, win, d, 1, "gaussian").build(1.1, 0.3, 0.02)
+    finally:
+        os.environ.pop("NFFT4GP_B200_POLY1D", None)
+    B = O.OracleAdditiveNFFT(X, win, d, 1, "gaussian").build(1.1, 0.3, 0.02)
+    x = rand_vec(n, 8)
+    assert rel_l2(A.matvec(x), B.matvec(x)) <= TOL
+    assert rel_l2(A.grad_matvec(x), B.grad_matvec(x)) <= TOL
+    A.free()
+    B.free()
+    code = (
+        "import numpy as np, sys\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import preconditioned_additive_gaussian_processes_with_fourier_acceleration_b200 as gpu\n"
+        "from oracle import oracle_api as O\n"
+        "assert gpu.lib().Nfft4GPB200Init(0) == 0\n"
+        "rng = np.random.default_rng(5); n, d = 40000, 4\n"
+        "X = rng.random((d, n)) * 3.0; win = np.arange(d, dtype=np.int32); x = rng.standard_normal(n)\n"
+        "A = gpu.AdditiveNFFTKernel(X, win, d, 1, 'matern12').build(1.3, 1.1, 0.05)\n"
+        "B = O.OracleAdditiveNFFT(X, win, d, 1, 'matern12').build(1.3, 1.1, 0.05)\n"
+        "e = np.linalg.norm(A.matvec(x) - B.matvec(x)) / np.linalg.norm(B.matvec(x))\n"
+        "print('REL', e); assert e <= 1e-10\n"
+    ) % (root, os.path.join(root, "tests"))
+    env = dict(os.environ, NFFT4GP_B200_POLY1D_ASYNC="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "REL" in r.stdout, r.stdout + r.stderr
