@@ -8,17 +8,15 @@
 //   gather:  f_i = sum_t h[c_i - 4 + t] p_t(v_i) = C_{c_i}(v_i),  C_c = sum_t h[c - 4 + t] p_t   -- ONE Horner evaluation
 //            (14 FMAs) per point from a 64 x 15 coefficient table per window instead of ten taps;
 //   spread:  g[c - 4 + t] += sum_k p_t[k] M_c[k],  M_c[k] = sum_{i in cell c} a_i v_i^k            -- 15 moments per point.
-// Per point and window the kernels read the scaled coordinate (8 B) and a 2-byte index instead of 80 B of taps + 4 B key + 8 B of
+// Per point and window the kernels read the in-cell offset v (8 B, exact) and a 2-byte index instead of 80 B of taps + 4 B key + 8 B of
 // permuted coefficient, and the prep / combine passes with their random 8-byte accesses disappear: points are sorted by cell
-// only INSIDE blocks of T consecutive points of the ORIGINAL order (done once per handle), so x and y are moved as coalesced
-// blocks through shared memory and the "permutation" is a shared-memory index.
-//   spread: the (window, block) items are cut into one wave of equal CTA ranges; a warp owns the runs of the cells c = warp (mod 16): lanes stride
-//           over the run accumulating 15 moments in registers, ONE transposing butterfly (16 values over 32 lanes in 16 shuffles)
-//           per run adds them to the CTA's 64 x 16 table in shared memory, which goes to the window's global table with fp64 REDs
-//           once per CTA.
-//   gather: CTA b keeps acc[T] for its block in shared memory and loops over the windows: coefficient table of the window to shared
-//           memory, a warp per run loads the cell's 15 coefficients into registers, Horner per point, acc[lp] += f; fused epilogue
-//           y = beta y + f^2 (acc + P mu a) for the block, coalesced.
+// only INSIDE blocks of T consecutive points of the ORIGINAL order (done once per handle, nfft_host.c:b200_poly1d_block_sort), so x
+// and y are moved as coalesced blocks through shared memory and the "permutation" is a shared-memory index.
+// Two generations of kernels live in this file:
+//   direct   (k_poly1d_spread, k_poly1d_gather<NCH>): 2 CTAs x 16 warps per SM, offsets / indices loaded from global memory per run,
+//            one transposing butterfly per run.  Kept for the gradient gather (NCH = 2), for a vector that is not 16-byte aligned
+//            and as a cross-check (NFFT4GP_B200_POLY1D_ASYNC=0).
+//   staged   (k_poly1d_spread_async, k_poly1d_gather_async): the production pair, described where it is defined below.
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -220,16 +218,10 @@ __global__ void k_poly1d_grid2coef(const double *__restrict__ grid, size_t grid_
 }
 
 // ---------------------------------------------------------------------------------------------------- gather: Horner + epilogue
-// degree-14 polynomial as E(v^2) + v O(v^2): two independent FMA chains of 7 instead of one of 14
+// degree-14 polynomial as E(v^2) + v O(v^2): two independent FMA chains of 7 instead of one of 14 (Estrin's scheme -- depth 5, three more
+// products -- was measured slower in the staged gather: 641 vs 606 us for 64 windows)
 __device__ __forceinline__ double p_horner(const double cf[PNC], double v)
 {
-#ifdef PESTRIN /* Estrin's scheme: 14 FMAs + 3 products, dependency depth 5 instead of 8 (A/B aid) */
-   const double v2 = v * v, v4 = v2 * v2, v8 = v4 * v4;
-   const double p0 = fma(cf[1], v, cf[0]), p1 = fma(cf[3], v, cf[2]), p2 = fma(cf[5], v, cf[4]), p3 = fma(cf[7], v, cf[6]);
-   const double p4 = fma(cf[9], v, cf[8]), p5 = fma(cf[11], v, cf[10]), p6 = fma(cf[13], v, cf[12]);
-   const double q0 = fma(p1, v2, p0), q1 = fma(p3, v2, p2), q2 = fma(p5, v2, p4), q3 = fma(cf[14], v2, p6);
-   return fma(fma(q3, v4, q2), v8, fma(q1, v4, q0));
-#else
    const double v2 = v * v;
    double e = cf[14], o = cf[13];
 #pragma unroll
@@ -240,7 +232,6 @@ __device__ __forceinline__ double p_horner(const double cf[PNC], double v)
          o = fma(o, v2, cf[k - 1]);
    }
    return fma(o, v, e);
-#endif
 }
 
 // NCH = 1: y = beta y + c0 (sum_w f_w + nw mu a)                                     (nfft_interface.c:428-494, 803-814)
