@@ -29,7 +29,10 @@ typedef struct
    int d;        /* window dimension 1..3                                        */
    int n;        /* number of points                                             */
    int nseg;     /* number of (cell, warp-range) segments (information only)     */
-   double *psi;  /* [n + pad][d*10] Kaiser-Bessel taps, cell-sorted point order  */
+   double *psi;  /* [n + pad][d*10] Kaiser-Bessel taps, cell-sorted point order; NULL on the table-free 2-D path */
+   double *pv;   /* 2-D windows on the table-free path (nfft2d_poly.cu): [n][2] in-cell offsets v = 2 u - 1 of the sorted points */
+   int *cells;   /* ... [ncell] packed keys of the occupied cells                 */
+   int ncell;
    double *xs;   /* [n][d] sorted scaled coordinates, kept only for 1-D / 2-D windows when the window is evaluated in the kernels
                     (NFFT4GP_B200_WINDOW_EVAL=1); NULL otherwise                  */
    int *key;     /* [n] packed cell index ((c1+32)<<12 | (c2+32)<<6 | (c3+32))    */
@@ -115,6 +118,11 @@ int b200k_poly1d_spread(const b200_poly1d_dev *p, const double *d_x, double s, d
 int b200k_poly1d_coef(const b200_poly1d_dev *p, int ch, const double *d_grids, size_t grid_stride, const double *d_wscale);
 int b200k_poly1d_gather(const b200_poly1d_dev *p, int nch, const double *d_x, double s, double c0, double mu, double ff, double beta,
                         double *d_y, size_t ystride);
+/* nfft2d_poly.cu: 2-D windows without tap tables (bivariate polynomial per cell, Vandermonde operands on the fp64 tensor cores) */
+int b200k_poly2d_prepare(void);
+int b200k_poly2d_offsets(const b200_win_dev *w, const double *d_xs);
+int b200k_spread2_poly(const b200_win_dev *w);
+int b200k_gather2_poly(const b200_win_dev *w, double *d_f);
 /* nfft2d_mma.cu: 2-D windows on the fp64 tensor cores (same data as the stream kernels) */
 int b200k_spread2_mma(const b200_win_dev *w);
 int b200k_gather2_mma(const b200_win_dev *w, double *d_f);

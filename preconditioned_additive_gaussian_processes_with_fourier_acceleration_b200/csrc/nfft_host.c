@@ -261,6 +261,8 @@ static void window_free_device(b200_window *w)
 {
    b200_win_dev *v = &w->dev;
    b200_free(v->psi);
+   b200_free(v->pv);
+   b200_free(v->cells);
    b200_free(v->xs);
    b200_free(v->key);
    b200_free(v->perm);
@@ -336,6 +338,18 @@ static double *window_scale_points(b200_window *w, const double *cols, int n_all
    return tmp;
 }
 
+/* 2-D windows take the table-free path of nfft2d_poly.cu from POLY2D_MIN_N points (about 60 per occupied cell: below that the
+ * per-cell work of that path -- 256 REDs / 8 coefficient loads per thread at every cell change -- outweighs the table traffic);
+ * NFFT4GP_B200_POLY2D=0 never, =1 always */
+#define POLY2D_MIN_N 65536
+static int window_wants_poly2d(int d, int n)
+{
+   const char *e = getenv("NFFT4GP_B200_POLY2D"), *ev = getenv("NFFT4GP_B200_WINDOW_EVAL");
+   if (d != 2 || (e && atoi(e) == 0) || (ev && atoi(ev) > 0))
+      return 0;
+   return (e && atoi(e) > 0) || n >= POLY2D_MIN_N;
+}
+
 static int window_setup_points(b200_window *w, const double *cols, int n_all, int lo, int hi)
 {
    /* n_all points define centre and scale (identical on every rank); this rank tabulates the block [lo, hi) only
@@ -399,8 +413,29 @@ static int window_setup_points(b200_window *w, const double *cols, int n_all, in
    {
       size_t pad = 16, gsz = ipow(B200_NOS, d), bsz = ipow(B200_NBAND, d);
       double *d_xs = (double *)b200_malloc(sizeof(double) * (size_t)n * d);
-      v->psi = (double *)b200_malloc(sizeof(double) * ((size_t)n + pad) * d * B200_TAPS);
-      b200_memset(v->psi, 0, sizeof(double) * ((size_t)n + pad) * d * B200_TAPS);
+      const int poly2d = window_wants_poly2d(d, n);
+      if (poly2d)
+      {
+         /* table-free 2-D path: 16 B of offsets per point instead of 160 B of taps, and the list of occupied cells */
+         int *hcells = (int *)b200_xmalloc(sizeof(int) * nbins), nc = 0;
+         for (i = 0; i < (int)nbins; i++)
+            if (binstart[i + 1] > binstart[i])
+               hcells[nc++] = i;
+         v->pv = (double *)b200_malloc(sizeof(double) * ((size_t)n + pad) * 2);
+         v->cells = (int *)b200_malloc(sizeof(int) * (size_t)(nc ? nc : 1));
+         v->ncell = nc;
+         if (!v->pv || !v->cells || b200k_poly2d_prepare() || b200_h2d(v->cells, hcells, sizeof(int) * (size_t)nc))
+         {
+            free(hcells);
+            return -1;
+         }
+         free(hcells);
+      }
+      else
+      {
+         v->psi = (double *)b200_malloc(sizeof(double) * ((size_t)n + pad) * d * B200_TAPS);
+         b200_memset(v->psi, 0, sizeof(double) * ((size_t)n + pad) * d * B200_TAPS);
+      }
       v->key = (int *)b200_malloc(sizeof(int) * (size_t)n);
       v->perm = (int *)b200_malloc(sizeof(int) * (size_t)n);
       v->inv = (int *)b200_malloc(sizeof(int) * (size_t)n);
@@ -505,10 +540,10 @@ static int window_setup_points(b200_window *w, const double *cols, int n_all, in
          w->h_nchunk = nch;
          free(hw);
       }
-      if (b200k_psi(v, d_xs) || b200_sync())
+      if ((poly2d ? b200k_poly2d_offsets(v, d_xs) : b200k_psi(v, d_xs)) || b200_sync())
          return -1;
       /* opt-in: 1-D / 2-D windows evaluate the window in the kernels from the coordinates (nfft12_stream.cu) */
-      if (d < 3 && getenv("NFFT4GP_B200_WINDOW_EVAL") && atoi(getenv("NFFT4GP_B200_WINDOW_EVAL")) > 0)
+      if (!poly2d && d < 3 && getenv("NFFT4GP_B200_WINDOW_EVAL") && atoi(getenv("NFFT4GP_B200_WINDOW_EVAL")) > 0)
          v->xs = d_xs;
       else
          b200_free(d_xs);

@@ -575,6 +575,8 @@ int b200k_spread(const b200_win_dev *w, int variant)
       return b200k_spread3_mma(w);
    if (w->d == 3 && variant != 0) // DFMA kernels (nfft3d_warp.cu); variant 0 = generic kernel (cross-check)
       return b200k_spread3_warp(w);
+   if (w->d == 2 && w->pv) // 2-D without tap tables (nfft2d_poly.cu): the plan holds offsets only, whatever variant is asked for
+      return b200k_spread2_poly(w);
    if (w->d == 2 && variant != 0 && variant != 1 && !w->xs) // 2-D: fp64 tensor-core kernels (nfft2d_mma.cu); variant 1 = DFMA stream kernels
       return b200k_spread2_mma(w);
    if (w->d < 3 && variant != 0) // 1-D / 2-D: streaming warp-per-range kernels (nfft12_stream.cu)
@@ -599,6 +601,8 @@ int b200k_gather(const b200_win_dev *w, double *d_f, int variant)
       return b200k_gather3_mma(w, d_f);
    if (w->d == 3 && variant != 0)
       return b200k_gather3_warp(w, d_f);
+   if (w->d == 2 && w->pv) // 2-D without tap tables (nfft2d_poly.cu)
+      return b200k_gather2_poly(w, d_f);
    if (w->d == 2 && variant != 0 && variant != 1 && !w->xs) // 2-D: fp64 tensor-core kernel (nfft2d_mma.cu); variant 1 = DFMA stream kernel
       return b200k_gather2_mma(w, d_f);
    if (w->d == 2 && variant != 0) // 1-D stays thread-per-point: 10 taps per point need no cross-lane reduction (measured 62 vs 152 us)

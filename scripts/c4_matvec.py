@@ -103,14 +103,21 @@ for dw in dims:
     # parity: rows of the N-GPU result against the dense Matern sums are the approximation's bar, so compare with the CPU oracle
     # on the same operator restricted to a sub-sample instead: build both on the first m points
     m = min(n, 20000)
+    poly2d = dw == 2 and n >= 65536 and os.environ.get("NFFT4GP_B200_POLY2D") != "0" and not os.environ.get("NFFT4GP_B200_WINDOW_EVAL")
     rel = None
     if rank == 0:
         from oracle import oracle_api as O
         Xs = np.ascontiguousarray(X[:, :m])
         os.environ["NFFT4GP_B200_POLY1D"] = "1" if dw == 1 else "0"
+        keep2 = os.environ.get("NFFT4GP_B200_POLY2D")
+        if poly2d:
+            os.environ["NFFT4GP_B200_POLY2D"] = "1"      # the sub-sample is below the automatic threshold: same path as the timed run
         As = pkg.AdditiveNFFTKernel(Xs, win, P, dw, "matern12")
         As.build(f, l, mu)
         os.environ.pop("NFFT4GP_B200_POLY1D", None)
+        os.environ.pop("NFFT4GP_B200_POLY2D", None)
+        if keep2 is not None:
+            os.environ["NFFT4GP_B200_POLY2D"] = keep2
         Bs = O.OracleAdditiveNFFT(Xs, win, P, dw, "matern12").build(f, l, mu)
         ys, yo = As.matvec(x[:m]), Bs.matvec(x[:m])
         rel = float(np.linalg.norm(ys - yo) / np.linalg.norm(yo))
@@ -132,6 +139,7 @@ for dw in dims:
             "per_class_us_rank0": {names[i]: round(sums[i] / reps * 1000, 1) for i in range(11) if cnts[i]},
             "launches_per_matvec_rank0": int(sum(cnts[i] for i in range(11)) / reps),
             "path": ("table-free polynomial path (nfft1d_poly.cu)" if dw == 1 and n >= 32768 and os.environ.get("NFFT4GP_B200_POLY1D") != "0" else
+                     "table-free bivariate polynomial path on the fp64 tensor cores (nfft2d_poly.cu)" if poly2d else
                      "tap tables, fp64 tensor-core kernels (nfft2d_mma.cu)" if dw == 2 else "tap tables, streaming kernels (nfft12_stream.cu)"),
             "parity_rel_l2_vs_oracle_on_first_20000_points": rel, "parity_rel_l2_sharded_vs_one_gpu": rel_1gpu}
     if rank == 0:

@@ -285,3 +285,39 @@ def test_poly1d_upper_end_point_and_direct_kernels(gpu):
     env = dict(os.environ, NFFT4GP_B200_POLY1D_ASYNC="0")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "REL" in r.stdout, r.stdout + r.stderr
+
+
+# ------------------------------------------------------------------------------------------------ 2-D windows: table-free path
+@pytest.mark.parametrize("n,d,kernel,force,cloud", [(70000, 4, "gaussian", False, "uniform"), (3000, 2, "matern12", True, "uniform"),
+                                                    (100000, 6, "matern12", False, "gaussian"), (257, 4, "gaussian", True, "uniform")])
+def test_poly2d_path_matches_oracle(gpu, n, d, kernel, force, cloud):
+    """Additive kernels of 2-D windows on the table-free path (nfft2d_poly.cu: bivariate degree-14 polynomial per grid cell, moments and
+    evaluation as Vandermonde GEMMs on the fp64 tensor cores; 28 B per point instead of 172 B of taps): matvec and gradient matvec
+    against the oracle for all (alpha, beta) branches, and against the tap-table kernels on the same data."""
+    import os
+    X = (uniform_cloud if cloud == "uniform" else gaussian_cloud)(n, d, seed=60 + d)
+    win = np.arange(d, dtype=np.int32)
+    f, l, mu = 1.3, 0.5 * n ** (1.0 / d) if cloud == "uniform" else 0.8, 0.02
+    if force:
+        os.environ["NFFT4GP_B200_POLY2D"] = "1"
+    try:
+        A = gpu.AdditiveNFFTKernel(X, win, d // 2, 2, kernel).build(f, l, mu)
+    finally:
+        os.environ.pop("NFFT4GP_B200_POLY2D", None)
+    B = O.OracleAdditiveNFFT(X, win, d // 2, 2, kernel).build(f, l, mu)
+    x = rand_vec(n, 5)
+    y0, g0 = rand_vec(n, 6), rand_vec(3 * n, 7)
+    for al, be in ((1.0, 0.0), (-1.0, 1.0), (0.7, 0.3)):
+        assert rel_l2(A.matvec(x, al, be, y0), B.matvec(x, al, be, y0)) <= TOL, (al, be)
+        assert rel_l2(A.grad_matvec(x, al, be, g0), B.grad_matvec(x, al, be, g0)) <= TOL, (al, be)
+    A.build(0.8, 1.7 * l, 0.2)                       # new hyper-parameters on the same points
+    B.build(0.8, 1.7 * l, 0.2)
+    assert rel_l2(A.matvec(x), B.matvec(x)) <= TOL
+    os.environ["NFFT4GP_B200_POLY2D"] = "0"
+    try:
+        T = gpu.AdditiveNFFTKernel(X, win, d // 2, 2, kernel).build(0.8, 1.7 * l, 0.2)
+    finally:
+        os.environ.pop("NFFT4GP_B200_POLY2D", None)
+    assert rel_l2(A.matvec(x), T.matvec(x)) <= 1e-12
+    for h in (A, B, T):
+        h.free()
