@@ -121,7 +121,8 @@ int b200k_poly1d_gather(const b200_poly1d_dev *p, int nch, const double *d_x, do
 /* nfft2d_poly.cu: 2-D windows without tap tables (bivariate polynomial per cell, Vandermonde operands on the fp64 tensor cores) */
 int b200k_poly2d_prepare(void);
 int b200k_poly2d_offsets(const b200_win_dev *w, const double *d_xs);
-int b200k_spread2_poly(const b200_win_dev *w);
+int b200k_spread2_poly(const b200_win_dev *w, const double *d_x, double s); /* d_x != NULL: coefficient s * d_x[perm] fetched in the kernel */
+int b200k_spread_fused_prep(const b200_win_dev *w, const double *d_x, double s);
 int b200k_gather2_poly(const b200_win_dev *w, double *d_f);
 /* nfft2d_mma.cu: 2-D windows on the fp64 tensor cores (same data as the stream kernels) */
 int b200k_spread2_mma(const b200_win_dev *w);

@@ -131,9 +131,12 @@ __device__ __forceinline__ void r_spread_step(const RSmem &sm, int wid, int ks, 
    r_dmma(c[1][1][0], c[1][1][1], a1, b1);
 }
 
+// FUSED: the coefficient of a sorted point is s x[perm[j]], fetched here one step ahead (the random 8-byte reads of the vector, which is
+// L2-resident, hide behind the tensor work of the current step) instead of a separate pass that writes it to a[] in sorted order
+template <bool FUSED>
 __global__ void __launch_bounds__(RWARPS * 32, RCTAS_PER_SM)
-k_spread2_poly(const double2 *__restrict__ pv, const int *__restrict__ key, const double *__restrict__ a, double *__restrict__ mom, int n,
-               int per_warp)
+k_spread2_poly(const double2 *__restrict__ pv, const int *__restrict__ key, const double *__restrict__ a, const int *__restrict__ perm, double s,
+               double *__restrict__ mom, int n, int per_warp)
 {
    __shared__ RSmem sm;
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -142,6 +145,17 @@ k_spread2_poly(const double2 *__restrict__ pv, const int *__restrict__ key, cons
    if (b64 >= n)
       return;
    const int jb = (int)b64, je = min(n, jb + per_warp);
+   // coefficient of the sorted point j (this lane's point of the step that is fetched now).  FUSED: `pnext` holds perm[j], loaded one
+   // step earlier; the vector entry is read now and the index of the step after is requested, so neither load waits for the other
+   int pnext = -1;
+   auto coef = [&](int j, bool ok) -> double
+   {
+      if (!FUSED)
+         return ok ? __ldg(a + j) : 0.0;
+      const double v = pnext >= 0 ? s * __ldg(a + pnext) : 0.0;
+      pnext = j + RBATCH < je ? __ldg(perm + j + RBATCH) : -1;
+      return v;
+   };
    double c[2][2][2];
 #pragma unroll
    for (int i = 0; i < 8; i++)
@@ -150,7 +164,9 @@ k_spread2_poly(const double2 *__restrict__ pv, const int *__restrict__ key, cons
    // the next step's point is fetched while the current step is computed (rows past the end of the range carry no weight)
    bool okn = jb + lane < je;
    double2 vn = okn ? __ldg(pv + jb + lane) : make_double2(0.0, 0.0);
-   double an = okn ? __ldg(a + jb + lane) : 0.0;
+   if (FUSED && okn)
+      pnext = __ldg(perm + jb + lane);
+   double an = coef(jb + lane, okn);
    int kn = okn ? __ldg(key + jb + lane) : -1;
    for (int j0 = jb; j0 < je; j0 += RBATCH)
    {
@@ -163,7 +179,7 @@ k_spread2_poly(const double2 *__restrict__ pv, const int *__restrict__ key, cons
          const int j = j0 + RBATCH + lane;
          okn = j < je;
          vn = okn ? __ldg(pv + j) : make_double2(0.0, 0.0);
-         an = okn ? __ldg(a + j) : 0.0;
+         an = coef(j, okn);
          kn = okn ? __ldg(key + j) : -1;
       }
       const int cnt = min(RBATCH, je - j0);
@@ -439,15 +455,20 @@ int b200k_poly2d_offsets(const b200_win_dev *w, const double *d_xs)
    return 0;
 }
 
-// w->a (sorted coefficients) -> w->grid (zeroed by the caller)
-int b200k_spread2_poly(const b200_win_dev *w)
+// w->a (sorted coefficients; d_x == NULL) or s * d_x[perm] (fused prep) -> w->grid (zeroed by the caller)
+int b200k_spread2_poly(const b200_win_dev *w, const double *d_x, double s)
 {
    if (w->n <= 0 || w->ncell <= 0)
       return 0;
    if (!g_mom2)
       return -1;
    int per, blocks = r_grid(w->n, &per);
-   k_spread2_poly<<<blocks, RWARPS * 32, 0, b200_stream()>>>(reinterpret_cast<const double2 *>(w->pv), w->key, w->a, g_mom2, w->n, per);
+   if (d_x)
+      k_spread2_poly<true><<<blocks, RWARPS * 32, 0, b200_stream()>>>(reinterpret_cast<const double2 *>(w->pv), w->key, d_x, w->perm, s, g_mom2,
+                                                                      w->n, per);
+   else
+      k_spread2_poly<false><<<blocks, RWARPS * 32, 0, b200_stream()>>>(reinterpret_cast<const double2 *>(w->pv), w->key, w->a, nullptr, 1.0, g_mom2,
+                                                                       w->n, per);
    B200_LAUNCHED();
    k_poly2d_mom2grid<<<w->ncell, 256, 0, b200_stream()>>>(w->cells, g_mom2, w->grid);
    B200_LAUNCHED();

@@ -585,6 +585,9 @@ static int window_build(b200_window *w, int kernel, double f, double l, double m
 static int window_spread(b200_window *w, const double *d_x, double s)
 {
    b200_win_dev *v = &w->dev;
+   int rc = b200k_spread_fused_prep(v, d_x, s); /* table-free 2-D windows fetch s * x[perm] inside the spread */
+   if (rc <= 0)
+      return rc;
    return (b200k_prep(v, d_x, s) || b200k_spread(v, g_variant_spread3)) ? -1 : 0;
 }
 

@@ -565,6 +565,16 @@ int b200k_gather_batch_end(void)
 
 static size_t grid_elems(int d) { return d == 1 ? 64 : (d == 2 ? 64 * 64 : 64 * 64 * 64); }
 
+// prep + spread in one launch for the paths that fetch their coefficient themselves (table-free 2-D windows); 1 = not such a window
+int b200k_spread_fused_prep(const b200_win_dev *w, const double *d_x, double s)
+{
+   if (!(w->d == 2 && w->pv))
+      return 1;
+   B200ProfScope prof_scope_(PC_SPREAD);
+   B200_CHECK(cudaMemsetAsync(w->grid, 0, sizeof(double) * grid_elems(w->d), b200_stream()));
+   return b200k_spread2_poly(w, d_x, s) ? -1 : 0;
+}
+
 int b200k_spread(const b200_win_dev *w, int variant)
 {
    B200ProfScope prof_scope_(PC_SPREAD);
@@ -576,7 +586,7 @@ int b200k_spread(const b200_win_dev *w, int variant)
    if (w->d == 3 && variant != 0) // DFMA kernels (nfft3d_warp.cu); variant 0 = generic kernel (cross-check)
       return b200k_spread3_warp(w);
    if (w->d == 2 && w->pv) // 2-D without tap tables (nfft2d_poly.cu): the plan holds offsets only, whatever variant is asked for
-      return b200k_spread2_poly(w);
+      return b200k_spread2_poly(w, nullptr, 1.0);
    if (w->d == 2 && variant != 0 && variant != 1 && !w->xs) // 2-D: fp64 tensor-core kernels (nfft2d_mma.cu); variant 1 = DFMA stream kernels
       return b200k_spread2_mma(w);
    if (w->d < 3 && variant != 0) // 1-D / 2-D: streaming warp-per-range kernels (nfft12_stream.cu)
