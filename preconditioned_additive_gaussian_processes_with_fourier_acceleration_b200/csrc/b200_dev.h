@@ -33,6 +33,7 @@ typedef struct
    double *pv;   /* 2-D windows on the table-free path (nfft2d_poly.cu): [n][2] in-cell offsets v = 2 u - 1 of the sorted points */
    int *cells;   /* ... [ncell] packed keys of the occupied cells                 */
    int ncell;
+   int f_orig;   /* ... the gather writes f / f2 in the ORIGINAL point order: the combine pass reads them without `inv` */
    double *xs;   /* [n][d] sorted scaled coordinates, kept only for 1-D / 2-D windows when the window is evaluated in the kernels
                     (NFFT4GP_B200_WINDOW_EVAL=1); NULL otherwise                  */
    int *key;     /* [n] packed cell index ((c1+32)<<12 | (c2+32)<<6 | (c3+32))    */

@@ -146,7 +146,7 @@ int b200_comm_build_local_windows(b200_additive *A)
       if (b200_comm_owns_window(A, i))
       {
          fp[nl] = A->win[i]->dev.f;
-         ip[nl] = A->win[i]->dev.inv;
+         ip[nl] = A->win[i]->dev.f_orig ? NULL : A->win[i]->dev.inv;
          nl++;
       }
    A->nlocal = nl;

@@ -59,10 +59,11 @@ struct RSmem
 {
    double x[4][RWARPS][RBATCH], y[4][RWARPS][RBATCH]; // [i]: v^(2^i) = v, v^2, v^4, v^8
    double a[RWARPS][RBATCH];
-   int key[RWARPS][RBATCH];
+   int key[RWARPS][RBATCH], out[RWARPS][RBATCH]; // out: where the gather writes the point's value
 };
-__device__ __forceinline__ void r_stage(RSmem &sm, int wid, int lane, double2 v, double a, int key)
+__device__ __forceinline__ void r_stage(RSmem &sm, int wid, int lane, double2 v, double a, int key, int out = 0)
 {
+   sm.out[wid][lane] = out;
    const double x2 = v.x * v.x, x4 = x2 * x2, y2 = v.y * v.y, y4 = y2 * y2;
    sm.x[0][wid][lane] = v.x;
    sm.x[1][wid][lane] = x2;
@@ -329,9 +330,12 @@ __device__ __forceinline__ double r_gather_group(const RSmem &sm, int wid, int q
 }
 
 __global__ void __launch_bounds__(RWARPS * 32, RCTAS_PER_SM)
-k_gather2_poly(const double2 *__restrict__ pv, const int *__restrict__ key, const double *__restrict__ ctab, double *__restrict__ f, int n,
-               int per_warp)
+k_gather2_poly(const double2 *__restrict__ pv, const int *__restrict__ key, const double *__restrict__ ctab, const int *__restrict__ perm,
+               double *__restrict__ f, int n, int per_warp)
 {
+   // perm != NULL: the value of the sorted point j goes to f[perm[j]] -- the ORIGINAL point order, so that the combine pass reads the
+   // window's results as a stream instead of gathering them through the inverse permutation (the scattered 8-byte stores ride on the
+   // tensor work here; the gathers cost a pass of their own there)
    __shared__ RSmem sm;
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
    const int g = lane >> 2, t = lane & 3;
@@ -345,18 +349,20 @@ k_gather2_poly(const double2 *__restrict__ pv, const int *__restrict__ key, cons
    bool okn = jb + lane < je;
    double2 vn = okn ? __ldg(pv + jb + lane) : make_double2(0.0, 0.0);
    int kn = okn ? __ldg(key + jb + lane) : -1;
+   int on = okn ? (perm ? __ldg(perm + jb + lane) : jb + lane) : 0;
    for (int j0 = jb; j0 < je; j0 += RBATCH)
    {
       const bool ok = okn;
       const int mykey = kn;
       __syncwarp();
-      r_stage(sm, wid, lane, vn, 0.0, kn);
+      r_stage(sm, wid, lane, vn, 0.0, kn, on);
       __syncwarp();
       {
          const int j = j0 + RBATCH + lane; // the next step's point is fetched while this step is computed
          okn = j < je;
          vn = okn ? __ldg(pv + j) : make_double2(0.0, 0.0);
          kn = okn ? __ldg(key + j) : -1;
+         on = okn ? (perm ? __ldg(perm + j) : j) : 0;
       }
       const int cnt = min(RBATCH, je - j0);
       if (__all_sync(0xffffffffu, mykey == cur || !ok))
@@ -366,7 +372,7 @@ k_gather2_poly(const double2 *__restrict__ pv, const int *__restrict__ key, cons
          {
             const double val = r_gather_group(sm, wid, q, g, t, hb);
             if (t == 0 && 8 * q + g < cnt)
-               f[j0 + 8 * q + g] = val;
+               f[sm.out[wid][8 * q + g]] = val;
          }
          continue;
       }
@@ -387,7 +393,7 @@ k_gather2_poly(const double2 *__restrict__ pv, const int *__restrict__ key, cons
             }
             const double val = r_gather_group(sm, wid, q, g, t, hb);
             if (t == 0 && p0 + g < cnt)
-               f[j0 + p0 + g] = val;
+               f[sm.out[wid][p0 + g]] = val;
             continue;
          }
          for (int p = p0; p < p1; p++)
@@ -400,7 +406,7 @@ k_gather2_poly(const double2 *__restrict__ pv, const int *__restrict__ key, cons
             }
             const double val = r_gather_group(sm, wid, q, g, t, hb);
             if (t == 0 && g == (p & 7))
-               f[j0 + p] = val;
+               f[sm.out[wid][p]] = val;
          }
       }
    }
@@ -475,7 +481,7 @@ int b200k_spread2_poly(const b200_win_dev *w, const double *d_x, double s)
    return 0;
 }
 
-// w->grid (Re h) -> d_f (sorted order)
+// w->grid (Re h) -> d_f (original point order if w->f_orig, else sorted order)
 int b200k_gather2_poly(const b200_win_dev *w, double *d_f)
 {
    if (w->n <= 0 || w->ncell <= 0)
@@ -485,7 +491,8 @@ int b200k_gather2_poly(const b200_win_dev *w, double *d_f)
    int per, blocks = r_grid(w->n, &per);
    k_poly2d_grid2coef<<<w->ncell, 256, 0, b200_stream()>>>(w->cells, w->grid, g_ctab2);
    B200_LAUNCHED();
-   k_gather2_poly<<<blocks, RWARPS * 32, 0, b200_stream()>>>(reinterpret_cast<const double2 *>(w->pv), w->key, g_ctab2, d_f, w->n, per);
+   k_gather2_poly<<<blocks, RWARPS * 32, 0, b200_stream()>>>(reinterpret_cast<const double2 *>(w->pv), w->key, g_ctab2, w->f_orig ? w->perm : nullptr,
+                                                             d_f, w->n, per);
    B200_LAUNCHED();
    return 0;
 }

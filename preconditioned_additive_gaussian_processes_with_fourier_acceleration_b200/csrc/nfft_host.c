@@ -424,6 +424,7 @@ static int window_setup_points(b200_window *w, const double *cols, int n_all, in
          v->pv = (double *)b200_malloc(sizeof(double) * ((size_t)n + pad) * 2);
          v->cells = (int *)b200_malloc(sizeof(int) * (size_t)(nc ? nc : 1));
          v->ncell = nc;
+         v->f_orig = 1;
          if (!v->pv || !v->cells || b200k_poly2d_prepare() || b200_h2d(v->cells, hcells, sizeof(int) * (size_t)nc))
          {
             free(hcells);
@@ -770,7 +771,7 @@ static int single_ensure_staging(b200_single *s, int n)
       s->d_invptr = (const int **)b200_malloc(sizeof(int *));
       s->d_c1w = (double *)b200_malloc(sizeof(double));
       fp = s->win->dev.f;
-      ip = s->win->dev.inv;
+      ip = s->win->dev.f_orig ? NULL : s->win->dev.inv;
       if (b200_h2d((void *)s->d_fptr, &fp, sizeof(fp)) || b200_h2d((void *)s->d_invptr, &ip, sizeof(ip)) || b200_sync())
          return -1;
    }
@@ -925,7 +926,7 @@ static int additive_ensure_device(b200_additive *A)
       for (i = 0; i < P; i++)
       {
          fp[i] = A->win[i]->dev.f;
-         ip[i] = A->win[i]->dev.inv;
+         ip[i] = A->win[i]->dev.f_orig ? NULL : A->win[i]->dev.inv;
       }
       if (b200_h2d((void *)A->d_fptr, fp, sizeof(double *) * (size_t)P) ||
           b200_h2d((void *)A->d_invptr, ip, sizeof(int *) * (size_t)P) || b200_sync())

@@ -440,7 +440,10 @@ __global__ void k_combine(int n, int P, const double *const *__restrict__ fptr, 
    const double ai = s * x[i];
    double acc = 0.0;
    for (int w = 0; w < P; w++)
-      acc += c0 * (__ldg(fptr[w] + invptr[w][i]) + mu * ai);
+   {
+      const int *iv = invptr[w]; // NULL: the window's results are already in the original order (table-free 2-D path)
+      acc += c0 * (__ldg(fptr[w] + (iv ? iv[i] : i)) + mu * ai);
+   }
    y[i] = (beta == 0.0 ? 0.0 : beta * y[i]) + acc;
 }
 
@@ -455,7 +458,8 @@ __global__ void k_combine_grad(int n, int P, const double *const *__restrict__ f
    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
    for (int w = 0; w < P; w++)
    {
-      int j = invptr[w][i];
+      const int *iv = invptr[w];
+      int j = iv ? iv[i] : i;
       a0 += f2 * (__ldg(fptr[w] + j) + mu * ai);
       a1 += c1w[w] * __ldg(f2ptr[w] + j);
       a2 += ff * ai;
