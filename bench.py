@@ -34,11 +34,19 @@ WORKLOAD = "C2: additive Gaussian NFFT matvec n={n} d=9 three 3-D windows N=32 n
 PROF_CLASSES = ["prep", "spread", "fft_fwd", "fft_inv", "gather", "combine", "vec", "nys", "csr", "gemv", "other"]
 
 
+CLOUD = "uniform"   # --cloud: "uniform" (the reference's synthetic data set) or "gaussian" (same variance per coordinate)
+
+
 def synthetic_problem(n, d=9, seed=906):
     """Reference-style synthetic cloud (Nfft4GPDatasetUniformRandom, SRC/utils/utils.c:266-286): n^(1/d) U(0,1),
-    feature-major; x = U(0,1) - 0.5 (TESTS/TEST1/foo.cpp:243-247); l resolved by N = 32."""
+    feature-major; x = U(0,1) - 0.5 (TESTS/TEST1/foo.cpp:243-247); l resolved by N = 32.
+    --cloud gaussian: N(0, 1) n^(1/d) / sqrt(12) per coordinate (the north star's second cloud: dense cells in the centre, empty ones
+    towards the bounding radius)."""
     rng = np.random.default_rng(seed)
-    X = rng.random((d, n)) * n ** (1.0 / d)
+    if CLOUD == "gaussian":
+        X = rng.standard_normal((d, n)) * n ** (1.0 / d) / np.sqrt(12.0)
+    else:
+        X = rng.random((d, n)) * n ** (1.0 / d)
     x = rng.random(n) - 0.5
     windows = np.arange(d, dtype=np.int32)
     side = n ** (1.0 / d)
@@ -185,8 +193,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(n=n), "l": hp["l"], "f": hp["f"], "mu": hp["mu"]},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic" if CLOUD == "uniform" else "synthetic (gaussian cloud)",
+        "config": {"workload": WORKLOAD.format(n=n), "cloud": CLOUD, "l": hp["l"], "f": hp["f"], "mu": hp["mu"]},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "host_cores": host_cores(), "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -329,6 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--cloud", choices=["uniform", "gaussian"], default="uniform", help="synthetic point cloud (default: the reference's uniform one)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pcg", action="store_true", help="skip the C3 AFN-PCG solve section")
@@ -336,6 +345,8 @@ def main():
     ap.add_argument("--pcg-mu", type=float, default=0.01)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global CLOUD
+    CLOUD = args.cloud
     if args.impl == "reference":
         return run_reference(args)
 
@@ -539,8 +550,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(n=n),
+        "data": "synthetic" if CLOUD == "uniform" else "synthetic (gaussian cloud)",
+        "config": {"workload": WORKLOAD.format(n=n), "cloud": CLOUD,
                    "parallelism": parallelism, "l": hp["l"], "f": hp["f"], "mu": hp["mu"],
                    "l2_policy": "inputs larger than L2: window tables streamed per step = 2 x 3 x 240 MB >> 126 MB"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 8 * nl * world, "d2h_bytes_per_step": 8 * nl * world,
