@@ -55,15 +55,17 @@ for mode in (1, 2):
     A.free()
 # ---- window sharding: gradient matvec (ONE allreduce of 3 n doubles), 3-D windows on the table path and 1-D windows on the polynomial path
 g0 = rng.random(3 * n) - 0.5
-for tag, dd, nw, dw, env in (("3-D windows", 9, 3, 3, None), ("1-D windows, polynomial path", 5, 5, 1, "1")):
+for tag, dd, nw, dw, env in (("3-D windows", 9, 3, 3, None), ("1-D windows, polynomial path", 5, 5, 1, "NFFT4GP_B200_POLY1D"),
+                             ("2-D windows, table-free path", 8, 4, 2, "NFFT4GP_B200_POLY2D")):
     Xg = np.ascontiguousarray(X[:dd])
     wing = np.arange(dd, dtype=np.int32)
     if env:
-        os.environ["NFFT4GP_B200_POLY1D"] = env
+        os.environ[env] = "1"
     A = pkg.AdditiveNFFTKernel(Xg, wing, nw, dw, "gaussian")
     assert L.Nfft4GPB200SetSharding(A.h, 1) == 0
     A.build(f, l, mu)
-    os.environ.pop("NFFT4GP_B200_POLY1D", None)
+    if env:
+        os.environ.pop(env, None)
     g = A.grad_matvec(x, 0.7, 0.3, g0)
     y = A.matvec(x, 0.7, 0.3, y0)
     if rank == 0:
@@ -74,6 +76,27 @@ for tag, dd, nw, dw, env in (("3-D windows", 9, 3, 3, None), ("1-D windows, poly
         ok = ok and eg <= 1e-10 and ey <= 1e-10
         B.free()
     A.free()
+# ---- point-block sharding of 2-D windows on the table-free path (every rank: its block of every window, allreduce of the grids)
+X2 = np.ascontiguousarray(X[:8])
+win2 = np.arange(8, dtype=np.int32)
+os.environ["NFFT4GP_B200_POLY2D"] = "1"
+A = pkg.AdditiveNFFTKernel(X2, win2, 4, 2, "matern12")
+assert L.Nfft4GPB200SetSharding(A.h, 2) == 0
+A.build(f, l, mu)
+os.environ.pop("NFFT4GP_B200_POLY2D", None)
+y = A.matvec(x, 0.7, 0.3, y0)
+t = torch.zeros(n, dtype=torch.float64, device="cuda")
+lo, hi = rank * n // world, (rank + 1) * n // world
+t[lo:hi] = torch.from_numpy(y[lo:hi]).cuda()
+dist.all_reduce(t)
+if rank == 0:
+    B = O.OracleAdditiveNFFT(X2, win2, 4, 2, "matern12").build(f, l, mu)
+    r2 = B.matvec(x, 0.7, 0.3, y0)
+    err = float(np.linalg.norm(t.cpu().numpy() - r2) / np.linalg.norm(r2))
+    print(f"mode 2 on {world} GPUs, 2-D windows, table-free path: rel l2 vs oracle {err:.2e}")
+    ok = ok and err <= 1e-10
+    B.free()
+A.free()
 # ---- window sharding: PCG with the allreduce inside the matvec (no CUDA-graph capture of the iteration: pcg_host.c)
 A = pkg.AdditiveNFFTKernel(X, win, 3, 3, "gaussian")
 assert L.Nfft4GPB200SetSharding(A.h, 1) == 0
